@@ -1,0 +1,203 @@
+/*
+ * hcjpeg.h — C ABI of libhcjpeg: a B200-native (sm_100a) baseline-JPEG decode / encode path that is a
+ * drop-in for the software model of hardcamls/video-coding (jpeg/model/src, common/src).
+ *
+ * The reference has no FFI of its own (it is 100 % OCaml); the entry points below are what thin OCaml
+ * `external` stubs bind so that `Hardcaml_jpeg_model.Decoder` / `.Encoder` can run on the GPU.  Each
+ * entry point cites the reference interface (file:line, relative to the reference root) it replaces.
+ * The matching stubs are in video-coding_b200/ocaml/ and described in INTEGRATION.md.
+ *
+ * Conventions: plain C, no exceptions across the boundary, the library never keeps a caller pointer
+ * after a call returns.  Every function returns an hcj_status (0 = ok).  Batched calls also fill a
+ * per-image status array: a bad image never poisons the rest of the batch.  There is NO CPU fallback:
+ * without a CUDA device every compute entry point returns HCJ_ERR_CUDA_*.
+ */
+#ifndef HCJPEG_H
+#define HCJPEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCJ_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes: one per exception the model can raise, plus stated extensions ------------- */
+typedef enum hcj_status {
+  HCJ_OK = 0,
+  HCJ_ERR_UNSUPPORTED_MARKER = -1,   /* decoder.ml:67  "unsupported marker code" */
+  HCJ_ERR_NO_DC_CODE = -2,           /* decoder.ml:92  "Can't find dc code" */
+  HCJ_ERR_NO_AC_CODE = -3,           /* decoder.ml:101 "Can't find ac code" */
+  HCJ_ERR_COEF_INDEX = -4,           /* decoder.ml:136 "coefficient index out of range:" */
+  HCJ_ERR_NO_COMPONENT = -5,         /* decoder.ml:228 "unable to find component identifier" */
+  HCJ_ERR_NO_QUANT_TABLE = -6,       /* decoder.ml:234 "unable to find quantisation table" */
+  HCJ_ERR_NO_HUFFMAN_TABLE = -7,     /* decoder.ml:243 "unable to find huffman table" */
+  HCJ_ERR_NO_FRAME_OR_SCAN = -8,     /* decoder.ml:291 "From start of frame or start of scan marker" */
+  HCJ_ERR_BITS_OUT_OF_BOUNDS = -9,   /* common/src/bitstream_reader.ml:32 "Bitstream_reader out of bounds" */
+  HCJ_ERR_PLANE_BOUNDS = -10,        /* common/src/plane.ml:47-59 "[Plane.get/set] out of bounds" */
+  HCJ_ERR_FRAME_INFER = -11,         /* common/src/frame.ml:44,55 chroma planes mismatch / cannot infer */
+  HCJ_ERR_NEED_3_COMPONENTS = -12,   /* decoder.ml:415-420 get_yuv_frame needs components.(1), .(2) */
+  HCJ_ERR_ENCODER_PARAMS = -13,      /* encoder.ml:274-282 "Failed to find identifier", bin/model.ml:76-82 */
+  /* stated extensions, and inputs on which the model does not terminate */
+  HCJ_ERR_NO_TERMINATOR = -20,       /* decoder.ml:261-281 loops forever when no marker follows the scan */
+  HCJ_ERR_RESTART_COUNT = -21,       /* restart extension: number of RSTn != ceil(MCUs / Ri) - 1 */
+  HCJ_ERR_UNSUPPORTED_GEOMETRY = -22,/* >4 scan components, sampling factor 0 or >4, >10 blocks/MCU, DC category >15, Pq>1 */
+  HCJ_ERR_DC_RANGE = -23,            /* an absolute DC value does not fit the int16 coefficient store */
+  HCJ_ERR_TRUNCATED = -24,           /* decoder.ml:24-29 find_marker spins forever on a truncated header */
+  HCJ_ERR_BAD_HUFFMAN_TABLE = -25,   /* tables.ml:497-499 array index out of bounds (over-subscribed DHT) */
+  HCJ_ERR_BUFFER_TOO_SMALL = -30,
+  HCJ_ERR_INVALID_ARG = -31,
+  HCJ_ERR_OUT_OF_MEMORY = -32,
+  HCJ_ERR_CUDA = -1000               /* -1000 - cudaError_t */
+} hcj_status;
+
+const char *hcj_strerror(int status);
+int hcj_version(void);
+
+/* ---- Decoder.Header (decoder.mli:5-21, decoder.ml:5-71; Markers, markers.ml) ------------------ */
+#define HCJ_MAX_COMPONENTS 4
+#define HCJ_MAX_TABLE_SEGMENTS 64
+
+typedef struct hcj_component { /* Markers.Component.t, markers.ml:6-13 */
+  int identifier, horizontal_sampling_factor, vertical_sampling_factor, quantization_table_identifier;
+} hcj_component;
+
+typedef struct hcj_scan_component { /* Markers.Scan_component.t, markers.ml:75-82 */
+  int selector, dc_coef_selector, ac_coef_selector;
+} hcj_scan_component;
+
+typedef struct hcj_dqt { /* Markers.Dqt.t, markers.ml:153-160 */
+  int length, element_precision, table_identifier;
+  int elements[64]; /* file (zig-zag) order */
+} hcj_dqt;
+
+typedef struct hcj_dht { /* Markers.Dht.t, markers.ml:200-208 */
+  int length, table_class, destination_identifier;
+  int lengths[16];
+  int nvalues;
+  uint8_t values[256];
+} hcj_dht;
+
+typedef struct hcj_header { /* Decoder.Header.t, decoder.ml:6-13 */
+  int has_frame; /* frame : Sof.t option */
+  int sof_length, sample_precision, width, height, number_of_components;
+  hcj_component components[HCJ_MAX_COMPONENTS];
+  int has_scan; /* scan : Sos.t option */
+  int sos_length, number_of_image_components;
+  hcj_scan_component scan_components[HCJ_MAX_COMPONENTS];
+  int start_of_predictor_selection, end_of_predictor_selection;
+  int successive_approximation_bit_high, successive_approximation_bit_low;
+  int has_restart_interval; /* restart_interval : Dri.t option */
+  int dri_length, restart_interval;
+  int n_quant_tables; /* list order: most recently parsed first (decoder.ml:51) */
+  hcj_dqt quant_tables[HCJ_MAX_TABLE_SEGMENTS];
+  int n_huffman_tables; /* likewise (decoder.ml:55) */
+  hcj_dht huffman_tables[HCJ_MAX_TABLE_SEGMENTS];
+  int64_t scan_byte_pos; /* Bits.bit_pos / 8 after the SOS header: first entropy-coded byte */
+} hcj_header;
+
+/* Decoder.Header.decode : Bits.t -> Header.t (decoder.ml:37-70).  Host only. */
+int hcj_header_decode(const uint8_t *jpeg, size_t len, hcj_header *out);
+
+/* Geometry fixed by Decoder.init (decoder.ml:304-345) and decode_seq (:374-383).  Host only. */
+typedef struct hcj_frame_info {
+  int width, height, ncomp;
+  int chroma; /* 420 / 422 / 444 as inferred by Frame.of_planes (frame.ml:42-61); 0 if not a YUV frame */
+  int hs[HCJ_MAX_COMPONENTS], vs[HCJ_MAX_COMPONENTS];
+  int decoded_width[HCJ_MAX_COMPONENTS], decoded_height[HCJ_MAX_COMPONENTS]; /* padded planes */
+  int actual_width[HCJ_MAX_COMPONENTS], actual_height[HCJ_MAX_COMPONENTS];   /* cropped planes */
+  int mcus_wide, mcus_high, blocks_per_mcu;
+  int64_t nblocks;
+  int restart_interval; /* 0 when absent */
+  size_t yuv_bytes;     /* Frame.output size: cropped planar Y,U,V (0 if chroma == 0) */
+  size_t planes_bytes;  /* get_decoded_planes: padded planes, scan order */
+  size_t rgb_bytes;     /* width*height*3 (0 if chroma == 0) */
+} hcj_frame_info;
+
+int hcj_frame_info_get(const uint8_t *jpeg, size_t len, hcj_frame_info *out);
+
+/* ---- context: one per GPU (the model's `Decoder.t` / `Encoder.t` values own no device state) -- */
+typedef struct hcj_ctx hcj_ctx;
+
+/* `cuda_stream` is a cudaStream_t (or NULL for a private stream); all work of this context is issued on it. */
+int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out);
+void hcj_ctx_destroy(hcj_ctx *ctx);
+int hcj_ctx_synchronize(hcj_ctx *ctx);
+/* Pinned host memory for zero-staging transfers (callers may also pass ordinary memory everywhere). */
+void *hcj_host_alloc(size_t bytes);
+void hcj_host_free(void *p);
+
+/* ---- decode --------------------------------------------------------------------------------- */
+typedef enum hcj_out_mode {
+  HCJ_OUT_YUV = 0,    /* Decoder.get_yuv_frame -> Frame.output: cropped planar Y,U,V (decoder.ml:403-420, frame.ml:66-70) */
+  HCJ_OUT_PLANES = 1, /* Decoder.get_decoded_planes: padded planes in scan order (decoder.ml:399-401) */
+  HCJ_OUT_RGB24 = 2   /* extension: Planar_444 up-sampling (tools/src/planar_444.ml:25-33,82-103) + stated YCbCr->RGB */
+} hcj_out_mode;
+
+#define HCJ_FLAG_RESTART_EXT 1u /* honour DRI / RSTn (T.81 semantics).  Without it: pure model semantics (decoder.ml:261-281) */
+#define HCJ_FLAG_DEFAULT HCJ_FLAG_RESTART_EXT
+
+/* Decoder.decode_a_frame (decoder.ml:422-427) for n independent images; host buffers in and out.
+ * out[i] must hold at least the size hcj_frame_info_get reports for `mode`.  Returns the first
+ * non-image error (CUDA, arguments); per-image results are in status[i]. */
+int hcj_decode_batch(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                     uint8_t *const *out, const size_t *out_capacity, int *status);
+
+/* The same in three steps, for pipelines that keep data resident in HBM. */
+typedef struct hcj_batch hcj_batch;
+/* Header.decode + init for every image, then upload (H2D) of the compressed bytes and tables. */
+int hcj_batch_create(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                     int *status, hcj_batch **out);
+/* Decoder.decode for the whole batch: kernels only, asynchronous on the context's stream. */
+int hcj_batch_decode(hcj_ctx *ctx, hcj_batch *b);
+/* D2H of the outputs and of the per-image statuses; synchronises. */
+int hcj_batch_fetch(hcj_ctx *ctx, hcj_batch *b, uint8_t *const *out, const size_t *out_capacity, int *status);
+/* Device pointer / size of image i's output (valid until the batch is destroyed). */
+int hcj_batch_device_output(hcj_batch *b, int i, void **dptr, size_t *bytes);
+int hcj_batch_count_kernels(const hcj_batch *b); /* kernels hcj_batch_decode launches */
+void hcj_batch_destroy(hcj_ctx *ctx, hcj_batch *b);
+
+/* Debug taps mirroring Decoder.For_testing (decoder.mli:62-85). */
+/* Component.coefs for every block of image i in decode_seq order: int16, zig-zag, DC *resolved* (absolute). */
+int hcj_batch_fetch_coefficients(hcj_ctx *ctx, hcj_batch *b, int i, int16_t *coefs, size_t capacity_blocks);
+/* For_testing.extract_entropy_coded_bits (decoder.ml:261-281): destuffed entropy-coded segment of image i. */
+int hcj_batch_fetch_entropy(hcj_ctx *ctx, hcj_batch *b, int i, uint8_t *out, size_t capacity, size_t *len);
+/* dequantize + Dct.Chen.inverse_8x8 + recon (decoder.ml:142-149,213-224; dct.ml:100-107) on caller-provided
+ * zig-zag blocks (DC absolute): out = nblocks*64 reconstructed samples, block-major (Component.recon). */
+int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const uint16_t quant_table[64], uint8_t *out);
+
+/* ---- encode --------------------------------------------------------------------------------- */
+/* Encoder.encode_420 / encode_422 / encode_444 (encoder.ml:522-541) for n frames of identical
+ * geometry.  yuv[i]: planar Y,U,V as Frame.input reads it (frame.ml:72-76).  chroma: 420/422/444.
+ * restart_interval 0 reproduces the model byte-for-byte; >0 is the stated DRI/RSTn extension. */
+int hcj_encode_batch(hcj_ctx *ctx, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
+                     int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
+                     int *status);
+size_t hcj_encode_bound(int width, int height, int chroma); /* worst-case bytes of one encoded frame */
+/* Encoder.write_headers (encoder.ml:371-418).  Host only. */
+int hcj_write_headers(int width, int height, int chroma, int quality, int restart_interval, uint8_t *out,
+                      size_t capacity, size_t *len);
+/* Block.quant (encoder.ml:56-66): quantised zig-zag blocks of one frame in encode_seq order. */
+int hcj_encode_quantized(hcj_ctx *ctx, const uint8_t *yuv, int width, int height, int chroma, int quality,
+                         int16_t *quant, size_t capacity_blocks);
+
+/* ---- on-device frame tools (tools/src) ------------------------------------------------------- */
+/* Ocompare.square_error / max_difference per plane (tools/src/ocompare.ml:8-52) of two host frames. */
+int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,
+                       int *max_difference);
+
+/* ---- timing helpers for benchmarks --------------------------------------------------------------- */
+/* One decode pass with a CUDA event between consecutive stages (on the context's stream); fills
+ * ms[0..*nstages) in launch order and synchronises.  Stage names: hcj_decode_stage_name(i). */
+int hcj_batch_decode_stages(hcj_ctx *ctx, hcj_batch *b, float *ms, int capacity, int *nstages);
+const char *hcj_decode_stage_name(int i);
+/* ms between two points on the context's stream */
+int hcj_timer_start(hcj_ctx *ctx);
+int hcj_timer_stop(hcj_ctx *ctx, float *ms); /* synchronises */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCJPEG_H */

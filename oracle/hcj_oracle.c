@@ -141,12 +141,14 @@ static void sof_decode(orc_bits *b, orc_sof *s) { /* markers.ml:49-59 */
   s->height = (int)get(b, 16);
   s->width = (int)get(b, 16);
   s->number_of_components = (int)get(b, 8);
+  if (s->number_of_components > 4) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY); /* stated domain limit */
   for (int i = 0; i < s->number_of_components; i++) component_decode(b, &s->components[i]);
 }
 static void sos_decode(orc_bits *b, orc_sos *s) { /* markers.ml:84-89,111-129 */
   s->present = 1;
   s->length = (int)get(b, 16);
   s->number_of_image_components = (int)get(b, 8);
+  if (s->number_of_image_components > 4) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY); /* stated domain limit */
   for (int i = 0; i < s->number_of_image_components; i++) {
     s->scan_components[i].selector = (int)get(b, 8);
     s->scan_components[i].dc_coef_selector = (int)get(b, 4);
@@ -174,6 +176,7 @@ static void dht_decode(orc_bits *b, orc_dht *h) { /* markers.ml:210-220: ONE tab
     h->lengths[i] = (int)get(b, 8);
     total += h->lengths[i];
   }
+  if (total > 256) orc_raise(ORC_ERR_BAD_HUFFMAN_TABLE); /* stated domain limit: more symbols than byte values */
   h->nvalues = total;
   for (int i = 0; i < total; i++) h->values[i] = (int)get(b, 8);
 }

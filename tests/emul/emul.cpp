@@ -1,0 +1,282 @@
+// emul.cpp — TEST INFRASTRUCTURE: compiles the kernels' per-thread building blocks (hcj_device.cuh)
+// and the host half (hcj_host.cpp) with g++ and drives them with plain loops that stand in for the CUDA
+// thread grid.  It lets `pytest -m "not gpu"` check the device logic against the oracle without a GPU.
+// Nothing in the product links or calls this file.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "hcj_device.cuh"
+#include "hcj_host.h"
+
+using namespace hcjdev;
+
+namespace {
+
+struct HostTables {
+  std::vector<hcj::HuffLut> luts;  // [comp][dc/ac]
+  Tables tab[HCJ_MAX_COMP];
+};
+
+int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj::ImagePlan *plan, HostTables *ht) {
+  int st = hcj::header_decode(jpeg, len, h);
+  if (st) return st;
+  st = hcj::plan_image(*h, flags, plan);
+  if (st) return st;
+  ht->luts.resize(plan->info.ncomp * 2);
+  for (int c = 0; c < plan->info.ncomp; c++) {
+    st = hcj::build_lut(h->huffman_tables[plan->dc_index[c]], &ht->luts[c * 2]);
+    if (st) return st;
+    st = hcj::build_lut(h->huffman_tables[plan->ac_index[c]], &ht->luts[c * 2 + 1]);
+    if (st) return st;
+  }
+  for (int c = 0; c < plan->info.ncomp; c++) {
+    Tables &t = ht->tab[c];
+    t.dc_primary = ht->luts[c * 2].primary.data();
+    t.dc_full = ht->luts[c * 2].full.data();
+    t.dc_max_bits = ht->luts[c * 2].max_bits;
+    t.ac_primary = ht->luts[c * 2 + 1].primary.data();
+    t.ac_full = ht->luts[c * 2 + 1].full.data();
+    t.ac_max_bits = ht->luts[c * 2 + 1].max_bits;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// k_idct / k_idct_blocks body.
+void emu_reconstruct_blocks(const int16_t *coefs, int64_t n, const uint16_t *qt, int force_wide, uint8_t *out) {
+  for (int64_t i = 0; i < n; i++) reconstruct_block(coefs + i * 64, qt, force_wide != 0, out + i * 64);
+}
+
+// Same, but forcing the 32-bit path regardless of the guard: used to probe where int32 stops being exact.
+void emu_idct32_unguarded(const int32_t *dequant_natural, int64_t n, int32_t *out) {
+  for (int64_t i = 0; i < n; i++) {
+    int32_t v[64];
+    memcpy(v, dequant_natural + i * 64, sizeof(v));
+    idct_8x8<int32_t>(v);
+    memcpy(out + i * 64, v, sizeof(v));
+  }
+}
+
+int emu_idct_l1_limit() { return HCJ_IDCT_L1_LIMIT; }
+
+// k_huff_restart: one "thread" per segment.  `entropy` = destuffed bytes, seg_off[nseg + 1] byte offsets.
+int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const uint8_t *entropy, const uint32_t *seg_off,
+                        uint32_t nseg, int16_t *coefs /* zeroed, nblocks * 64 */) {
+  hcj_header *h = new hcj_header;
+  hcj::ImagePlan plan;
+  HostTables ht;
+  int st = prepare(jpeg, (size_t)len, flags, h, &plan, &ht);
+  delete h;
+  if (st) return st;
+  const hcj_frame_info &f = plan.info;
+  uint32_t nmcu = (uint32_t)(f.mcus_wide * f.mcus_high), bpm = (uint32_t)f.blocks_per_mcu;
+  uint32_t ri = f.restart_interval ? (uint32_t)f.restart_interval : nmcu;
+  std::vector<uint32_t> words((seg_off[nseg] + 15) / 4 + 4, 0);
+  memcpy(words.data(), entropy, seg_off[nseg]);
+  for (uint32_t seg = 0; seg < nseg; seg++) {  // <- thread index
+    uint32_t seg_bits = (seg_off[seg + 1] - seg_off[seg]) * 8;
+    uint32_t mcu0 = seg * ri, mcu1 = mcu0 + ri < nmcu ? mcu0 + ri : nmcu;
+    BitReader br;
+    br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
+    int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+    int16_t *out = coefs + (int64_t)mcu0 * bpm * 64;
+    for (uint32_t mcu = mcu0; mcu < mcu1; mcu++)
+      for (uint32_t k = 0; k < bpm; k++, out += 64) {
+        int comp = plan.blk_comp[k];
+        int err = decode_block_exact(br, ht.tab[comp], seg_bits, pred[comp], out);
+        if (err) return err;
+      }
+  }
+  return 0;
+}
+
+// k_huff_spec: T emulated threads per chunk, subsequences of S bits.  Returns status; rounds_out gets the
+// largest number of fix-point rounds any chunk needed.
+int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entropy, uint32_t ent_len, int T, uint32_t S,
+                           int16_t *coefs /* zeroed */, int *rounds_out) {
+  hcj_header *h = new hcj_header;
+  hcj::ImagePlan plan;
+  HostTables ht;
+  int st = prepare(jpeg, (size_t)len, 0, h, &plan, &ht);
+  delete h;
+  if (st) return st;
+  const hcj_frame_info &f = plan.info;
+  std::vector<uint32_t> words((ent_len + 15) / 4 + 4, 0);
+  memcpy(words.data(), entropy, ent_len);
+  uint8_t blk_comp[HCJ_MAX_BPM + 2];
+  for (int k = 0; k < f.blocks_per_mcu; k++) blk_comp[k] = (uint8_t)plan.blk_comp[k];
+  ScanCtx sc;
+  sc.words = words.data();
+  sc.total_bits = ent_len * 8;
+  sc.bpm = (uint32_t)f.blocks_per_mcu;
+  sc.blk_comp = blk_comp;
+  for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
+  const uint32_t L = sc.total_bits;
+  const int64_t nblocks = f.nblocks;
+  int max_rounds = 0;
+  if (L <= 16) {
+    BitReader br;
+    br.init(sc.words, 0, L);
+    int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+    for (int64_t blk = 0; blk < nblocks; blk++) {
+      int comp = blk_comp[blk % sc.bpm];
+      int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+      if (err) return err;
+    }
+    return 0;
+  }
+  struct Carry {
+    uint32_t p = 0, cz = 0;
+    int64_t nstart = 0;
+    int32_t dc[HCJ_MAX_COMP] = {0, 0, 0, 0};
+  } carry;
+  const uint32_t nsub = (L + S - 1) / S;
+  unsigned long long err_key = ~0ull;
+  for (uint32_t base = 0; base < nsub; base += T) {
+    const int nact = (int)(nsub - base < (uint32_t)T ? nsub - base : (uint32_t)T);
+    std::vector<SubResult> r(nact);
+    std::vector<uint32_t> sp(nact), scz(nact), endp(nact), endcz(nact), hi(nact);
+    // phase A
+    for (int t = 0; t < nact; t++) {
+      uint32_t i = base + t, lo = i * S;
+      hi[t] = lo + S < L ? lo + S : L;
+      sp[t] = t == 0 ? carry.p : lo;
+      scz[t] = t == 0 ? carry.cz : 0;
+      subseq_sync(sc, sp[t], scz[t], hi[t], r[t]);
+      endp[t] = r[t].p;
+      endcz[t] = r[t].cz;
+    }
+    // phase B (Jacobi rounds: all threads read the ends of the previous round)
+    int rounds = 0;
+    for (;;) {
+      std::vector<uint32_t> np(endp), ncz(endcz);
+      bool any = false;
+      for (int t = 0; t < nact; t++) {
+        uint32_t nsp = t == 0 ? carry.p : endp[t - 1], nscz = t == 0 ? carry.cz : endcz[t - 1];
+        if (nsp != sp[t] || nscz != scz[t]) {
+          sp[t] = nsp;
+          scz[t] = nscz;
+          subseq_sync(sc, nsp, nscz, hi[t], r[t]);
+          if (r[t].p != endp[t] || r[t].cz != endcz[t]) {
+            any = true;
+            np[t] = r[t].p;
+            ncz[t] = r[t].cz;
+          }
+        }
+      }
+      endp = np;
+      endcz = ncz;
+      rounds++;
+      if (!any) break;
+    }
+    if (rounds > max_rounds) max_rounds = rounds;
+    // phase C
+    int64_t ex_n = 0;
+    int32_t ex_dc[HCJ_MAX_COMP] = {0, 0, 0, 0};
+    for (int t = 0; t < nact; t++) {
+      int32_t pred[HCJ_MAX_COMP];
+      for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + ex_dc[k];
+      int64_t blk = carry.nstart + ex_n - 1;
+      bool last = base + t == nsub - 1;
+      uint32_t err_pos = 0;
+      int err = subseq_write(sc, sp[t], scz[t], last ? 0xffffffffu : hi[t], blk, pred, nblocks, coefs, &err_pos);
+      unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
+      if (err && key < err_key) err_key = key;  // the kernel's atomicMin
+      ex_n += r[t].nstart;
+      for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] += r[t].dcsum[k];
+    }
+    carry.p = r[nact - 1].p;
+    carry.cz = r[nact - 1].cz;
+    carry.nstart += ex_n;
+    for (int k = 0; k < HCJ_MAX_COMP; k++) carry.dc[k] += ex_dc[k];
+  }
+  if (rounds_out) *rounds_out = max_rounds;
+  return err_key == ~0ull ? 0 : -(int)(err_key & 0xff);
+}
+
+// k_fdct_quant body for one 8x8 block of pixels (row-major), quant table in zig-zag order.
+void emu_fdct_quant(const uint8_t *pix, const uint16_t *qt, int16_t *out_zigzag, int32_t *out_fdct) {
+  int32_t v[64];
+  for (int i = 0; i < 64; i++) v[i] = (int32_t)pix[i] - 128;
+  fdct_8x8(v);
+  if (out_fdct) memcpy(out_fdct, v, sizeof(v));
+  for (int z = 0; z < 64; z++) {
+    uint32_t recip = (uint32_t)((1ull << 32) / (4u * qt[z])) + 1u;
+    out_zigzag[z] = (int16_t)quantize(v[zigzag_inverse(z)], qt[z], recip);
+  }
+}
+
+// Exhaustive check of the reciprocal quantiser against truncating division; returns mismatches.
+int64_t emu_quantize_check(int fmax) {
+  int64_t bad = 0;
+  for (uint32_t q = 1; q <= 255; q++) {
+    uint32_t recip = (uint32_t)((1ull << 32) / (4u * q)) + 1u;
+    for (int f = -fmax; f <= fmax; f++) {
+      int32_t want = f < 0 ? (f - (int)q * 2) / ((int)q * 4) : (f + (int)q * 2) / ((int)q * 4);
+      if (quantize(f, q, recip) != want) bad++;
+    }
+  }
+  return bad;
+}
+
+// k_block_bits / k_pack symbol stream for a whole frame of quantised blocks -> entropy-coded bytes with
+// stuffing, 1-fill and (optionally) RSTn, i.e. everything between the SOS header and EOI.
+struct ByteWriter {
+  std::vector<uint8_t> *out;
+  uint64_t acc = 0;
+  int nacc = 0;
+  void operator()(uint32_t bits, uint32_t n) {
+    if (!n) return;
+    acc = (acc << n) | (bits & ((1u << n) - 1u));
+    nacc += (int)n;
+    while (nacc >= 8) {
+      uint8_t b = (uint8_t)(acc >> (nacc - 8));
+      out->push_back(b);
+      if (b == 0xff) out->push_back(0);
+      nacc -= 8;
+    }
+  }
+  void pad() {
+    if (nacc) (*this)((1u << (8 - nacc)) - 1u, (uint32_t)(8 - nacc));
+  }
+};
+
+int64_t emu_entropy_encode(const int16_t *quant, int width, int height, int chroma, int restart_interval, uint8_t *out,
+                           int64_t cap) {
+  hcj::EncodePlan p;
+  if (hcj::plan_encode(width, height, chroma, 75, restart_interval, &p)) return -1;
+  uint32_t dc[2][16], ac[2][256];
+  hcj::encoder_tables(0, 2, dc[0], ac[0]);
+  hcj::encoder_tables(1, 3, dc[1], ac[1]);
+  std::vector<uint8_t> bytes;
+  ByteWriter w;
+  w.out = &bytes;
+  int32_t pred[3] = {0, 0, 0};
+  int64_t nmcu = (int64_t)p.mcus_wide * p.mcus_high;
+  int rst = 0;
+  for (int64_t mcu = 0; mcu < nmcu; mcu++) {
+    if (restart_interval && mcu && mcu % restart_interval == 0) {
+      w.pad();
+      bytes.push_back(0xff);
+      bytes.push_back((uint8_t)(0xd0 + (rst++ & 7)));
+      pred[0] = pred[1] = pred[2] = 0;
+    }
+    for (int k = 0; k < p.bpm; k++) {
+      const int16_t *q = quant + (mcu * p.bpm + k) * 64;
+      int c = p.blk_comp[k];
+      if (!encode_block_fields(q, (int32_t)q[0] - pred[c], dc[c ? 1 : 0], ac[c ? 1 : 0], w)) return -2;
+      pred[c] = q[0];
+    }
+  }
+  w.pad();
+  if ((int64_t)bytes.size() > cap) return -3;
+  memcpy(out, bytes.data(), bytes.size());
+  return (int64_t)bytes.size();
+}
+
+}  // extern "C"

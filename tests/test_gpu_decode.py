@@ -1,0 +1,237 @@
+"""GPU parity tests of the decode path: every call goes through the C ABI (libhcjpeg.so) and is compared
+bit-for-bit with the CPU oracle on the same inputs, plus the reference's golden fixtures."""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def hcj():
+    import hcjpeg
+
+    assert hcjpeg.lib() is not None
+    return hcjpeg
+
+
+@pytest.fixture(scope="module")
+def ctx(hcj):
+    c = hcj.Context(0)
+    yield c
+    c.close()
+
+
+def oracle_rgb(orc, dec):
+    y, u, v = orc.upsample_to_444(dec.cropped[:3], dec.chroma)
+    h, w = y.shape
+
+    def fit(p):  # Planar_444 leaves the odd last column / row of a fresh (zero) plane untouched
+        out = np.zeros((h, w), np.uint8)
+        out[: min(h, p.shape[0]), : min(w, p.shape[1])] = p[:h, :w]
+        return out
+
+    return orc.ycbcr_to_rgb24(y, fit(u), fit(v))
+
+
+# ---- config 0: the reference's own fixtures -----------------------------------------------------------
+def test_mouse480_golden(hcj, ctx, orc, data):
+    """jpeg/test/mouse-decode.t + SURVEY B.2 hashes, through the model-shaped mirror."""
+    from hcjpeg.model import Decoder
+
+    jpg = data("Mouse480.jpg")
+    frame = Decoder.decode_a_frame(jpg, ctx)
+    out = io.BytesIO()
+    frame.output(out)
+    assert sha(out.getvalue()) == "f17981ec39aee6fb10ea5fa078b397ba4df460cab8eadbbce98a916f21b2b97d"
+    assert out.getvalue() == orc.decode(jpg).yuv()
+    assert frame.chroma_subsampling == 420 and (frame.width, frame.height) == (480, 320)
+    ent = Decoder.For_testing.extract_entropy_coded_bits(jpg, ctx)
+    assert len(ent) == 6281 and sha(ent) == "5daa43a6323e8df1e2b04baff0f22770c85e60039693dc7bbf10a59272aac56a"
+    coefs = Decoder.For_testing.coefficients(jpg, ctx)
+    assert sha(coefs.astype("<i2").tobytes()) == "1f750d078cb2a5a395cd24b6b34befce4d4078efbb96c1caea01fcc5ae9d1356"
+    d = Decoder(jpg, ctx)
+    planes = d.get_decoded_planes()
+    want = orc.decode(jpg).planes
+    assert [p.plane.shape for p in planes] == [w.shape for w in want]
+    assert all(np.array_equal(p.plane, w) for p, w in zip(planes, want))
+
+
+def test_mini_jpg_golden(hcj, ctx, orc, data):
+    outs, st = ctx.decode_batch([data("mini.jpg")])
+    assert st == [0]
+    assert sha(outs[0]) == "0e85b2f317212070b18c48f0190d5ffeb80913aa9447755c9407ff4bcb6098b6"
+
+
+def test_cram_psnr_flow(hcj, ctx, orc, goldens, data):
+    """jpeg/test/model-encode-and-decode.t re-run as oracle-encode -> GPU-decode: exact SSE goldens."""
+    sse = {(420, 95): (5605, 1404, 1166), (420, 50): (64890, 9410, 7446), (420, 30): (113632, 11096, 8747),
+           (422, 75): (32263, 8169, 6414), (444, 75): (32263, 10908, 9357)}
+    for run in goldens["cram_encode_decode"]["runs"]:
+        chroma, q = int(run["chroma"]), run["quality"]
+        src = data(run["input"])
+        outs, st = ctx.decode_batch([orc.encode(src, 64, 64, chroma, q)])
+        assert st == [0]
+        a, b = np.frombuffer(src, np.uint8), outs[0]
+        y = 64 * 64
+        c = (len(src) - y) // 2
+        got = tuple(int(((a[s].astype(int) - b[s].astype(int)) ** 2).sum()) for s in (slice(0, y), slice(y, y + c), slice(y + c, y + 2 * c)))
+        assert got == sse[(chroma, q)]
+        dev_sse, dev_max = ctx.compare_planes(a[:y], b[:y])
+        assert dev_sse == got[0] and dev_max == int(np.abs(a[:y].astype(int) - b[:y].astype(int)).max())
+
+
+# ---- oracle parity on seeded synthetic images -----------------------------------------------------------
+CASES = [
+    # (chroma, quality, w, h, restart_interval)
+    (420, 75, 256, 192, 0), (420, 75, 256, 192, 8), (422, 50, 200, 120, 0), (444, 95, 160, 96, 0),
+    (420, 10, 333, 77, 0), (420, 95, 52, 44, 0), (444, 75, 17, 9, 0), (420, 75, 16, 16, 1),
+    (422, 75, 130, 70, 3), (444, 100, 64, 64, 2), (420, 1, 96, 80, 0), (420, 75, 8, 8, 0),
+]
+
+
+@pytest.mark.parametrize("mode_name", ["yuv", "planes", "rgb"])
+def test_batch_matches_oracle(hcj, ctx, orc, mode_name):
+    mode = {"yuv": hcj.OUT_YUV, "planes": hcj.OUT_PLANES, "rgb": hcj.OUT_RGB24}[mode_name]
+    jpgs = [orc.encode(synth.frame(100 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(CASES)]
+    outs, st = ctx.decode_batch(jpgs, mode)
+    assert st == [0] * len(jpgs)
+    for jpg, out, case in zip(jpgs, outs, CASES):
+        dec = orc.decode(jpg)
+        if mode == hcj.OUT_YUV:
+            want = dec.yuv()
+        elif mode == hcj.OUT_PLANES:
+            want = b"".join(p.tobytes() for p in dec.planes)
+        else:
+            want = oracle_rgb(orc, dec).tobytes()
+        assert bytes(out) == want, case
+
+
+def test_coefficients_and_entropy_taps(hcj, ctx, orc):
+    jpgs = [orc.encode(synth.frame(200 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(CASES[:6])]
+    with ctx.batch(jpgs, hcj.OUT_PLANES) as b:
+        b.decode()
+        for i, jpg in enumerate(jpgs):
+            dec = orc.decode(jpg, want_blocks=True)
+            assert np.array_equal(b.coefficients(i), dec.coefs_abs_dc().astype(np.int16))
+            assert len(b.entropy(i)) == dec.entropy_len
+        assert b.kernels() >= 3
+
+
+def test_restart_extension_equivalence(hcj, ctx, orc):
+    """Stated extension pin: decode(DRI stream) == pure-model decode of the same blocks coded without DRI."""
+    w, h = 208, 112
+    yuv = synth.frame(7, w, h, 420)
+    twin = orc.decode(orc.encode(yuv, w, h, 420, 75), restart_ext=False).yuv()
+    for ri in (1, 5, 8, 1000):
+        outs, st = ctx.decode_batch([orc.encode(yuv, w, h, 420, 75, restart_interval=ri)])
+        assert st == [0] and bytes(outs[0]) == twin
+    # pure model semantics (flag off) on a DRI stream: the model stops at RST0 and decodes garbage; so do we
+    jpg = orc.encode(yuv, w, h, 420, 75, restart_interval=8)
+    outs, st = ctx.decode_batch([jpg], flags=0)
+    try:
+        want = orc.decode(jpg, restart_ext=False).yuv()
+        assert st == [0] and bytes(outs[0]) == want
+    except orc.OracleError as e:
+        assert st == [e.status]
+
+
+def test_pillow_streams(hcj, ctx, orc):
+    """Third-party (libjpeg-turbo) streams: custom Huffman tables, restart markers."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    base = np.clip(rng.normal(128, 40, (120, 168, 3)), 0, 255).astype(np.uint8)
+    img = Image.fromarray(base)
+    jpgs = []
+    for kw in (dict(subsampling=2), dict(subsampling=0, optimize=True), dict(subsampling=2, restart_marker_blocks=3),
+               dict(subsampling=1, quality=95, optimize=True), dict(subsampling=2, quality=30, restart_marker_blocks=1)):
+        buf = io.BytesIO()
+        img.save(buf, "JPEG", **kw)
+        jpgs.append(buf.getvalue())
+    outs, st = ctx.decode_batch(jpgs)
+    for jpg, out, s in zip(jpgs, outs, st):
+        try:
+            want = orc.decode(jpg).yuv()
+        except orc.OracleError as e:
+            assert s == e.status
+            continue
+        assert s == 0 and bytes(out) == want
+
+
+def test_corrupt_streams_do_not_poison_batch(hcj, ctx, orc, data):
+    good = data("Mouse480.jpg")
+    start = orc.header_decode(good).scan_bit_pos // 8
+    rng = np.random.default_rng(11)
+    batch = [good]
+    for trial in range(24):
+        bad = bytearray(good)
+        for _ in range(3):
+            v = int(rng.integers(0, 255))
+            bad[int(rng.integers(start, len(bad) - 2))] = v if v != 0xFF else 0x7F
+        batch.append(bytes(bad))
+    batch += [good[:100], good[: len(good) - 2], b"", good[:2] + b"\xff\xc2" + good[4:], good]
+    outs, st = ctx.decode_batch(batch)
+    want_good = orc.decode(good).yuv()
+    assert st[0] == 0 and st[-1] == 0 and bytes(outs[0]) == want_good and bytes(outs[-1]) == want_good
+    statuses = set()
+    for jpg, out, s in zip(batch, outs, st):
+        try:
+            want, ws = orc.decode(jpg).yuv(), 0
+        except orc.OracleError as e:
+            want, ws = None, e.status
+        if s == -23 or ws == -23:
+            continue
+        assert s == ws, (s, ws)
+        statuses.add(s)
+        if ws == 0:
+            assert bytes(out) == want
+    assert len(statuses) >= 3
+
+
+def test_idct_blocks_tap(hcj, ctx, orc):
+    rng = np.random.default_rng(6)
+    qt = orc.quant_scale(False, 50).astype(np.uint16)
+    coefs = np.where(rng.random((5000, 64)) < 0.2, rng.integers(-300, 300, (5000, 64)), 0).astype(np.int16)
+    coefs[:, 0] = rng.integers(-1024, 1024, 5000)
+    coefs[-50:] = rng.integers(-32768, 32767, (50, 64))  # far above the int32 guard: 64-bit path
+    got = ctx.idct_blocks(coefs, qt)
+    inv = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+    for b in list(range(0, 5000, 13)) + list(range(4950, 5000)):
+        d = np.zeros(64, np.int64)
+        d[inv] = coefs[b].astype(np.int64) * qt
+        want = np.clip(orc.chen_inverse(d), -128, 127) + 128
+        assert got[b].tolist() == want.tolist(), b
+
+
+# ---- full-size configurations ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ri", [0, 8])
+def test_1080p_420_full_size(hcj, ctx, orc, ri):
+    """BASELINE configs 2/3 at full size: a handful of distinct 1080p images against the oracle, then a
+    larger batch checked through a size-independent property (identical inputs -> identical outputs,
+    distinct inputs -> the oracle's checksum of checksums)."""
+    w, h = 1920, 1080
+    uniq = [orc.encode(synth.frame(2000 + i, w, h, 420), w, h, 420, 75, restart_interval=ri) for i in range(3)]
+    want = [sha(orc.decode(j).yuv()) for j in uniq]
+    batch = [uniq[i % 3] for i in range(48)]
+    outs, st = ctx.decode_batch(batch)
+    assert st == [0] * 48
+    assert [sha(o) for o in outs] == [want[i % 3] for i in range(48)]
+
+
+def test_4k_444_rgb_full_size(hcj, ctx, orc):
+    """BASELINE config 4: 3840x2160 4:4:4 q95 -> RGB24."""
+    w, h = 3840, 2160
+    jpg = orc.encode(synth.frame(4000, w, h, 444), w, h, 444, 95)
+    outs, st = ctx.decode_batch([jpg, jpg], hcj.OUT_RGB24)
+    assert st == [0, 0]
+    want = oracle_rgb(orc, orc.decode(jpg)).tobytes()
+    assert bytes(outs[0]) == want and bytes(outs[1]) == want

@@ -1,0 +1,115 @@
+"""GPU parity tests of the encoder mirror: byte-identical files versus the oracle / the reference's
+mini.jpg, through the C ABI."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def hcj():
+    import hcjpeg
+
+    assert hcjpeg.lib() is not None
+    return hcjpeg
+
+
+@pytest.fixture(scope="module")
+def ctx(hcj):
+    c = hcj.Context(0)
+    yield c
+    c.close()
+
+
+def test_mini_jpg_byte_identity(hcj, ctx, data):
+    """jpeg/test_data/mini.jpg == Encoder.encode_420 mini64x64.420 q75, via the model-shaped mirror."""
+    from hcjpeg.model import Encoder, Frame, Writer
+
+    frame = Frame.frombytes(data("mini64x64.420"), 420, 64, 64)
+    writer = Writer.create()
+    Encoder.encode_420(frame=frame, quality=75, writer=writer, ctx=ctx)
+    assert writer.get_buffer() == data("mini.jpg")
+
+
+def test_survey_hashes(hcj, ctx, data):
+    from test_oracle_goldens import SURVEY_HASHES
+
+    for (chroma, q), (n, h) in sorted(SURVEY_HASHES.items()):
+        outs, st = ctx.encode_batch([data("mini64x64.%d" % chroma)], 64, 64, chroma, q)
+        assert st == [0] and (len(outs[0]), sha(outs[0])) == (n, h), (chroma, q)
+
+
+CASES = [
+    # (chroma, quality, w, h, restart_interval)
+    (420, 75, 256, 192, 0), (420, 75, 256, 192, 8), (422, 50, 200, 120, 0), (444, 95, 160, 96, 0),
+    (420, 10, 336, 80, 0), (420, 95, 52, 44, 0), (444, 75, 17, 9, 0), (420, 75, 16, 16, 1),
+    (422, 75, 130, 70, 3), (444, 100, 64, 64, 2), (420, 1, 96, 80, 0), (420, 100, 64, 48, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_encode_matches_oracle(hcj, ctx, orc, case):
+    chroma, q, w, h, ri = case
+    frames = [synth.frame(300 + i, w, h, chroma) for i in range(3)]
+    outs, st = ctx.encode_batch(frames, w, h, chroma, q, ri)
+    assert st == [0, 0, 0]
+    for f, o in zip(frames, outs):
+        assert o == orc.encode(f, w, h, chroma, q, restart_interval=ri)
+
+
+def test_quantized_tap(hcj, ctx, orc):
+    w, h = 128, 80
+    f = synth.frame(5, w, h, 420)
+    _, quant, _ = orc.encode(f, w, h, 420, 60, want_blocks=True)
+    got = ctx.encode_quantized(f, w, h, 420, 60)
+    assert np.array_equal(got, quant.astype(np.int16))
+
+
+def test_extreme_content(hcj, ctx, orc):
+    """Saturated / checkerboard content: long codes, many stuffed FF bytes, ZRL runs."""
+    w, h = 64, 64
+    rng = np.random.default_rng(9)
+    frames = [
+        bytes(rng.choice([0, 255], w * h * 3).astype(np.uint8)),
+        bytes(np.full(w * h * 3, 255, np.uint8)),
+        bytes(np.zeros(w * h * 3, np.uint8)),
+        bytes((np.indices((h * 3, w)).sum(0) % 2 * 255).astype(np.uint8)),
+    ]
+    for q in (100, 75, 5):
+        outs, st = ctx.encode_batch(frames, w, h, 444, q)
+        assert st == [0] * 4
+        for f, o in zip(frames, outs):
+            assert o == orc.encode(f, w, h, 444, q), q
+
+
+def test_plane_bounds_status(hcj, ctx, orc):
+    """W = 17 at 4:2:0: per-component rounding disagrees and the model raises."""
+    f = synth.frame(1, 17, 16, 420)
+    with pytest.raises(orc.OracleError) as e:
+        orc.encode(f, 17, 16, 420, 75)
+    with pytest.raises(hcj.HcjError) as g:
+        ctx.encode_batch([f], 17, 16, 420, 75)
+    assert g.value.status == e.value.status == -10
+
+
+@pytest.mark.parametrize("ri", [0, 8])
+def test_1080p_encode_full_size(hcj, ctx, orc, ri):
+    """BASELINE config 5 at full size + encode -> decode round trip through both device paths."""
+    w, h = 1920, 1080
+    frames = [synth.frame(5000 + i, w, h, 420) for i in range(2)]
+    want = [orc.encode(f, w, h, 420, 75, restart_interval=ri) for f in frames]
+    outs, st = ctx.encode_batch([frames[i % 2] for i in range(8)], w, h, 420, 75, ri)
+    assert st == [0] * 8
+    assert [sha(o) for o in outs] == [sha(want[i % 2]) for i in range(8)]
+    dec, st = ctx.decode_batch(outs[:2])
+    assert st == [0, 0]
+    for j, d in zip(want, dec):
+        assert bytes(d) == orc.decode(j).yuv()

@@ -1,0 +1,619 @@
+// hcj_api.cu — the C ABI of libhcjpeg (include/hcjpeg.h): contexts, batches, orchestration.
+//
+// Host work per image is what the model does before its block loop (Header.decode + init); everything
+// else is queued on the context's CUDA stream.  No CPU fallback exists: if CUDA is unavailable every
+// compute entry point fails with HCJ_ERR_CUDA - cudaError.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hcjpeg.h"
+#include "hcj_host.h"
+#include "hcj_internal.h"
+#include "hcj_kernels.cuh"
+
+
+using hcj::align_up;
+
+struct hcj_batch {
+  int n = 0, mode = 0;
+  unsigned flags = 0;
+  std::vector<HcjImageDesc> descs;
+  std::vector<int> host_status;
+  std::vector<size_t> out_bytes;
+  std::vector<void *> owned;  // device allocations
+  hcjk::DecodeBatchDev dev;
+  size_t coef_bytes = 0;
+  int kernels = 0;
+};
+
+extern "C" {
+
+int hcj_version(void) { return HCJ_VERSION; }
+
+const char *hcj_strerror(int status) {
+  switch (status) {
+    case HCJ_OK: return "ok";
+    case HCJ_ERR_UNSUPPORTED_MARKER: return "unsupported marker code";
+    case HCJ_ERR_NO_DC_CODE: return "Can't find dc code";
+    case HCJ_ERR_NO_AC_CODE: return "Can't find ac code";
+    case HCJ_ERR_COEF_INDEX: return "coefficient index out of range:";
+    case HCJ_ERR_NO_COMPONENT: return "unable to find component identifier";
+    case HCJ_ERR_NO_QUANT_TABLE: return "unable to find quantisation table";
+    case HCJ_ERR_NO_HUFFMAN_TABLE: return "unable to find huffman table";
+    case HCJ_ERR_NO_FRAME_OR_SCAN: return "From start of frame or start of scan marker";
+    case HCJ_ERR_BITS_OUT_OF_BOUNDS: return "Bitstream_reader out of bounds";
+    case HCJ_ERR_PLANE_BOUNDS: return "[Plane.get/set] out of bounds";
+    case HCJ_ERR_FRAME_INFER: return "Could not infer chroma subsampling";
+    case HCJ_ERR_NEED_3_COMPONENTS: return "index out of bounds (get_yuv_frame needs 3 components)";
+    case HCJ_ERR_ENCODER_PARAMS: return "invalid encoder parameters";
+    case HCJ_ERR_NO_TERMINATOR: return "no marker terminates the entropy-coded segment (the model would not return)";
+    case HCJ_ERR_RESTART_COUNT: return "restart marker count does not match the restart interval";
+    case HCJ_ERR_UNSUPPORTED_GEOMETRY: return "outside the supported domain (components / sampling factors / DC category / Pq)";
+    case HCJ_ERR_DC_RANGE: return "resolved DC does not fit int16";
+    case HCJ_ERR_TRUNCATED: return "truncated header (the model would not return)";
+    case HCJ_ERR_BAD_HUFFMAN_TABLE: return "index out of bounds (over-subscribed Huffman table)";
+    case HCJ_ERR_BUFFER_TOO_SMALL: return "output buffer too small";
+    case HCJ_ERR_INVALID_ARG: return "invalid argument";
+    case HCJ_ERR_OUT_OF_MEMORY: return "out of device memory";
+    default: break;
+  }
+  if (status <= HCJ_ERR_CUDA) return cudaGetErrorString((cudaError_t)(HCJ_ERR_CUDA - status));
+  return "unknown status";
+}
+
+int hcj_header_decode(const uint8_t *jpeg, size_t len, hcj_header *out) {
+  if (!jpeg || !out) return HCJ_ERR_INVALID_ARG;
+  return hcj::header_decode(jpeg, len, out);
+}
+
+int hcj_frame_info_get(const uint8_t *jpeg, size_t len, hcj_frame_info *out) {
+  if (!jpeg || !out) return HCJ_ERR_INVALID_ARG;
+  hcj_header *h = new (std::nothrow) hcj_header;
+  if (!h) return HCJ_ERR_OUT_OF_MEMORY;
+  int st = hcj::header_decode(jpeg, len, h);
+  hcj::ImagePlan plan;
+  if (st == HCJ_OK) st = hcj::plan_image(*h, HCJ_FLAG_DEFAULT, &plan);
+  if (st == HCJ_OK) *out = plan.info;
+  delete h;
+  return st;
+}
+
+int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out) {
+  if (!out) return HCJ_ERR_INVALID_ARG;
+  *out = nullptr;
+  CU_TRY(cudaSetDevice(device));
+  hcj_ctx *c = new (std::nothrow) hcj_ctx;
+  if (!c) return HCJ_ERR_OUT_OF_MEMORY;
+  c->device = device;
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return HCJ_ERR_CUDA - (int)e;
+    }
+    c->own_stream = true;
+  }
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  *out = c;
+  return HCJ_OK;
+}
+
+void hcj_ctx_destroy(hcj_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &f : c->pool) cudaFree(f.p);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int hcj_ctx_synchronize(hcj_ctx *c) {
+  if (!c) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return HCJ_OK;
+}
+
+void *hcj_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void hcj_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int hcj_timer_start(hcj_ctx *c) {
+  if (!c) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaEventRecord(c->ev0, c->stream));
+  return HCJ_OK;
+}
+int hcj_timer_stop(hcj_ctx *c, float *ms) {
+  if (!c || !ms) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaEventRecord(c->ev1, c->stream));
+  CU_TRY(cudaEventSynchronize(c->ev1));
+  CU_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return HCJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+static int batch_alloc(hcj_ctx *c, hcj_batch *b, void **p, size_t bytes) {
+  int st = c->alloc(p, bytes);
+  if (st == HCJ_OK) b->owned.push_back(*p);
+  return st;
+}
+
+void hcj_batch_destroy(hcj_ctx *c, hcj_batch *b) {
+  if (!b) return;
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : b->owned) c->release(p);
+  }
+  delete b;
+}
+
+int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                     int *status, hcj_batch **out) {
+  if (!c || !out || n < 0 || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > 2) return HCJ_ERR_INVALID_ARG;
+  *out = nullptr;
+  CU_TRY(cudaSetDevice(c->device));
+  hcj_batch *b = new (std::nothrow) hcj_batch;
+  if (!b) return HCJ_ERR_OUT_OF_MEMORY;
+  b->n = n;
+  b->mode = mode;
+  b->flags = flags;
+  b->descs.assign(n, HcjImageDesc());
+  b->host_status.assign(n, HCJ_OK);
+  b->out_bytes.assign(n, 0);
+  memset(&b->dev, 0, sizeof(b->dev));
+
+  std::vector<HcjTableSet> table_sets;
+  std::vector<uint16_t> prim_pool, full_pool, qt_pool;
+  std::map<std::string, uint32_t> set_index;
+  std::vector<uint32_t> list_restart, list_spec;
+  size_t file_bytes = 0, ent_bytes = 0, nsegs = 0, out_total = 0, plane_total = 0;
+  uint64_t total_blocks = 0;
+  uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0;
+  const int tile_mcus = 42;  // upper bound on MCUs per IDCT tile (256 threads / 6 blocks for 4:2:0)
+  hcj_header *h = new (std::nothrow) hcj_header;
+  if (!h) {
+    delete b;
+    return HCJ_ERR_OUT_OF_MEMORY;
+  }
+
+  for (int i = 0; i < n; i++) {
+    HcjImageDesc &d = b->descs[i];
+    memset(&d, 0, sizeof(d));
+    hcj::ImagePlan plan;
+    int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], h) : HCJ_ERR_INVALID_ARG;
+    if (st == HCJ_OK) st = hcj::plan_image(*h, flags, &plan);
+    const hcj_frame_info &f = plan.info;
+    // table set of this image: one (dc, ac) pair per distinct binding among its scan components
+    int pair_of[HCJ_MAX_COMPONENTS] = {0, 0, 0, 0}, npairs = 0, pair_dc[HCJ_MAX_COMPONENTS], pair_ac[HCJ_MAX_COMPONENTS];
+    std::string key;
+    if (st == HCJ_OK) {
+      for (int k = 0; k < f.ncomp; k++) {
+        int p = -1;
+        for (int j = 0; j < npairs; j++)
+          if (pair_dc[j] == plan.dc_index[k] && pair_ac[j] == plan.ac_index[k]) p = j;
+        if (p < 0) {
+          p = npairs++;
+          pair_dc[p] = plan.dc_index[k];
+          pair_ac[p] = plan.ac_index[k];
+          for (int which = 0; which < 2; which++) {
+            const hcj_dht &t = h->huffman_tables[which ? pair_ac[p] : pair_dc[p]];
+            key.push_back((char)t.table_class);
+            for (int q = 0; q < 16; q++) key.push_back((char)t.lengths[q]);
+            key.append(reinterpret_cast<const char *>(t.values), (size_t)t.nvalues);
+          }
+        }
+        pair_of[k] = p;
+      }
+      auto it = set_index.find(key);
+      if (it != set_index.end()) {
+        d.table_set = it->second;
+      } else {
+        HcjTableSet ts;
+        memset(&ts, 0, sizeof(ts));
+        ts.npairs = (uint32_t)npairs;
+        ts.primary_off = (uint32_t)prim_pool.size();
+        std::vector<uint16_t> prim_local, full_local;
+        for (int p = 0; p < npairs && st == HCJ_OK; p++)
+          for (int which = 0; which < 2 && st == HCJ_OK; which++) {
+            hcj::HuffLut lut;
+            st = hcj::build_lut(h->huffman_tables[which ? pair_ac[p] : pair_dc[p]], &lut);
+            if (st != HCJ_OK) break;
+            ts.meta[p][which].max_bits = (uint32_t)lut.max_bits;
+            ts.meta[p][which].full_off = (uint32_t)(full_pool.size() + full_local.size());
+            prim_local.insert(prim_local.end(), lut.primary.begin(), lut.primary.end());
+            full_local.insert(full_local.end(), lut.full.begin(), lut.full.end());
+            while (full_local.size() % 8) full_local.push_back(0);
+          }
+        if (st == HCJ_OK) {
+          prim_pool.insert(prim_pool.end(), prim_local.begin(), prim_local.end());
+          full_pool.insert(full_pool.end(), full_local.begin(), full_local.end());
+          d.table_set = (uint32_t)table_sets.size();
+          set_index[key] = d.table_set;
+          table_sets.push_back(ts);
+        }
+      }
+    }
+    if (st == HCJ_OK && (mode == HCJ_OUT_YUV || mode == HCJ_OUT_RGB24)) {
+      if (f.ncomp < 3) st = HCJ_ERR_NEED_3_COMPONENTS;  // decoder.ml:415-420
+      else if (f.chroma == 0) st = HCJ_ERR_FRAME_INFER;  // frame.ml:44,55
+    }
+    b->host_status[i] = st;
+    if (st != HCJ_OK) continue;
+
+    d.valid = 1;
+    d.file_off = file_bytes;
+    d.file_len = (uint32_t)len[i];
+    d.scan_start = (uint32_t)h->scan_byte_pos;
+    if (d.scan_start > d.file_len) d.scan_start = d.file_len;
+    file_bytes += align_up(len[i] + 16, 16);
+    d.ent_off = ent_bytes;
+    d.ent_cap = (uint32_t)align_up(len[i] - d.scan_start + 32, 16);
+    ent_bytes += d.ent_cap;
+    d.ncomp = f.ncomp;
+    d.bpm = f.blocks_per_mcu;
+    d.mcus_wide = f.mcus_wide;
+    d.mcus_high = f.mcus_high;
+    d.nmcu = (uint32_t)(f.mcus_wide * f.mcus_high);
+    d.nblocks = (uint32_t)f.nblocks;
+    d.ri = (uint32_t)f.restart_interval;
+    d.nseg_expected = d.ri ? (d.nmcu + d.ri - 1) / d.ri : 1;
+    d.seg_off = (uint32_t)nsegs;
+    nsegs += d.nseg_expected + 1;
+    d.coef_off = total_blocks;
+    total_blocks += d.nblocks;
+    d.chroma = f.chroma;
+    d.width = f.width;
+    d.height = f.height;
+    d.qt_off = (uint32_t)qt_pool.size();
+    size_t out_i = mode == HCJ_OUT_YUV ? f.yuv_bytes : mode == HCJ_OUT_PLANES ? f.planes_bytes : f.rgb_bytes;
+    d.out_off = out_total;
+    d.out_bytes = out_i;
+    b->out_bytes[i] = out_i;
+    out_total += align_up(out_i, 256);
+    size_t plane_acc = 0, yuv_acc = 0;
+    int first_blk = 0;
+    for (int k = 0; k < f.ncomp; k++) {
+      HcjCompGeom &g = d.comp[k];
+      g.hs = f.hs[k];
+      g.vs = f.vs[k];
+      g.decoded_w = f.decoded_width[k];
+      g.decoded_h = f.decoded_height[k];
+      g.actual_w = f.actual_width[k];
+      g.actual_h = f.actual_height[k];
+      g.pair = pair_of[k];
+      g.qt = k;
+      g.first_blk = first_blk;
+      first_blk += g.hs * g.vs;
+      g.plane_off = (mode == HCJ_OUT_RGB24 ? plane_total : 0) + plane_acc;
+      plane_acc += (size_t)g.decoded_w * g.decoded_h;
+      g.out_off = yuv_acc;
+      yuv_acc += (size_t)g.actual_w * g.actual_h;
+      const hcj_dqt &q = h->quant_tables[plan.qt_index[k]];
+      for (int e = 0; e < 64; e++) {
+        qt_pool.push_back((uint16_t)q.elements[e]);
+        if (q.elements[e] > 255) d.wide_idct = 1;
+      }
+    }
+    if (mode == HCJ_OUT_RGB24) plane_total += align_up(plane_acc, 256);
+    for (int k = 0; k < f.blocks_per_mcu && k < HCJ_MAX_BPM; k++) {
+      d.blk_comp[k] = (uint8_t)plan.blk_comp[k];
+      d.blk_bx[k] = (uint8_t)plan.blk_bx[k];
+      d.blk_by[k] = (uint8_t)plan.blk_by[k];
+    }
+    if (d.ri) {
+      list_restart.push_back((uint32_t)i);
+      max_segments = std::max(max_segments, d.nseg_expected);
+    } else {
+      list_spec.push_back((uint32_t)i);
+    }
+    int tm_max = std::max(1, std::min(tile_mcus, 256 / d.bpm));
+    uint32_t tiles = (uint32_t)((d.mcus_wide + tm_max - 1) / tm_max) * (uint32_t)d.mcus_high;
+    max_tiles = std::max(max_tiles, tiles);
+    max_rows = std::max(max_rows, (uint32_t)f.height);
+    max_width = std::max(max_width, (uint32_t)f.width);
+  }
+  delete h;
+  if (status)
+    for (int i = 0; i < n; i++) status[i] = b->host_status[i];
+
+  // ---- device buffers
+  hcjk::DecodeBatchDev &dv = b->dev;
+  int st = HCJ_OK;
+  void *p = nullptr;
+#define BALLOC(field, type, bytes)                          \
+  if (st == HCJ_OK) {                                       \
+    st = batch_alloc(c, b, &p, (bytes));                    \
+    dv.field = reinterpret_cast<type>(p);                   \
+  }
+  HcjImageDesc *d_descs = nullptr;
+  uint8_t *d_files = nullptr;
+  HcjTableSet *d_sets = nullptr;
+  uint16_t *d_prim = nullptr, *d_full = nullptr, *d_qt = nullptr;
+  uint32_t *d_lr = nullptr, *d_ls = nullptr;
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_descs, sizeof(HcjImageDesc) * std::max(n, 1));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_files, file_bytes + 16);
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_sets, sizeof(HcjTableSet) * std::max<size_t>(table_sets.size(), 1));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_prim, 2 * std::max<size_t>(prim_pool.size(), 8));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_full, 2 * std::max<size_t>(full_pool.size(), 8));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_qt, 2 * std::max<size_t>(qt_pool.size(), 8));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_lr, 4 * std::max<size_t>(list_restart.size(), 1));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_ls, 4 * std::max<size_t>(list_spec.size(), 1));
+  BALLOC(states, HcjImageState *, sizeof(HcjImageState) * std::max(n, 1));
+  BALLOC(entropy, uint8_t *, ent_bytes + 16);
+  BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
+  b->coef_bytes = (size_t)total_blocks * 128;
+  BALLOC(coefs, int16_t *, b->coef_bytes + 16);
+  BALLOC(out, uint8_t *, out_total + 16);
+  if (mode == HCJ_OUT_RGB24) BALLOC(planes, uint8_t *, plane_total + 16);
+#undef BALLOC
+  if (st != HCJ_OK) {
+    hcj_batch_destroy(c, b);
+    return st;
+  }
+  dv.n = n;
+  dv.descs = d_descs;
+  dv.files = d_files;
+  dv.table_sets = d_sets;
+  dv.lut_primary = d_prim;
+  dv.lut_full = d_full;
+  dv.qtables = d_qt;
+  dv.list_restart = d_lr;
+  dv.n_restart = (int)list_restart.size();
+  dv.max_segments = max_segments;
+  dv.list_spec = d_ls;
+  dv.n_spec = (int)list_spec.size();
+  dv.max_idct_tiles = max_tiles;
+  dv.tile_mcus = tile_mcus;
+  dv.max_rgb_rows = max_rows;
+  dv.max_width = max_width;
+  dv.total_blocks = total_blocks;
+  b->kernels = 1 + (dv.n_restart ? 1 : 0) + (dv.n_spec ? 1 : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
+
+  // ---- upload
+  cudaStream_t s = c->stream;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void *dst, const void *src, size_t bytes) {
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+  };
+  up(d_descs, b->descs.data(), sizeof(HcjImageDesc) * n);
+  up(d_sets, table_sets.data(), sizeof(HcjTableSet) * table_sets.size());
+  up(d_prim, prim_pool.data(), 2 * prim_pool.size());
+  up(d_full, full_pool.data(), 2 * full_pool.size());
+  up(d_qt, qt_pool.data(), 2 * qt_pool.size());
+  up(d_lr, list_restart.data(), 4 * list_restart.size());
+  up(d_ls, list_spec.data(), 4 * list_spec.size());
+  // compressed files: merge copies of images that are adjacent in host memory with matching padding
+  for (int i = 0; i < n && e == cudaSuccess;) {
+    if (!b->descs[i].valid) {
+      i++;
+      continue;
+    }
+    int j = i;
+    size_t bytes = len[i];
+    while (j + 1 < n && b->descs[j + 1].valid && jpeg[j + 1] == jpeg[i] + (b->descs[j + 1].file_off - b->descs[i].file_off)) {
+      j++;
+      bytes = (size_t)(b->descs[j].file_off - b->descs[i].file_off) + len[j];
+    }
+    up(d_files + b->descs[i].file_off, jpeg[i], bytes);
+    i = j + 1;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // host staging vectors go out of scope
+  if (e != cudaSuccess) {
+    hcj_batch_destroy(c, b);
+    return HCJ_ERR_CUDA - (int)e;
+  }
+  *out = b;
+  return HCJ_OK;
+}
+
+int hcj_batch_count_kernels(const hcj_batch *b) { return b ? b->kernels : 0; }
+
+int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
+  if (!c || !b) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  if (b->n == 0) return HCJ_OK;
+  // Coefficient blocks start as zero (clear_block, decoder.ml:112-116,160); decoders store non-zeros.
+  CU_TRY(cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s));
+  CU_TRY(cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s));  // overwritten by k_destuff for valid images
+  hcjk::launch_destuff(b->dev, s);
+  hcjk::launch_huff_restart(b->dev, s);
+  hcjk::launch_huff_spec(b->dev, s);
+  hcjk::launch_idct(b->dev, b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2, s);
+  if (b->mode == HCJ_OUT_RGB24) hcjk::launch_rgb(b->dev, s);
+  CU_TRY(cudaGetLastError());
+  return HCJ_OK;
+}
+
+static const char *kStageNames[] = {"zero_coefficients", "destuff", "huffman_restart", "huffman_speculative", "idct", "rgb"};
+const char *hcj_decode_stage_name(int i) { return i >= 0 && i < 6 ? kStageNames[i] : ""; }
+
+int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, int *nstages) {
+  if (!c || !b || !ms || !nstages || capacity < 6) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  cudaEvent_t ev[7];
+  for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
+  const int mode = b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2;
+  cudaEventRecord(ev[0], s);
+  cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s);
+  cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s);
+  cudaEventRecord(ev[1], s);
+  hcjk::launch_destuff(b->dev, s);
+  cudaEventRecord(ev[2], s);
+  hcjk::launch_huff_restart(b->dev, s);
+  cudaEventRecord(ev[3], s);
+  hcjk::launch_huff_spec(b->dev, s);
+  cudaEventRecord(ev[4], s);
+  hcjk::launch_idct(b->dev, mode, s);
+  cudaEventRecord(ev[5], s);
+  if (b->mode == HCJ_OUT_RGB24) hcjk::launch_rgb(b->dev, s);
+  cudaEventRecord(ev[6], s);
+  cudaError_t e = cudaEventSynchronize(ev[6]);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+  for (auto &x : ev) cudaEventDestroy(x);
+  *nstages = 6;
+  return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
+static int fetch_states(hcj_ctx *c, hcj_batch *b, std::vector<HcjImageState> *states) {
+  states->assign(std::max(b->n, 1), HcjImageState());
+  if (b->n)
+    CU_TRY(cudaMemcpyAsync(states->data(), b->dev.states, sizeof(HcjImageState) * b->n, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < b->n; i++) {
+    HcjImageState &st = (*states)[i];
+    if (b->host_status[i] != HCJ_OK) st.status = b->host_status[i];
+    else if (st.status == 0 && st.err_key != HCJ_NO_ERR_KEY) st.status = -(int)(st.err_key & 0xff);
+  }
+  return HCJ_OK;
+}
+
+int hcj_batch_fetch(hcj_ctx *c, hcj_batch *b, uint8_t *const *out, const size_t *out_capacity, int *status) {
+  if (!c || !b || (b->n > 0 && (!out || !out_capacity))) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  std::vector<int> st(b->host_status);
+  for (int i = 0; i < b->n; i++) {
+    if (st[i] != HCJ_OK) continue;
+    if (!out[i] || out_capacity[i] < b->out_bytes[i]) {
+      st[i] = HCJ_ERR_BUFFER_TOO_SMALL;
+      continue;
+    }
+    CU_TRY(cudaMemcpyAsync(out[i], b->dev.out + b->descs[i].out_off, b->out_bytes[i], cudaMemcpyDeviceToHost, c->stream));
+  }
+  std::vector<HcjImageState> states;
+  int r = fetch_states(c, b, &states);
+  if (r != HCJ_OK) return r;
+  for (int i = 0; i < b->n; i++)
+    if (st[i] == HCJ_OK && states[i].status != 0) st[i] = states[i].status;
+  if (status)
+    for (int i = 0; i < b->n; i++) status[i] = st[i];
+  return HCJ_OK;
+}
+
+int hcj_batch_device_output(hcj_batch *b, int i, void **dptr, size_t *bytes) {
+  if (!b || i < 0 || i >= b->n || !dptr || !bytes) return HCJ_ERR_INVALID_ARG;
+  if (b->host_status[i] != HCJ_OK) return b->host_status[i];
+  *dptr = b->dev.out + b->descs[i].out_off;
+  *bytes = b->out_bytes[i];
+  return HCJ_OK;
+}
+
+int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                     uint8_t *const *out, const size_t *out_capacity, int *status) {
+  hcj_batch *b = nullptr;
+  int st = hcj_batch_create(c, jpeg, len, n, mode, flags, status, &b);
+  if (st != HCJ_OK) return st;
+  st = hcj_batch_decode(c, b);
+  if (st == HCJ_OK) st = hcj_batch_fetch(c, b, out, out_capacity, status);
+  hcj_batch_destroy(c, b);
+  return st;
+}
+
+int hcj_batch_fetch_coefficients(hcj_ctx *c, hcj_batch *b, int i, int16_t *coefs, size_t capacity_blocks) {
+  if (!c || !b || i < 0 || i >= b->n || !coefs) return HCJ_ERR_INVALID_ARG;
+  if (b->host_status[i] != HCJ_OK) return b->host_status[i];
+  const HcjImageDesc &d = b->descs[i];
+  if (capacity_blocks < d.nblocks) return HCJ_ERR_BUFFER_TOO_SMALL;
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMemcpyAsync(coefs, b->dev.coefs + d.coef_off * 64, (size_t)d.nblocks * 128, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<HcjImageState> states;
+  int r = fetch_states(c, b, &states);
+  return r != HCJ_OK ? r : states[i].status;
+}
+
+int hcj_batch_fetch_entropy(hcj_ctx *c, hcj_batch *b, int i, uint8_t *out, size_t capacity, size_t *len) {
+  if (!c || !b || i < 0 || i >= b->n || !out || !len) return HCJ_ERR_INVALID_ARG;
+  if (b->host_status[i] != HCJ_OK) return b->host_status[i];
+  CU_TRY(cudaSetDevice(c->device));
+  std::vector<HcjImageState> states;
+  int r = fetch_states(c, b, &states);
+  if (r != HCJ_OK) return r;
+  *len = states[i].ent_len;
+  if (states[i].status == HCJ_ERR_NO_TERMINATOR) return states[i].status;
+  if (capacity < states[i].ent_len) return HCJ_ERR_BUFFER_TOO_SMALL;
+  CU_TRY(cudaMemcpy(out, b->dev.entropy + b->descs[i].ent_off, states[i].ent_len, cudaMemcpyDeviceToHost));
+  return HCJ_OK;
+}
+
+int hcj_idct_blocks(hcj_ctx *c, const int16_t *coefs, size_t nblocks, const uint16_t quant_table[64], uint8_t *out) {
+  if (!c || !coefs || !quant_table || !out) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  void *d_c = nullptr, *d_q = nullptr, *d_o = nullptr;
+  int st = c->alloc(&d_c, nblocks * 128 + 16);
+  if (st == HCJ_OK) st = c->alloc(&d_q, 256);
+  if (st == HCJ_OK) st = c->alloc(&d_o, nblocks * 64 + 16);
+  cudaError_t e = cudaSuccess;
+  if (st == HCJ_OK) {
+    bool wide = false;
+    for (int i = 0; i < 64; i++) wide |= quant_table[i] > 255;
+    e = cudaMemcpyAsync(d_c, coefs, nblocks * 128, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, quant_table, 128, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+      hcjk::launch_idct_blocks((const int16_t *)d_c, nblocks, (const uint16_t *)d_q, wide, (uint8_t *)d_o, c->stream);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, nblocks * 64, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  c->release(d_c);
+  c->release(d_q);
+  c->release(d_o);
+  if (st != HCJ_OK) return st;
+  return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
+int hcj_compare_planes(hcj_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error, int *max_difference) {
+  if (!c || !a || !b || !square_error || !max_difference) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  void *d_a = nullptr, *d_b = nullptr, *d_r = nullptr;
+  int st = c->alloc(&d_a, n + 16);
+  if (st == HCJ_OK) st = c->alloc(&d_b, n + 16);
+  if (st == HCJ_OK) st = c->alloc(&d_r, 256);
+  cudaError_t e = cudaSuccess;
+  unsigned long long res[2] = {0, 0};
+  if (st == HCJ_OK) {
+    e = cudaMemcpyAsync(d_a, a, n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, b, n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_r, 0, 16, c->stream);
+    if (e == cudaSuccess) {
+      hcjk::launch_compare((const uint8_t *)d_a, (const uint8_t *)d_b, n, (unsigned long long *)d_r,
+                           (int *)((char *)d_r + 8), c->stream);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res, d_r, 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  c->release(d_a);
+  c->release(d_b);
+  c->release(d_r);
+  if (st != HCJ_OK) return st;
+  if (e != cudaSuccess) return HCJ_ERR_CUDA - (int)e;
+  *square_error = (int64_t)res[0];
+  *max_difference = (int)(res[1] & 0xffffffffu);
+  return HCJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,583 @@
+// hcj_encode.cu — encoder mirror (Encoder.encode_420/422/444, jpeg/model/src/encoder.ml) for sm_100a.
+//
+//   k_fdct_quant   E2,E4-E6  zero-padded block fetch, level shift, Chen FDCT, quantise, zig-zag
+//   k_block_bits   E7,E8     per block: DC differential + (run, size) symbols -> code length in bits
+//   k_scan_bits    per frame: exclusive prefix sum of block bit lengths (one CTA walks the frame)
+//   k_pack         E8,E9     per block: write code + magnitude fields at their bit offset (big-endian
+//                            32-bit words, atomicOr only on the two boundary words), 1-fill at the end of
+//                            every segment (flush_with_1s, bitstream_writer.ml:45-49)
+//   k_seg_count    E9        per segment: stuffed byte count (bytes + number of FF bytes)
+//   k_seg_scan     per frame: prefix sum of segment sizes -> output offsets; copies the header
+//   k_stuff        E9,E10    per segment: byte copy with FF -> FF 00, RSTn between segments, EOI
+//
+// Results are byte-identical to the model's Writer.get_buffer (tests/test_gpu_encode.py).
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "hcj_device.cuh"
+#include "hcj_host.h"
+#include "hcj_internal.h"
+#include "hcj_kernels.cuh"
+
+namespace hcjk {
+using namespace hcjdev;
+
+// ---- K6 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fdct_quant(EncodeBatchDev e) {
+  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t frame = blockIdx.y;
+  if (blk >= e.nblocks) return;
+  const uint32_t mcu = blk / e.bpm, k = blk - mcu * e.bpm;
+  const int c = e.blk_comp[k];
+  const int my = mcu / e.mcus_wide, mx = mcu - my * e.mcus_wide;
+  const int x0 = (mx * e.hs[c] + e.blk_bx[k]) * 8, y0 = (my * e.vs[c] + e.blk_by[k]) * 8;
+  const uint8_t *src = e.src + (uint64_t)frame * e.frame_bytes + e.src_off[c];
+  const int sw = e.src_w[c], sh = e.src_h[c];
+  int32_t v[64];
+  // level_shifted_input_block over the zero-initialised padded plane (encoder.ml:81-90, plane.ml:11-17)
+  const bool inside = x0 + 8 <= sw && y0 + 8 <= sh;
+  if (inside && ((((uintptr_t)src + (size_t)y0 * sw + x0) & 7u) == 0) && (sw & 7) == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      uint2 u = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(y0 + y) * sw + x0));
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        v[y * 8 + x] = (int32_t)((u.x >> (8 * x)) & 0xffu) - 128;
+        v[y * 8 + 4 + x] = (int32_t)((u.y >> (8 * x)) & 0xffu) - 128;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+#pragma unroll
+      for (int x = 0; x < 8; x++) {
+        int px = x0 + x, py = y0 + y;
+        int p = (px < sw && py < sh) ? (int)__ldg(src + (size_t)py * sw + px) : 0;
+        v[y * 8 + x] = p - 128;
+      }
+  }
+  fdct_8x8(v);
+  const uint16_t *qt = e.qt + (c ? 64 : 0);
+  const uint32_t *qr = e.qrecip + (c ? 64 : 0);
+  uint32_t packed[32];
+#pragma unroll
+  for (int z = 0; z < 64; z += 2) {  // quant (encoder.ml:103-108): zig-zag position z <- natural inverse(z)
+    int32_t a = quantize(v[zigzag_inverse(z)], __ldg(qt + z), __ldg(qr + z));
+    int32_t b = quantize(v[zigzag_inverse(z + 1)], __ldg(qt + z + 1), __ldg(qr + z + 1));
+    packed[z >> 1] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk) * 64);
+#pragma unroll
+  for (int j = 0; j < 8; j++) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+}
+
+// Index (within the frame) of the block whose DC is this block's predictor, or -1 (start of a segment).
+__device__ __forceinline__ int64_t dc_pred_block(const EncodeBatchDev &e, uint32_t blk) {
+  const uint32_t mcu = blk / e.bpm, k = blk - mcu * e.bpm;
+  const int c = e.blk_comp[k];
+  if (e.blk_bx[k] != 0 || e.blk_by[k] != 0) return (int64_t)blk - 1;  // previous block of the same component, same MCU
+  if (mcu == 0 || (e.restart_interval && mcu % e.restart_interval == 0)) return -1;
+  // last block of component c in the previous MCU
+  uint32_t first = 0;
+  for (int j = 0; j < c; j++) first += e.hs[j] * e.vs[j];
+  return (int64_t)(mcu - 1) * e.bpm + first + e.hs[c] * e.vs[c] - 1;
+}
+
+struct BitCounter {
+  uint32_t bits = 0;
+  __device__ __forceinline__ void operator()(uint32_t, uint32_t n) { bits += n; }
+};
+
+struct EncTablesSmem {
+  uint32_t dc[2][16];
+  uint32_t ac[2][256];
+};
+
+__device__ __forceinline__ void load_enc_tables(EncTablesSmem &t, const EncodeBatchDev &e) {
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) t.dc[i >> 4][i & 15] = e.dc_codes[i];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) t.ac[i >> 8][i & 255] = e.ac_codes[i];
+}
+
+// ---- K7a -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *status) {
+  __shared__ EncTablesSmem t;
+  load_enc_tables(t, e);
+  __syncthreads();
+  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t frame = blockIdx.y;
+  if (blk >= e.nblocks) return;
+  const int16_t *q = e.quant + ((uint64_t)frame * e.nblocks + blk) * 64;
+  int16_t loc[64];
+  const uint4 *src = reinterpret_cast<const uint4 *>(q);
+#pragma unroll
+  for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(loc + 8 * j) = __ldg(src + j);
+  int64_t pb = dc_pred_block(e, blk);
+  int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
+  const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
+  BitCounter cnt;
+  bool ok = encode_block_fields(loc, (int32_t)loc[0] - pred, t.dc[tsel], t.ac[tsel], cnt);
+  if (!ok) atomicCAS(status + frame, 0, HCJ_ERR_ENCODER_PARAMS);
+  e.blk_bits[(uint64_t)frame * (e.nblocks + 1) + blk] = cnt.bits;
+}
+
+// ---- K7b: in-place exclusive scan of blk_bits per frame; entry [nblocks] receives the total ---------
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_bits(EncodeBatchDev e) {
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  uint32_t *bits = e.blk_bits + (uint64_t)blockIdx.x * (e.nblocks + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < e.nblocks; base += SCAN_THREADS) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < e.nblocks ? bits[i] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_THREADS / 32; k++) {
+      uint32_t t = s_warp[k];
+      if (k < warp) wbase += t;
+      total += t;
+    }
+    if (i < e.nblocks) bits[i] = carry + wbase + incl - v;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bits[e.nblocks] = carry;
+}
+
+// Segment s of a frame covers blocks [s * ri * bpm, min((s + 1) * ri * bpm, nblocks)).  Its packed bits
+// start at byte  floor(P[first] / 8) + s  of the frame's raw buffer (P = exclusive bit prefix): segments
+// are byte aligned and never overlap because each one wastes less than a byte of rounding.
+__device__ __forceinline__ uint32_t seg_first_block(const EncodeBatchDev &e, uint32_t s) {
+  return e.restart_interval ? min(s * e.restart_interval * e.bpm, e.nblocks) : (s ? e.nblocks : 0u);
+}
+
+struct BitPacker {
+  uint32_t *words;  // big-endian 32-bit words of the raw buffer
+  uint64_t acc;     // pending bits, right-aligned
+  uint32_t nacc;    // number of pending bits (< 32 between calls)
+  uint32_t widx;    // next word to write
+  bool first;
+  __device__ __forceinline__ void init(uint8_t *raw, uint64_t bitpos) {
+    words = reinterpret_cast<uint32_t *>(raw);
+    widx = (uint32_t)(bitpos >> 5);
+    nacc = (uint32_t)(bitpos & 31u);  // leading bits of the first word belong to the previous block: zeros here
+    acc = 0;
+    first = true;
+  }
+  __device__ __forceinline__ void flush_word(uint32_t w) {
+    uint32_t le = bswap32(w);
+    if (first) {
+      atomicOr(words + widx, le);
+      first = false;
+    } else {
+      words[widx] = le;
+    }
+    widx++;
+  }
+  __device__ __forceinline__ void operator()(uint32_t bits, uint32_t n) {
+    if (n == 0) return;
+    acc = (acc << n) | (uint64_t)(bits & ((1u << n) - 1u));
+    nacc += n;
+    if (nacc >= 32u) {
+      nacc -= 32u;
+      flush_word((uint32_t)(acc >> nacc));
+      acc &= (1ull << nacc) - 1ull;
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (nacc) {
+      uint32_t le = bswap32((uint32_t)(acc << (32u - nacc)));
+      atomicOr(words + widx, le);
+    }
+  }
+};
+
+// ---- K7c -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pack(EncodeBatchDev e) {
+  __shared__ EncTablesSmem t;
+  load_enc_tables(t, e);
+  __syncthreads();
+  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t frame = blockIdx.y;
+  if (blk >= e.nblocks) return;
+  const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
+  const uint32_t seg = e.restart_interval ? (blk / e.bpm) / e.restart_interval : 0;
+  const uint32_t first = seg_first_block(e, seg), next = seg_first_block(e, seg + 1);
+  const uint32_t seg_byte = (P[first] >> 3) + seg;
+  const uint64_t bitpos = (uint64_t)seg_byte * 8 + (P[blk] - P[first]);
+
+  int16_t loc[64];
+  const uint4 *src = reinterpret_cast<const uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk) * 64);
+#pragma unroll
+  for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(loc + 8 * j) = __ldg(src + j);
+  int64_t pb = dc_pred_block(e, blk);
+  int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
+  const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
+  BitPacker pk;
+  pk.init(e.raw + (uint64_t)frame * e.raw_stride, bitpos);
+  encode_block_fields(loc, (int32_t)loc[0] - pred, t.dc[tsel], t.ac[tsel], pk);
+  if (blk + 1 == next) {  // last block of the segment: flush_with_1s
+    uint32_t segbits = P[next] - P[first];
+    uint32_t pad = (8u - (segbits & 7u)) & 7u;
+    pk((1u << pad) - 1u, pad);
+  }
+  pk.finish();
+}
+
+// ---- K8a: stuffed size of every segment ------------------------------------------------------------
+__device__ __forceinline__ void seg_raw_range(const EncodeBatchDev &e, const uint32_t *P, uint32_t seg, uint32_t &byte0,
+                                              uint32_t &nbytes) {
+  const uint32_t first = seg_first_block(e, seg), next = seg_first_block(e, seg + 1);
+  byte0 = (P[first] >> 3) + seg;
+  nbytes = (P[next] - P[first] + 7u) >> 3;
+}
+
+__global__ void __launch_bounds__(128) k_seg_count(EncodeBatchDev e) {
+  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31;
+  if (seg >= e.nseg) return;
+  const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
+  uint32_t byte0, nbytes;
+  seg_raw_range(e, P, seg, byte0, nbytes);
+  const uint8_t *raw = e.raw + (uint64_t)frame * e.raw_stride + byte0;
+  uint32_t ff = 0;
+  for (uint32_t i = lane; i < nbytes; i += 32) ff += raw[i] == 0xffu;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ff += __shfl_xor_sync(0xffffffffu, ff, s);
+  if (lane == 0) e.seg_bytes[(uint64_t)frame * (e.nseg + 1) + seg] = nbytes + ff;
+}
+
+// ---- K8b: per frame, exclusive scan of segment sizes (+2 bytes of RSTn after each but the last),
+//      starting after the header; copies the header; writes the frame's total length -------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_seg_scan(EncodeBatchDev e) {
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  const uint32_t frame = blockIdx.x;
+  uint32_t *sb = e.seg_bytes + (uint64_t)frame * (e.nseg + 1);
+  uint8_t *out = e.out + (uint64_t)frame * e.out_stride;
+  for (uint32_t i = threadIdx.x; i < e.header_len; i += SCAN_THREADS) out[i] = e.header[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t carry = e.header_len;
+  for (uint32_t base = 0; base < e.nseg; base += SCAN_THREADS) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < e.nseg ? sb[i] + (i + 1 < e.nseg ? 2u : 0u) : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_THREADS / 32; k++) {
+      uint32_t t = s_warp[k];
+      if (k < warp) wbase += t;
+      total += t;
+    }
+    if (i < e.nseg) sb[i] = carry + wbase + incl - v;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sb[e.nseg] = carry;
+    out[carry] = 0xff;  // complete_and_write_eoi (encoder.ml:507-510)
+    out[carry + 1] = 0xd9;
+    e.out_len[frame] = carry + 2;
+  }
+}
+
+// ---- K8c: copy with byte stuffing; one warp per segment ---------------------------------------------
+__global__ void __launch_bounds__(128) k_stuff(EncodeBatchDev e) {
+  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31;
+  if (seg >= e.nseg) return;
+  const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
+  const uint32_t *sb = e.seg_bytes + (uint64_t)frame * (e.nseg + 1);
+  uint32_t byte0, nbytes;
+  seg_raw_range(e, P, seg, byte0, nbytes);
+  const uint8_t *raw = e.raw + (uint64_t)frame * e.raw_stride + byte0;
+  uint8_t *out = e.out + (uint64_t)frame * e.out_stride;
+  uint32_t opos = sb[seg];
+  for (uint32_t base = 0; base < nbytes; base += 32 * 8) {  // 8 bytes per lane per round
+    uint32_t i0 = base + lane * 8;
+    uint8_t v[8];
+    uint32_t n = 0, ff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      bool in = i0 + k < nbytes;
+      v[k] = in ? raw[i0 + k] : 0;
+      n += in;
+      ff += in && v[k] == 0xffu;
+    }
+    uint32_t cnt = n + ff, incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t o = opos + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (i0 + k < nbytes) {
+        out[o++] = v[k];
+        if (v[k] == 0xffu) out[o++] = 0x00;  // Writer.flush ~stuffing:true (bitstream_writer.ml:25-29)
+      }
+    opos += total;
+  }
+  if (lane == 0 && seg + 1 < e.nseg) {  // stated extension: RSTn, n = segment index mod 8
+    out[opos] = 0xff;
+    out[opos + 1] = (uint8_t)(0xd0 + (seg & 7u));
+  }
+}
+
+void launch_encode(const EncodeBatchDev &e, cudaStream_t s) {
+  if (e.n == 0) return;
+  dim3 gb((e.nblocks + 127) / 128, e.n);
+  k_fdct_quant<<<gb, 128, 0, s>>>(e);
+}
+
+int encode_kernel_count() { return 8; }
+
+// Gathers the per-frame totals of the bit scan into a dense array for one small D2H copy.
+__global__ void k_gather_totals(EncodeBatchDev e, uint32_t *totals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < e.n) totals[i] = e.blk_bits[(uint64_t)i * (e.nblocks + 1) + e.nblocks];
+}
+
+static void launch_bit_lengths(const EncodeBatchDev &e, int *d_status, uint32_t *d_totals, cudaStream_t s) {
+  dim3 gb((e.nblocks + 127) / 128, e.n);
+  k_block_bits<<<gb, 128, 0, s>>>(e, d_status);
+  k_scan_bits<<<e.n, SCAN_THREADS, 0, s>>>(e);
+  k_gather_totals<<<(e.n + 127) / 128, 128, 0, s>>>(e, d_totals);
+}
+
+static void launch_entropy(const EncodeBatchDev &e, cudaStream_t s) {
+  dim3 gb((e.nblocks + 127) / 128, e.n);
+  k_pack<<<gb, 128, 0, s>>>(e);
+  dim3 gs((e.nseg + 3) / 4, e.n);
+  k_seg_count<<<gs, 128, 0, s>>>(e);
+  k_seg_scan<<<e.n, SCAN_THREADS, 0, s>>>(e);
+  k_stuff<<<gs, 128, 0, s>>>(e);
+}
+
+}  // namespace hcjk
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+namespace {
+
+struct EncodeSetup {
+  hcj::EncodePlan plan;
+  hcjk::EncodeBatchDev dev;
+  std::vector<void *> owned;
+  std::vector<uint8_t> header;
+  int *d_status = nullptr;
+};
+
+int setup_encode(hcj_ctx *c, int n, int width, int height, int chroma, int quality, int restart_interval, bool entropy,
+                 EncodeSetup *S) {
+  int st = hcj::plan_encode(width, height, chroma, quality, restart_interval, &S->plan);
+  if (st != HCJ_OK) return st;
+  const hcj::EncodePlan &p = S->plan;
+  hcjk::EncodeBatchDev &e = S->dev;
+  memset(&e, 0, sizeof(e));
+  e.n = n;
+  e.ncomp = p.ncomp;
+  e.bpm = p.bpm;
+  uint64_t off = 0;
+  for (int i = 0; i < 3; i++) {
+    e.hs[i] = p.hs[i];
+    e.vs[i] = p.vs[i];
+    e.plane_w[i] = p.plane_w[i];
+    e.plane_h[i] = p.plane_h[i];
+    e.src_w[i] = p.src_w[i];
+    e.src_h[i] = p.src_h[i];
+    e.src_off[i] = off;
+    off += (uint64_t)p.src_w[i] * p.src_h[i];
+  }
+  e.frame_bytes = off;
+  e.mcus_wide = p.mcus_wide;
+  e.mcus_high = p.mcus_high;
+  e.nblocks = (uint32_t)p.nblocks;
+  e.restart_interval = (uint32_t)restart_interval;
+  uint32_t nmcu = (uint32_t)(p.mcus_wide * p.mcus_high);
+  e.nseg = restart_interval ? (nmcu + restart_interval - 1) / restart_interval : 1;
+  for (int k = 0; k < p.bpm; k++) {
+    e.blk_comp[k] = (uint8_t)p.blk_comp[k];
+    e.blk_bx[k] = (uint8_t)p.blk_bx[k];
+    e.blk_by[k] = (uint8_t)p.blk_by[k];
+  }
+  hcj::write_headers(p, &S->header);
+  e.header_len = (uint32_t)S->header.size();
+
+  std::vector<uint32_t> tables(64 * 2 + 32 + 512);
+  uint16_t qt16[128];
+  for (int t = 0; t < 2; t++)
+    for (int i = 0; i < 64; i++) {
+      qt16[t * 64 + i] = p.qt[t][i];
+      tables[t * 64 + i] = (uint32_t)((1ull << 32) / (4u * p.qt[t][i])) + 1u;  // reciprocal of 4q
+    }
+  hcj::encoder_tables(0, 2, &tables[128], &tables[160]);
+  hcj::encoder_tables(1, 3, &tables[144], &tables[160 + 256]);
+
+  auto alloc = [&](void **ptr, size_t bytes) {
+    if (st != HCJ_OK) return;
+    st = c->alloc(ptr, bytes);
+    if (st == HCJ_OK) S->owned.push_back(*ptr);
+  };
+  void *d_tables = nullptr, *d_qt = nullptr, *d_hdr = nullptr;
+  alloc(&d_tables, tables.size() * 4);
+  alloc(&d_qt, sizeof(qt16));
+  alloc(&d_hdr, S->header.size() + 16);
+  alloc((void **)&e.src, e.frame_bytes * (uint64_t)n + 16);
+  alloc((void **)&e.quant, (uint64_t)n * e.nblocks * 128 + 16);
+  alloc((void **)&S->d_status, 4 * (size_t)std::max(n, 1));
+  if (entropy) {
+    alloc((void **)&e.blk_bits, (uint64_t)n * (e.nblocks + 1) * 4);
+    alloc((void **)&e.seg_bytes, (uint64_t)n * (e.nseg + 1) * 4);
+    alloc((void **)&e.out_len, 4 * (size_t)std::max(n, 1));
+  }
+  if (st != HCJ_OK) return st;
+  e.qrecip = reinterpret_cast<const uint32_t *>(d_tables);
+  e.dc_codes = e.qrecip + 128;
+  e.ac_codes = e.qrecip + 160;
+  e.qt = reinterpret_cast<const uint16_t *>(d_qt);
+  e.header = reinterpret_cast<const uint8_t *>(d_hdr);
+  CU_TRY(cudaMemcpyAsync(d_tables, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(d_qt, qt16, sizeof(qt16), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(d_hdr, S->header.data(), S->header.size(), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemsetAsync(S->d_status, 0, 4 * (size_t)std::max(n, 1), c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));  // `tables` / `qt16` are stack / local storage
+  return HCJ_OK;
+}
+
+void teardown_encode(hcj_ctx *c, EncodeSetup *S) {
+  cudaStreamSynchronize(c->stream);
+  for (void *p : S->owned) c->release(p);
+  S->owned.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t hcj_encode_bound(int width, int height, int chroma) {
+  hcj::EncodePlan p;
+  if (hcj::plan_encode(width, height, chroma, 75, 0, &p) != HCJ_OK) return 0;
+  return 1024 + (size_t)p.nblocks * 432 + 16;  // header + 2 x 216 bytes per block (all bytes stuffed) + EOI
+}
+
+int hcj_write_headers(int width, int height, int chroma, int quality, int restart_interval, uint8_t *out, size_t capacity,
+                      size_t *len) {
+  if (!out || !len) return HCJ_ERR_INVALID_ARG;
+  hcj::EncodePlan p;
+  int st = hcj::plan_encode(width, height, chroma, quality, restart_interval, &p);
+  if (st != HCJ_OK) return st;
+  std::vector<uint8_t> h;
+  hcj::write_headers(p, &h);
+  *len = h.size();
+  if (h.size() > capacity) return HCJ_ERR_BUFFER_TOO_SMALL;
+  memcpy(out, h.data(), h.size());
+  return HCJ_OK;
+}
+
+int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
+                     int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len, int *status) {
+  if (!c || n < 0 || (n > 0 && (!yuv || !out || !out_capacity || !out_len))) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  EncodeSetup S;
+  int st = setup_encode(c, n, width, height, chroma, quality, restart_interval, true, &S);
+  if (st != HCJ_OK) {
+    teardown_encode(c, &S);
+    return st;
+  }
+  hcjk::EncodeBatchDev &e = S.dev;
+  cudaStream_t s = c->stream;
+  cudaError_t err = cudaSuccess;
+  for (int i = 0; i < n && err == cudaSuccess; i++)
+    err = cudaMemcpyAsync(const_cast<uint8_t *>(e.src) + (uint64_t)i * e.frame_bytes, yuv[i], e.frame_bytes,
+                          cudaMemcpyHostToDevice, s);
+  std::vector<uint32_t> lens(std::max(n, 1));
+  std::vector<int> dev_status(std::max(n, 1), 0);
+  if (err == cudaSuccess && n > 0) {
+    // phase 1: coefficients and the bit length of every block; the totals size the byte buffers
+    hcjk::launch_encode(e, s);
+    hcjk::launch_bit_lengths(e, S.d_status, e.out_len, s);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(lens.data(), e.out_len, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    uint64_t max_bits = 0;
+    for (int i = 0; i < n; i++) max_bits = std::max<uint64_t>(max_bits, lens[i]);
+    e.raw_stride = hcj::align_up(max_bits / 8 + e.nseg + 64, 256);
+    e.out_stride = hcj::align_up(e.header_len + 2 * e.raw_stride + 2ull * e.nseg + 16, 256);  // every byte stuffed
+    if (err == cudaSuccess) {
+      st = c->alloc((void **)&e.raw, (uint64_t)n * e.raw_stride);
+      if (st == HCJ_OK) S.owned.push_back(e.raw);
+      if (st == HCJ_OK) st = c->alloc((void **)&e.out, (uint64_t)n * e.out_stride);
+      if (st == HCJ_OK) S.owned.push_back(e.out);
+    }
+    if (st != HCJ_OK) {
+      teardown_encode(c, &S);
+      return st;
+    }
+    // phase 2: pack, stuff, assemble
+    if (err == cudaSuccess) err = cudaMemsetAsync(e.raw, 0, (uint64_t)n * e.raw_stride, s);  // the packer ORs into zeroed words
+    if (err == cudaSuccess) {
+      hcjk::launch_entropy(e, s);
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(lens.data(), e.out_len, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dev_status.data(), S.d_status, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    for (int i = 0; i < n && err == cudaSuccess; i++) {
+      int sti = dev_status[i];
+      out_len[i] = lens[i];
+      if (sti == HCJ_OK && (!out[i] || out_capacity[i] < lens[i])) sti = HCJ_ERR_BUFFER_TOO_SMALL;
+      if (sti == HCJ_OK)
+        err = cudaMemcpyAsync(out[i], e.out + (uint64_t)i * e.out_stride, lens[i], cudaMemcpyDeviceToHost, s);
+      if (status) status[i] = sti;
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  }
+  teardown_encode(c, &S);
+  return err == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)err;
+}
+
+int hcj_encode_quantized(hcj_ctx *c, const uint8_t *yuv, int width, int height, int chroma, int quality, int16_t *quant,
+                         size_t capacity_blocks) {
+  if (!c || !yuv || !quant) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  EncodeSetup S;
+  int st = setup_encode(c, 1, width, height, chroma, quality, 0, false, &S);
+  if (st == HCJ_OK && capacity_blocks < S.dev.nblocks) st = HCJ_ERR_BUFFER_TOO_SMALL;
+  cudaError_t err = cudaSuccess;
+  if (st == HCJ_OK) {
+    hcjk::EncodeBatchDev &e = S.dev;
+    err = cudaMemcpyAsync(const_cast<uint8_t *>(e.src), yuv, e.frame_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (err == cudaSuccess) {
+      hcjk::launch_encode(e, c->stream);
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(quant, e.quant, (size_t)e.nblocks * 128, cudaMemcpyDeviceToHost, c->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  }
+  teardown_encode(c, &S);
+  if (st != HCJ_OK) return st;
+  return err == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)err;
+}
+
+}  // extern "C"

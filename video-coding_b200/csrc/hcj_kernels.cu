@@ -1,0 +1,649 @@
+// hcj_kernels.cu — decode kernels for sm_100a.
+//
+//   k_destuff        D3  extract_entropy_coded_bits (decoder.ml:261-281) + restart-marker scan
+//   k_huff_restart   D6  huffman_decode per restart interval (stated extension), DC resolved in-thread
+//   k_huff_spec      D6  huffman_decode of a scan without restart markers: self-synchronising
+//                        speculative subsequence decode, block-wide fix-point, prefix sums for block
+//                        indices and DC predictors (decoder.ml:118-165,347-397)
+//   k_idct           D7-D11 dequantise + inverse zig-zag + Chen IDCT + clip + store (+ crop)
+//   k_rgb            D12/D13 Planar_444 up-sampling + stated YCbCr->RGB
+//
+// None of this is GEMM-shaped: no tensor cores.  The entropy kernels are issue/latency bound, the
+// IDCT kernel is HBM bound (DESIGN.md has the byte counts).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hcj_device.cuh"
+#include "hcj_kernels.cuh"
+
+namespace hcjk {
+
+using namespace hcjdev;
+
+// ================================================================================================
+// K1: destuff + marker scan.  One CTA per image walks the scan in 4 KiB tiles; within a tile every
+// thread classifies 16 bytes from (previous byte, byte) pairs exactly as the model's recursive
+// search_for_marker does, a block scan turns the keep flags into output offsets.
+// ================================================================================================
+constexpr int DS_THREADS = 256;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
+  const int img = blockIdx.x;
+  const HcjImageDesc &d = b.descs[img];
+  if (!d.valid) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t *file = b.files + d.file_off;
+  uint8_t *ent = b.entropy + d.ent_off;
+  uint32_t *segs = b.seg_offs + d.seg_off;
+  const bool restart = d.ri > 0;
+  const uint32_t start = d.scan_start, flen = d.file_len, nseg_expected = d.nseg_expected;
+
+  __shared__ uint8_t s_last[DS_THREADS];
+  __shared__ uint32_t s_warp[DS_THREADS / 32];
+  __shared__ uint32_t s_min[DS_THREADS / 32];
+
+  uint32_t carry_out = 0, carry_mark = 0;
+  uint32_t prev_tile_last = 0;
+  bool found = false;
+
+  for (uint32_t base = start & ~15u; base < flen && !found; base += DS_THREADS * 16) {
+    const uint32_t off = base + tid * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (off < flen) v = __ldg(reinterpret_cast<const uint4 *>(file + off));
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    s_last[tid] = (uint8_t)(v.w >> 24);
+    __syncthreads();
+    uint32_t prev = tid == 0 ? prev_tile_last : s_last[tid - 1];
+
+    uint32_t emit = 0, mark = 0, term = 0, ffmask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+      uint32_t pos = off + i;
+      uint32_t p = pos == start ? 0u : prev;  // the model starts with prev = '\x00' (decoder.ml:279)
+      bool in = pos >= start && pos < flen;
+      if (in) {
+        if (p == 0xffu) {
+          if (c == 0u) {
+            emit |= 1u << i;
+            ffmask |= 1u << i;  // this slot emits the deferred FF
+          } else if (restart && (c & 0xf8u) == 0xd0u) {
+            mark |= 1u << i;
+          } else {
+            term |= 1u << i;
+          }
+        } else if (c != 0xffu) {
+          emit |= 1u << i;
+        }
+      }
+      prev = c;
+    }
+    // first terminator of the tile
+    uint32_t tpos = term ? off + (uint32_t)__ffs((int)term) - 1u : 0xffffffffu;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) tpos = min(tpos, __shfl_xor_sync(0xffffffffu, tpos, s));
+    if (lane == 0) s_min[warp] = tpos;
+    __syncthreads();
+    uint32_t tmin = s_min[0];
+#pragma unroll
+    for (int k = 1; k < DS_THREADS / 32; k++) tmin = min(tmin, s_min[k]);
+    if (tmin != 0xffffffffu) {
+      found = true;
+      // drop everything at or after the terminator
+      if (off + 16 > tmin) {
+        uint32_t keep = tmin > off ? (1u << (tmin - off)) - 1u : 0u;
+        emit &= keep;
+        mark &= keep;
+      }
+    }
+    // block exclusive scan of (markers << 16 | emitted bytes)
+    uint32_t cnt = ((uint32_t)__popc(mark) << 16) | (uint32_t)__popc(emit);
+    uint32_t incl = warp_incl_scan(cnt, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < DS_THREADS / 32; k++) {
+      uint32_t t = s_warp[k];
+      if (k < warp) wbase += t;
+      total += t;
+    }
+    uint32_t excl = wbase + incl - cnt;
+    uint32_t opos = carry_out + (excl & 0xffffu);
+    uint32_t mk = carry_mark + (excl >> 16);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (emit & (1u << i)) {
+        uint32_t c = (ffmask & (1u << i)) ? 0xffu : (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+        ent[opos++] = (uint8_t)c;
+      } else if (mark & (1u << i)) {
+        mk++;
+        if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+      }
+    }
+    carry_out += total & 0xffffu;
+    carry_mark += total >> 16;
+    prev_tile_last = s_last[DS_THREADS - 1];
+    __syncthreads();  // s_last / s_warp / s_min are rewritten by the next tile
+  }
+  if (tid == 0) {
+    HcjImageState st;
+    st.ent_len = carry_out;
+    st.nseg_found = carry_mark + 1;
+    st.status = HCJ_DEV_OK;
+    st.pad_ = 0;
+    st.err_key = HCJ_NO_ERR_KEY;
+    if (!found) st.status = HCJ_DEV_NO_TERMINATOR;
+    else if (restart && st.nseg_found != nseg_expected) st.status = HCJ_DEV_RESTART_COUNT;
+    segs[0] = 0;
+    segs[nseg_expected] = carry_out;
+    b.states[img] = st;
+  }
+}
+
+void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
+  if (b.n > 0) k_destuff<<<b.n, DS_THREADS, 0, s>>>(b);
+}
+
+// ================================================================================================
+// Huffman tables in shared memory, shared by K2 and K3.
+// ================================================================================================
+struct SmemTables {
+  uint16_t primary[HCJ_MAX_COMP * 2 * HCJ_LUT_SIZE];  // [pair][dc/ac][HCJ_LUT_SIZE]
+  uint32_t max_bits[HCJ_MAX_COMP * 2];
+  const uint16_t *full[HCJ_MAX_COMP * 2];
+  uint8_t comp_pair[HCJ_MAX_COMP];
+  uint8_t blk_comp[HCJ_MAX_BPM + 2];
+};
+
+__device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev &b, const HcjImageDesc &d) {
+  const HcjTableSet &ts = b.table_sets[d.table_set];
+  const uint32_t n = ts.npairs * 2 * HCJ_LUT_SIZE;
+  const uint4 *src = reinterpret_cast<const uint4 *>(b.lut_primary + ts.primary_off);
+  uint4 *dst = reinterpret_cast<uint4 *>(st.primary);
+  for (uint32_t i = threadIdx.x; i < n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (threadIdx.x < HCJ_MAX_COMP * 2) {
+    const HcjTableMeta &m = ts.meta[threadIdx.x >> 1][threadIdx.x & 1];
+    st.max_bits[threadIdx.x] = m.max_bits;
+    st.full[threadIdx.x] = b.lut_full + m.full_off;
+  }
+  if (threadIdx.x < HCJ_MAX_COMP) st.comp_pair[threadIdx.x] = (uint8_t)d.comp[threadIdx.x].pair;
+  if (threadIdx.x < HCJ_MAX_BPM) st.blk_comp[threadIdx.x] = d.blk_comp[threadIdx.x];
+}
+
+__device__ __forceinline__ Tables tables_of(const SmemTables &st, uint32_t comp) {
+  uint32_t pr = st.comp_pair[comp];
+  Tables t;
+  t.dc_primary = st.primary + (pr * 2 + 0) * HCJ_LUT_SIZE;
+  t.ac_primary = st.primary + (pr * 2 + 1) * HCJ_LUT_SIZE;
+  t.dc_full = st.full[pr * 2 + 0];
+  t.ac_full = st.full[pr * 2 + 1];
+  t.dc_max_bits = st.max_bits[pr * 2 + 0];
+  t.ac_max_bits = st.max_bits[pr * 2 + 1];
+  return t;
+}
+
+__device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32_t bit_pos) {
+  atomicMin(&st->err_key, ((unsigned long long)bit_pos << 8) | (unsigned long long)(-code));
+}
+
+// ================================================================================================
+// K2: one thread per restart interval.  Intervals are byte aligned and start with every DC predictor
+// at 0, so a thread owns its MCUs outright and writes resolved coefficients straight to HBM.
+// ================================================================================================
+constexpr int HR_THREADS = 128;
+
+__global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
+  __shared__ SmemTables st;
+  const uint32_t img = b.list_restart[blockIdx.y];
+  const HcjImageDesc &d = b.descs[img];
+  const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
+  if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
+  load_tables(st, b, d);
+  __syncthreads();
+  HcjImageState *state = b.states + img;
+  if (seg >= d.nseg_expected || state->status != 0) return;
+
+  const uint32_t *segs = b.seg_offs + d.seg_off;
+  const uint32_t seg_begin = segs[seg], seg_end = segs[seg + 1];
+  const uint32_t seg_bits = (seg_end - seg_begin) * 8u;
+  const uint32_t ri = d.ri ? d.ri : d.nmcu;
+  const uint32_t mcu0 = seg * ri, mcu1 = min(mcu0 + ri, d.nmcu);
+  const uint32_t bpm = d.bpm;
+  int16_t *coefs = b.coefs + (d.coef_off + (uint64_t)mcu0 * bpm) * 64;
+
+  BitReader br;
+  br.init(reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off), seg_begin * 8u, seg_end * 8u);
+  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
+    for (uint32_t k = 0; k < bpm; k++, coefs += 64) {
+      const uint32_t comp = st.blk_comp[k];
+      const Tables t = tables_of(st, comp);
+      int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
+      int err = decode_block_exact(br, t, seg_bits, pred, coefs);
+      if (err) {
+        raise_status(state, err, br.pos);
+        return;
+      }
+      if (comp == 0) p0 = pred;
+      else if (comp == 1) p1 = pred;
+      else if (comp == 2) p2 = pred;
+      else p3 = pred;
+    }
+  }
+}
+
+void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
+  if (b.n_restart == 0) return;
+  dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.n_restart);
+  k_huff_restart<<<grid, HR_THREADS, 0, s>>>(b);
+}
+
+// ================================================================================================
+// K3: scans without restart markers.  One CTA per image; subsequences of SPEC_BITS bits, one per
+// thread, processed in chunks of SPEC_THREADS.  Per chunk:
+//   A  every thread decodes its subsequence from a guessed state (block 0 of an MCU, DC next),
+//      thread 0 from the exact state carried over from the previous chunk;
+//   B  fix-point: re-decode from the end state of the left neighbour until no end state changes
+//      (after k rounds the first k+1 subsequences are exact, so this terminates; JPEG streams
+//      self-synchronise within a few hundred bits, so it takes 2-4 rounds in practice);
+//   C  block-wide exclusive scans of (blocks begun, DC sums) give every thread its block index and
+//      DC predictors; a final exact pass stores the coefficients.
+// ================================================================================================
+constexpr int SPEC_THREADS = 512;
+constexpr uint32_t SPEC_BITS = 1024;
+
+struct SpecCarry {
+  uint32_t p, cz;
+  int64_t nstart;
+  int32_t dc[HCJ_MAX_COMP];
+};
+
+__device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t *s_warp, int32_t &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  __syncthreads();  // s_warp may still be read from the previous scan
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int32_t base = 0;
+  total = 0;
+#pragma unroll
+  for (int k = 0; k < SPEC_THREADS / 32; k++) {
+    int32_t t = s_warp[k];
+    if (k < warp) base += t;
+    total += t;
+  }
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
+  __shared__ SmemTables st;
+  __shared__ ScanCtx sc;
+  __shared__ uint2 s_end[SPEC_THREADS];
+  __shared__ int32_t s_scan[SPEC_THREADS / 32];
+  __shared__ SpecCarry carry;
+
+  const uint32_t img = b.list_spec[blockIdx.x];
+  const HcjImageDesc &d = b.descs[img];
+  HcjImageState *state = b.states + img;
+  const int t = threadIdx.x;
+  load_tables(st, b, d);
+  __syncthreads();
+  if (t == 0) {
+    sc.words = reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off);
+    sc.total_bits = state->ent_len * 8u;
+    sc.bpm = d.bpm;
+    sc.blk_comp = st.blk_comp;
+    carry.p = 0;
+    carry.cz = 0;
+    carry.nstart = 0;
+    for (int k = 0; k < HCJ_MAX_COMP; k++) carry.dc[k] = 0;
+  }
+  if (t < d.ncomp) sc.tab[t] = tables_of(st, t);
+  __syncthreads();
+  if (state->status != 0) return;
+
+  const uint32_t L = sc.total_bits;
+  const int64_t nblocks = d.nblocks;
+  int16_t *coefs = b.coefs + d.coef_off * 64;
+
+  if (L <= 16u) {
+    // Degenerate scans: the model's `show` bound (bitstream_reader.ml:32) is in play; decode serially.
+    if (t == 0) {
+      BitReader br;
+      br.init(sc.words, 0, L);
+      int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+      for (int64_t blk = 0; blk < nblocks; blk++) {
+        uint32_t comp = st.blk_comp[blk % d.bpm];
+        int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+        if (err) {
+          raise_status(state, err, br.pos);
+          break;
+        }
+      }
+    }
+    return;
+  }
+
+  const uint32_t nsub = (L + SPEC_BITS - 1) / SPEC_BITS;
+  for (uint32_t base = 0; base < nsub; base += SPEC_THREADS) {
+    const uint32_t i = base + t;
+    const bool active = i < nsub;
+    const bool last = i == nsub - 1;
+    const uint32_t lo = i * SPEC_BITS;
+    const uint32_t hi = active ? min(lo + SPEC_BITS, L) : 0u;
+
+    // ---- A: speculative first pass
+    uint2 mystart = t == 0 ? make_uint2(carry.p, carry.cz) : make_uint2(lo, 0u);
+    SubResult r;
+    r.p = mystart.x;
+    r.cz = mystart.y;
+    r.nstart = 0;
+    r.dcsum[0] = r.dcsum[1] = r.dcsum[2] = r.dcsum[3] = 0;
+    if (active) subseq_sync(sc, mystart.x, mystart.y, hi, r);
+    s_end[t] = make_uint2(r.p, r.cz);
+    __syncthreads();
+
+    // ---- B: fix-point over the chunk
+    for (;;) {
+      uint2 ns = t == 0 ? make_uint2(carry.p, carry.cz) : s_end[t - 1];
+      int changed = 0;
+      if (active && (ns.x != mystart.x || ns.y != mystart.y)) {
+        mystart = ns;
+        uint2 old = make_uint2(r.p, r.cz);
+        subseq_sync(sc, ns.x, ns.y, hi, r);
+        changed = (r.p != old.x) | (r.cz != old.y);
+      }
+      __syncthreads();  // every s_end[t - 1] has been read
+      if (changed) s_end[t] = make_uint2(r.p, r.cz);
+      if (!__syncthreads_or(changed)) break;
+    }
+
+    // ---- C: prefix sums, then the exact pass that stores coefficients
+    int32_t tot_n, tot0, tot1, tot2, tot3;
+    int32_t ex_n = block_excl_scan(active ? (int32_t)r.nstart : 0, s_scan, tot_n);
+    int32_t ex0 = block_excl_scan(active ? r.dcsum[0] : 0, s_scan, tot0);
+    int32_t ex1 = block_excl_scan(active ? r.dcsum[1] : 0, s_scan, tot1);
+    int32_t ex2 = block_excl_scan(active ? r.dcsum[2] : 0, s_scan, tot2);
+    int32_t ex3 = block_excl_scan(active ? r.dcsum[3] : 0, s_scan, tot3);
+    if (active) {
+      int32_t pred[HCJ_MAX_COMP] = {carry.dc[0] + ex0, carry.dc[1] + ex1, carry.dc[2] + ex2, carry.dc[3] + ex3};
+      int64_t blk = carry.nstart + ex_n - 1;
+      uint32_t err_pos = 0;
+      int err = subseq_write(sc, mystart.x, mystart.y, last ? 0xffffffffu : hi, blk, pred, nblocks, coefs, &err_pos);
+      if (err) raise_status(state, err, err_pos);
+    }
+    __syncthreads();  // all reads of carry done
+    const uint32_t last_t = min(nsub - base, (uint32_t)SPEC_THREADS) - 1;
+    if (t == (int)last_t) {
+      carry.p = r.p;
+      carry.cz = r.cz;
+      carry.nstart += tot_n;
+      carry.dc[0] += tot0;
+      carry.dc[1] += tot1;
+      carry.dc[2] += tot2;
+      carry.dc[3] += tot3;
+    }
+    __syncthreads();
+  }
+}
+
+void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
+  if (b.n_spec == 0) return;
+  k_huff_spec<<<b.n_spec, SPEC_THREADS, 0, s>>>(b);
+}
+
+// ================================================================================================
+// K5: fused dequantise + inverse zig-zag + Chen IDCT + clip/level shift + store (+ crop).
+//
+// A CTA owns up to `tile_mcus` consecutive MCUs of one MCU row.  Their coefficient blocks are one
+// contiguous run in HBM (block order = decode_seq order) and are staged into shared memory with
+// 16-byte cp.async copies; block rows are padded to 144 bytes so that the per-thread 16-byte reads are
+// bank-conflict free.  One thread reconstructs one 8x8 block entirely in registers; threads are ordered
+// (component, block row, MCU, block column) so that a warp stores 32 horizontally adjacent blocks:
+// every store instruction writes 256 contiguous bytes of one image row.
+// ================================================================================================
+constexpr int IDCT_MAX_THREADS = 256;
+constexpr int IDCT_ROW_U4 = 9;  // 144 bytes per staged block
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void unpack8(const uint4 &u, int16_t *c) {
+  c[0] = (int16_t)(u.x & 0xffffu);
+  c[1] = (int16_t)(u.x >> 16);
+  c[2] = (int16_t)(u.y & 0xffffu);
+  c[3] = (int16_t)(u.y >> 16);
+  c[4] = (int16_t)(u.z & 0xffffu);
+  c[5] = (int16_t)(u.z >> 16);
+  c[6] = (int16_t)(u.w & 0xffffu);
+  c[7] = (int16_t)(u.w >> 16);
+}
+
+__device__ __forceinline__ void store_block_rows(const uint8_t pix[64], uint8_t *dst, int stride, int x, int y,
+                                                 int w_limit, int h_limit) {
+  // dst: plane base; (x, y): top-left sample of the block; samples outside w_limit x h_limit are cropped.
+  const bool fast = (x + 8 <= w_limit) && ((((uintptr_t)dst + (size_t)y * stride + x) & 7u) == 0) && ((stride & 7) == 0);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (y + r >= h_limit) break;
+    uint8_t *row = dst + (size_t)(y + r) * stride + x;
+    if (fast) {
+      uint2 v;
+      v.x = pix[r * 8 + 0] | (pix[r * 8 + 1] << 8) | (pix[r * 8 + 2] << 16) | ((uint32_t)pix[r * 8 + 3] << 24);
+      v.y = pix[r * 8 + 4] | (pix[r * 8 + 5] << 8) | (pix[r * 8 + 6] << 16) | ((uint32_t)pix[r * 8 + 7] << 24);
+      *reinterpret_cast<uint2 *>(row) = v;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (x + i < w_limit) row[i] = pix[r * 8 + i];
+    }
+  }
+}
+
+// mode: 0 = HCJ_OUT_YUV (cropped planes, packed), 1 = padded planes into b.out, 2 = padded planes into b.planes
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct(DecodeBatchDev b, int mode) {
+  extern __shared__ uint4 s_tile[];
+  const HcjImageDesc &d = b.descs[blockIdx.y];
+  if (!d.valid) return;
+  const int bpm = d.bpm;
+  const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / bpm);
+  const int tiles_per_row = (d.mcus_wide + tm_max - 1) / tm_max;
+  const int tm_bal = (d.mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
+  const int tile = blockIdx.x;
+  if (tile >= tiles_per_row * d.mcus_high) return;
+  const int my = tile / tiles_per_row, tx = tile - my * tiles_per_row;
+  const int m0 = tx * tm_bal;
+  const int tm = min(tm_bal, d.mcus_wide - m0);
+  const int nblk = tm * bpm;
+  const int tid = threadIdx.x;
+
+  const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)my * d.mcus_wide + m0) * bpm) * 64;
+  for (int g = tid; g < nblk * 8; g += blockDim.x) cp_async16(&s_tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+  cp_async_wait_all();
+  __syncthreads();
+  if (tid >= nblk) return;
+
+  // thread -> (component, block row, MCU, block column)
+  int rem = tid, c = 0;
+  for (; c < d.ncomp - 1; c++) {
+    int n = tm * d.comp[c].hs * d.comp[c].vs;
+    if (rem < n) break;
+    rem -= n;
+  }
+  const HcjCompGeom &g = d.comp[c];
+  const int rowlen = tm * g.hs;
+  const int by = rem / rowlen, r2 = rem - by * rowlen;
+  const int m = r2 / g.hs, bx = r2 - m * g.hs;
+  const int slot = m * bpm + g.first_blk + by * g.hs + bx;
+
+  int16_t coef[64];
+#pragma unroll
+  for (int j = 0; j < 8; j++) unpack8(s_tile[slot * IDCT_ROW_U4 + j], coef + 8 * j);
+  uint16_t q[64];
+  const uint4 *qsrc = reinterpret_cast<const uint4 *>(b.qtables + d.qt_off + g.qt * 64);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint4 u = __ldg(qsrc + j);
+    unpack8(u, reinterpret_cast<int16_t *>(q) + 8 * j);
+  }
+  uint8_t pix[64];
+  reconstruct_block(coef, q, d.wide_idct != 0, pix);
+
+  const int x = ((m0 + m) * g.hs + bx) * 8, y = (my * g.vs + by) * 8;
+  if (mode == 0) {
+    store_block_rows(pix, b.out + d.out_off + g.out_off, g.actual_w, x, y, g.actual_w, g.actual_h);
+  } else {
+    uint8_t *base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
+    store_block_rows(pix, base, g.decoded_w, x, y, g.decoded_w, g.decoded_h);
+  }
+}
+
+void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
+  if (b.n == 0 || b.max_idct_tiles == 0) return;
+  dim3 grid(b.max_idct_tiles, b.n);
+  size_t smem = (size_t)IDCT_MAX_THREADS * IDCT_ROW_U4 * sizeof(uint4);
+  k_idct<<<grid, IDCT_MAX_THREADS, smem, s>>>(b, mode);
+}
+
+// Debug tap: Component.recon of caller-provided blocks (hcj_idct_blocks).
+__global__ void k_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, int force_wide, uint8_t *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblocks) return;
+  int16_t c[64];
+  uint16_t q[64];
+  const uint4 *src = reinterpret_cast<const uint4 *>(coefs + i * 64);
+  const uint4 *qs = reinterpret_cast<const uint4 *>(qt);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    unpack8(__ldg(src + j), c + 8 * j);
+    unpack8(__ldg(qs + j), reinterpret_cast<int16_t *>(q) + 8 * j);
+  }
+  uint8_t pix[64];
+  reconstruct_block(c, q, force_wide != 0, pix);
+  uint4 *dst = reinterpret_cast<uint4 *>(out + i * 64);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint4 v;
+    uint32_t *vv = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      vv[k] = pix[j * 16 + k * 4] | (pix[j * 16 + k * 4 + 1] << 8) | (pix[j * 16 + k * 4 + 2] << 16) |
+              ((uint32_t)pix[j * 16 + k * 4 + 3] << 24);
+    dst[j] = v;
+  }
+}
+
+void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
+                        cudaStream_t s) {
+  if (nblocks == 0) return;
+  k_idct_blocks<<<(unsigned)((nblocks + 127) / 128), 128, 0, s>>>(coefs, nblocks, qt, force_wide ? 1 : 0, out);
+}
+
+// ================================================================================================
+// K9: Planar_444 up-sampling (tools/src/planar_444.ml:25-33,82-103) + YCbCr -> RGB24 (stated formula,
+// JFIF full range, 16-bit fixed point).  One thread per 4 horizontally adjacent pixels.
+// Reads the padded planes written by k_idct (mode 2); the up-sampling clamps at the CROPPED plane
+// edge, as Planar_444 does on the cropped frame.
+// ================================================================================================
+__device__ __forceinline__ int up_sample(const uint8_t *p, int stride, int w, int h, int x, int y, int hs_log, int vs_log) {
+  // hs_log / vs_log: 1 if this axis is subsampled by 2.  (x, y) in full-resolution coordinates.
+  int cx = x >> hs_log, cy = y >> vs_log;
+  int cx1 = min(cx + 1, w - 1), cy1 = min(cy + 1, h - 1);
+  int a = p[cy * stride + cx];
+  bool ox = hs_log && (x & 1), oy = vs_log && (y & 1);
+  if (!ox && !oy) return a;
+  if (ox && !oy) return (a + p[cy * stride + cx1] + 1) >> 1;
+  if (!ox && oy) return (a + p[cy1 * stride + cx] + 1) >> 1;
+  // the model's edge columns use avg2 of the two rows (planar_444.ml:97-102); with cx1 == cx that is
+  // what avg4(a, a, c, c) would NOT give after rounding, so treat the edge explicitly
+  if (cx1 == cx) return (a + p[cy1 * stride + cx] + 1) >> 1;
+  return (a + p[cy * stride + cx1] + p[cy1 * stride + cx] + p[cy1 * stride + cx1] + 2) >> 2;
+}
+
+__global__ void k_rgb(DecodeBatchDev b) {
+  const HcjImageDesc &d = b.descs[blockIdx.z];
+  if (!d.valid || d.chroma == 0) return;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (y >= d.height || x0 >= d.width) return;
+  const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
+  const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off,
+                *pv = b.planes + d.comp[2].plane_off;
+  uint8_t *dst = b.out + d.out_off + ((size_t)y * d.width + x0) * 3;
+  uint8_t rgb[12];
+  const int n = min(4, d.width - x0);
+  for (int i = 0; i < n; i++) {
+    int x = x0 + i;
+    int Y = py[y * d.comp[0].decoded_w + x];
+    int Cb = up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log) - 128;
+    int Cr = up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log) - 128;
+    int r = Y + ((91881 * Cr + 32768) >> 16);
+    int g = Y + ((-22554 * Cb - 46802 * Cr + 32768) >> 16);
+    int bl = Y + ((116130 * Cb + 32768) >> 16);
+    rgb[3 * i + 0] = (uint8_t)min(255, max(0, r));
+    rgb[3 * i + 1] = (uint8_t)min(255, max(0, g));
+    rgb[3 * i + 2] = (uint8_t)min(255, max(0, bl));
+  }
+  if (n == 4 && ((uintptr_t)dst & 3u) == 0) {
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(rgb);
+    d32[0] = s32[0];
+    d32[1] = s32[1];
+    d32[2] = s32[2];
+  } else {
+    for (int i = 0; i < 3 * n; i++) dst[i] = rgb[i];
+  }
+}
+
+void launch_rgb(const DecodeBatchDev &b, cudaStream_t s) {
+  if (b.n == 0 || b.max_rgb_rows == 0) return;
+  dim3 block(128);
+  dim3 grid((b.max_width / 4 + 127 + 1) / 128, b.max_rgb_rows, b.n);
+  k_rgb<<<grid, block, 0, s>>>(b);
+}
+
+// Ocompare.square_error / max_difference (tools/src/ocompare.ml:8-52).
+__global__ void k_compare(const uint8_t *a, const uint8_t *bb, size_t n, unsigned long long *sse, int *maxdiff) {
+  unsigned long long acc = 0;
+  int mx = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int dlt = abs((int)a[i] - (int)bb[i]);
+    acc += (unsigned long long)(dlt * dlt);
+    mx = max(mx, dlt);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sse, acc);
+    atomicMax(maxdiff, mx);
+  }
+}
+
+void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff, cudaStream_t s) {
+  if (n == 0) return;
+  size_t want = (n + 255) / 256;
+  unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  k_compare<<<blocks, 256, 0, s>>>(a, b, n, sse, maxdiff);
+}
+
+}  // namespace hcjk

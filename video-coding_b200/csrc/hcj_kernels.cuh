@@ -1,0 +1,81 @@
+// hcj_kernels.cuh — launch wrappers of the CUDA kernels (hcj_kernels.cu), called by hcj_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hcj_common.h"
+
+namespace hcjk {
+
+// Everything the decode kernels need about one batch resident in HBM.
+struct DecodeBatchDev {
+  int n;                          // images
+  const HcjImageDesc *descs;      // [n]
+  HcjImageState *states;          // [n]
+  const uint8_t *files;           // compressed files, each starting at a 16-byte boundary
+  uint8_t *entropy;               // destuffed entropy-coded bytes per image
+  uint32_t *seg_offs;             // per image: nseg_expected + 1 byte offsets into its entropy bytes
+  const HcjTableSet *table_sets;
+  const uint16_t *lut_primary;    // primary LUT pool
+  const uint16_t *lut_full;       // full LUT pool
+  const uint16_t *qtables;        // quant tables pool, zig-zag order
+  int16_t *coefs;                 // [total blocks][64], zig-zag, DC resolved
+  uint8_t *planes;                // padded planes (scratch for RGB mode, the output for PLANES mode)
+  uint8_t *out;                   // outputs
+  // launch geometry, computed on the host
+  const uint32_t *list_restart;   // images decoded per restart interval
+  int n_restart;
+  uint32_t max_segments;          // max nseg_expected over list_restart
+  const uint32_t *list_spec;      // images decoded speculatively (no restart markers)
+  int n_spec;
+  uint32_t max_idct_tiles;        // max over images of tiles_per_row * mcus_high
+  int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
+  uint32_t max_rgb_rows;          // max image height (RGB mode)
+  uint32_t max_width;
+  uint64_t total_blocks;
+};
+
+void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
+void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
+void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
+void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s);
+void launch_rgb(const DecodeBatchDev &b, cudaStream_t s);
+void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
+                        cudaStream_t s);
+void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff,
+                    cudaStream_t s);
+
+// ---- encoder ----
+struct EncodeBatchDev {
+  int n;                      // frames
+  int ncomp, bpm;
+  int hs[3], vs[3];
+  int plane_w[3], plane_h[3]; // padded geometry (never materialised: reads outside src are 0)
+  int src_w[3], src_h[3];
+  uint64_t src_off[3];        // offset of each source plane inside one frame
+  uint64_t frame_bytes;       // bytes of one source frame
+  int mcus_wide, mcus_high;
+  uint32_t nblocks;           // per frame
+  uint32_t restart_interval;  // 0 = none
+  uint32_t nseg;              // segments per frame (1 if no restart)
+  uint8_t blk_comp[HCJ_MAX_BPM + 2], blk_bx[HCJ_MAX_BPM + 2], blk_by[HCJ_MAX_BPM + 2];
+  const uint8_t *src;         // [n] frames
+  const uint16_t *qt;         // [2][64] zig-zag
+  const uint32_t *qrecip;     // [2][64] reciprocals of 4q
+  const uint32_t *dc_codes;   // [2][16]  (bits << 8) | length
+  const uint32_t *ac_codes;   // [2][256]
+  int16_t *quant;             // [n][nblocks][64] zig-zag, DC absolute
+  uint32_t *blk_bits;         // [n][nblocks] bit length of each block's code, later exclusive offsets per segment
+  uint32_t *seg_bytes;        // [n][nseg] stuffed byte length of every segment
+  uint8_t *raw;               // [n][raw_stride] unstuffed packed bits, segments byte-aligned
+  uint64_t raw_stride;
+  uint8_t *out;               // [n][out_stride] finished files
+  uint64_t out_stride;
+  uint32_t *out_len;          // [n]
+  const uint8_t *header;      // shared header bytes
+  uint32_t header_len;
+};
+void launch_encode(const EncodeBatchDev &e, cudaStream_t s);
+int encode_kernel_count();
+
+}  // namespace hcjk
