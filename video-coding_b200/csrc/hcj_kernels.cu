@@ -566,6 +566,8 @@ void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt
 __device__ __forceinline__ int up_sample(const uint8_t *p, int stride, int w, int h, int x, int y, int hs_log, int vs_log) {
   // hs_log / vs_log: 1 if this axis is subsampled by 2.  (x, y) in full-resolution coordinates.
   int cx = x >> hs_log, cy = y >> vs_log;
+  // odd luma sizes: Planar_444 never writes the last column / row of the (zero-initialised) 4:4:4 plane
+  if (cx >= w || cy >= h) return 0;
   int cx1 = min(cx + 1, w - 1), cy1 = min(cy + 1, h - 1);
   int a = p[cy * stride + cx];
   bool ox = hs_log && (x & 1), oy = vs_log && (y & 1);
