@@ -153,8 +153,8 @@ def peaks():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="restart8", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: per workload)")
@@ -202,7 +202,7 @@ def main():
         v = float(np.mean([x["value"] for x in vals]))
         cb = dict(vals[-1], value=v)
         print(json.dumps({
-            "impl": "reference", "metric": "decoded megapixels/sec" if kind == "decode" else "encoded megapixels/sec",
+            "impl": "reference", "metric": "%s megapixels/sec (%dx%d %d baseline)" % ("decoded" if kind == "decode" else "encoded", w, h, chroma),
             "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean([float(x["sample"].split(",")[-1].split()[0]) for x in vals])),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -250,11 +250,11 @@ def main():
         # ---- value: resident inputs, kernels only
         b = ctx.batch(batch_jpgs, mode)
         assert all(s == 0 for s in b.host_status)
+        sampler.start()
         for _ in range(max(args.warmup, 3)):
             b.decode()
         ctx.synchronize()
         barrier()
-        sampler.start()
         ctx.timer_start()
         for _ in range(args.steps):
             b.decode()
@@ -282,7 +282,8 @@ def main():
             "rgb": nblocks * 64 + out_bytes,
             "zero_coefficients": 128 * nblocks,
         }
-        kernels_only = {k: v for k, v in stages.items() if k != "zero_coefficients" and v > 0}
+        stages = {k: v for k, v in stages.items() if v > 0.02}  # stages that did not launch read as ~0.003 ms
+        kernels_only = {k: v for k, v in stages.items() if k != "zero_coefficients"}
         dom = max(kernels_only, key=kernels_only.get)
         peak, peak_src = peaks()
         achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9

@@ -30,8 +30,8 @@ def lib():
         L = C.CDLL(build())
         L.emu_reconstruct_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_idct32_unguarded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
-        L.emu_decode_segments.argtypes = [C.c_char_p, C.c_int64, C.c_uint, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p]
-        L.emu_decode_speculative.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_int)]
+        L.emu_decode_segments.argtypes = [C.c_char_p, C.c_int64, C.c_uint, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emu_decode_speculative.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
         L.emu_fdct_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_quantize_check.argtypes = [C.c_int]
         L.emu_quantize_check.restype = C.c_int64
@@ -84,7 +84,9 @@ def decode_segments(jpeg, nblocks, scan_start, restart, flags=1):
     ent, segs = split_entropy(jpeg, scan_start, restart)
     so = np.array(segs, np.uint32)
     coefs = np.zeros((nblocks, 64), np.int16)
-    st = lib().emu_decode_segments(jpeg, len(jpeg), flags, ent, so.ctypes.data, len(segs) - 1, coefs.ctypes.data)
+    wide = np.zeros(nblocks // 32 + 2, np.uint32)
+    st = lib().emu_decode_segments(jpeg, len(jpeg), flags, ent, so.ctypes.data, len(segs) - 1, coefs.ctypes.data, wide.ctypes.data)
+    decode_segments.wide = wide
     return st, coefs
 
 
@@ -92,7 +94,9 @@ def decode_speculative(jpeg, nblocks, scan_start, T=64, S=1024):
     ent, _ = split_entropy(jpeg, scan_start, False)
     coefs = np.zeros((nblocks, 64), np.int16)
     rounds = C.c_int()
-    st = lib().emu_decode_speculative(jpeg, len(jpeg), ent, len(ent), T, S, coefs.ctypes.data, C.byref(rounds))
+    wide = np.zeros(nblocks // 32 + 2, np.uint32)
+    st = lib().emu_decode_speculative(jpeg, len(jpeg), ent, len(ent), T, S, coefs.ctypes.data, C.byref(rounds), wide.ctypes.data)
+    decode_speculative.wide = wide
     return st, coefs, rounds.value
 
 

@@ -17,6 +17,7 @@ namespace {
 struct HostTables {
   std::vector<hcj::HuffLut> luts;  // [comp][dc/ac]
   Tables tab[HCJ_MAX_COMP];
+  int32_t quant[HCJ_MAX_COMP * 128];
 };
 
 int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj::ImagePlan *plan, HostTables *ht) {
@@ -31,6 +32,11 @@ int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj:
     st = hcj::build_lut(h->huffman_tables[plan->ac_index[c]], &ht->luts[c * 2 + 1]);
     if (st) return st;
   }
+  for (int c = 0; c < plan->info.ncomp; c++)
+    for (int e = 0; e < 64; e++) {
+      ht->quant[c * 128 + e] = h->quant_tables[plan->qt_index[c]].elements[e];
+      ht->quant[c * 128 + 64 + e] = HCJ_QD(e, h->quant_tables[plan->qt_index[c]].elements[e] & 0xff);
+    }
   for (int c = 0; c < plan->info.ncomp; c++) {
     Tables &t = ht->tab[c];
     t.dc_primary = ht->luts[c * 2].primary.data();
@@ -66,7 +72,7 @@ int emu_idct_l1_limit() { return HCJ_IDCT_L1_LIMIT; }
 
 // k_huff_restart: one "thread" per segment.  `entropy` = destuffed bytes, seg_off[nseg + 1] byte offsets.
 int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const uint8_t *entropy, const uint32_t *seg_off,
-                        uint32_t nseg, int16_t *coefs /* zeroed, nblocks * 64 */) {
+                        uint32_t nseg, int16_t *coefs /* zeroed, nblocks * 64 */, uint32_t *wide_flags /* zeroed */) {
   hcj_header *h = new hcj_header;
   hcj::ImagePlan plan;
   HostTables ht;
@@ -78,27 +84,50 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
   uint32_t ri = f.restart_interval ? (uint32_t)f.restart_interval : nmcu;
   std::vector<uint32_t> words((seg_off[nseg] + 15) / 4 + 4, 0);
   memcpy(words.data(), entropy, seg_off[nseg]);
+  uint8_t blk_comp[HCJ_MAX_BPM + 2];
+  for (uint32_t k = 0; k < bpm; k++) blk_comp[k] = (uint8_t)plan.blk_comp[k];
+  ScanCtx sc;
+  sc.words = words.data();
+  sc.total_bits = 0;
+  sc.bpm = bpm;
+  sc.blk_comp = blk_comp;
+  for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
+  sc.quant = ht.quant;
+  sc.wide_flags = wide_flags;
+  sc.blk_base = 0;
+  unsigned long long err_key = ~0ull;
   for (uint32_t seg = 0; seg < nseg; seg++) {  // <- thread index
     uint32_t seg_bits = (seg_off[seg + 1] - seg_off[seg]) * 8;
     uint32_t mcu0 = seg * ri, mcu1 = mcu0 + ri < nmcu ? mcu0 + ri : nmcu;
-    BitReader br;
-    br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
-    int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-    int16_t *out = coefs + (int64_t)mcu0 * bpm * 64;
-    for (uint32_t mcu = mcu0; mcu < mcu1; mcu++)
-      for (uint32_t k = 0; k < bpm; k++, out += 64) {
-        int comp = plan.blk_comp[k];
-        int err = decode_block_exact(br, ht.tab[comp], seg_bits, pred[comp], out);
-        if (err) return err;
-      }
+    int err = 0;
+    uint32_t err_pos = 0;
+    if (seg_bits > 16) {
+      int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+      err = subseq_write(sc, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
+                         (int64_t)mcu1 * bpm, coefs, &err_pos);
+    } else {
+      BitReader br;
+      br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
+      int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+      int64_t blk = (int64_t)mcu0 * bpm;
+      for (uint32_t mcu = mcu0; mcu < mcu1 && !err; mcu++)
+        for (uint32_t k = 0; k < bpm && !err; k++, blk++) {
+          int comp = plan.blk_comp[k];
+          err = decode_block_exact(br, ht.tab[comp], seg_bits, pred[comp], coefs + blk * 64);
+          flag_wide_block(sc, blk);
+          err_pos = br.pos;
+        }
+    }
+    unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
+    if (err && key < err_key) err_key = key;
   }
-  return 0;
+  return err_key == ~0ull ? 0 : -(int)(err_key & 0xff);
 }
 
 // k_huff_spec: T emulated threads per chunk, subsequences of S bits.  Returns status; rounds_out gets the
 // largest number of fix-point rounds any chunk needed.
 int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entropy, uint32_t ent_len, int T, uint32_t S,
-                           int16_t *coefs /* zeroed */, int *rounds_out) {
+                           int16_t *coefs /* zeroed */, int *rounds_out, uint32_t *wide_flags /* zeroed, nblocks / 32 + 1 */) {
   hcj_header *h = new hcj_header;
   hcj::ImagePlan plan;
   HostTables ht;
@@ -116,6 +145,9 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
   sc.bpm = (uint32_t)f.blocks_per_mcu;
   sc.blk_comp = blk_comp;
   for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
+  sc.quant = ht.quant;
+  sc.wide_flags = wide_flags;
+  sc.blk_base = 0;
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = f.nblocks;
   int max_rounds = 0;
@@ -126,6 +158,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
     for (int64_t blk = 0; blk < nblocks; blk++) {
       int comp = blk_comp[blk % sc.bpm];
       int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+      flag_wide_block(sc, blk);
       if (err) return err;
     }
     return 0;
@@ -184,7 +217,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       int64_t blk = carry.nstart + ex_n - 1;
       bool last = base + t == nsub - 1;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, sp[t], scz[t], last ? 0xffffffffu : hi[t], blk, pred, nblocks, coefs, &err_pos);
+      int err = subseq_write(sc, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, &err_pos);
       unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
       if (err && key < err_key) err_key = key;  // the kernel's atomicMin
       ex_n += r[t].nstart;

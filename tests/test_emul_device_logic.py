@@ -201,3 +201,41 @@ def test_entropy_encode_matches_oracle(orc, data, chroma, ri):
     hdr = orc.write_headers(64, 64, chroma, 75, ri)
     body = emul.entropy_encode(quant.astype(np.int16), 64, 64, chroma, ri)
     assert hdr + body + b"\xff\xd9" == jpg
+
+
+def _patch_dqt(jpg, value):
+    """Overwrite every 8-bit quant table entry: blows the dequantised magnitudes past the int32 guard."""
+    b = bytearray(jpg)
+    i = 0
+    while True:
+        i = b.find(b"\xff\xdb", i)
+        if i < 0:
+            break
+        b[i + 5 : i + 5 + 64] = bytes([value]) * 64
+        i += 69
+    return bytes(b)
+
+
+def test_wide_block_flags(orc, data):
+    """Entropy decoders flag blocks whose sum(|dequantised coef|) may reach the IDCT guard; an unflagged
+    block is certainly below it (so k_idct may skip its own check)."""
+    limit = emul.lib().emu_idct_l1_limit()
+    for jpg in (data("Mouse480.jpg"), _patch_dqt(orc.encode(data("mini64x64.444"), 64, 64, 444, 100), 255)):
+        dec = orc.decode(jpg, want_blocks=True)
+        l1 = np.abs(dec.dequant.astype(np.int64)).sum(1)
+        start = _scan_start(orc, jpg)
+        st, got = emul.decode_segments(jpg, dec.nblocks, start, restart=False)
+        flags_seq = emul.decode_segments.wide
+        st2, got2, _ = emul.decode_speculative(jpg, dec.nblocks, start, T=16, S=1024)
+        flags_spec = emul.decode_speculative.wide
+        assert st == 0 and st2 == 0
+        for flags in (flags_seq, flags_spec):
+            bit = np.array([(flags[b >> 5] >> (b & 31)) & 1 for b in range(dec.nblocks)])
+            assert not np.any((l1 >= limit) & (bit == 0))
+        if l1.max() < limit // 4:
+            assert flags_seq.sum() == 0 and flags_spec.sum() == 0
+        else:
+            assert flags_seq.sum() > 0
+        # and the reconstruction is exact either way
+        qts = [np.array(list(orc.header_decode(jpg).quant_tables[i].elements), np.int64) for i in range(2)]
+        assert np.array_equal(got, dec.coefs_abs_dc().astype(np.int16))

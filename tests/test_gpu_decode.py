@@ -212,6 +212,36 @@ def test_idct_blocks_tap(hcj, ctx, orc):
         assert got[b].tolist() == want.tolist(), b
 
 
+def test_wide_idct_path(hcj, ctx, orc, data):
+    """Quant tables patched to 255 / 16-bit tables: blocks exceed the 32-bit IDCT guard and must take the
+    64-bit path (flagged by the entropy decoders) and still match the model bit for bit."""
+    from test_emul_device_logic import _patch_dqt
+
+    base = orc.encode(data("mini64x64.444"), 64, 64, 444, 100)
+    big = _patch_dqt(base, 255)
+    # 16-bit table: rewrite DQT segments with Pq = 1 and large entries
+    b16 = bytearray()
+    i = 0
+    src = bytearray(base)
+    while i < len(src):
+        if src[i] == 0xFF and src[i + 1] == 0xDB:
+            tq = src[i + 4] & 15
+            b16 += bytes([0xFF, 0xDB, 0x00, 0x83, 0x10 | tq]) + b"".join(bytes([1 + (k % 3), 0x2C]) for k in range(64))
+            i += 69
+        else:
+            b16.append(src[i])
+            i += 1
+    batch = [base, big, bytes(b16), data("Mouse480.jpg")]
+    for restart_free in (True,):
+        outs, st = ctx.decode_batch(batch)
+        for jpg, out, s in zip(batch, outs, st):
+            assert s == 0 and bytes(out) == orc.decode(jpg).yuv()
+    yuv = synth.frame(77, 96, 64, 420)
+    jr = _patch_dqt(orc.encode(yuv, 96, 64, 420, 90, restart_interval=2), 200)
+    outs, st = ctx.decode_batch([jr])
+    assert st == [0] and bytes(outs[0]) == orc.decode(jr).yuv()
+
+
 # ---- full-size configurations ---------------------------------------------------------------------------
 @pytest.mark.parametrize("ri", [0, 8])
 def test_1080p_420_full_size(hcj, ctx, orc, ri):

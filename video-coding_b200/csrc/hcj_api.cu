@@ -184,7 +184,8 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   memset(&b->dev, 0, sizeof(b->dev));
 
   std::vector<HcjTableSet> table_sets;
-  std::vector<uint16_t> prim_pool, full_pool, qt_pool;
+  std::vector<uint16_t> prim_pool, full_pool;
+  std::vector<int32_t> qt_pool;
   std::map<std::string, uint32_t> set_index;
   std::vector<uint32_t> list_restart, list_spec;
   size_t file_bytes = 0, ent_bytes = 0, nsegs = 0, out_total = 0, plane_total = 0;
@@ -310,10 +311,12 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       g.out_off = yuv_acc;
       yuv_acc += (size_t)g.actual_w * g.actual_h;
       const hcj_dqt &q = h->quant_tables[plan.qt_index[k]];
-      for (int e = 0; e < 64; e++) {
-        qt_pool.push_back((uint16_t)q.elements[e]);
+      for (int e = 0; e < 64; e++) {  // plain values, used by the 64-bit path
+        qt_pool.push_back((int32_t)q.elements[e]);
         if (q.elements[e] > 255) d.wide_idct = 1;
       }
+      for (int e = 0; e < 64; e++)  // "dp2a form" used by the 32-bit path (see HCJ_QD in hcj_device.cuh)
+        qt_pool.push_back((e & 1) ? (int32_t)(q.elements[e] & 0xff) << 8 : (int32_t)(q.elements[e] & 0xff));
     }
     if (mode == HCJ_OUT_RGB24) plane_total += align_up(plane_acc, 256);
     for (int k = 0; k < f.blocks_per_mcu && k < HCJ_MAX_BPM; k++) {
@@ -349,14 +352,15 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   HcjImageDesc *d_descs = nullptr;
   uint8_t *d_files = nullptr;
   HcjTableSet *d_sets = nullptr;
-  uint16_t *d_prim = nullptr, *d_full = nullptr, *d_qt = nullptr;
+  uint16_t *d_prim = nullptr, *d_full = nullptr;
+  int32_t *d_qt = nullptr;
   uint32_t *d_lr = nullptr, *d_ls = nullptr;
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_descs, sizeof(HcjImageDesc) * std::max(n, 1));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_files, file_bytes + 16);
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_sets, sizeof(HcjTableSet) * std::max<size_t>(table_sets.size(), 1));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_prim, 2 * std::max<size_t>(prim_pool.size(), 8));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_full, 2 * std::max<size_t>(full_pool.size(), 8));
-  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_qt, 2 * std::max<size_t>(qt_pool.size(), 8));
+  if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_qt, 4 * std::max<size_t>(qt_pool.size(), 8));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_lr, 4 * std::max<size_t>(list_restart.size(), 1));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_ls, 4 * std::max<size_t>(list_spec.size(), 1));
   BALLOC(states, HcjImageState *, sizeof(HcjImageState) * std::max(n, 1));
@@ -364,6 +368,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
   b->coef_bytes = (size_t)total_blocks * 128;
   BALLOC(coefs, int16_t *, b->coef_bytes + 16);
+  BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4);
   BALLOC(out, uint8_t *, out_total + 16);
   if (mode == HCJ_OUT_RGB24) BALLOC(planes, uint8_t *, plane_total + 16);
 #undef BALLOC
@@ -400,7 +405,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   up(d_sets, table_sets.data(), sizeof(HcjTableSet) * table_sets.size());
   up(d_prim, prim_pool.data(), 2 * prim_pool.size());
   up(d_full, full_pool.data(), 2 * full_pool.size());
-  up(d_qt, qt_pool.data(), 2 * qt_pool.size());
+  up(d_qt, qt_pool.data(), 4 * qt_pool.size());
   up(d_lr, list_restart.data(), 4 * list_restart.size());
   up(d_ls, list_spec.data(), 4 * list_spec.size());
   // compressed files: merge copies of images that are adjacent in host memory with matching padding
@@ -436,6 +441,7 @@ int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
   if (b->n == 0) return HCJ_OK;
   // Coefficient blocks start as zero (clear_block, decoder.ml:112-116,160); decoders store non-zeros.
   CU_TRY(cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s));
+  CU_TRY(cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s));
   CU_TRY(cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s));  // overwritten by k_destuff for valid images
   hcjk::launch_destuff(b->dev, s);
   hcjk::launch_huff_restart(b->dev, s);
@@ -458,6 +464,7 @@ int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, i
   const int mode = b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2;
   cudaEventRecord(ev[0], s);
   cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s);
+  cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
   cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s);
   cudaEventRecord(ev[1], s);
   hcjk::launch_destuff(b->dev, s);

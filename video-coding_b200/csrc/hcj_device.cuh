@@ -47,7 +47,8 @@ struct BitReader {
   uint32_t end_bits;
   uint32_t pos;
   uint32_t widx;
-  uint32_t w0, w1;
+  uint32_t w0, w1;  // big-endian words widx, widx + 1: the 32-bit window lives in these
+  uint32_t wn;      // word widx + 2, requested one refill ahead so that its latency is never waited for
 
   HCJ_HD void init(const uint32_t *words_, uint32_t pos_, uint32_t end_bits_) {
     words = words_;
@@ -56,6 +57,7 @@ struct BitReader {
     widx = pos_ >> 5;
     w0 = load_be_word(words, widx, end_bits);
     w1 = load_be_word(words, widx + 1, end_bits);
+    wn = load_be_word(words, widx + 2, end_bits);
   }
   // The next 32 bits, MSB-aligned.
   HCJ_HD uint32_t window() const {
@@ -73,7 +75,8 @@ struct BitReader {
     if (nidx != widx) {
       widx = nidx;
       w0 = w1;
-      w1 = load_be_word(words, nidx + 1, end_bits);
+      w1 = wn;
+      wn = load_be_word(words, nidx + 2, end_bits);
     }
   }
 };
@@ -158,13 +161,59 @@ struct ScanCtx {
   uint32_t bpm;                // blocks per MCU
   const uint8_t *blk_comp;     // [bpm] block-in-MCU -> scan component
   Tables tab[HCJ_MAX_COMP];    // per scan component
+  const int32_t *quant;        // [HCJ_MAX_COMP][128]: per scan component, 64 plain entries (+ 64 in dp2a form)
+  uint32_t *wide_flags;        // bit (blk_base + blk): the block needs the 64-bit IDCT (see HCJ_IDCT_L1_LIMIT)
+  uint64_t blk_base;           // index of the image's first block in the batch
 };
+
+// A block's sum(|dequantised coefficient|) may be accumulated by up to four threads (a block is at most
+// 63 * 31 + 31 bits long, subsequences are at least 1024 bits): each flags the block when its share reaches
+// a quarter of the limit, so an unflagged block is certainly below HCJ_IDCT_L1_LIMIT.
+#define HCJ_WIDE_SHARE (HCJ_IDCT_L1_LIMIT_VALUE / 4)
+#define HCJ_IDCT_L1_LIMIT_VALUE 60000
+
+HCJ_HD void flag_wide_block(const ScanCtx &sc, int64_t blk) {
+  uint64_t g = sc.blk_base + (uint64_t)blk;
+#if defined(__CUDA_ARCH__)
+  atomicOr(sc.wide_flags + (g >> 5), 1u << (g & 31u));
+#else
+  sc.wide_flags[g >> 5] |= 1u << (g & 31u);
+#endif
+}
 
 struct SubResult {
   uint32_t p, cz;     // end state: cz = (c << 8) | z
   uint32_t nstart;    // DC symbols (blocks begun) decoded
   int32_t dcsum[HCJ_MAX_COMP];
 };
+
+// One symbol, DC or AC, decoded with the same instruction stream (lanes of a warp are rarely all in the
+// same phase, so separate DC / AC branches would both be executed on almost every iteration).
+struct Symbol {
+  uint32_t e;      // LUT entry, 0 = undefined code
+  uint32_t nbits;  // code length + magnitude bits
+  uint32_t run, size;
+  int32_t value;   // extended magnitude (0 when size == 0)
+};
+
+HCJ_HD Symbol read_symbol(const BitReader &br, const Tables &t, bool isdc) {
+  Symbol s;
+  const uint32_t win = br.window();
+  const uint16_t *prim = isdc ? t.dc_primary : t.ac_primary;
+  uint32_t e = prim[win >> (32 - HCJ_LUT_BITS)];
+  if (e == 0u) {
+    const uint32_t mb = isdc ? t.dc_max_bits : t.ac_max_bits;
+    if (mb > HCJ_LUT_BITS) e = (isdc ? t.dc_full : t.ac_full)[win >> (32u - mb)];
+  }
+  const uint32_t len = e >> 8, rs = e & 0xffu;
+  s.e = e;
+  s.size = isdc ? rs : rs & 15u;
+  s.run = isdc ? 0u : rs >> 4;
+  s.nbits = len + s.size;
+  const uint32_t mbits = s.size ? (win << len) >> (32u - s.size) : 0u;
+  s.value = s.size ? extend(mbits, s.size) : 0;
+  return s;
+}
 
 HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
@@ -173,38 +222,29 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
   BitReader br;
   br.init(sc.words, p, sc.total_bits);
   uint32_t comp = sc.blk_comp[c];
+  Tables t = sc.tab[comp];
   while (br.pos < hi) {
-    const Tables &t = sc.tab[comp];
-    uint32_t win = br.window();
-    if (z == 0u) {
-      uint32_t e = lut_lookup(t.dc_primary, t.dc_full, t.dc_max_bits, win);
-      if (e == 0u) {  // undefined code: resynchronise one bit later
-        br.skip(1);
-        continue;
-      }
-      uint32_t len = e >> 8, cat = e & 0xffu;
-      int32_t diff = cat ? extend((win << len) >> (32u - cat), cat) : 0;
-      br.skip(len + cat);
-      d0 += comp == 0u ? diff : 0;
-      d1 += comp == 1u ? diff : 0;
-      d2 += comp == 2u ? diff : 0;
-      d3 += comp == 3u ? diff : 0;
-      nstart++;
-      z = 1;
-    } else {
-      uint32_t e = lut_lookup(t.ac_primary, t.ac_full, t.ac_max_bits, win);
-      if (e == 0u) {
-        br.skip(1);
-        continue;
-      }
-      uint32_t rs = e & 0xffu;
-      br.skip((e >> 8) + (rs & 15u));
-      z = rs ? z + (rs >> 4) + 1u : 64u;
-      if (z >= 64u) {  // block complete (EOB, coefficient 63, or an overlong run while speculating)
-        z = 0;
-        c = c + 1u == sc.bpm ? 0u : c + 1u;
-        comp = sc.blk_comp[c];
-      }
+    const bool isdc = z == 0u;
+    const Symbol s = read_symbol(br, t, isdc);
+    if (s.e == 0u) {  // undefined code: resynchronise one bit later
+      br.skip(1);
+      continue;
+    }
+    br.skip(s.nbits);
+    const int32_t diff = isdc ? s.value : 0;
+    d0 += comp == 0u ? diff : 0;
+    d1 += comp == 1u ? diff : 0;
+    d2 += comp == 2u ? diff : 0;
+    d3 += comp == 3u ? diff : 0;
+    nstart += isdc ? 1u : 0u;
+    // next zig-zag index: 1 after a DC; 64 on EOB; past 63 closes the block too (coefficient 63, or an
+    // overlong run met while speculating)
+    z = isdc ? 1u : ((s.e & 0xffu) ? z + s.run + 1u : 64u);
+    if (z >= 64u) {
+      z = 0;
+      c = c + 1u == sc.bpm ? 0u : c + 1u;
+      comp = sc.blk_comp[c];
+      t = sc.tab[comp];
     }
   }
   r.p = br.pos;
@@ -216,62 +256,73 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
   r.dcsum[3] = d3;
 }
 
-// Final pass over one subsequence from its exact start state.  `blk` is the index (within the image)
-// of the block in progress (start of a block: the index of the previous one), `pred` the DC predictors
-// at the start state.  Stores coefficients (zig-zag, DC resolved) into the zero-initialised `coefs`.
-// `hi` = end of the subsequence; the last subsequence passes 0xffffffff and runs until `nblocks` blocks
-// are complete, reading zero bits past the end exactly as the model's reader does.
-HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi, int64_t blk, int32_t pred[HCJ_MAX_COMP],
-                        int64_t nblocks, int16_t *__restrict__ coefs, uint32_t *err_pos) {
+// Final pass over one subsequence (or one restart interval) from its exact start state.  `blk` is the
+// index (within the image) of the block in progress (at the start of a block: the index of the previous
+// one), `pred` the DC predictors at the start state.  Stores coefficients (zig-zag, DC resolved) into the
+// zero-initialised `coefs`.  Decodes the symbols that start before `hi` and belong to blocks < `nblocks`;
+// with hi = 0xffffffff it runs until block nblocks - 1 is complete, reading zero bits past the end of
+// the data exactly as the model's reader does.
+HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
+                        int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, uint32_t *err_pos) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   BitReader br;
-  br.init(sc.words, p, sc.total_bits);
+  br.init(sc.words, p, end_bits);
   uint32_t comp = sc.blk_comp[c];
+  Tables t = sc.tab[comp];
+  const int32_t *q = sc.quant + comp * 128;
   int32_t p0 = pred[0], p1 = pred[1], p2 = pred[2], p3 = pred[3];
   if (z != 0u && blk >= nblocks) return HCJ_DEV_OK;
   int16_t *out = coefs + blk * 64;
+  uint32_t share = 0;  // this thread's part of the block's sum(|dequantised coefficient|)
+  int err = HCJ_DEV_OK;
   while (br.pos < hi) {
-    const Tables &t = sc.tab[comp];
-    uint32_t win = br.window();
-    if (z == 0u) {
-      if (blk + 1 >= nblocks) break;  // every block of the frame is complete
-      uint32_t e = lut_lookup(t.dc_primary, t.dc_full, t.dc_max_bits, win);
-      if (e == 0u) return *err_pos = br.pos, HCJ_DEV_NO_DC_CODE;
-      uint32_t len = e >> 8, cat = e & 0xffu;
-      int32_t diff = cat ? extend((win << len) >> (32u - cat), cat) : 0;
-      br.skip(len + cat);
-      int32_t v;
-      if (comp == 0u) v = (p0 += diff);
-      else if (comp == 1u) v = (p1 += diff);
-      else if (comp == 2u) v = (p2 += diff);
-      else v = (p3 += diff);
-      if (v < -32768 || v > 32767) return *err_pos = br.pos, HCJ_DEV_DC_RANGE;
+    const bool isdc = z == 0u;
+    if (isdc && blk + 1 >= nblocks) break;  // every block is complete
+    const Symbol s = read_symbol(br, t, isdc);
+    if (s.e == 0u) {
+      err = isdc ? HCJ_DEV_NO_DC_CODE : HCJ_DEV_NO_AC_CODE;
+      break;
+    }
+    br.skip(s.nbits);
+    const bool eob = !isdc && (s.e & 0xffu) == 0u;
+    const uint32_t zi = isdc ? 0u : z + s.run;  // where this symbol's value goes
+    if (zi >= 64u && !eob) {
+      err = HCJ_DEV_COEF_INDEX;
+      break;
+    }
+    int32_t v = s.value;
+    if (isdc) {
+      const int32_t pv = (comp == 0u ? p0 : comp == 1u ? p1 : comp == 2u ? p2 : p3) + v;
+      p0 = comp == 0u ? pv : p0;
+      p1 = comp == 1u ? pv : p1;
+      p2 = comp == 2u ? pv : p2;
+      p3 = comp == 3u ? pv : p3;
+      v = pv;
+      if (pv < -32768 || pv > 32767) {
+        err = HCJ_DEV_DC_RANGE;
+        break;
+      }
       blk++;
-      out = coefs + blk * 64;
-      out[0] = (int16_t)v;
-      z = 1;
-    } else {
-      uint32_t e = lut_lookup(t.ac_primary, t.ac_full, t.ac_max_bits, win);
-      if (e == 0u) return *err_pos = br.pos, HCJ_DEV_NO_AC_CODE;
-      uint32_t len = e >> 8, rs = e & 0xffu, size = rs & 15u;
-      uint32_t mbits = size ? (win << len) >> (32u - size) : 0u;
-      br.skip(len + size);
-      if (rs == 0u) {
-        z = 64;
-      } else {
-        z += rs >> 4;
-        if (z >= 64u) return *err_pos = br.pos, HCJ_DEV_COEF_INDEX;
-        if (size) out[z] = (int16_t)extend(mbits, size);
-        z++;
-      }
-      if (z >= 64u) {
-        z = 0;
-        c = c + 1u == sc.bpm ? 0u : c + 1u;
-        comp = sc.blk_comp[c];
-      }
+      out += 64;
+    }
+    if (isdc || (s.size != 0u && !eob)) {
+      out[zi] = (int16_t)v;
+      share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)q[zi];
+    }
+    z = eob ? 64u : zi + 1u;
+    if (z >= 64u) {
+      if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
+      share = 0;
+      z = 0;
+      c = c + 1u == sc.bpm ? 0u : c + 1u;
+      comp = sc.blk_comp[c];
+      t = sc.tab[comp];
+      q = sc.quant + comp * 128;
     }
   }
-  return HCJ_DEV_OK;
+  if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
+  if (err) *err_pos = br.pos;
+  return err;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +333,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
 // block is below HCJ_IDCT_L1_LIMIT (derivation in DESIGN.md; checked in tests/test_emul_idct.py).
 // T = int64_t is the model's arithmetic verbatim and is taken for the (pathological) blocks above.
 // ------------------------------------------------------------------------------------------------
-#define HCJ_IDCT_L1_LIMIT 60000
+#define HCJ_IDCT_L1_LIMIT HCJ_IDCT_L1_LIMIT_VALUE
 
 template <typename T>
 HCJ_HD T mul181(T a) {
@@ -309,26 +360,28 @@ HCJ_HD void idct_row(T *b) {  // dct.ml:11-54
   x4 = x4 - x6;
   x6 = x5 + x7;
   x5 = x5 - x7;
-  x7 = x8 + x3;
-  x8 = x8 - x3;
-  x3 = x0 + x2;
-  x0 = x0 - x2;
-  x2 = mul181<T>(x4 + x5);
-  x4 = mul181<T>(x4 - x5);
-  b[0 * STRIDE] = (x7 + x1) >> 8;
-  b[1 * STRIDE] = (x3 + x2) >> 8;
-  b[2 * STRIDE] = (x0 + x4) >> 8;
-  b[3 * STRIDE] = (x8 + x6) >> 8;
-  b[4 * STRIDE] = (x8 - x6) >> 8;
-  b[5 * STRIDE] = (x0 - x4) >> 8;
-  b[6 * STRIDE] = (x3 - x2) >> 8;
-  b[7 * STRIDE] = (x7 - x1) >> 8;
+  // third + fourth stage (dct.ml:39-53) written as three-input sums: x7 = x8 + x3, x8' = x8 - x3,
+  // x3' = x0 + x2, x0' = x0 - x2 are only ever used inside the output sums, and two's-complement
+  // addition is associative, so the results are bit-identical while an IADD3 does two adds at once.
+  const T y2 = mul181<T>(x4 + x5);
+  const T y4 = mul181<T>(x4 - x5);
+  b[0 * STRIDE] = (x8 + x3 + x1) >> 8;
+  b[1 * STRIDE] = (x0 + x2 + y2) >> 8;
+  b[2 * STRIDE] = (x0 - x2 + y4) >> 8;
+  b[3 * STRIDE] = (x8 - x3 + x6) >> 8;
+  b[4 * STRIDE] = (x8 - x3 - x6) >> 8;
+  b[5 * STRIDE] = (x0 - x2 - y4) >> 8;
+  b[6 * STRIDE] = (x0 + x2 - y2) >> 8;
+  b[7 * STRIDE] = (x8 + x3 - x1) >> 8;
 }
 
-template <typename T, int STRIDE>
+// BIAS is added to every output before the final >> 14 (x0 reaches each output exactly once): with
+// BIAS = 128 << 14 the outputs are the model's values + 128, i.e. the level shift of recon
+// (decoder.ml:220) folded into the transform at no cost.
+template <typename T, int STRIDE, int BIAS = 0>
 HCJ_HD void idct_col(T *b) {  // dct.ml:56-98
   const T W1 = 2841, W2 = 2676, W3 = 2408, W5 = 1609, W6 = 1108, W7 = 565;
-  T x0 = b[0 * STRIDE] * 256 + 8192, x1 = b[4 * STRIDE] * 256, x2 = b[6 * STRIDE], x3 = b[2 * STRIDE],
+  T x0 = b[0 * STRIDE] * 256 + (8192 + BIAS), x1 = b[4 * STRIDE] * 256, x2 = b[6 * STRIDE], x3 = b[2 * STRIDE],
     x4 = b[1 * STRIDE], x5 = b[7 * STRIDE], x6 = b[5 * STRIDE], x7 = b[3 * STRIDE], x8;
   x8 = W7 * (x4 + x5) + 4;
   x4 = (x8 + (W1 - W7) * x4) >> 3;
@@ -345,28 +398,41 @@ HCJ_HD void idct_col(T *b) {  // dct.ml:56-98
   x4 = x4 - x6;
   x6 = x5 + x7;
   x5 = x5 - x7;
-  x7 = x8 + x3;
-  x8 = x8 - x3;
-  x3 = x0 + x2;
-  x0 = x0 - x2;
-  x2 = mul181<T>(x4 + x5);
-  x4 = mul181<T>(x4 - x5);
-  b[0 * STRIDE] = (x7 + x1) >> 14;
-  b[1 * STRIDE] = (x3 + x2) >> 14;
-  b[2 * STRIDE] = (x0 + x4) >> 14;
-  b[3 * STRIDE] = (x8 + x6) >> 14;
-  b[4 * STRIDE] = (x8 - x6) >> 14;
-  b[5 * STRIDE] = (x0 - x4) >> 14;
-  b[6 * STRIDE] = (x3 - x2) >> 14;
-  b[7 * STRIDE] = (x7 - x1) >> 14;
+  // third + fourth stage (dct.ml:83-97) written as three-input sums: x7 = x8 + x3, x8' = x8 - x3,
+  // x3' = x0 + x2, x0' = x0 - x2 are only ever used inside the output sums, and two's-complement
+  // addition is associative, so the results are bit-identical while an IADD3 does two adds at once.
+  const T y2 = mul181<T>(x4 + x5);
+  const T y4 = mul181<T>(x4 - x5);
+  b[0 * STRIDE] = (x8 + x3 + x1) >> 14;
+  b[1 * STRIDE] = (x0 + x2 + y2) >> 14;
+  b[2 * STRIDE] = (x0 - x2 + y4) >> 14;
+  b[3 * STRIDE] = (x8 - x3 + x6) >> 14;
+  b[4 * STRIDE] = (x8 - x3 - x6) >> 14;
+  b[5 * STRIDE] = (x0 - x2 - y4) >> 14;
+  b[6 * STRIDE] = (x0 + x2 - y2) >> 14;
+  b[7 * STRIDE] = (x8 + x3 - x1) >> 14;
 }
 
-template <typename T>
+template <typename T, int BIAS = 0>
 HCJ_HD void idct_8x8(T v[64]) {  // dct.ml:100-107: all rows, then all columns
 #pragma unroll
   for (int i = 0; i < 8; i++) idct_row<T, 1>(v + 8 * i);
 #pragma unroll
-  for (int i = 0; i < 8; i++) idct_col<T, 8>(v + i);
+  for (int i = 0; i < 8; i++) idct_col<T, 8, BIAS>(v + i);
+}
+
+// Four samples clamped to [0, 255] and packed little-endian (sample 0 in the low byte):
+// clip to [-128, 127] then + 128 (decoder.ml:213-224) == clamp(v + 128, 0, 255).
+HCJ_HD uint32_t pack4_sat(int32_t p0, int32_t p1, int32_t p2, int32_t p3) {
+#if defined(__CUDA_ARCH__)
+  uint32_t t, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(p3), "r"(p2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(p1), "r"(p0), "r"(t));
+  return d;
+#else
+  auto c = [](int32_t v) { return (uint32_t)(v < 0 ? 0 : v > 255 ? 255 : v); };
+  return c(p0) | (c(p1) << 8) | (c(p2) << 16) | (c(p3) << 24);
+#endif
 }
 
 // Zigzag.inverse (zigzag.ml:3-69) as a compile-time function so that fully unrolled loops index
@@ -386,37 +452,86 @@ HCJ_HD constexpr int zigzag_forward(int i) {
 }
 
 // dequantize + inverse zig-zag (decoder.ml:142-149), IDCT, clip and level shift (decoder.ml:213-224).
-// c[i]: zig-zag coefficients with c[0] the resolved DC; q[i]: quant table in file (zig-zag) order.
-// pix[k]: reconstructed sample k = x + 8*y.  `force_wide`: quant entries above 255 are present.
-HCJ_HD void reconstruct_block(const int16_t c[64], const uint16_t q[64], bool force_wide, uint8_t pix[64]) {
+// cw[j]: zig-zag coefficients 2j (low half) and 2j+1 (high half) as int16, coefficient 0 the resolved DC;
+// q[i]: quant table in file (zig-zag) order; out[2r], out[2r+1]: the 8 samples of row r, packed.
+// The fast version works in 32 bits and returns false (leaving `out` unspecified) when the block's
+// sum(|dequantised coefficient|) reaches HCJ_IDCT_L1_LIMIT; the caller then takes the wide version.
+// lo16(cw) * q_lo and hi16(cw) * q_hi for quant entries <= 255: one dp2a each (signed halves of `cw`
+// times the unsigned bytes 0 / 1 of the second operand), i.e. unpack + dequantise in one instruction.
+// The table is kept in "dp2a form" (HCJ_QD): entry i holds q[i] for even i and q[i] << 8 for odd i.
+#define HCJ_QD(i, q) (((i) & 1) ? (int32_t)(q) << 8 : (int32_t)(q))
+HCJ_HD int32_t dequant_lo(uint32_t cw, int32_t q) {
+#if defined(__CUDA_ARCH__)
+  int32_t d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(cw), "r"(q), "r"(0));
+  return d;
+#else
+  return (int32_t)(int16_t)(cw & 0xffffu) * q;
+#endif
+}
+HCJ_HD int32_t dequant_hi(uint32_t cw, int32_t q) {
+#if defined(__CUDA_ARCH__)
+  int32_t d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(cw), "r"(q), "r"(0));
+  return d;
+#else
+  return (int32_t)(int16_t)(cw >> 16) * (q >> 8);
+#endif
+}
+
+// GUARD = false: the caller already knows the block is below the limit (wide-block flags written by
+// the entropy decoders), so the sum is not formed.
+template <bool GUARD = true>
+HCJ_HD bool reconstruct_fast(const uint32_t cw[32], const int32_t *__restrict__ qd /* dp2a form */, uint32_t out[16]) {
   int32_t v[64];
   uint32_t l1 = 0;
-  bool wide = force_wide;
-  if (!force_wide) {
 #pragma unroll
-    for (int i = 0; i < 64; i++) {
-      int32_t d = (int32_t)c[i] * (int32_t)q[i];
-      v[zigzag_inverse(i)] = d;
-      l1 += (uint32_t)(d < 0 ? -d : d);
-    }
-    wide = l1 >= (uint32_t)HCJ_IDCT_L1_LIMIT;
+  for (int j = 0; j < 32; j++) {
+    int32_t d0 = dequant_lo(cw[j], qd[2 * j]), d1 = dequant_hi(cw[j], qd[2 * j + 1]);
+    v[zigzag_inverse(2 * j)] = d0;
+    v[zigzag_inverse(2 * j + 1)] = d1;
+    if (GUARD) l1 += (uint32_t)(d0 < 0 ? -d0 : d0) + (uint32_t)(d1 < 0 ? -d1 : d1);
   }
-  if (!wide) {
-    idct_8x8<int32_t>(v);
+  if (GUARD && l1 >= (uint32_t)HCJ_IDCT_L1_LIMIT) return false;
+  idct_8x8<int32_t, (128 << 14)>(v);
 #pragma unroll
-    for (int k = 0; k < 64; k++) {
-      int32_t s = v[k] < -128 ? -128 : v[k] > 127 ? 127 : v[k];
-      pix[k] = (uint8_t)(s + 128);
-    }
-  } else {
-    int64_t w[64];
-    for (int i = 0; i < 64; i++) w[zigzag_inverse(i)] = (int64_t)c[i] * (int64_t)q[i];
-    idct_8x8<int64_t>(w);
-    for (int k = 0; k < 64; k++) {
-      int64_t s = w[k] < -128 ? -128 : w[k] > 127 ? 127 : w[k];
-      pix[k] = (uint8_t)(s + 128);
-    }
+  for (int r = 0; r < 8; r++) {
+    out[2 * r] = pack4_sat(v[8 * r], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3]);
+    out[2 * r + 1] = pack4_sat(v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
   }
+  return true;
+}
+
+// The model's arithmetic verbatim (64-bit), for blocks above the guard or quant entries above 255.
+HCJ_HD void reconstruct_wide(const uint32_t *cw, const int32_t *q, uint32_t *out) {
+  int64_t w[64];
+  for (int j = 0; j < 32; j++) {
+    int64_t lo = (int16_t)(cw[j] & 0xffffu), hi = (int16_t)(cw[j] >> 16);
+    w[zigzag_inverse(2 * j)] = lo * (int64_t)q[2 * j];
+    w[zigzag_inverse(2 * j + 1)] = hi * (int64_t)q[2 * j + 1];
+  }
+  idct_8x8<int64_t>(w);
+  for (int k = 0; k < 16; k++) {
+    uint32_t word = 0;
+    for (int i = 0; i < 4; i++) {
+      int64_t sv = w[4 * k + i] < -128 ? -128 : w[4 * k + i] > 127 ? 127 : w[4 * k + i];
+      word |= (uint32_t)(sv + 128) << (8 * i);
+    }
+    out[k] = word;
+  }
+}
+
+// Convenience form used by the debug tap and the CPU emulation.
+HCJ_HD void reconstruct_block(const int16_t c[64], const uint16_t q[64], bool force_wide, uint8_t pix[64]) {
+  uint32_t cw[32], out[16];
+  int32_t q32[64], qd[64];
+  for (int j = 0; j < 32; j++) cw[j] = (uint32_t)(uint16_t)c[2 * j] | ((uint32_t)(uint16_t)c[2 * j + 1] << 16);
+  for (int i = 0; i < 64; i++) {
+    q32[i] = q[i];
+    qd[i] = HCJ_QD(i, q[i]);
+  }
+  if (force_wide || !reconstruct_fast<true>(cw, qd, out)) reconstruct_wide(cw, q32, out);
+  for (int k = 0; k < 64; k++) pix[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // IDCT kernel is HBM bound (DESIGN.md has the byte counts).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "hcj_device.cuh"
 #include "hcj_kernels.cuh"
@@ -163,6 +164,7 @@ struct SmemTables {
   const uint16_t *full[HCJ_MAX_COMP * 2];
   uint8_t comp_pair[HCJ_MAX_COMP];
   uint8_t blk_comp[HCJ_MAX_BPM + 2];
+  int32_t quant[HCJ_MAX_COMP * 128];  // per scan component: 64 plain entries + 64 in dp2a form
 };
 
 __device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev &b, const HcjImageDesc &d) {
@@ -178,6 +180,7 @@ __device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev
   }
   if (threadIdx.x < HCJ_MAX_COMP) st.comp_pair[threadIdx.x] = (uint8_t)d.comp[threadIdx.x].pair;
   if (threadIdx.x < HCJ_MAX_BPM) st.blk_comp[threadIdx.x] = d.blk_comp[threadIdx.x];
+  for (uint32_t i = threadIdx.x; i < (uint32_t)d.ncomp * 128; i += blockDim.x) st.quant[i] = __ldg(b.qtables + d.qt_off + i);
 }
 
 __device__ __forceinline__ Tables tables_of(const SmemTables &st, uint32_t comp) {
@@ -192,6 +195,20 @@ __device__ __forceinline__ Tables tables_of(const SmemTables &st, uint32_t comp)
   return t;
 }
 
+__device__ __forceinline__ void fill_scan_ctx(ScanCtx &sc, const SmemTables &st, const DecodeBatchDev &b,
+                                              const HcjImageDesc &d, uint32_t total_bits) {
+  if (threadIdx.x == 0) {
+    sc.words = reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off);
+    sc.total_bits = total_bits;
+    sc.bpm = d.bpm;
+    sc.blk_comp = st.blk_comp;
+    sc.quant = st.quant;
+    sc.wide_flags = b.wide_flags;
+    sc.blk_base = d.coef_off;
+  }
+  if (threadIdx.x < (uint32_t)d.ncomp) sc.tab[threadIdx.x] = tables_of(st, threadIdx.x);
+}
+
 __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32_t bit_pos) {
   atomicMin(&st->err_key, ((unsigned long long)bit_pos << 8) | (unsigned long long)(-code));
 }
@@ -200,15 +217,18 @@ __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32
 // K2: one thread per restart interval.  Intervals are byte aligned and start with every DC predictor
 // at 0, so a thread owns its MCUs outright and writes resolved coefficients straight to HBM.
 // ================================================================================================
-constexpr int HR_THREADS = 128;
+constexpr int HR_THREADS = 256;
 
 __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
   __shared__ SmemTables st;
+  __shared__ ScanCtx sc;
   const uint32_t img = b.list_restart[blockIdx.y];
   const HcjImageDesc &d = b.descs[img];
   const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
   if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
   load_tables(st, b, d);
+  __syncthreads();
+  fill_scan_ctx(sc, st, b, d, 0);
   __syncthreads();
   HcjImageState *state = b.states + img;
   if (seg >= d.nseg_expected || state->status != 0) return;
@@ -219,17 +239,27 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
   const uint32_t ri = d.ri ? d.ri : d.nmcu;
   const uint32_t mcu0 = seg * ri, mcu1 = min(mcu0 + ri, d.nmcu);
   const uint32_t bpm = d.bpm;
-  int16_t *coefs = b.coefs + (d.coef_off + (uint64_t)mcu0 * bpm) * 64;
+  int16_t *coefs = b.coefs + d.coef_off * 64;
 
+  if (seg_bits > 16u) {
+    int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+    uint32_t err_pos = 0;
+    int err = subseq_write(sc, seg_begin * 8u, 0u, 0xffffffffu, seg_end * 8u, (int64_t)mcu0 * bpm - 1, pred,
+                           (int64_t)mcu1 * bpm, coefs, &err_pos);
+    if (err) raise_status(state, err, err_pos);
+    return;
+  }
+  // Degenerate interval: the model's `show` bound (bitstream_reader.ml:32) is in play.
   BitReader br;
-  br.init(reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off), seg_begin * 8u, seg_end * 8u);
+  br.init(sc.words, seg_begin * 8u, seg_end * 8u);
   int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  int64_t blk = (int64_t)mcu0 * bpm;
   for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
-    for (uint32_t k = 0; k < bpm; k++, coefs += 64) {
+    for (uint32_t k = 0; k < bpm; k++, blk++) {
       const uint32_t comp = st.blk_comp[k];
-      const Tables t = tables_of(st, comp);
       int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
-      int err = decode_block_exact(br, t, seg_bits, pred, coefs);
+      int err = decode_block_exact(br, sc.tab[comp], seg_bits, pred, coefs + blk * 64);
+      flag_wide_block(sc, blk);
       if (err) {
         raise_status(state, err, br.pos);
         return;
@@ -303,17 +333,13 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   const int t = threadIdx.x;
   load_tables(st, b, d);
   __syncthreads();
+  fill_scan_ctx(sc, st, b, d, state->ent_len * 8u);
   if (t == 0) {
-    sc.words = reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off);
-    sc.total_bits = state->ent_len * 8u;
-    sc.bpm = d.bpm;
-    sc.blk_comp = st.blk_comp;
     carry.p = 0;
     carry.cz = 0;
     carry.nstart = 0;
     for (int k = 0; k < HCJ_MAX_COMP; k++) carry.dc[k] = 0;
   }
-  if (t < d.ncomp) sc.tab[t] = tables_of(st, t);
   __syncthreads();
   if (state->status != 0) return;
 
@@ -330,6 +356,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       for (int64_t blk = 0; blk < nblocks; blk++) {
         uint32_t comp = st.blk_comp[blk % d.bpm];
         int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+        flag_wide_block(sc, blk);
         if (err) {
           raise_status(state, err, br.pos);
           break;
@@ -384,7 +411,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       int32_t pred[HCJ_MAX_COMP] = {carry.dc[0] + ex0, carry.dc[1] + ex1, carry.dc[2] + ex2, carry.dc[3] + ex3};
       int64_t blk = carry.nstart + ex_n - 1;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, mystart.x, mystart.y, last ? 0xffffffffu : hi, blk, pred, nblocks, coefs, &err_pos);
+      int err = subseq_write(sc, mystart.x, mystart.y, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, &err_pos);
       if (err) raise_status(state, err, err_pos);
     }
     __syncthreads();  // all reads of carry done
@@ -426,129 +453,255 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-__device__ __forceinline__ void unpack8(const uint4 &u, int16_t *c) {
-  c[0] = (int16_t)(u.x & 0xffffu);
-  c[1] = (int16_t)(u.x >> 16);
-  c[2] = (int16_t)(u.y & 0xffffu);
-  c[3] = (int16_t)(u.y >> 16);
-  c[4] = (int16_t)(u.z & 0xffffu);
-  c[5] = (int16_t)(u.z >> 16);
-  c[6] = (int16_t)(u.w & 0xffffu);
-  c[7] = (int16_t)(u.w >> 16);
-}
-
-__device__ __forceinline__ void store_block_rows(const uint8_t pix[64], uint8_t *dst, int stride, int x, int y,
+__device__ __forceinline__ void store_block_rows(const uint32_t pix[16], uint8_t *dst, int stride, int x, int y,
                                                  int w_limit, int h_limit) {
   // dst: plane base; (x, y): top-left sample of the block; samples outside w_limit x h_limit are cropped.
-  const bool fast = (x + 8 <= w_limit) && ((((uintptr_t)dst + (size_t)y * stride + x) & 7u) == 0) && ((stride & 7) == 0);
+  uint8_t *row = dst + (size_t)y * stride + x;
+  const bool fast = (x + 8 <= w_limit) && (((uintptr_t)row & 7u) == 0) && ((stride & 7) == 0);
+  if (fast) {
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    if (y + r >= h_limit) break;
-    uint8_t *row = dst + (size_t)(y + r) * stride + x;
-    if (fast) {
-      uint2 v;
-      v.x = pix[r * 8 + 0] | (pix[r * 8 + 1] << 8) | (pix[r * 8 + 2] << 16) | ((uint32_t)pix[r * 8 + 3] << 24);
-      v.y = pix[r * 8 + 4] | (pix[r * 8 + 5] << 8) | (pix[r * 8 + 6] << 16) | ((uint32_t)pix[r * 8 + 7] << 24);
-      *reinterpret_cast<uint2 *>(row) = v;
-    } else {
+    for (int r = 0; r < 8; r++)
+      if (y + r < h_limit) *reinterpret_cast<uint2 *>(row + (size_t)r * stride) = make_uint2(pix[2 * r], pix[2 * r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      if (y + r >= h_limit) break;
 #pragma unroll
       for (int i = 0; i < 8; i++)
-        if (x + i < w_limit) row[i] = pix[r * 8 + i];
+        if (x + i < w_limit) row[(size_t)r * stride + i] = (uint8_t)(pix[2 * r + (i >> 2)] >> (8 * (i & 3)));
     }
   }
 }
 
-// mode: 0 = HCJ_OUT_YUV (cropped planes, packed), 1 = padded planes into b.out, 2 = padded planes into b.planes
-__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct(DecodeBatchDev b, int mode) {
-  extern __shared__ uint4 s_tile[];
-  const HcjImageDesc &d = b.descs[blockIdx.y];
-  if (!d.valid) return;
+// Rare path kept out of line so that its 64-bit temporaries do not cost the fast path registers.
+__device__ __noinline__ void wide_block_store(const uint32_t *cw, const int32_t *q, uint8_t *dst, int stride, int x, int y,
+                                              int w_limit, int h_limit) {
+  uint32_t pix[16];
+  reconstruct_wide(cw, q, pix);
+  store_block_rows(pix, dst, stride, x, y, w_limit, h_limit);
+}
+
+struct IdctTile {
+  const HcjImageDesc *d;  // nullptr: nothing to do
+  int my, m0, tm, nblk;
+};
+
+__device__ __forceinline__ IdctTile idct_tile(const DecodeBatchDev &b, uint32_t tile_id) {
+  IdctTile t;
+  t.d = nullptr;
+  t.my = t.m0 = t.tm = t.nblk = 0;
+  const uint32_t img = tile_id / b.max_idct_tiles, tile = tile_id - img * b.max_idct_tiles;
+  const HcjImageDesc &d = b.descs[img];
+  if (!d.valid) return t;
   const int bpm = d.bpm;
   const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / bpm);
   const int tiles_per_row = (d.mcus_wide + tm_max - 1) / tm_max;
   const int tm_bal = (d.mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
-  const int tile = blockIdx.x;
-  if (tile >= tiles_per_row * d.mcus_high) return;
-  const int my = tile / tiles_per_row, tx = tile - my * tiles_per_row;
-  const int m0 = tx * tm_bal;
-  const int tm = min(tm_bal, d.mcus_wide - m0);
-  const int nblk = tm * bpm;
-  const int tid = threadIdx.x;
+  if (tile >= (uint32_t)(tiles_per_row * d.mcus_high)) return t;
+  t.my = tile / tiles_per_row;
+  t.m0 = (tile - t.my * tiles_per_row) * tm_bal;
+  t.tm = min(tm_bal, d.mcus_wide - t.m0);
+  t.nblk = t.tm * bpm;
+  t.d = &d;
+  return t;
+}
 
-  const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)my * d.mcus_wide + m0) * bpm) * 64;
-  for (int g = tid; g < nblk * 8; g += blockDim.x) cp_async16(&s_tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+// Persistent CTAs (2 per SM) walk the batch's tiles with a stride of gridDim.x; the coefficient tile and
+// the quant tables of tile i+1 are in flight (cp.async) while tile i is being transformed.
+// mode: 0 = HCJ_OUT_YUV (cropped planes, packed), 1 = padded planes into b.out, 2 = padded planes into b.planes
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeBatchDev b, int mode) {
+  extern __shared__ uint4 s_dyn[];
+  uint4 *s_tile[2] = {s_dyn, s_dyn + IDCT_MAX_THREADS * IDCT_ROW_U4};
+  int32_t *s_qbase = reinterpret_cast<int32_t *>(s_dyn + 2 * IDCT_MAX_THREADS * IDCT_ROW_U4);
+  int32_t *s_q[2] = {s_qbase, s_qbase + HCJ_MAX_COMP * 128};
+  const int tid = threadIdx.x;
+  const uint32_t total = (uint32_t)b.n * b.max_idct_tiles;
+
+  auto issue = [&](uint32_t tile_id, int buf) {
+    const IdctTile t = idct_tile(b, tile_id);
+    if (t.d) {
+      const HcjImageDesc &d = *t.d;
+      const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm) * 64;
+      for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS)
+        cp_async16(&s_tile[buf][(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+      if (tid < d.ncomp * 32) cp_async16(s_q[buf] + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  uint32_t cur = blockIdx.x;
+  int buf = 0;
+  if (cur < total) issue(cur, 0);
+  for (; cur < total; cur += gridDim.x, buf ^= 1) {
+    const uint32_t next = cur + gridDim.x;
+    if (next < total) {
+      issue(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    const IdctTile t = idct_tile(b, cur);
+    if (t.d && tid < t.nblk) {
+      const HcjImageDesc &d = *t.d;
+      // thread -> (component, block row, MCU, block column)
+      int rem = tid, c = 0;
+      for (; c < d.ncomp - 1; c++) {
+        int n = t.tm * d.comp[c].hs * d.comp[c].vs;
+        if (rem < n) break;
+        rem -= n;
+      }
+      const HcjCompGeom &g = d.comp[c];
+      const int rowlen = t.tm * g.hs;
+      const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
+      const int r2 = rem - by * rowlen;
+      const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
+      const int bx = r2 - m * g.hs;
+      const int slot = m * d.bpm + g.first_blk + by * g.hs + bx;
+
+      uint32_t cw[32];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint4 u = s_tile[buf][slot * IDCT_ROW_U4 + j];
+        cw[4 * j] = u.x;
+        cw[4 * j + 1] = u.y;
+        cw[4 * j + 2] = u.z;
+        cw[4 * j + 3] = u.w;
+      }
+      uint32_t pix[16];
+      const int32_t *q = s_q[buf] + c * 128;
+      const int x = ((t.m0 + m) * g.hs + bx) * 8, y = (t.my * g.vs + by) * 8;
+      uint8_t *base;
+      int stride, w_limit, h_limit;
+      if (mode == 0) {
+        base = b.out + d.out_off + g.out_off;
+        stride = w_limit = g.actual_w;
+        h_limit = g.actual_h;
+      } else {
+        base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
+        stride = w_limit = g.decoded_w;
+        h_limit = g.decoded_h;
+      }
+      const uint64_t gblk = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm + slot;
+      const bool wide = d.wide_idct || ((__ldg(b.wide_flags + (gblk >> 5)) >> (gblk & 31u)) & 1u);
+      if (wide || !reconstruct_fast<false>(cw, q + 64, pix))
+        wide_block_store(reinterpret_cast<const uint32_t *>(&s_tile[buf][slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
+      else
+        store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
+    }
+    __syncthreads();  // the buffer is refilled by the next iteration's prefetch
+  }
+}
+
+// One tile per CTA: load (cp.async) -> transform -> store; latency is hidden by the other resident CTAs.
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct(DecodeBatchDev b, int mode) {
+  extern __shared__ uint4 s_dyn[];
+  uint4 *s_tile = s_dyn;
+  int32_t *s_q = reinterpret_cast<int32_t *>(s_dyn + IDCT_MAX_THREADS * IDCT_ROW_U4);
+  const int tid = threadIdx.x;
+  const IdctTile t = idct_tile(b, blockIdx.y * b.max_idct_tiles + blockIdx.x);
+  if (!t.d) return;
+  const HcjImageDesc &d = *t.d;
+  const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm) * 64;
+  for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&s_tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+  if (tid < d.ncomp * 32) cp_async16(s_q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
   cp_async_wait_all();
   __syncthreads();
-  if (tid >= nblk) return;
-
+  if (tid >= t.nblk) return;
   // thread -> (component, block row, MCU, block column)
   int rem = tid, c = 0;
   for (; c < d.ncomp - 1; c++) {
-    int n = tm * d.comp[c].hs * d.comp[c].vs;
+    int n = t.tm * d.comp[c].hs * d.comp[c].vs;
     if (rem < n) break;
     rem -= n;
   }
   const HcjCompGeom &g = d.comp[c];
-  const int rowlen = tm * g.hs;
-  const int by = rem / rowlen, r2 = rem - by * rowlen;
-  const int m = r2 / g.hs, bx = r2 - m * g.hs;
-  const int slot = m * bpm + g.first_blk + by * g.hs + bx;
-
-  int16_t coef[64];
-#pragma unroll
-  for (int j = 0; j < 8; j++) unpack8(s_tile[slot * IDCT_ROW_U4 + j], coef + 8 * j);
-  uint16_t q[64];
-  const uint4 *qsrc = reinterpret_cast<const uint4 *>(b.qtables + d.qt_off + g.qt * 64);
+  const int rowlen = t.tm * g.hs;
+  const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
+  const int r2 = rem - by * rowlen;
+  const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
+  const int bx = r2 - m * g.hs;
+  const int slot = m * d.bpm + g.first_blk + by * g.hs + bx;
+  uint32_t cw[32];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    uint4 u = __ldg(qsrc + j);
-    unpack8(u, reinterpret_cast<int16_t *>(q) + 8 * j);
+    uint4 u = s_tile[slot * IDCT_ROW_U4 + j];
+    cw[4 * j] = u.x;
+    cw[4 * j + 1] = u.y;
+    cw[4 * j + 2] = u.z;
+    cw[4 * j + 3] = u.w;
   }
-  uint8_t pix[64];
-  reconstruct_block(coef, q, d.wide_idct != 0, pix);
-
-  const int x = ((m0 + m) * g.hs + bx) * 8, y = (my * g.vs + by) * 8;
+  uint32_t pix[16];
+  const int32_t *q = s_q + c * 128;
+  const int x = ((t.m0 + m) * g.hs + bx) * 8, y = (t.my * g.vs + by) * 8;
+  uint8_t *base;
+  int stride, w_limit, h_limit;
   if (mode == 0) {
-    store_block_rows(pix, b.out + d.out_off + g.out_off, g.actual_w, x, y, g.actual_w, g.actual_h);
+    base = b.out + d.out_off + g.out_off;
+    stride = w_limit = g.actual_w;
+    h_limit = g.actual_h;
   } else {
-    uint8_t *base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
-    store_block_rows(pix, base, g.decoded_w, x, y, g.decoded_w, g.decoded_h);
+    base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
+    stride = w_limit = g.decoded_w;
+    h_limit = g.decoded_h;
   }
+  const uint64_t gblk = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm + slot;
+  const bool wide = d.wide_idct || ((__ldg(b.wide_flags + (gblk >> 5)) >> (gblk & 31u)) & 1u);
+  if (wide || !reconstruct_fast<false>(cw, q + 64, pix)) {
+    wide_block_store(reinterpret_cast<const uint32_t *>(&s_tile[slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
+    return;
+  }
+  store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
 }
 
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   if (b.n == 0 || b.max_idct_tiles == 0) return;
-  dim3 grid(b.max_idct_tiles, b.n);
-  size_t smem = (size_t)IDCT_MAX_THREADS * IDCT_ROW_U4 * sizeof(uint4);
-  k_idct<<<grid, IDCT_MAX_THREADS, smem, s>>>(b, mode);
+  static int grid = 0, persistent = 0;
+  const size_t smem1 = (size_t)IDCT_MAX_THREADS * IDCT_ROW_U4 * sizeof(uint4) + HCJ_MAX_COMP * 128 * sizeof(int32_t);
+  if (!grid) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem1));
+    grid = 2 * sms;
+    const char *e = getenv("HCJ_IDCT_PERSISTENT");
+    persistent = e && e[0] == '1';
+  }
+  if (persistent) {
+    uint64_t total = (uint64_t)b.n * b.max_idct_tiles;
+    k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * smem1, s>>>(b, mode);
+  } else {
+    k_idct<<<dim3(b.max_idct_tiles, b.n), IDCT_MAX_THREADS, smem1, s>>>(b, mode);
+  }
 }
 
 // Debug tap: Component.recon of caller-provided blocks (hcj_idct_blocks).
 __global__ void k_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, int force_wide, uint8_t *out) {
+  __shared__ int32_t s_q[128];
+  if (threadIdx.x < 64) {
+    s_q[threadIdx.x] = qt[threadIdx.x];
+    s_q[64 + threadIdx.x] = HCJ_QD(threadIdx.x, qt[threadIdx.x]);
+  }
+  __syncthreads();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nblocks) return;
-  int16_t c[64];
-  uint16_t q[64];
+  uint32_t cw[32], pix[16];
   const uint4 *src = reinterpret_cast<const uint4 *>(coefs + i * 64);
-  const uint4 *qs = reinterpret_cast<const uint4 *>(qt);
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    unpack8(__ldg(src + j), c + 8 * j);
-    unpack8(__ldg(qs + j), reinterpret_cast<int16_t *>(q) + 8 * j);
+    uint4 u = __ldg(src + j);
+    cw[4 * j] = u.x;
+    cw[4 * j + 1] = u.y;
+    cw[4 * j + 2] = u.z;
+    cw[4 * j + 3] = u.w;
   }
-  uint8_t pix[64];
-  reconstruct_block(c, q, force_wide != 0, pix);
+  if (force_wide || !reconstruct_fast<true>(cw, s_q + 64, pix)) {
+    wide_block_store(reinterpret_cast<const uint32_t *>(coefs + i * 64), s_q, out + i * 64, 8, 0, 0, 8, 8);
+    return;
+  }
   uint4 *dst = reinterpret_cast<uint4 *>(out + i * 64);
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint4 v;
-    uint32_t *vv = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      vv[k] = pix[j * 16 + k * 4] | (pix[j * 16 + k * 4 + 1] << 8) | (pix[j * 16 + k * 4 + 2] << 16) |
-              ((uint32_t)pix[j * 16 + k * 4 + 3] << 24);
-    dst[j] = v;
-  }
+  for (int j = 0; j < 4; j++) dst[j] = make_uint4(pix[4 * j], pix[4 * j + 1], pix[4 * j + 2], pix[4 * j + 3]);
 }
 
 void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,

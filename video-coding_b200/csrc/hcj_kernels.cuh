@@ -18,8 +18,9 @@ struct DecodeBatchDev {
   const HcjTableSet *table_sets;
   const uint16_t *lut_primary;    // primary LUT pool
   const uint16_t *lut_full;       // full LUT pool
-  const uint16_t *qtables;        // quant tables pool, zig-zag order
+  const int32_t *qtables;         // quant tables pool, zig-zag order, one int32 per entry
   int16_t *coefs;                 // [total blocks][64], zig-zag, DC resolved
+  uint32_t *wide_flags;           // 1 bit per block: take the 64-bit IDCT (zeroed before every decode)
   uint8_t *planes;                // padded planes (scratch for RGB mode, the output for PLANES mode)
   uint8_t *out;                   // outputs
   // launch geometry, computed on the host
