@@ -83,7 +83,7 @@ def split_entropy(jpeg, scan_start, restart):
 def decode_segments(jpeg, nblocks, scan_start, restart, flags=1):
     ent, segs = split_entropy(jpeg, scan_start, restart)
     so = np.array(segs, np.uint32)
-    coefs = np.zeros((nblocks, 64), np.int16)
+    coefs = np.full((nblocks, 64), 0x5A5A, np.int16)  # garbage: the decoders clear the blocks themselves
     wide = np.zeros(nblocks // 32 + 2, np.uint32)
     st = lib().emu_decode_segments(jpeg, len(jpeg), flags, ent, so.ctypes.data, len(segs) - 1, coefs.ctypes.data, wide.ctypes.data)
     decode_segments.wide = wide
@@ -92,7 +92,7 @@ def decode_segments(jpeg, nblocks, scan_start, restart, flags=1):
 
 def decode_speculative(jpeg, nblocks, scan_start, T=64, S=1024):
     ent, _ = split_entropy(jpeg, scan_start, False)
-    coefs = np.zeros((nblocks, 64), np.int16)
+    coefs = np.full((nblocks, 64), 0x5A5A, np.int16)  # garbage: the decoders clear the blocks themselves
     rounds = C.c_int()
     wide = np.zeros(nblocks // 32 + 2, np.uint32)
     st = lib().emu_decode_speculative(jpeg, len(jpeg), ent, len(ent), T, S, coefs.ctypes.data, C.byref(rounds), wide.ctypes.data)

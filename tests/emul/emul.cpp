@@ -16,8 +16,11 @@ namespace {
 
 struct HostTables {
   std::vector<hcj::HuffLut> luts;  // [comp][dc/ac]
+  std::vector<uint16_t> lut;       // all primary tables back to back (what the kernels keep in shared memory)
   Tables tab[HCJ_MAX_COMP];
   int32_t quant[HCJ_MAX_COMP * 128];
+  uint8_t blk_comp[HCJ_MAX_BPM + 2];
+  Local local() const { return Local{lut.data(), quant, blk_comp}; }
 };
 
 int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj::ImagePlan *plan, HostTables *ht) {
@@ -39,13 +42,16 @@ int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj:
     }
   for (int c = 0; c < plan->info.ncomp; c++) {
     Tables &t = ht->tab[c];
-    t.dc_primary = ht->luts[c * 2].primary.data();
+    t.dc_off = (uint32_t)ht->lut.size();
+    ht->lut.insert(ht->lut.end(), ht->luts[c * 2].primary.begin(), ht->luts[c * 2].primary.end());
     t.dc_full = ht->luts[c * 2].full.data();
     t.dc_max_bits = ht->luts[c * 2].max_bits;
-    t.ac_primary = ht->luts[c * 2 + 1].primary.data();
+    t.ac_off = (uint32_t)ht->lut.size();
+    ht->lut.insert(ht->lut.end(), ht->luts[c * 2 + 1].primary.begin(), ht->luts[c * 2 + 1].primary.end());
     t.ac_full = ht->luts[c * 2 + 1].full.data();
     t.ac_max_bits = ht->luts[c * 2 + 1].max_bits;
   }
+  for (int k = 0; k < plan->info.blocks_per_mcu; k++) ht->blk_comp[k] = (uint8_t)plan->blk_comp[k];
   return 0;
 }
 
@@ -84,16 +90,14 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
   uint32_t ri = f.restart_interval ? (uint32_t)f.restart_interval : nmcu;
   std::vector<uint32_t> words((seg_off[nseg] + 15) / 4 + 4, 0);
   memcpy(words.data(), entropy, seg_off[nseg]);
-  uint8_t blk_comp[HCJ_MAX_BPM + 2];
-  for (uint32_t k = 0; k < bpm; k++) blk_comp[k] = (uint8_t)plan.blk_comp[k];
+  const Local L = ht.local();
   ScanCtx sc;
   sc.words = words.data();
   sc.total_bits = 0;
   sc.bpm = bpm;
-  sc.blk_comp = blk_comp;
   for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
-  sc.quant = ht.quant;
   sc.wide_flags = wide_flags;
+  sc.debug = 0;
   sc.blk_base = 0;
   unsigned long long err_key = ~0ull;
   for (uint32_t seg = 0; seg < nseg; seg++) {  // <- thread index
@@ -103,8 +107,8 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
     uint32_t err_pos = 0;
     if (seg_bits > 16) {
       int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-      err = subseq_write(sc, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
-                         (int64_t)mcu1 * bpm, coefs, &err_pos);
+      err = subseq_write(sc, L, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
+                         (int64_t)mcu1 * bpm, coefs, -2, &err_pos);
     } else {
       BitReader br;
       br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
@@ -113,7 +117,7 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
       for (uint32_t mcu = mcu0; mcu < mcu1 && !err; mcu++)
         for (uint32_t k = 0; k < bpm && !err; k++, blk++) {
           int comp = plan.blk_comp[k];
-          err = decode_block_exact(br, ht.tab[comp], seg_bits, pred[comp], coefs + blk * 64);
+          err = decode_block_exact(br, L, ht.tab[comp], seg_bits, pred[comp], coefs + blk * 64);
           flag_wide_block(sc, blk);
           err_pos = br.pos;
         }
@@ -137,16 +141,15 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
   const hcj_frame_info &f = plan.info;
   std::vector<uint32_t> words((ent_len + 15) / 4 + 4, 0);
   memcpy(words.data(), entropy, ent_len);
-  uint8_t blk_comp[HCJ_MAX_BPM + 2];
-  for (int k = 0; k < f.blocks_per_mcu; k++) blk_comp[k] = (uint8_t)plan.blk_comp[k];
+  const Local LT = ht.local();
+  const uint8_t *blk_comp = ht.blk_comp;
   ScanCtx sc;
   sc.words = words.data();
   sc.total_bits = ent_len * 8;
   sc.bpm = (uint32_t)f.blocks_per_mcu;
-  sc.blk_comp = blk_comp;
   for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
-  sc.quant = ht.quant;
   sc.wide_flags = wide_flags;
+  sc.debug = 0;
   sc.blk_base = 0;
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = f.nblocks;
@@ -157,7 +160,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
     int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
     for (int64_t blk = 0; blk < nblocks; blk++) {
       int comp = blk_comp[blk % sc.bpm];
-      int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+      int err = decode_block_exact(br, LT, sc.tab[comp], L, pred[comp], coefs + blk * 64);
       flag_wide_block(sc, blk);
       if (err) return err;
     }
@@ -180,7 +183,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       hi[t] = lo + S < L ? lo + S : L;
       sp[t] = t == 0 ? carry.p : lo;
       scz[t] = t == 0 ? carry.cz : 0;
-      subseq_sync(sc, sp[t], scz[t], hi[t], r[t]);
+      subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t]);
       endp[t] = r[t].p;
       endcz[t] = r[t].cz;
     }
@@ -194,7 +197,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
         if (nsp != sp[t] || nscz != scz[t]) {
           sp[t] = nsp;
           scz[t] = nscz;
-          subseq_sync(sc, nsp, nscz, hi[t], r[t]);
+          subseq_sync(sc, LT, nsp, nscz, hi[t], r[t]);
           if (r[t].p != endp[t] || r[t].cz != endcz[t]) {
             any = true;
             np[t] = r[t].p;
@@ -208,21 +211,47 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       if (!any) break;
     }
     if (rounds > max_rounds) max_rounds = rounds;
-    // phase C
+    // phase C: first every thread clears the block it begins last (its neighbour finishes it) ...
+    {
+      int64_t acc = 0;
+      for (int t = 0; t < nact; t++) {
+        int64_t trailing = r[t].nstart > 0 ? carry.nstart + acc - 1 + (int64_t)r[t].nstart : -2;
+        if (trailing >= 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
+        acc += r[t].nstart;
+      }
+    }
+    // ... then (after the barrier) the exact pass; run the emulated threads in REVERSE order so that a
+    // right neighbour really does store into a shared block before its owner gets to it
+    std::vector<int64_t> exn(nact);
+    std::vector<int32_t> exd(nact * HCJ_MAX_COMP);
+    {
+      int64_t acc = 0;
+      int32_t accd[HCJ_MAX_COMP] = {0, 0, 0, 0};
+      for (int t = 0; t < nact; t++) {
+        exn[t] = acc;
+        for (int k = 0; k < HCJ_MAX_COMP; k++) exd[t * HCJ_MAX_COMP + k] = accd[k];
+        acc += r[t].nstart;
+        for (int k = 0; k < HCJ_MAX_COMP; k++) accd[k] += r[t].dcsum[k];
+      }
+    }
     int64_t ex_n = 0;
     int32_t ex_dc[HCJ_MAX_COMP] = {0, 0, 0, 0};
-    for (int t = 0; t < nact; t++) {
+    for (int tt = 0; tt < nact; tt++) {
+      const int t = nact - 1 - tt;
+      ex_n = exn[t];
+      for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] = exd[t * HCJ_MAX_COMP + k];
       int32_t pred[HCJ_MAX_COMP];
       for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + ex_dc[k];
       int64_t blk = carry.nstart + ex_n - 1;
       bool last = base + t == nsub - 1;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, &err_pos);
+      const int64_t trailing = r[t].nstart > 0 ? blk + (int64_t)r[t].nstart : -2;
+      int err = subseq_write(sc, LT, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, trailing, &err_pos);
       unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
       if (err && key < err_key) err_key = key;  // the kernel's atomicMin
-      ex_n += r[t].nstart;
-      for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] += r[t].dcsum[k];
     }
+    ex_n = exn[nact - 1] + r[nact - 1].nstart;
+    for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] = exd[(nact - 1) * HCJ_MAX_COMP + k] + r[nact - 1].dcsum[k];
     carry.p = r[nact - 1].p;
     carry.cz = r[nact - 1].cz;
     carry.nstart += ex_n;

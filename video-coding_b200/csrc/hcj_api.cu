@@ -4,6 +4,7 @@
 // else is queued on the context's CUDA stream.  No CPU fallback exists: if CUDA is unavailable every
 // compute entry point fails with HCJ_ERR_CUDA - cudaError.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -393,6 +394,10 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   dv.max_rgb_rows = max_rows;
   dv.max_width = max_width;
   dv.total_blocks = total_blocks;
+  {
+    const char *e = getenv("HCJ_DEBUG");
+    dv.debug = e ? atoi(e) : 0;
+  }
   b->kernels = 1 + (dv.n_restart ? 1 : 0) + (dv.n_spec ? 1 : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
 
   // ---- upload
@@ -439,8 +444,8 @@ int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   if (b->n == 0) return HCJ_OK;
-  // Coefficient blocks start as zero (clear_block, decoder.ml:112-116,160); decoders store non-zeros.
-  CU_TRY(cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s));
+  // Coefficient blocks are cleared (clear_block, decoder.ml:112-116,160) by the entropy kernels themselves,
+  // block by block, right before they store into them (see zero_block in hcj_device.cuh).
   CU_TRY(cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s));
   CU_TRY(cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s));  // overwritten by k_destuff for valid images
   hcjk::launch_destuff(b->dev, s);
@@ -452,7 +457,7 @@ int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
   return HCJ_OK;
 }
 
-static const char *kStageNames[] = {"zero_coefficients", "destuff", "huffman_restart", "huffman_speculative", "idct", "rgb"};
+static const char *kStageNames[] = {"clear_flags", "destuff", "huffman_restart", "huffman_speculative", "idct", "rgb"};
 const char *hcj_decode_stage_name(int i) { return i >= 0 && i < 6 ? kStageNames[i] : ""; }
 
 int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, int *nstages) {
@@ -463,7 +468,6 @@ int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, i
   for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
   const int mode = b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2;
   cudaEventRecord(ev[0], s);
-  cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s);
   cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
   cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s);
   cudaEventRecord(ev[1], s);

@@ -8,6 +8,10 @@
 
 #define HCJ_LUT_BITS 10                    // primary Huffman LUT index width
 #define HCJ_LUT_SIZE (1 << HCJ_LUT_BITS)
+#define HCJ_LUT_NSUB 8                     // second-level sub-tables per Huffman table (shared memory)
+#define HCJ_LUT_SUB_BITS 6                 // each covers the 16 - HCJ_LUT_BITS bits below an unresolved prefix
+#define HCJ_LUT_SUB_SIZE (1 << HCJ_LUT_SUB_BITS)
+#define HCJ_LUT_ENTRIES (HCJ_LUT_SIZE + HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE)  // per table, uint16 each
 #define HCJ_MAX_BPM 10                     // blocks per MCU (T.81 limit)
 #define HCJ_MAX_COMP 4
 
@@ -22,9 +26,13 @@
 #define HCJ_DEV_DC_RANGE (-23)
 
 // One Huffman table as the kernels see it.
-//   primary[i] (i = next HCJ_LUT_BITS bits): (length << 8) | data, or 0 = "not resolved here"
-//   full table (2^max_bits entries, same encoding, 0 = None in Tables.Lut, tables.ml:492) lives in
-//   global memory at full_off and is consulted only when the primary entry is 0.
+//   primary[i] (i = next HCJ_LUT_BITS bits): (length << 8) | data;
+//                0x8000 | k = "longer code: look in sub-table k"; 0 = "not resolved here"
+//   sub-table k (HCJ_LUT_SUB_SIZE entries, indexed by the max_bits - HCJ_LUT_BITS bits that follow the
+//                prefix): same encoding as the full table
+//   full table (2^max_bits entries, (length << 8) | data, 0 = None in Tables.Lut, tables.ml:492) lives in
+//   global memory at full_off and is consulted only when the primary entry is 0 (tables with more than
+//   HCJ_LUT_NSUB unresolved prefixes; never the case for the Annex K tables).
 struct HcjTableMeta {
   uint32_t full_off;  // offset (in uint16 entries) into the batch's full-LUT pool
   uint32_t max_bits;  // Tables.Lut.max_bits (tables.ml:491)
@@ -33,7 +41,7 @@ struct HcjTableMeta {
 // A table set = the (dc, ac) pairs used by the scan components of one image, de-duplicated.
 struct HcjTableSet {
   HcjTableMeta meta[HCJ_MAX_COMP][2];  // [pair][0 = dc, 1 = ac]
-  uint32_t primary_off;                // offset (uint16 entries) of primary[pair][dc/ac][HCJ_LUT_SIZE]
+  uint32_t primary_off;                // offset (uint16 entries) of lut[pair][dc/ac][HCJ_LUT_ENTRIES]
   uint32_t npairs;
 };
 

@@ -29,17 +29,27 @@ HCJ_HD uint32_t bswap32(uint32_t x) {
 #endif
 }
 
-HCJ_HD uint32_t load_be_word(const uint32_t *__restrict__ words, uint32_t idx, uint32_t end_bits) {
-  uint32_t bitbase = idx << 5;
-  if (bitbase >= end_bits) return 0u;
+// Raw (little-endian, unmasked) word `idx` of the stream, 0 past the end.  Kept separate from
+// be_word() so that the value of a look-ahead load is not touched (= waited for) before it is needed.
+HCJ_HD uint32_t load_raw_word(const uint32_t *__restrict__ words, uint32_t idx, uint32_t end_bits) {
+  if ((idx << 5) >= end_bits) return 0u;
 #if defined(__CUDA_ARCH__)
-  uint32_t w = bswap32(__ldg(words + idx));
+  return __ldg(words + idx);
 #else
-  uint32_t w = bswap32(words[idx]);
+  return words[idx];
 #endif
-  uint32_t rem = end_bits - bitbase;
+}
+// Big-endian view of a raw word with the bits at or beyond end_bits cleared.
+HCJ_HD uint32_t be_word(uint32_t raw, uint32_t idx, uint32_t end_bits) {
+  uint32_t w = bswap32(raw);
+  const uint32_t bitbase = idx << 5;
+  if (bitbase >= end_bits) return 0u;
+  const uint32_t rem = end_bits - bitbase;
   if (rem < 32u) w &= ~(0xffffffffu >> rem);
   return w;
+}
+HCJ_HD uint32_t load_be_word(const uint32_t *__restrict__ words, uint32_t idx, uint32_t end_bits) {
+  return be_word(load_raw_word(words, idx, end_bits), idx, end_bits);
 }
 
 struct BitReader {
@@ -48,7 +58,7 @@ struct BitReader {
   uint32_t pos;
   uint32_t widx;
   uint32_t w0, w1;  // big-endian words widx, widx + 1: the 32-bit window lives in these
-  uint32_t wn;      // word widx + 2, requested one refill ahead so that its latency is never waited for
+  uint32_t wn_raw;  // raw word widx + 2, requested one refill ahead so that its latency is never waited for
 
   HCJ_HD void init(const uint32_t *words_, uint32_t pos_, uint32_t end_bits_) {
     words = words_;
@@ -57,7 +67,7 @@ struct BitReader {
     widx = pos_ >> 5;
     w0 = load_be_word(words, widx, end_bits);
     w1 = load_be_word(words, widx + 1, end_bits);
-    wn = load_be_word(words, widx + 2, end_bits);
+    wn_raw = load_raw_word(words, widx + 2, end_bits);
   }
   // The next 32 bits, MSB-aligned.
   HCJ_HD uint32_t window() const {
@@ -75,23 +85,38 @@ struct BitReader {
     if (nidx != widx) {
       widx = nidx;
       w0 = w1;
-      w1 = wn;
-      wn = load_be_word(words, nidx + 2, end_bits);
+      w1 = be_word(wn_raw, nidx + 1, end_bits);
+      wn_raw = load_raw_word(words, nidx + 2, end_bits);
     }
   }
 };
 
 // Huffman tables of one scan component as the decode loops see them.
 struct Tables {
-  const uint16_t *dc_primary, *ac_primary;  // HCJ_LUT_SIZE entries each (shared memory in the kernels)
-  const uint16_t *dc_full, *ac_full;        // 2^max_bits entries (global memory)
+  uint32_t dc_off, ac_off;            // offsets (entries) of the table's HCJ_LUT_ENTRIES in Local::lut
+  const uint16_t *dc_full, *ac_full;  // 2^max_bits entries (global memory)
   uint32_t dc_max_bits, ac_max_bits;
 };
 
+// The hot lookup tables of the CTA's image.  In the kernels these point into __shared__ arrays and the
+// struct is built in the kernel body and passed by value, so that after inlining the compiler knows
+// the address space and emits LDS (a generic load costs a long-scoreboard round trip per symbol).
+struct Local {
+  const uint16_t *lut;      // [pair][dc/ac][HCJ_LUT_ENTRIES]
+  const int32_t *quant;     // [scan component][128]: 64 plain entries + 64 in dp2a form
+  const uint8_t *blk_comp;  // [bpm] block-in-MCU -> scan component
+};
+
 // Tables.Lut lookup (decoder.ml:89-105): (length << 8) | data, 0 = None.
-HCJ_HD uint32_t lut_lookup(const uint16_t *primary, const uint16_t *full, uint32_t max_bits, uint32_t win) {
+HCJ_HD uint32_t lut_lookup(const uint16_t *lut, uint32_t off, const uint16_t *full, uint32_t max_bits, uint32_t win) {
+  const uint16_t *primary = lut + off;
   uint32_t e = primary[win >> (32 - HCJ_LUT_BITS)];
-  if (e == 0u && max_bits > HCJ_LUT_BITS) e = full[win >> (32u - max_bits)];
+  if (e & 0x8000u) {  // longer code: sub-table indexed by the bits that follow the prefix
+    const uint32_t sub = (win >> (32u - max_bits)) & ((1u << (max_bits - HCJ_LUT_BITS)) - 1u);
+    e = primary[HCJ_LUT_SIZE + (e & (HCJ_LUT_NSUB - 1)) * HCJ_LUT_SUB_SIZE + sub];
+  } else if (e == 0u && max_bits > HCJ_LUT_BITS) {
+    e = full[win >> (32u - max_bits)];
+  }
   return e;
 }
 
@@ -101,18 +126,34 @@ HCJ_HD int32_t extend(uint32_t bits, uint32_t cat) {
   return (bits >> (cat - 1u)) ? v : v - (int32_t)(1u << cat) + 1;
 }
 
+// Clears one 128-byte coefficient block (clear_block, decoder.ml:112-116) with full-sector stores.  Done
+// by the thread that begins the block right before its first coefficient store: the sector is then
+// resident (dirty) in L2 when the scattered 2-byte stores arrive, so they neither fetch the line from HBM
+// nor need a separate clearing pass over the whole coefficient buffer.
+HCJ_HD void zero_block(int16_t *blk) {
+#if defined(__CUDA_ARCH__)
+  uint4 *p = reinterpret_cast<uint4 *>(blk);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int j = 0; j < 8; j++) p[j] = z;
+#else
+  for (int j = 0; j < 64; j++) blk[j] = 0;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Exact decode of one 8x8 block (Decoder.huffman_decode, decoder.ml:118-140) into a zero-initialised
-// int16 block in zig-zag order; slot 0 receives the RESOLVED dc (pred + diff, decoder.ml:143).
+// int16 block (cleared here) in zig-zag order; slot 0 receives the RESOLVED dc (pred + diff, decoder.ml:143).
 // `seg_bits` is the length of the reader the model would be using (for the `show` bound, reader.ml:32).
 // Returns 0 or the status of the exception the model raises.
 // ------------------------------------------------------------------------------------------------
-HCJ_HD int decode_block_exact(BitReader &br, const Tables &t, uint32_t seg_bits, int32_t &dc_pred,
+HCJ_HD int decode_block_exact(BitReader &br, const Local L, const Tables &t, uint32_t seg_bits, int32_t &dc_pred,
                               int16_t *__restrict__ blk) {
+  zero_block(blk);
   const bool careful = seg_bits <= 16u;
   if (careful && t.dc_max_bits >= seg_bits) return HCJ_DEV_BITS_OOB;
   uint32_t win = br.window();
-  uint32_t e = lut_lookup(t.dc_primary, t.dc_full, t.dc_max_bits, win);
+  uint32_t e = lut_lookup(L.lut, t.dc_off, t.dc_full, t.dc_max_bits, win);
   if (e == 0u) return HCJ_DEV_NO_DC_CODE;
   uint32_t len = e >> 8, cat = e & 0xffu;
   int32_t diff = 0;
@@ -128,7 +169,7 @@ HCJ_HD int decode_block_exact(BitReader &br, const Tables &t, uint32_t seg_bits,
   while (k < 64u) {
     if (careful && t.ac_max_bits >= seg_bits) return HCJ_DEV_BITS_OOB;
     win = br.window();
-    e = lut_lookup(t.ac_primary, t.ac_full, t.ac_max_bits, win);
+    e = lut_lookup(L.lut, t.ac_off, t.ac_full, t.ac_max_bits, win);
     if (e == 0u) return HCJ_DEV_NO_AC_CODE;
     len = e >> 8;
     uint32_t rs = e & 0xffu, size = rs & 15u;
@@ -159,9 +200,8 @@ struct ScanCtx {
   const uint32_t *words;       // destuffed bytes of the image (16-byte aligned)
   uint32_t total_bits;         // 8 * destuffed length
   uint32_t bpm;                // blocks per MCU
-  const uint8_t *blk_comp;     // [bpm] block-in-MCU -> scan component
   Tables tab[HCJ_MAX_COMP];    // per scan component
-  const int32_t *quant;        // [HCJ_MAX_COMP][128]: per scan component, 64 plain entries (+ 64 in dp2a form)
+  int debug;                   // experiment switches
   uint32_t *wide_flags;        // bit (blk_base + blk): the block needs the 64-bit IDCT (see HCJ_IDCT_L1_LIMIT)
   uint64_t blk_base;           // index of the image's first block in the batch
 };
@@ -196,15 +236,11 @@ struct Symbol {
   int32_t value;   // extended magnitude (0 when size == 0)
 };
 
-HCJ_HD Symbol read_symbol(const BitReader &br, const Tables &t, bool isdc) {
+HCJ_HD Symbol read_symbol(const BitReader &br, const Local L, const Tables &t, bool isdc) {
   Symbol s;
   const uint32_t win = br.window();
-  const uint16_t *prim = isdc ? t.dc_primary : t.ac_primary;
-  uint32_t e = prim[win >> (32 - HCJ_LUT_BITS)];
-  if (e == 0u) {
-    const uint32_t mb = isdc ? t.dc_max_bits : t.ac_max_bits;
-    if (mb > HCJ_LUT_BITS) e = (isdc ? t.dc_full : t.ac_full)[win >> (32u - mb)];
-  }
+  const uint32_t e = lut_lookup(L.lut, isdc ? t.dc_off : t.ac_off, isdc ? t.dc_full : t.ac_full,
+                                isdc ? t.dc_max_bits : t.ac_max_bits, win);
   const uint32_t len = e >> 8, rs = e & 0xffu;
   s.e = e;
   s.size = isdc ? rs : rs & 15u;
@@ -215,17 +251,17 @@ HCJ_HD Symbol read_symbol(const BitReader &br, const Tables &t, bool isdc) {
   return s;
 }
 
-HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
+HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   uint32_t nstart = 0;
   int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
   BitReader br;
   br.init(sc.words, p, sc.total_bits);
-  uint32_t comp = sc.blk_comp[c];
+  uint32_t comp = L.blk_comp[c];
   Tables t = sc.tab[comp];
   while (br.pos < hi) {
     const bool isdc = z == 0u;
-    const Symbol s = read_symbol(br, t, isdc);
+    const Symbol s = read_symbol(br, L, t, isdc);
     if (s.e == 0u) {  // undefined code: resynchronise one bit later
       br.skip(1);
       continue;
@@ -243,7 +279,7 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
     if (z >= 64u) {
       z = 0;
       c = c + 1u == sc.bpm ? 0u : c + 1u;
-      comp = sc.blk_comp[c];
+      comp = L.blk_comp[c];
       t = sc.tab[comp];
     }
   }
@@ -259,17 +295,21 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
 // Final pass over one subsequence (or one restart interval) from its exact start state.  `blk` is the
 // index (within the image) of the block in progress (at the start of a block: the index of the previous
 // one), `pred` the DC predictors at the start state.  Stores coefficients (zig-zag, DC resolved) into the
-// zero-initialised `coefs`.  Decodes the symbols that start before `hi` and belong to blocks < `nblocks`;
+// `coefs`.  Decodes the symbols that start before `hi` and belong to blocks < `nblocks`;
 // with hi = 0xffffffff it runs until block nblocks - 1 is complete, reading zero bits past the end of
 // the data exactly as the model's reader does.
-HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
-                        int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, uint32_t *err_pos) {
+// Every block is cleared by the thread that begins it, just before the DC store, except block
+// `prezeroed_blk`: a block this thread begins but another thread finishes must have been cleared before
+// that other thread's pass starts (the speculative kernel does so in a separate step); pass -2 if none.
+HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
+                        int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, int64_t prezeroed_blk,
+                        uint32_t *err_pos) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   BitReader br;
   br.init(sc.words, p, end_bits);
-  uint32_t comp = sc.blk_comp[c];
+  uint32_t comp = L.blk_comp[c];
   Tables t = sc.tab[comp];
-  const int32_t *q = sc.quant + comp * 128;
+  const int32_t *q = L.quant + comp * 128;
   int32_t p0 = pred[0], p1 = pred[1], p2 = pred[2], p3 = pred[3];
   if (z != 0u && blk >= nblocks) return HCJ_DEV_OK;
   int16_t *out = coefs + blk * 64;
@@ -278,7 +318,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
   while (br.pos < hi) {
     const bool isdc = z == 0u;
     if (isdc && blk + 1 >= nblocks) break;  // every block is complete
-    const Symbol s = read_symbol(br, t, isdc);
+    const Symbol s = read_symbol(br, L, t, isdc);
     if (s.e == 0u) {
       err = isdc ? HCJ_DEV_NO_DC_CODE : HCJ_DEV_NO_AC_CODE;
       break;
@@ -304,9 +344,10 @@ HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
       }
       blk++;
       out += 64;
+      if (blk != prezeroed_blk) zero_block(out);
     }
     if (isdc || (s.size != 0u && !eob)) {
-      out[zi] = (int16_t)v;
+      if (!(sc.debug & 1)) out[zi] = (int16_t)v;
       share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)q[zi];
     }
     z = eob ? 64u : zi + 1u;
@@ -315,9 +356,9 @@ HCJ_HD int subseq_write(const ScanCtx &sc, uint32_t p, uint32_t cz, uint32_t hi,
       share = 0;
       z = 0;
       c = c + 1u == sc.bpm ? 0u : c + 1u;
-      comp = sc.blk_comp[c];
+      comp = L.blk_comp[c];
       t = sc.tab[comp];
-      q = sc.quant + comp * 128;
+      q = L.quant + comp * 128;
     }
   }
   if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);

@@ -291,17 +291,33 @@ int build_lut(const hcj_dht &t, HuffLut *lut) {
     for (int64_t i = first; i < first + count; i++) lut->full[i] = (uint16_t)((c.length << 8) | c.data);
   }
   // Primary table over the next HCJ_LUT_BITS bits: an entry is resolved here when every full-table
-  // slot under the prefix agrees on a code no longer than the prefix.
-  lut->primary.assign(HCJ_LUT_SIZE, 0);
+  // slot under the prefix agrees on a code no longer than the prefix.  Other prefixes get one of the
+  // HCJ_LUT_NSUB sub-tables (a verbatim slice of the full table); if those run out the entry stays 0
+  // and the kernels consult the full table in global memory.
+  lut->primary.assign(HCJ_LUT_ENTRIES, 0);
+  int nsub = 0;
   for (int p = 0; p < HCJ_LUT_SIZE; p++) {
     if (max_bits <= HCJ_LUT_BITS) {
       lut->primary[p] = lut->full[p >> (HCJ_LUT_BITS - max_bits)];
     } else {
       int sh = max_bits - HCJ_LUT_BITS;
-      uint16_t e = lut->full[(size_t)p << sh];
-      bool same = (e != 0) && ((e >> 8) <= HCJ_LUT_BITS);
-      for (size_t i = 1; same && i < ((size_t)1 << sh); i++) same = lut->full[((size_t)p << sh) + i] == e;
-      lut->primary[p] = same ? e : 0;
+      size_t n = (size_t)1 << sh, base = (size_t)p << sh;
+      uint16_t e = lut->full[base];
+      bool same = ((e >> 8) <= HCJ_LUT_BITS);
+      bool any = e != 0;
+      for (size_t i = 1; i < n; i++) {
+        same = same && lut->full[base + i] == e;
+        any = any || lut->full[base + i] != 0;
+      }
+      if (same) {
+        lut->primary[p] = e;  // includes "all None" (0): the full-table lookup then finds None as well
+      } else if (any && nsub < HCJ_LUT_NSUB && sh <= HCJ_LUT_SUB_BITS) {
+        for (size_t i = 0; i < n; i++) lut->primary[HCJ_LUT_SIZE + nsub * HCJ_LUT_SUB_SIZE + i] = lut->full[base + i];
+        lut->primary[p] = (uint16_t)(0x8000 | nsub);
+        nsub++;
+      } else {
+        lut->primary[p] = 0;
+      }
     }
   }
   return HCJ_OK;

@@ -32,7 +32,7 @@ int plan_image(const hcj_header &h, unsigned flags, ImagePlan *plan);
 struct HuffLut {
   int max_bits = 0;
   std::vector<uint16_t> full;     // 2^max_bits entries: (length << 8) | data, 0 = None
-  std::vector<uint16_t> primary;  // HCJ_LUT_SIZE entries
+  std::vector<uint16_t> primary;  // HCJ_LUT_ENTRIES entries: primary table, then HCJ_LUT_NSUB sub-tables
 };
 int build_lut(const hcj_dht &t, HuffLut *lut);
 

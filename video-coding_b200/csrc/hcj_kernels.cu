@@ -159,7 +159,7 @@ void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
 // Huffman tables in shared memory, shared by K2 and K3.
 // ================================================================================================
 struct SmemTables {
-  uint16_t primary[HCJ_MAX_COMP * 2 * HCJ_LUT_SIZE];  // [pair][dc/ac][HCJ_LUT_SIZE]
+  uint16_t primary[HCJ_MAX_COMP * 2 * HCJ_LUT_ENTRIES];  // [pair][dc/ac][primary + sub-tables]
   uint32_t max_bits[HCJ_MAX_COMP * 2];
   const uint16_t *full[HCJ_MAX_COMP * 2];
   uint8_t comp_pair[HCJ_MAX_COMP];
@@ -169,7 +169,7 @@ struct SmemTables {
 
 __device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev &b, const HcjImageDesc &d) {
   const HcjTableSet &ts = b.table_sets[d.table_set];
-  const uint32_t n = ts.npairs * 2 * HCJ_LUT_SIZE;
+  const uint32_t n = ts.npairs * 2 * HCJ_LUT_ENTRIES;
   const uint4 *src = reinterpret_cast<const uint4 *>(b.lut_primary + ts.primary_off);
   uint4 *dst = reinterpret_cast<uint4 *>(st.primary);
   for (uint32_t i = threadIdx.x; i < n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -186,8 +186,8 @@ __device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev
 __device__ __forceinline__ Tables tables_of(const SmemTables &st, uint32_t comp) {
   uint32_t pr = st.comp_pair[comp];
   Tables t;
-  t.dc_primary = st.primary + (pr * 2 + 0) * HCJ_LUT_SIZE;
-  t.ac_primary = st.primary + (pr * 2 + 1) * HCJ_LUT_SIZE;
+  t.dc_off = (pr * 2 + 0) * HCJ_LUT_ENTRIES;
+  t.ac_off = (pr * 2 + 1) * HCJ_LUT_ENTRIES;
   t.dc_full = st.full[pr * 2 + 0];
   t.ac_full = st.full[pr * 2 + 1];
   t.dc_max_bits = st.max_bits[pr * 2 + 0];
@@ -201,9 +201,8 @@ __device__ __forceinline__ void fill_scan_ctx(ScanCtx &sc, const SmemTables &st,
     sc.words = reinterpret_cast<const uint32_t *>(b.entropy + d.ent_off);
     sc.total_bits = total_bits;
     sc.bpm = d.bpm;
-    sc.blk_comp = st.blk_comp;
-    sc.quant = st.quant;
     sc.wide_flags = b.wide_flags;
+    sc.debug = b.debug;
     sc.blk_base = d.coef_off;
   }
   if (threadIdx.x < (uint32_t)d.ncomp) sc.tab[threadIdx.x] = tables_of(st, threadIdx.x);
@@ -217,65 +216,160 @@ __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32
 // K2: one thread per restart interval.  Intervals are byte aligned and start with every DC predictor
 // at 0, so a thread owns its MCUs outright and writes resolved coefficients straight to HBM.
 // ================================================================================================
-constexpr int HR_THREADS = 256;
+constexpr int HR_THREADS = 512;
+constexpr int HR_STAGE_WORDS = 32 * 33;  // per warp: 32 lanes x (32 words + 1 pad)
 
+// The exact pass of one restart interval per lane (same symbol semantics as subseq_write), with the
+// coefficient block of every lane staged in shared memory and written out by the whole warp as one
+// 128-byte line when it completes: scattered 2-byte stores cost one L2 partial-sector transaction per
+// symbol and were the bottleneck of this kernel (profiles/r01_notes.md).
 __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
-  __shared__ SmemTables st;
-  __shared__ ScanCtx sc;
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
+
   const uint32_t img = b.list_restart[blockIdx.y];
   const HcjImageDesc &d = b.descs[img];
   const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
   if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
+  for (int j = lane; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
   load_tables(st, b, d);
   __syncthreads();
   fill_scan_ctx(sc, st, b, d, 0);
   __syncthreads();
   HcjImageState *state = b.states + img;
-  if (seg >= d.nseg_expected || state->status != 0) return;
+  const Local L{st.primary, st.quant, st.blk_comp};
+  const bool valid = seg < d.nseg_expected && state->status == 0;
 
   const uint32_t *segs = b.seg_offs + d.seg_off;
-  const uint32_t seg_begin = segs[seg], seg_end = segs[seg + 1];
+  const uint32_t seg_begin = valid ? segs[seg] : 0u, seg_end = valid ? segs[seg + 1] : 0u;
   const uint32_t seg_bits = (seg_end - seg_begin) * 8u;
   const uint32_t ri = d.ri ? d.ri : d.nmcu;
-  const uint32_t mcu0 = seg * ri, mcu1 = min(mcu0 + ri, d.nmcu);
+  const uint32_t mcu0 = min(seg * ri, d.nmcu), mcu1 = min(mcu0 + ri, d.nmcu);
   const uint32_t bpm = d.bpm;
   int16_t *coefs = b.coefs + d.coef_off * 64;
+  uint32_t *coefs32 = reinterpret_cast<uint32_t *>(coefs);
 
-  if (seg_bits > 16u) {
-    int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-    uint32_t err_pos = 0;
-    int err = subseq_write(sc, seg_begin * 8u, 0u, 0xffffffffu, seg_end * 8u, (int64_t)mcu0 * bpm - 1, pred,
-                           (int64_t)mcu1 * bpm, coefs, &err_pos);
-    if (err) raise_status(state, err, err_pos);
-    return;
-  }
-  // Degenerate interval: the model's `show` bound (bitstream_reader.ml:32) is in play.
-  BitReader br;
-  br.init(sc.words, seg_begin * 8u, seg_end * 8u);
-  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-  int64_t blk = (int64_t)mcu0 * bpm;
-  for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
-    for (uint32_t k = 0; k < bpm; k++, blk++) {
-      const uint32_t comp = st.blk_comp[k];
-      int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
-      int err = decode_block_exact(br, sc.tab[comp], seg_bits, pred, coefs + blk * 64);
-      flag_wide_block(sc, blk);
-      if (err) {
-        raise_status(state, err, br.pos);
-        return;
+  if (valid && seg_bits <= 16u) {
+    // Degenerate interval: the model's `show` bound (bitstream_reader.ml:32) is in play; decode it with
+    // the literal per-block routine and direct stores.
+    BitReader br;
+    br.init(sc.words, seg_begin * 8u, seg_end * 8u);
+    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    int64_t blk = (int64_t)mcu0 * bpm;
+    for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
+      for (uint32_t k = 0; k < bpm; k++, blk++) {
+        const uint32_t comp = st.blk_comp[k];
+        int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
+        int err = decode_block_exact(br, L, sc.tab[comp], seg_bits, pred, coefs + blk * 64);
+        flag_wide_block(sc, blk);
+        if (err) {
+          raise_status(state, err, br.pos);
+          mcu = mcu1;
+          break;
+        }
+        if (comp == 0) p0 = pred;
+        else if (comp == 1) p1 = pred;
+        else if (comp == 2) p2 = pred;
+        else p3 = pred;
       }
-      if (comp == 0) p0 = pred;
-      else if (comp == 1) p1 = pred;
-      else if (comp == 2) p2 = pred;
-      else p3 = pred;
     }
   }
+
+  // ---- warp-synchronous symbol loop
+  bool active = valid && seg_bits > 16u && mcu1 > mcu0;
+  const int32_t nblocks_end = (int32_t)(mcu1 * bpm);
+  int32_t blk = (int32_t)(mcu0 * bpm) - 1;
+  uint32_t c = 0, z = 0, share = 0;
+  uint32_t comp = st.blk_comp[0];
+  Tables t = sc.tab[comp];
+  const int32_t *q = st.quant + comp * 128;
+  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  BitReader br;
+  br.init(sc.words, seg_begin * 8u, active ? seg_end * 8u : 0u);
+  int16_t *mine = reinterpret_cast<int16_t *>(stage + lane * 33);
+  int err = HCJ_DEV_OK;
+
+  while (__any_sync(0xffffffffu, active)) {
+    bool done_blk = false;
+    if (active) {
+      const bool isdc = z == 0u;
+      if (isdc && blk + 1 >= nblocks_end) {
+        active = false;
+      } else {
+        const Symbol s = read_symbol(br, L, t, isdc);
+        if (s.e == 0u) {
+          err = isdc ? HCJ_DEV_NO_DC_CODE : HCJ_DEV_NO_AC_CODE;
+          active = false;
+        } else {
+          br.skip(s.nbits);
+          const bool eob = !isdc && (s.e & 0xffu) == 0u;
+          const uint32_t zi = isdc ? 0u : z + s.run;
+          int32_t v = s.value;
+          if (zi >= 64u && !eob) {
+            err = HCJ_DEV_COEF_INDEX;
+            active = false;
+          } else {
+            if (isdc) {
+              const int32_t pv = (comp == 0u ? p0 : comp == 1u ? p1 : comp == 2u ? p2 : p3) + v;
+              p0 = comp == 0u ? pv : p0;
+              p1 = comp == 1u ? pv : p1;
+              p2 = comp == 2u ? pv : p2;
+              p3 = comp == 3u ? pv : p3;
+              v = pv;
+              blk++;
+              if (pv < -32768 || pv > 32767) {
+                err = HCJ_DEV_DC_RANGE;
+                active = false;
+              }
+            }
+            if (isdc || (s.size != 0u && !eob)) {
+              mine[zi] = (int16_t)v;
+              share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)q[zi];
+            }
+            z = eob ? 64u : zi + 1u;
+            if (z >= 64u && active) {
+              done_blk = true;
+              if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
+              share = 0;
+              z = 0;
+              c = c + 1u == bpm ? 0u : c + 1u;
+              comp = st.blk_comp[c];
+              t = sc.tab[comp];
+              q = st.quant + comp * 128;
+            }
+          }
+        }
+      }
+    }
+    // write out the blocks completed in this step: one 128-byte line per block, all lanes cooperating
+    uint32_t mask = __ballot_sync(0xffffffffu, done_blk);
+    while (mask) {
+      const int l = __ffs((int)mask) - 1;
+      mask &= mask - 1u;
+      const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
+      const uint32_t w = stage[l * 33 + lane];
+      stage[l * 33 + lane] = 0u;
+      coefs32[(size_t)bidx * 32 + lane] = w;
+    }
+  }
+  if (err) raise_status(state, err, br.pos);
 }
 
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.n_restart == 0) return;
+  const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
+                      (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
   dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.n_restart);
-  k_huff_restart<<<grid, HR_THREADS, 0, s>>>(b);
+  k_huff_restart<<<grid, HR_THREADS, smem, s>>>(b);
 }
 
 // ================================================================================================
@@ -342,6 +436,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   }
   __syncthreads();
   if (state->status != 0) return;
+  const Local LT{st.primary, st.quant, st.blk_comp};
 
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = d.nblocks;
@@ -355,7 +450,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
       for (int64_t blk = 0; blk < nblocks; blk++) {
         uint32_t comp = st.blk_comp[blk % d.bpm];
-        int err = decode_block_exact(br, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+        int err = decode_block_exact(br, LT, sc.tab[comp], L, pred[comp], coefs + blk * 64);
         flag_wide_block(sc, blk);
         if (err) {
           raise_status(state, err, br.pos);
@@ -381,7 +476,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
     r.cz = mystart.y;
     r.nstart = 0;
     r.dcsum[0] = r.dcsum[1] = r.dcsum[2] = r.dcsum[3] = 0;
-    if (active) subseq_sync(sc, mystart.x, mystart.y, hi, r);
+    if (active) subseq_sync(sc, LT, mystart.x, mystart.y, hi, r);
     s_end[t] = make_uint2(r.p, r.cz);
     __syncthreads();
 
@@ -392,7 +487,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       if (active && (ns.x != mystart.x || ns.y != mystart.y)) {
         mystart = ns;
         uint2 old = make_uint2(r.p, r.cz);
-        subseq_sync(sc, ns.x, ns.y, hi, r);
+        subseq_sync(sc, LT, ns.x, ns.y, hi, r);
         changed = (r.p != old.x) | (r.cz != old.y);
       }
       __syncthreads();  // every s_end[t - 1] has been read
@@ -407,11 +502,17 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
     int32_t ex1 = block_excl_scan(active ? r.dcsum[1] : 0, s_scan, tot1);
     int32_t ex2 = block_excl_scan(active ? r.dcsum[2] : 0, s_scan, tot2);
     int32_t ex3 = block_excl_scan(active ? r.dcsum[3] : 0, s_scan, tot3);
+    // The last block a thread begins is finished by its right neighbour, whose pass may reach it first:
+    // clear it now, before anybody stores into it.
+    const int64_t blk0 = carry.nstart + ex_n - 1;
+    const int64_t trailing = active && r.nstart > 0 ? blk0 + (int64_t)r.nstart : -2;
+    if (trailing >= 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
+    __syncthreads();
     if (active) {
       int32_t pred[HCJ_MAX_COMP] = {carry.dc[0] + ex0, carry.dc[1] + ex1, carry.dc[2] + ex2, carry.dc[3] + ex3};
-      int64_t blk = carry.nstart + ex_n - 1;
+      int64_t blk = blk0;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, mystart.x, mystart.y, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, &err_pos);
+      int err = subseq_write(sc, LT, mystart.x, mystart.y, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, trailing, &err_pos);
       if (err) raise_status(state, err, err_pos);
     }
     __syncthreads();  // all reads of carry done

@@ -34,6 +34,7 @@ struct DecodeBatchDev {
   uint32_t max_rgb_rows;          // max image height (RGB mode)
   uint32_t max_width;
   uint64_t total_blocks;
+  int debug;                      // experiment switches (HCJ_DEBUG env var); 0 in production
 };
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
