@@ -369,7 +369,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
   b->coef_bytes = (size_t)total_blocks * 128;
   BALLOC(coefs, int16_t *, b->coef_bytes + 16);
-  BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4);
+  BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4 + 64);  // + slack: k_idct stages 48 bytes per tile
   BALLOC(out, uint8_t *, out_total + 16);
   if (mode == HCJ_OUT_RGB24) BALLOC(planes, uint8_t *, plane_total + 16);
 #undef BALLOC

@@ -607,90 +607,123 @@ __device__ __forceinline__ IdctTile idct_tile(const DecodeBatchDev &b, uint32_t 
   return t;
 }
 
-// Persistent CTAs (2 per SM) walk the batch's tiles with a stride of gridDim.x; the coefficient tile and
-// the quant tables of tile i+1 are in flight (cp.async) while tile i is being transformed.
+// Persistent CTAs (2 per SM): each owns a contiguous range of the batch's tiles and keeps the coefficient
+// tile, the quant tables and the wide-block flags of tile i+1 in flight (cp.async) while tile i is being
+// transformed.  The thread -> block mapping depends only on (image geometry, tile width): it is computed
+// when either changes and kept in registers, so the per-tile overhead is a handful of instructions.
 // mode: 0 = HCJ_OUT_YUV (cropped planes, packed), 1 = padded planes into b.out, 2 = padded planes into b.planes
+constexpr int IDCT_TILE_U4 = IDCT_MAX_THREADS * IDCT_ROW_U4;
+constexpr int IDCT_Q_I32 = HCJ_MAX_COMP * 128;
+constexpr int IDCT_FLAG_U4 = 3;  // 256 blocks = 8 flag words, at any alignment inside 3 x 16 bytes
+
+struct IdctStage {  // one pipeline stage in shared memory
+  uint4 tile[IDCT_TILE_U4];
+  int32_t q[IDCT_Q_I32];
+  uint4 flags[IDCT_FLAG_U4 + 1];
+};
+
+__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, uint32_t tile_id, IdctStage &st, int tid) {
+  const IdctTile t = idct_tile(b, tile_id);
+  if (t.d) {
+    const HcjImageDesc &d = *t.d;
+    const uint64_t blk0 = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm;
+    const int16_t *src = b.coefs + blk0 * 64;
+    for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&st.tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+    if (tid < d.ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
+    if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (blk0 >> 7) + tid);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
 __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeBatchDev b, int mode) {
   extern __shared__ uint4 s_dyn[];
-  uint4 *s_tile[2] = {s_dyn, s_dyn + IDCT_MAX_THREADS * IDCT_ROW_U4};
-  int32_t *s_qbase = reinterpret_cast<int32_t *>(s_dyn + 2 * IDCT_MAX_THREADS * IDCT_ROW_U4);
-  int32_t *s_q[2] = {s_qbase, s_qbase + HCJ_MAX_COMP * 128};
+  IdctStage *stages = reinterpret_cast<IdctStage *>(s_dyn);
   const int tid = threadIdx.x;
   const uint32_t total = (uint32_t)b.n * b.max_idct_tiles;
+  const uint32_t chunk = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t begin = min(blockIdx.x * chunk, total), end = min(begin + chunk, total);
+  if (begin >= end) return;
 
-  auto issue = [&](uint32_t tile_id, int buf) {
-    const IdctTile t = idct_tile(b, tile_id);
-    if (t.d) {
-      const HcjImageDesc &d = *t.d;
-      const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm) * 64;
-      for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS)
-        cp_async16(&s_tile[buf][(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
-      if (tid < d.ncomp * 32) cp_async16(s_q[buf] + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
+  // per-thread mapping, valid for (map_img, map_tm)
+  const HcjImageDesc *map_img = nullptr;
+  int map_tm = -1;
+  bool mine = false;          // this thread has a block in the tile
+  int slot = 0, qoff = 0;     // staged block index, quant table offset
+  int xoff = 0, yoff = 0;     // sample offset of the block inside the tile's MCU row
+  int hs8 = 0, vs8 = 0;       // samples per MCU of this component
+  int stride = 0, w_limit = 0, h_limit = 0;
+  uint64_t plane_off = 0;     // component plane offset inside the image's output / plane buffer
 
-  uint32_t cur = blockIdx.x;
+  idct_issue(b, begin, stages[0], tid);
   int buf = 0;
-  if (cur < total) issue(cur, 0);
-  for (; cur < total; cur += gridDim.x, buf ^= 1) {
-    const uint32_t next = cur + gridDim.x;
-    if (next < total) {
-      issue(next, buf ^ 1);
+  for (uint32_t cur = begin; cur < end; cur++, buf ^= 1) {
+    IdctStage &st = stages[buf];
+    if (cur + 1 < end) {
+      idct_issue(b, cur + 1, stages[buf ^ 1], tid);
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
     const IdctTile t = idct_tile(b, cur);
-    if (t.d && tid < t.nblk) {
+    if (t.d) {
       const HcjImageDesc &d = *t.d;
-      // thread -> (component, block row, MCU, block column)
-      int rem = tid, c = 0;
-      for (; c < d.ncomp - 1; c++) {
-        int n = t.tm * d.comp[c].hs * d.comp[c].vs;
-        if (rem < n) break;
-        rem -= n;
+      if (t.d != map_img || t.tm != map_tm) {  // CTA-uniform: new image or a narrower last tile in the row
+        map_img = t.d;
+        map_tm = t.tm;
+        mine = tid < t.nblk;
+        int rem = tid, c = 0;
+        for (; c < d.ncomp - 1; c++) {
+          int n = t.tm * d.comp[c].hs * d.comp[c].vs;
+          if (rem < n) break;
+          rem -= n;
+        }
+        const HcjCompGeom &g = d.comp[c];
+        const int rowlen = t.tm * g.hs;
+        const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
+        const int r2 = rem - by * rowlen;
+        const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
+        const int bx = r2 - m * g.hs;
+        slot = m * d.bpm + g.first_blk + by * g.hs + bx;
+        qoff = c * 128;
+        hs8 = g.hs * 8;
+        vs8 = g.vs * 8;
+        xoff = m * hs8 + bx * 8;
+        yoff = by * 8;
+        if (mode == 0) {
+          plane_off = g.out_off;
+          stride = w_limit = g.actual_w;
+          h_limit = g.actual_h;
+        } else {
+          plane_off = g.plane_off;
+          stride = w_limit = g.decoded_w;
+          h_limit = g.decoded_h;
+        }
       }
-      const HcjCompGeom &g = d.comp[c];
-      const int rowlen = t.tm * g.hs;
-      const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
-      const int r2 = rem - by * rowlen;
-      const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
-      const int bx = r2 - m * g.hs;
-      const int slot = m * d.bpm + g.first_blk + by * g.hs + bx;
-
-      uint32_t cw[32];
+      if (mine) {
+        uint32_t cw[32];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        uint4 u = s_tile[buf][slot * IDCT_ROW_U4 + j];
-        cw[4 * j] = u.x;
-        cw[4 * j + 1] = u.y;
-        cw[4 * j + 2] = u.z;
-        cw[4 * j + 3] = u.w;
+        for (int j = 0; j < 8; j++) {
+          uint4 u = st.tile[slot * IDCT_ROW_U4 + j];
+          cw[4 * j] = u.x;
+          cw[4 * j + 1] = u.y;
+          cw[4 * j + 2] = u.z;
+          cw[4 * j + 3] = u.w;
+        }
+        const uint64_t blk0 = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm;
+        const uint32_t fbit = (uint32_t)(blk0 & 127u) + slot;  // bit index inside the staged flag chunks
+        const bool wide = d.wide_idct || ((reinterpret_cast<const uint32_t *>(st.flags)[fbit >> 5] >> (fbit & 31u)) & 1u);
+        uint8_t *base = (mode == 2 ? b.planes : b.out + d.out_off) + plane_off;
+        const int x = t.m0 * hs8 + xoff, y = t.my * vs8 + yoff;
+        const int32_t *q = st.q + qoff;
+        uint32_t pix[16];
+        if (wide || !reconstruct_fast<false>(cw, q + 64, pix))
+          wide_block_store(reinterpret_cast<const uint32_t *>(&st.tile[slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
+        else
+          store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
       }
-      uint32_t pix[16];
-      const int32_t *q = s_q[buf] + c * 128;
-      const int x = ((t.m0 + m) * g.hs + bx) * 8, y = (t.my * g.vs + by) * 8;
-      uint8_t *base;
-      int stride, w_limit, h_limit;
-      if (mode == 0) {
-        base = b.out + d.out_off + g.out_off;
-        stride = w_limit = g.actual_w;
-        h_limit = g.actual_h;
-      } else {
-        base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
-        stride = w_limit = g.decoded_w;
-        h_limit = g.decoded_h;
-      }
-      const uint64_t gblk = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm + slot;
-      const bool wide = d.wide_idct || ((__ldg(b.wide_flags + (gblk >> 5)) >> (gblk & 31u)) & 1u);
-      if (wide || !reconstruct_fast<false>(cw, q + 64, pix))
-        wide_block_store(reinterpret_cast<const uint32_t *>(&s_tile[buf][slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
-      else
-        store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
     }
-    __syncthreads();  // the buffer is refilled by the next iteration's prefetch
+    __syncthreads();  // this stage is refilled by the next iteration's prefetch
   }
 }
 
@@ -763,14 +796,14 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem1));
+    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(IdctStage)));
     grid = 2 * sms;
     const char *e = getenv("HCJ_IDCT_PERSISTENT");
-    persistent = e && e[0] == '1';
+    persistent = !(e && e[0] == '0');  // default; HCJ_IDCT_PERSISTENT=0 selects the one-tile-per-CTA kernel
   }
   if (persistent) {
     uint64_t total = (uint64_t)b.n * b.max_idct_tiles;
-    k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * smem1, s>>>(b, mode);
+    k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * sizeof(IdctStage), s>>>(b, mode);
   } else {
     k_idct<<<dim3(b.max_idct_tiles, b.n), IDCT_MAX_THREADS, smem1, s>>>(b, mode);
   }
