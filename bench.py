@@ -113,12 +113,16 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def mark(self):
+        """Samples before this point (input generation, warm-up of nvidia-smi itself) are ignored."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -131,6 +135,7 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self.rows = self.rows[self.first:]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -213,27 +218,27 @@ def main():
     import torch
 
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from hcjpeg import shard
+
+    dist_mod = dist if world > 1 else None
+
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        shard.barrier(dist_mod, torch.cuda.synchronize)
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, dist_mod, "cuda")
 
     ctx = hcjpeg.Context(local)
     mode = {"yuv": hcjpeg.OUT_YUV, "rgb": hcjpeg.OUT_RGB24, "jpeg": None}[out_name]
     mp_per_step = batch_n * w * h / 1e6
     sampler = ClockSampler(local)
+    sampler.start()
     result = {}
 
     if args.workload != "encode":
@@ -250,7 +255,7 @@ def main():
         # ---- value: resident inputs, kernels only
         b = ctx.batch(batch_jpgs, mode)
         assert all(s == 0 for s in b.host_status)
-        sampler.start()
+        sampler.mark()
         for _ in range(max(args.warmup, 3)):
             b.decode()
         ctx.synchronize()
@@ -339,7 +344,7 @@ def main():
         for _ in range(max(args.warmup, 3)):
             ctx.encode_batch(batch_frames[:64], w, h, chroma, quality, ri)
         barrier()
-        sampler.start()
+        sampler.mark()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             outs, st = ctx.encode_batch(batch_frames, w, h, chroma, quality, ri, capacity=1 << 20)

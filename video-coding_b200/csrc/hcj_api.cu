@@ -31,6 +31,7 @@ struct hcj_batch {
   hcjk::DecodeBatchDev dev;
   size_t coef_bytes = 0;
   int kernels = 0;
+  std::vector<uint32_t> list_restart, list_spec;  // host copies (sorted by image index) for chunked launches
 };
 
 extern "C" {
@@ -104,6 +105,7 @@ int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out) {
   }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   *out = c;
   return HCJ_OK;
 }
@@ -115,6 +117,8 @@ void hcj_ctx_destroy(hcj_ctx *c) {
   for (auto &f : c->pool) cudaFree(f.p);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -394,6 +398,14 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   dv.max_rgb_rows = max_rows;
   dv.max_width = max_width;
   dv.total_blocks = total_blocks;
+  dv.img_lo = 0;
+  dv.img_hi = (uint32_t)n;
+  dv.lr_lo = 0;
+  dv.lr_hi = (uint32_t)list_restart.size();
+  dv.ls_lo = 0;
+  dv.ls_hi = (uint32_t)list_spec.size();
+  b->list_restart = list_restart;
+  b->list_spec = list_spec;
   {
     const char *e = getenv("HCJ_DEBUG");
     dv.debug = e ? atoi(e) : 0;
@@ -532,15 +544,78 @@ int hcj_batch_device_output(hcj_batch *b, int i, void **dptr, size_t *bytes) {
   return HCJ_OK;
 }
 
+// One-call form.  The batch is decoded in chunks of images: while the kernels of chunk k+1 run on the
+// context's stream, the frames of chunk k travel to the host on a second stream (D2H dominates the
+// end-to-end time: 3 MB out per 0.4 MB in for 1080p 4:2:0).
 int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      uint8_t *const *out, const size_t *out_capacity, int *status) {
   hcj_batch *b = nullptr;
   int st = hcj_batch_create(c, jpeg, len, n, mode, flags, status, &b);
   if (st != HCJ_OK) return st;
-  st = hcj_batch_decode(c, b);
-  if (st == HCJ_OK) st = hcj_batch_fetch(c, b, out, out_capacity, status);
+  if (n > 0 && (!out || !out_capacity)) {
+    hcj_batch_destroy(c, b);
+    return HCJ_ERR_INVALID_ARG;
+  }
+  cudaStream_t s = c->stream, cs = c->copy_stream;
+  cudaError_t e = cudaSuccess;
+  const int chunk = std::max(16, std::min(128, (n + 7) / 8));
+  const int nchunks = n ? (n + chunk - 1) / chunk : 0;
+  while ((int)c->chunk_events.size() < nchunks + 1) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
+    c->chunk_events.push_back(ev);
+  }
+  std::vector<int> host_st(b->host_status);
+  if (n > 0 && (int)c->chunk_events.size() >= nchunks + 1) {
+    e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * n, s);
+    const int kmode = mode == HCJ_OUT_YUV ? 0 : mode == HCJ_OUT_PLANES ? 1 : 2;
+    size_t lr = 0, ls = 0;
+    for (int k = 0; k < nchunks && e == cudaSuccess; k++) {
+      hcjk::DecodeBatchDev dv = b->dev;
+      dv.img_lo = (uint32_t)(k * chunk);
+      dv.img_hi = (uint32_t)std::min(n, (k + 1) * chunk);
+      dv.lr_lo = (uint32_t)lr;
+      while (lr < b->list_restart.size() && b->list_restart[lr] < dv.img_hi) lr++;
+      dv.lr_hi = (uint32_t)lr;
+      dv.ls_lo = (uint32_t)ls;
+      while (ls < b->list_spec.size() && b->list_spec[ls] < dv.img_hi) ls++;
+      dv.ls_hi = (uint32_t)ls;
+      hcjk::launch_destuff(dv, s);
+      hcjk::launch_huff_restart(dv, s);
+      hcjk::launch_huff_spec(dv, s);
+      hcjk::launch_idct(dv, kmode, s);
+      if (mode == HCJ_OUT_RGB24) hcjk::launch_rgb(dv, s);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaEventRecord(c->chunk_events[k], s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, c->chunk_events[k], 0);
+      for (uint32_t i = dv.img_lo; i < dv.img_hi && e == cudaSuccess; i++) {
+        if (host_st[i] != HCJ_OK) continue;
+        if (!out[i] || out_capacity[i] < b->out_bytes[i]) {
+          host_st[i] = HCJ_ERR_BUFFER_TOO_SMALL;
+          continue;
+        }
+        e = cudaMemcpyAsync(out[i], b->dev.out + b->descs[i].out_off, b->out_bytes[i], cudaMemcpyDeviceToHost, cs);
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    std::vector<HcjImageState> states;
+    if (e == cudaSuccess) {
+      int r = fetch_states(c, b, &states);
+      if (r != HCJ_OK) {
+        hcj_batch_destroy(c, b);
+        return r;
+      }
+      for (int i = 0; i < n; i++)
+        if (host_st[i] == HCJ_OK && states[i].status != 0) host_st[i] = states[i].status;
+    }
+  } else if (n > 0) {
+    e = cudaErrorMemoryAllocation;
+  }
+  if (status)
+    for (int i = 0; i < n; i++) status[i] = host_st[i];
   hcj_batch_destroy(c, b);
-  return st;
+  return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
 }
 
 int hcj_batch_fetch_coefficients(hcj_ctx *c, hcj_batch *b, int i, int16_t *coefs, size_t capacity_blocks) {

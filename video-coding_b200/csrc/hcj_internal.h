@@ -27,6 +27,8 @@ struct hcj_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the kernels of the next chunk
+  std::vector<cudaEvent_t> chunk_events;
   std::vector<hcj::FreeBlock> pool;  // device memory recycled between batches (grow-only)
 
   int alloc(void **p, size_t bytes) {

@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
-  const int img = blockIdx.x;
+  const int img = blockIdx.x + b.img_lo;
   const HcjImageDesc &d = b.descs[img];
   if (!d.valid) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
 }
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.n > 0) k_destuff<<<b.n, DS_THREADS, 0, s>>>(b);
+  if (b.img_hi > b.img_lo) k_destuff<<<b.img_hi - b.img_lo, DS_THREADS, 0, s>>>(b);
 }
 
 // ================================================================================================
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
   uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
 
-  const uint32_t img = b.list_restart[blockIdx.y];
+  const uint32_t img = b.list_restart[blockIdx.y + b.lr_lo];
   const HcjImageDesc &d = b.descs[img];
   const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
   if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
 }
 
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.n_restart == 0) return;
+  if (b.lr_hi <= b.lr_lo) return;
   const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
                       (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
   static bool configured = false;
@@ -368,7 +368,7 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
     cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.n_restart);
+  dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.lr_hi - b.lr_lo);
   k_huff_restart<<<grid, HR_THREADS, smem, s>>>(b);
 }
 
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   __shared__ int32_t s_scan[SPEC_THREADS / 32];
   __shared__ SpecCarry carry;
 
-  const uint32_t img = b.list_spec[blockIdx.x];
+  const uint32_t img = b.list_spec[blockIdx.x + b.ls_lo];
   const HcjImageDesc &d = b.descs[img];
   HcjImageState *state = b.states + img;
   const int t = threadIdx.x;
@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
 }
 
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.n_spec == 0) return;
-  k_huff_spec<<<b.n_spec, SPEC_THREADS, 0, s>>>(b);
+  if (b.ls_hi <= b.ls_lo) return;
+  k_huff_spec<<<b.ls_hi - b.ls_lo, SPEC_THREADS, 0, s>>>(b);
 }
 
 // ================================================================================================
@@ -591,8 +591,8 @@ __device__ __forceinline__ IdctTile idct_tile(const DecodeBatchDev &b, uint32_t 
   IdctTile t;
   t.d = nullptr;
   t.my = t.m0 = t.tm = t.nblk = 0;
-  const uint32_t img = tile_id / b.max_idct_tiles, tile = tile_id - img * b.max_idct_tiles;
-  const HcjImageDesc &d = b.descs[img];
+  const uint32_t rel = tile_id / b.max_idct_tiles, tile = tile_id - rel * b.max_idct_tiles;
+  const HcjImageDesc &d = b.descs[rel + b.img_lo];
   if (!d.valid) return t;
   const int bpm = d.bpm;
   const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / bpm);
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeB
   extern __shared__ uint4 s_dyn[];
   IdctStage *stages = reinterpret_cast<IdctStage *>(s_dyn);
   const int tid = threadIdx.x;
-  const uint32_t total = (uint32_t)b.n * b.max_idct_tiles;
+  const uint32_t total = (b.img_hi - b.img_lo) * b.max_idct_tiles;
   const uint32_t chunk = (total + gridDim.x - 1) / gridDim.x;
   const uint32_t begin = min(blockIdx.x * chunk, total), end = min(begin + chunk, total);
   if (begin >= end) return;
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct(DecodeBatchDev b, 
 }
 
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
-  if (b.n == 0 || b.max_idct_tiles == 0) return;
+  if (b.img_hi <= b.img_lo || b.max_idct_tiles == 0) return;
   static int grid = 0, persistent = 0;
   const size_t smem1 = (size_t)IDCT_MAX_THREADS * IDCT_ROW_U4 * sizeof(uint4) + HCJ_MAX_COMP * 128 * sizeof(int32_t);
   if (!grid) {
@@ -802,10 +802,10 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
     persistent = !(e && e[0] == '0');  // default; HCJ_IDCT_PERSISTENT=0 selects the one-tile-per-CTA kernel
   }
   if (persistent) {
-    uint64_t total = (uint64_t)b.n * b.max_idct_tiles;
+    uint64_t total = (uint64_t)(b.img_hi - b.img_lo) * b.max_idct_tiles;
     k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * sizeof(IdctStage), s>>>(b, mode);
   } else {
-    k_idct<<<dim3(b.max_idct_tiles, b.n), IDCT_MAX_THREADS, smem1, s>>>(b, mode);
+    k_idct<<<dim3(b.max_idct_tiles, b.img_hi - b.img_lo), IDCT_MAX_THREADS, smem1, s>>>(b, mode);
   }
 }
 
@@ -868,7 +868,7 @@ __device__ __forceinline__ int up_sample(const uint8_t *p, int stride, int w, in
 }
 
 __global__ void k_rgb(DecodeBatchDev b) {
-  const HcjImageDesc &d = b.descs[blockIdx.z];
+  const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
   if (!d.valid || d.chroma == 0) return;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
   if (y >= d.height || x0 >= d.width) return;
@@ -902,9 +902,9 @@ __global__ void k_rgb(DecodeBatchDev b) {
 }
 
 void launch_rgb(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.n == 0 || b.max_rgb_rows == 0) return;
+  if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
   dim3 block(128);
-  dim3 grid((b.max_width / 4 + 127 + 1) / 128, b.max_rgb_rows, b.n);
+  dim3 grid((b.max_width / 4 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
   k_rgb<<<grid, block, 0, s>>>(b);
 }
 
