@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
   __shared__ uint8_t s_last[DS_THREADS];
   __shared__ uint32_t s_warp[DS_THREADS / 32];
   __shared__ uint32_t s_min[DS_THREADS / 32];
+  // Compacted bytes of the tile, placed at the same 16-byte phase as their destination so that they
+  // leave as aligned 16-byte words; [0, phase) holds the not yet written tail of the previous tile.
+  __shared__ __align__(16) uint8_t s_out[DS_THREADS * 16 + 32];
 
   uint32_t carry_out = 0, carry_mark = 0;
   uint32_t prev_tile_last = 0;
@@ -119,23 +122,37 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
       total += t;
     }
     uint32_t excl = wbase + incl - cnt;
+    const uint32_t phase = carry_out & 15u;
     uint32_t opos = carry_out + (excl & 0xffffu);
+    uint32_t so = phase + (excl & 0xffffu);
     uint32_t mk = carry_mark + (excl >> 16);
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       if (emit & (1u << i)) {
         uint32_t c = (ffmask & (1u << i)) ? 0xffu : (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-        ent[opos++] = (uint8_t)c;
+        s_out[so++] = (uint8_t)c;
+        opos++;
       } else if (mark & (1u << i)) {
         mk++;
         if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
       }
     }
+    __syncthreads();
+    const uint32_t avail = phase + (total & 0xffffu);  // bytes staged, including the carried tail
+    const uint32_t nfull = avail >> 4;
+    uint4 *dst = reinterpret_cast<uint4 *>(ent + (carry_out - phase));
+    for (uint32_t k = tid; k < nfull; k += DS_THREADS) dst[k] = reinterpret_cast<const uint4 *>(s_out)[k];
+    uint8_t tail = 0;
+    const uint32_t ntail = avail & 15u;
+    if ((uint32_t)tid < ntail) tail = s_out[nfull * 16 + tid];
+    __syncthreads();
+    if ((uint32_t)tid < ntail) s_out[tid] = tail;
     carry_out += total & 0xffffu;
     carry_mark += total >> 16;
     prev_tile_last = s_last[DS_THREADS - 1];
     __syncthreads();  // s_last / s_warp / s_min are rewritten by the next tile
   }
+  if ((uint32_t)tid < (carry_out & 15u)) ent[(carry_out & ~15u) + tid] = s_out[tid];  // last partial word
   if (tid == 0) {
     HcjImageState st;
     st.ent_len = carry_out;
