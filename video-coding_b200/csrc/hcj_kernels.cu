@@ -240,7 +240,7 @@ constexpr int HR_STAGE_WORDS = 32 * 33;  // per warp: 32 lanes x (32 words + 1 p
 // coefficient block of every lane staged in shared memory and written out by the whole warp as one
 // 128-byte line when it completes: scattered 2-byte stores cost one L2 partial-sector transaction per
 // symbol and were the bottleneck of this kernel (profiles/r01_notes.md).
-__global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
+__global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b) {
   extern __shared__ uint4 s_dyn4[];
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
@@ -303,11 +303,15 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
   uint32_t c = 0, z = 0, share = 0;
   uint32_t comp = st.blk_comp[0];
   Tables t = sc.tab[comp];
-  const int32_t *q = st.quant + comp * 128;
-  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  // shared-memory byte addresses, computed once (the compiler otherwise re-derives them from %tid in the loop)
+  const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t mine_sa = stage_sa + (uint32_t)lane * 33u * 4u;
+  const uint32_t quant_sa = (uint32_t)__cvta_generic_to_shared(st.quant);
+  uint32_t q_sa = quant_sa + comp * 512u;
+  int32_t pcur = 0;                        // DC predictor of the current block's component
+  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // predictors of the scan components (written back at block ends)
   BitReader br;
   br.init(sc.words, seg_begin * 8u, active ? seg_end * 8u : 0u);
-  int16_t *mine = reinterpret_cast<int16_t *>(stage + lane * 33);
   int err = HCJ_DEV_OK;
 
   while (__any_sync(0xffffffffu, active)) {
@@ -325,27 +329,22 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
           br.skip(s.nbits);
           const bool eob = !isdc && (s.e & 0xffu) == 0u;
           const uint32_t zi = isdc ? 0u : z + s.run;
-          int32_t v = s.value;
           if (zi >= 64u && !eob) {
             err = HCJ_DEV_COEF_INDEX;
             active = false;
           } else {
-            if (isdc) {
-              const int32_t pv = (comp == 0u ? p0 : comp == 1u ? p1 : comp == 2u ? p2 : p3) + v;
-              p0 = comp == 0u ? pv : p0;
-              p1 = comp == 1u ? pv : p1;
-              p2 = comp == 2u ? pv : p2;
-              p3 = comp == 3u ? pv : p3;
-              v = pv;
-              blk++;
-              if (pv < -32768 || pv > 32767) {
-                err = HCJ_DEV_DC_RANGE;
-                active = false;
-              }
+            pcur += isdc ? s.value : 0;
+            const int32_t v = isdc ? pcur : s.value;
+            blk += isdc ? 1 : 0;
+            if (isdc && (pcur < -32768 || pcur > 32767)) {
+              err = HCJ_DEV_DC_RANGE;
+              active = false;
             }
             if (isdc || (s.size != 0u && !eob)) {
-              mine[zi] = (int16_t)v;
-              share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)q[zi];
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(mine_sa + zi * 2u), "h"((short)v) : "memory");
+              int32_t qv;
+              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qv) : "r"(q_sa + zi * 4u));
+              share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)qv;
             }
             z = eob ? 64u : zi + 1u;
             if (z >= 64u && active) {
@@ -353,10 +352,15 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
               if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
               share = 0;
               z = 0;
+              p0 = comp == 0u ? pcur : p0;
+              p1 = comp == 1u ? pcur : p1;
+              p2 = comp == 2u ? pcur : p2;
+              p3 = comp == 3u ? pcur : p3;
               c = c + 1u == bpm ? 0u : c + 1u;
               comp = st.blk_comp[c];
+              pcur = comp == 0u ? p0 : comp == 1u ? p1 : comp == 2u ? p2 : p3;
               t = sc.tab[comp];
-              q = st.quant + comp * 128;
+              q_sa = quant_sa + comp * 512u;
             }
           }
         }
@@ -368,8 +372,10 @@ __global__ void __launch_bounds__(HR_THREADS) k_huff_restart(DecodeBatchDev b) {
       const int l = __ffs((int)mask) - 1;
       mask &= mask - 1u;
       const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
-      const uint32_t w = stage[l * 33 + lane];
-      stage[l * 33 + lane] = 0u;
+      const uint32_t sa = stage_sa + ((uint32_t)l * 33u + (uint32_t)lane) * 4u;
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sa) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(0u) : "memory");
       coefs32[(size_t)bidx * 32 + lane] = w;
     }
   }
@@ -390,24 +396,49 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 }
 
 // ================================================================================================
-// K3: scans without restart markers.  One CTA per image; subsequences of SPEC_BITS bits, one per
-// thread, processed in chunks of SPEC_THREADS.  Per chunk:
-//   A  every thread decodes its subsequence from a guessed state (block 0 of an MCU, DC next),
-//      thread 0 from the exact state carried over from the previous chunk;
-//   B  fix-point: re-decode from the end state of the left neighbour until no end state changes
-//      (after k rounds the first k+1 subsequences are exact, so this terminates; JPEG streams
-//      self-synchronise within a few hundred bits, so it takes 2-4 rounds in practice);
-//   C  block-wide exclusive scans of (blocks begun, DC sums) give every thread its block index and
-//      DC predictors; a final exact pass stores the coefficients.
+// K3: scans without restart markers.  One CTA per image; subsequences of SPEC_BITS bits; windows of up to
+// SPEC_WINDOW subsequences whose decoder states live in shared memory (16 bits each: position relative to
+// the subsequence boundary, block-in-MCU, zig-zag index).  Per window:
+//   A  every subsequence is decoded from a guessed state (block 0 of an MCU, DC next), the first one
+//      from the exact state carried over from the previous window;
+//   B  fix-point over the whole window: a subsequence whose left neighbour's end state differs from the
+//      start state it last used is decoded again; rounds repeat until nothing changes.  Reads of the
+//      neighbour's state are unsynchronised within a round (chaotic relaxation): the fix-point is unique
+//      because subsequence 0 is exact, so the order of updates does not matter, and after k rounds the
+//      first k+1 subsequences are exact, so it terminates.  JPEG streams self-synchronise within a few
+//      hundred bits, but the block-in-MCU phase can take several subsequences to lock: doing the rounds
+//      over the whole window (not per 512-thread chunk) keeps their number at the length of the
+//      longest unsynchronised run instead of the sum over chunks;
+//   C  exclusive scans over the window of (blocks begun, DC sums per component) give every subsequence
+//      its first block index and DC predictors; the exact pass stores the coefficients.
+// Undefined codes / overlong runs met while speculating are skipped deterministically; only the exact
+// pass reports them.
 // ================================================================================================
 constexpr int SPEC_THREADS = 512;
 constexpr uint32_t SPEC_BITS = 1024;
+constexpr int SPEC_PER_THREAD = 4;
+constexpr int SPEC_WINDOW = SPEC_THREADS * SPEC_PER_THREAD;
 
 struct SpecCarry {
   uint32_t p, cz;
   int64_t nstart;
   int32_t dc[HCJ_MAX_COMP];
 };
+
+struct SpecWindow {
+  uint16_t start[SPEC_WINDOW];       // packed state the subsequence was last decoded from
+  uint16_t end[SPEC_WINDOW];         // packed state at its end (relative to the next boundary)
+  int32_t nstart[SPEC_WINDOW + 1];   // blocks begun; after the scan: exclusive prefix (entry n = total)
+  int32_t dc[HCJ_MAX_COMP][SPEC_WINDOW + 1];
+};
+
+__device__ __forceinline__ uint32_t spec_pack(uint32_t p, uint32_t base, uint32_t cz) {
+  return ((p - base) << 10) | ((cz >> 8) << 6) | (cz & 63u);
+}
+__device__ __forceinline__ void spec_unpack(uint32_t s, uint32_t base, uint32_t &p, uint32_t &cz) {
+  p = base + (s >> 10);
+  cz = (((s >> 6) & 15u) << 8) | (s & 63u);
+}
 
 __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t *s_warp, int32_t &total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -431,10 +462,30 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t *s_warp, i
   return base + incl - v;
 }
 
+// In-place exclusive scan of a[0..n) (n <= SPEC_WINDOW), a[n] = total; every thread owns 4 consecutive entries.
+__device__ __forceinline__ void window_scan(int32_t *a, int n, int32_t *s_warp) {
+  const int i0 = threadIdx.x * SPEC_PER_THREAD;
+  int32_t v[SPEC_PER_THREAD], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SPEC_PER_THREAD; k++) {
+    v[k] = i0 + k < n ? a[i0 + k] : 0;
+    sum += v[k];
+  }
+  int32_t total;
+  int32_t run = block_excl_scan(sum, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < SPEC_PER_THREAD; k++) {
+    if (i0 + k < n) a[i0 + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 0) a[n] = total;
+}
+
 __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
-  __shared__ SmemTables st;
-  __shared__ ScanCtx sc;
-  __shared__ uint2 s_end[SPEC_THREADS];
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  SpecWindow &win = *reinterpret_cast<SpecWindow *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
   __shared__ int32_t s_scan[SPEC_THREADS / 32];
   __shared__ SpecCarry carry;
 
@@ -479,69 +530,85 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   }
 
   const uint32_t nsub = (L + SPEC_BITS - 1) / SPEC_BITS;
-  for (uint32_t base = 0; base < nsub; base += SPEC_THREADS) {
-    const uint32_t i = base + t;
-    const bool active = i < nsub;
-    const bool last = i == nsub - 1;
-    const uint32_t lo = i * SPEC_BITS;
-    const uint32_t hi = active ? min(lo + SPEC_BITS, L) : 0u;
+  for (uint32_t wbase = 0; wbase < nsub; wbase += SPEC_WINDOW) {
+    const int n = (int)min(nsub - wbase, (uint32_t)SPEC_WINDOW);
 
     // ---- A: speculative first pass
-    uint2 mystart = t == 0 ? make_uint2(carry.p, carry.cz) : make_uint2(lo, 0u);
-    SubResult r;
-    r.p = mystart.x;
-    r.cz = mystart.y;
-    r.nstart = 0;
-    r.dcsum[0] = r.dcsum[1] = r.dcsum[2] = r.dcsum[3] = 0;
-    if (active) subseq_sync(sc, LT, mystart.x, mystart.y, hi, r);
-    s_end[t] = make_uint2(r.p, r.cz);
+    for (int j = t; j < n; j += SPEC_THREADS) {
+      const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+      uint32_t p = lo, cz = 0;
+      if (j == 0) {
+        p = carry.p;
+        cz = carry.cz;
+      }
+      SubResult r;
+      subseq_sync(sc, LT, p, cz, hi, r);
+      win.start[j] = (uint16_t)spec_pack(p, lo, cz);
+      win.end[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
+      win.nstart[j] = (int32_t)r.nstart;
+#pragma unroll
+      for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+    }
     __syncthreads();
 
-    // ---- B: fix-point over the chunk
+    // ---- B: fix-point over the window
     for (;;) {
-      uint2 ns = t == 0 ? make_uint2(carry.p, carry.cz) : s_end[t - 1];
       int changed = 0;
-      if (active && (ns.x != mystart.x || ns.y != mystart.y)) {
-        mystart = ns;
-        uint2 old = make_uint2(r.p, r.cz);
-        subseq_sync(sc, LT, ns.x, ns.y, hi, r);
-        changed = (r.p != old.x) | (r.cz != old.y);
+      for (int j = t; j < n; j += SPEC_THREADS) {
+        if (j == 0) continue;  // exact by construction
+        const uint32_t ns = win.end[j - 1];
+        if (ns == win.start[j]) continue;
+        const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+        uint32_t p, cz;
+        spec_unpack(ns, lo, p, cz);
+        SubResult r;
+        subseq_sync(sc, LT, p, cz, hi, r);
+        win.start[j] = (uint16_t)ns;
+        const uint32_t ne = spec_pack(r.p, hi, r.cz);
+        if (ne != win.end[j]) {
+          win.end[j] = (uint16_t)ne;
+          changed = 1;
+        }
+        win.nstart[j] = (int32_t)r.nstart;
+#pragma unroll
+        for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
       }
-      __syncthreads();  // every s_end[t - 1] has been read
-      if (changed) s_end[t] = make_uint2(r.p, r.cz);
       if (!__syncthreads_or(changed)) break;
     }
 
-    // ---- C: prefix sums, then the exact pass that stores coefficients
-    int32_t tot_n, tot0, tot1, tot2, tot3;
-    int32_t ex_n = block_excl_scan(active ? (int32_t)r.nstart : 0, s_scan, tot_n);
-    int32_t ex0 = block_excl_scan(active ? r.dcsum[0] : 0, s_scan, tot0);
-    int32_t ex1 = block_excl_scan(active ? r.dcsum[1] : 0, s_scan, tot1);
-    int32_t ex2 = block_excl_scan(active ? r.dcsum[2] : 0, s_scan, tot2);
-    int32_t ex3 = block_excl_scan(active ? r.dcsum[3] : 0, s_scan, tot3);
-    // The last block a thread begins is finished by its right neighbour, whose pass may reach it first:
-    // clear it now, before anybody stores into it.
-    const int64_t blk0 = carry.nstart + ex_n - 1;
-    const int64_t trailing = active && r.nstart > 0 ? blk0 + (int64_t)r.nstart : -2;
-    if (trailing >= 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
+    // ---- C: prefix sums over the window, then the exact pass that stores coefficients
+    window_scan(win.nstart, n, s_scan);
+    for (int k = 0; k < d.ncomp; k++) window_scan(win.dc[k], n, s_scan);
     __syncthreads();
-    if (active) {
-      int32_t pred[HCJ_MAX_COMP] = {carry.dc[0] + ex0, carry.dc[1] + ex1, carry.dc[2] + ex2, carry.dc[3] + ex3};
-      int64_t blk = blk0;
+    // The last block a subsequence begins is finished by its right neighbour, whose pass may reach it
+    // first: clear it now, before anybody stores into it.
+    for (int j = t; j < n; j += SPEC_THREADS) {
+      const int32_t begun = win.nstart[j + 1] - win.nstart[j];
+      const int64_t trailing = carry.nstart + win.nstart[j] - 1 + begun;
+      if (begun > 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
+    }
+    __syncthreads();
+    for (int j = t; j < n; j += SPEC_THREADS) {
+      const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+      const bool last = wbase + j == nsub - 1;
+      uint32_t p, cz;
+      spec_unpack(win.start[j], lo, p, cz);
+      int32_t pred[HCJ_MAX_COMP];
+#pragma unroll
+      for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + (k < d.ncomp ? win.dc[k][j] : 0);
+      const int32_t begun = win.nstart[j + 1] - win.nstart[j];
+      const int64_t blk = carry.nstart + win.nstart[j] - 1;
+      const int64_t trailing = begun > 0 ? blk + begun : -2;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, LT, mystart.x, mystart.y, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, trailing, &err_pos);
+      int err = subseq_write(sc, LT, p, cz, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, trailing, &err_pos);
       if (err) raise_status(state, err, err_pos);
     }
-    __syncthreads();  // all reads of carry done
-    const uint32_t last_t = min(nsub - base, (uint32_t)SPEC_THREADS) - 1;
-    if (t == (int)last_t) {
-      carry.p = r.p;
-      carry.cz = r.cz;
-      carry.nstart += tot_n;
-      carry.dc[0] += tot0;
-      carry.dc[1] += tot1;
-      carry.dc[2] += tot2;
-      carry.dc[3] += tot3;
+    __syncthreads();  // all reads of carry and of the window are done
+    if (t == 0) {
+      const uint32_t hi = min((wbase + n) * SPEC_BITS, L);
+      spec_unpack(win.end[n - 1], hi, carry.p, carry.cz);
+      carry.nstart += win.nstart[n];
+      for (int k = 0; k < d.ncomp; k++) carry.dc[k] += win.dc[k][n];
     }
     __syncthreads();
   }
@@ -549,7 +616,13 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
 
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.ls_hi <= b.ls_lo) return;
-  k_huff_spec<<<b.ls_hi - b.ls_lo, SPEC_THREADS, 0, s>>>(b);
+  const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + sizeof(SpecWindow);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_huff_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  k_huff_spec<<<b.ls_hi - b.ls_lo, SPEC_THREADS, smem, s>>>(b);
 }
 
 // ================================================================================================
