@@ -391,6 +391,8 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   dv.list_restart = d_lr;
   dv.n_restart = (int)list_restart.size();
   dv.max_segments = max_segments;
+  dv.max_pairs = 1;
+  for (const HcjTableSet &ts : table_sets) dv.max_pairs = std::max(dv.max_pairs, ts.npairs);
   dv.list_spec = d_ls;
   dv.n_spec = (int)list_spec.size();
   dv.max_idct_tiles = max_tiles;

@@ -176,7 +176,7 @@ void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
 // Huffman tables in shared memory, shared by K2 and K3.
 // ================================================================================================
 struct SmemTables {
-  uint16_t primary[HCJ_MAX_COMP * 2 * HCJ_LUT_ENTRIES];  // [pair][dc/ac][primary + sub-tables]
+  uint16_t *primary;  // [pair][dc/ac][primary + sub-tables]: lives right behind the kernel's other dynamic shared memory
   uint32_t max_bits[HCJ_MAX_COMP * 2];
   const uint16_t *full[HCJ_MAX_COMP * 2];
   uint8_t comp_pair[HCJ_MAX_COMP];
@@ -184,11 +184,12 @@ struct SmemTables {
   int32_t quant[HCJ_MAX_COMP * 128];  // per scan component: 64 plain entries + 64 in dp2a form
 };
 
-__device__ __forceinline__ void load_tables(SmemTables &st, const DecodeBatchDev &b, const HcjImageDesc &d) {
+__device__ __forceinline__ void load_tables(SmemTables &st, uint16_t *lut_smem, const DecodeBatchDev &b, const HcjImageDesc &d) {
   const HcjTableSet &ts = b.table_sets[d.table_set];
+  if (threadIdx.x == 0) st.primary = lut_smem;
   const uint32_t n = ts.npairs * 2 * HCJ_LUT_ENTRIES;
   const uint4 *src = reinterpret_cast<const uint4 *>(b.lut_primary + ts.primary_off);
-  uint4 *dst = reinterpret_cast<uint4 *>(st.primary);
+  uint4 *dst = reinterpret_cast<uint4 *>(lut_smem);
   for (uint32_t i = threadIdx.x; i < n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
   if (threadIdx.x < HCJ_MAX_COMP * 2) {
     const HcjTableMeta &m = ts.meta[threadIdx.x >> 1][threadIdx.x & 1];
@@ -225,6 +226,9 @@ __device__ __forceinline__ void fill_scan_ctx(ScanCtx &sc, const SmemTables &st,
   if (threadIdx.x < (uint32_t)d.ncomp) sc.tab[threadIdx.x] = tables_of(st, threadIdx.x);
 }
 
+// Shared memory for the LUTs of one image: as many (dc, ac) pairs as any image of the batch uses.
+static inline size_t lut_smem_bytes(const DecodeBatchDev &b) { return (size_t)b.max_pairs * 2 * HCJ_LUT_ENTRIES * sizeof(uint16_t); }
+
 __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32_t bit_pos) {
   atomicMin(&st->err_key, ((unsigned long long)bit_pos << 8) | (unsigned long long)(-code));
 }
@@ -233,92 +237,53 @@ __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32
 // K2: one thread per restart interval.  Intervals are byte aligned and start with every DC predictor
 // at 0, so a thread owns its MCUs outright and writes resolved coefficients straight to HBM.
 // ================================================================================================
-constexpr int HR_THREADS = 512;
 constexpr int HR_STAGE_WORDS = 32 * 33;  // per warp: 32 lanes x (32 words + 1 pad)
 
-// The exact pass of one restart interval per lane (same symbol semantics as subseq_write), with the
-// coefficient block of every lane staged in shared memory and written out by the whole warp as one
-// 128-byte line when it completes: scattered 2-byte stores cost one L2 partial-sector transaction per
-// symbol and were the bottleneck of this kernel (profiles/r01_notes.md).
-__global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b) {
-  extern __shared__ uint4 s_dyn4[];
-  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
-  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
-  uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
+// ------------------------------------------------------------------------------------------------
+// Warp-synchronous exact pass (the symbol semantics of subseq_write), shared by K2 and K3.
+//
+// Every lane decodes its own run of symbols: from state (p, cz) while symbols start before `hi` and
+// belong to blocks < nblocks_end.  A block the lane begins is staged in the lane's row of `stage`
+// (shared memory, 33-word stride) and, once complete, written out by the whole warp as one 128-byte
+// line: scattered 2-byte stores cost one L2 partial-sector transaction per symbol and were the
+// bottleneck of the entropy kernels.  Two kinds of blocks are only partly decoded by a lane (K3 only):
+// the one in progress at its start state (begun by the left neighbour) takes direct 2-byte stores, and
+// the one in progress when it stops is drained from the stage with 2-byte stores; both kinds have been
+// cleared in global memory before the pass.
+// ------------------------------------------------------------------------------------------------
+struct PassIn {
+  uint32_t p, cz, hi, end_bits;
+  int32_t blk;          // index of the block in progress (start of a block: the previous one)
+  int32_t pred[HCJ_MAX_COMP];
+  int32_t nblocks_end;  // blocks >= this are not decoded
+  bool valid;
+};
 
-  const uint32_t img = b.list_restart[blockIdx.y + b.lr_lo];
-  const HcjImageDesc &d = b.descs[img];
-  const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
-  if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
-  for (int j = lane; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
-  load_tables(st, b, d);
-  __syncthreads();
-  fill_scan_ctx(sc, st, b, d, 0);
-  __syncthreads();
-  HcjImageState *state = b.states + img;
-  const Local L{st.primary, st.quant, st.blk_comp};
-  const bool valid = seg < d.nseg_expected && state->status == 0;
-
-  const uint32_t *segs = b.seg_offs + d.seg_off;
-  const uint32_t seg_begin = valid ? segs[seg] : 0u, seg_end = valid ? segs[seg + 1] : 0u;
-  const uint32_t seg_bits = (seg_end - seg_begin) * 8u;
-  const uint32_t ri = d.ri ? d.ri : d.nmcu;
-  const uint32_t mcu0 = min(seg * ri, d.nmcu), mcu1 = min(mcu0 + ri, d.nmcu);
-  const uint32_t bpm = d.bpm;
-  int16_t *coefs = b.coefs + d.coef_off * 64;
+__device__ __forceinline__ int warp_exact_pass(const ScanCtx &sc, const SmemTables &st, const Local L, uint32_t *stage,
+                                               int lane, const PassIn &in, int16_t *coefs, uint32_t *err_pos) {
   uint32_t *coefs32 = reinterpret_cast<uint32_t *>(coefs);
-
-  if (valid && seg_bits <= 16u) {
-    // Degenerate interval: the model's `show` bound (bitstream_reader.ml:32) is in play; decode it with
-    // the literal per-block routine and direct stores.
-    BitReader br;
-    br.init(sc.words, seg_begin * 8u, seg_end * 8u);
-    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-    int64_t blk = (int64_t)mcu0 * bpm;
-    for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
-      for (uint32_t k = 0; k < bpm; k++, blk++) {
-        const uint32_t comp = st.blk_comp[k];
-        int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
-        int err = decode_block_exact(br, L, sc.tab[comp], seg_bits, pred, coefs + blk * 64);
-        flag_wide_block(sc, blk);
-        if (err) {
-          raise_status(state, err, br.pos);
-          mcu = mcu1;
-          break;
-        }
-        if (comp == 0) p0 = pred;
-        else if (comp == 1) p1 = pred;
-        else if (comp == 2) p2 = pred;
-        else p3 = pred;
-      }
-    }
-  }
-
-  // ---- warp-synchronous symbol loop
-  bool active = valid && seg_bits > 16u && mcu1 > mcu0;
-  const int32_t nblocks_end = (int32_t)(mcu1 * bpm);
-  int32_t blk = (int32_t)(mcu0 * bpm) - 1;
-  uint32_t c = 0, z = 0, share = 0;
-  uint32_t comp = st.blk_comp[0];
+  const uint32_t bpm = sc.bpm;
+  uint32_t c = in.cz >> 8, z = in.cz & 0xffu, share = 0;
+  int32_t blk = in.blk;
+  bool active = in.valid && !(z != 0u && blk >= in.nblocks_end);
+  bool leading = z != 0u;  // the block in progress was begun by another thread
+  uint32_t comp = st.blk_comp[c];
   Tables t = sc.tab[comp];
-  // shared-memory byte addresses, computed once (the compiler otherwise re-derives them from %tid in the loop)
   const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
   const uint32_t mine_sa = stage_sa + (uint32_t)lane * 33u * 4u;
   const uint32_t quant_sa = (uint32_t)__cvta_generic_to_shared(st.quant);
   uint32_t q_sa = quant_sa + comp * 512u;
-  int32_t pcur = 0;                        // DC predictor of the current block's component
-  int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // predictors of the scan components (written back at block ends)
+  int32_t p0 = in.pred[0], p1 = in.pred[1], p2 = in.pred[2], p3 = in.pred[3];
+  int32_t pcur = comp == 0u ? p0 : comp == 1u ? p1 : comp == 2u ? p2 : p3;
   BitReader br;
-  br.init(sc.words, seg_begin * 8u, active ? seg_end * 8u : 0u);
+  br.init(sc.words, in.p, active ? in.end_bits : 0u);
   int err = HCJ_DEV_OK;
 
   while (__any_sync(0xffffffffu, active)) {
     bool done_blk = false;
     if (active) {
       const bool isdc = z == 0u;
-      if (isdc && blk + 1 >= nblocks_end) {
+      if (br.pos >= in.hi || (isdc && blk + 1 >= in.nblocks_end)) {
         active = false;
       } else {
         const Symbol s = read_symbol(br, L, t, isdc);
@@ -341,14 +306,16 @@ __global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b
               active = false;
             }
             if (isdc || (s.size != 0u && !eob)) {
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(mine_sa + zi * 2u), "h"((short)v) : "memory");
+              if (leading) coefs[(size_t)blk * 64 + zi] = (int16_t)v;
+              else asm volatile("st.shared.u16 [%0], %1;" ::"r"(mine_sa + zi * 2u), "h"((short)v) : "memory");
               int32_t qv;
               asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qv) : "r"(q_sa + zi * 4u));
               share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)qv;
             }
             z = eob ? 64u : zi + 1u;
             if (z >= 64u && active) {
-              done_blk = true;
+              done_blk = !leading;
+              leading = false;
               if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
               share = 0;
               z = 0;
@@ -379,17 +346,110 @@ __global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b
       coefs32[(size_t)bidx * 32 + lane] = w;
     }
   }
-  if (err) raise_status(state, err, br.pos);
+  // a block this lane began but does not finish: hand its coefficients over with 2-byte stores
+  if (z != 0u && !leading && !err && in.valid) {
+    for (uint32_t w = 0; w < 32u; w++) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(mine_sa + w * 4u) : "memory");
+      if (v) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine_sa + w * 4u), "r"(0u) : "memory");
+        if (v & 0xffffu) coefs[(size_t)blk * 64 + 2u * w] = (int16_t)(v & 0xffffu);
+        if (v >> 16) coefs[(size_t)blk * 64 + 2u * w + 1u] = (int16_t)(v >> 16);
+      }
+    }
+  } else if (err) {  // leave the stage clean for the next pass of this warp
+    for (uint32_t w = 0; w < 32u; w++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(mine_sa + w * 4u), "r"(0u) : "memory");
+  }
+  if (share >= (uint32_t)HCJ_WIDE_SHARE && blk >= 0) flag_wide_block(sc, blk);
+  *err_pos = br.pos;
+  return err;
+}
+
+constexpr int HR_THREADS = 512;
+
+// The exact pass of one restart interval per lane (same symbol semantics as subseq_write), with the
+// coefficient block of every lane staged in shared memory and written out by the whole warp as one
+// 128-byte line when it completes: scattered 2-byte stores cost one L2 partial-sector transaction per
+// symbol and were the bottleneck of this kernel (profiles/r01_notes.md).
+__global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b) {
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
+
+  const uint32_t img = b.list_restart[blockIdx.y + b.lr_lo];
+  const HcjImageDesc &d = b.descs[img];
+  const uint32_t seg = blockIdx.x * HR_THREADS + threadIdx.x;
+  if (blockIdx.x * HR_THREADS >= d.nseg_expected) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
+  for (int j = lane; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
+  uint16_t *lut_smem = reinterpret_cast<uint16_t *>(s_stage + (HR_THREADS / 32) * HR_STAGE_WORDS);
+  load_tables(st, lut_smem, b, d);
+  __syncthreads();
+  fill_scan_ctx(sc, st, b, d, 0);
+  __syncthreads();
+  HcjImageState *state = b.states + img;
+  const Local L{lut_smem, st.quant, st.blk_comp};
+  const bool valid = seg < d.nseg_expected && state->status == 0;
+
+  const uint32_t *segs = b.seg_offs + d.seg_off;
+  const uint32_t seg_begin = valid ? segs[seg] : 0u, seg_end = valid ? segs[seg + 1] : 0u;
+  const uint32_t seg_bits = (seg_end - seg_begin) * 8u;
+  const uint32_t ri = d.ri ? d.ri : d.nmcu;
+  const uint32_t mcu0 = min(seg * ri, d.nmcu), mcu1 = min(mcu0 + ri, d.nmcu);
+  const uint32_t bpm = d.bpm;
+  int16_t *coefs = b.coefs + d.coef_off * 64;
+
+  if (valid && seg_bits <= 16u) {
+    // Degenerate interval: the model's `show` bound (bitstream_reader.ml:32) is in play; decode it with
+    // the literal per-block routine and direct stores.
+    BitReader br;
+    br.init(sc.words, seg_begin * 8u, seg_end * 8u);
+    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    int64_t blk = (int64_t)mcu0 * bpm;
+    for (uint32_t mcu = mcu0; mcu < mcu1; mcu++) {
+      for (uint32_t k = 0; k < bpm; k++, blk++) {
+        const uint32_t comp = st.blk_comp[k];
+        int32_t pred = comp == 0 ? p0 : comp == 1 ? p1 : comp == 2 ? p2 : p3;
+        int err = decode_block_exact(br, L, sc.tab[comp], seg_bits, pred, coefs + blk * 64);
+        flag_wide_block(sc, blk);
+        if (err) {
+          raise_status(state, err, br.pos);
+          mcu = mcu1;
+          break;
+        }
+        if (comp == 0) p0 = pred;
+        else if (comp == 1) p1 = pred;
+        else if (comp == 2) p2 = pred;
+        else p3 = pred;
+      }
+    }
+  }
+
+  // ---- warp-synchronous exact pass over the interval
+  PassIn in;
+  in.valid = valid && seg_bits > 16u && mcu1 > mcu0;
+  in.p = seg_begin * 8u;
+  in.cz = 0u;
+  in.hi = 0xffffffffu;
+  in.end_bits = seg_end * 8u;
+  in.blk = (int32_t)(mcu0 * bpm) - 1;
+  in.pred[0] = in.pred[1] = in.pred[2] = in.pred[3] = 0;
+  in.nblocks_end = (int32_t)(mcu1 * bpm);
+  uint32_t err_pos = 0;
+  int err = warp_exact_pass(sc, st, L, stage, lane, in, coefs, &err_pos);
+  if (err) raise_status(state, err, err_pos);
 }
 
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.lr_hi <= b.lr_lo) return;
   const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
-                      (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
-  static bool configured = false;
-  if (!configured) {
+                      (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t) + lut_smem_bytes(b);
+  static size_t configured = 0;
+  if (smem > configured) {
     cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    configured = smem;
   }
   dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.lr_hi - b.lr_lo);
   k_huff_restart<<<grid, HR_THREADS, smem, s>>>(b);
@@ -416,7 +476,7 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 // ================================================================================================
 constexpr int SPEC_THREADS = 512;
 constexpr uint32_t SPEC_BITS = 1024;
-constexpr int SPEC_PER_THREAD = 4;
+constexpr int SPEC_PER_THREAD = 2;
 constexpr int SPEC_WINDOW = SPEC_THREADS * SPEC_PER_THREAD;
 
 struct SpecCarry {
@@ -462,7 +522,7 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t *s_warp, i
   return base + incl - v;
 }
 
-// In-place exclusive scan of a[0..n) (n <= SPEC_WINDOW), a[n] = total; every thread owns 4 consecutive entries.
+// In-place exclusive scan of a[0..n) (n <= SPEC_WINDOW), a[n] = total; every thread owns SPEC_PER_THREAD consecutive entries.
 __device__ __forceinline__ void window_scan(int32_t *a, int n, int32_t *s_warp) {
   const int i0 = threadIdx.x * SPEC_PER_THREAD;
   int32_t v[SPEC_PER_THREAD], sum = 0;
@@ -486,6 +546,11 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
   SpecWindow &win = *reinterpret_cast<SpecWindow *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
+  uint32_t *stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15))) +
+                    (threadIdx.x >> 5) * HR_STAGE_WORDS;
+  for (int j = threadIdx.x & 31; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
+  uint16_t *lut_smem = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15)) +
+                                                    (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t));
   __shared__ int32_t s_scan[SPEC_THREADS / 32];
   __shared__ SpecCarry carry;
 
@@ -493,7 +558,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[img];
   HcjImageState *state = b.states + img;
   const int t = threadIdx.x;
-  load_tables(st, b, d);
+  load_tables(st, lut_smem, b, d);
   __syncthreads();
   fill_scan_ctx(sc, st, b, d, state->ent_len * 8u);
   if (t == 0) {
@@ -504,7 +569,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   }
   __syncthreads();
   if (state->status != 0) return;
-  const Local LT{st.primary, st.quant, st.blk_comp};
+  const Local LT{lut_smem, st.quant, st.blk_comp};
 
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = d.nblocks;
@@ -588,19 +653,22 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       if (begun > 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
     }
     __syncthreads();
-    for (int j = t; j < n; j += SPEC_THREADS) {
-      const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
-      const bool last = wbase + j == nsub - 1;
-      uint32_t p, cz;
-      spec_unpack(win.start[j], lo, p, cz);
-      int32_t pred[HCJ_MAX_COMP];
+    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {  // warp-uniform trip count
+      const int j = j0 + t;
+      PassIn in;
+      in.valid = j < n;
+      const int jj = in.valid ? j : 0;
+      const uint32_t lo = (wbase + jj) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+      const bool last = wbase + jj == nsub - 1;
+      spec_unpack(win.start[jj], lo, in.p, in.cz);
 #pragma unroll
-      for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + (k < d.ncomp ? win.dc[k][j] : 0);
-      const int32_t begun = win.nstart[j + 1] - win.nstart[j];
-      const int64_t blk = carry.nstart + win.nstart[j] - 1;
-      const int64_t trailing = begun > 0 ? blk + begun : -2;
+      for (int k = 0; k < HCJ_MAX_COMP; k++) in.pred[k] = carry.dc[k] + (k < d.ncomp ? win.dc[k][jj] : 0);
+      in.blk = (int32_t)(carry.nstart + win.nstart[jj] - 1);
+      in.hi = last ? 0xffffffffu : hi;
+      in.end_bits = L;
+      in.nblocks_end = (int32_t)nblocks;
       uint32_t err_pos = 0;
-      int err = subseq_write(sc, LT, p, cz, last ? 0xffffffffu : hi, L, blk, pred, nblocks, coefs, trailing, &err_pos);
+      int err = warp_exact_pass(sc, st, LT, stage, t & 31, in, coefs, &err_pos);
       if (err) raise_status(state, err, err_pos);
     }
     __syncthreads();  // all reads of carry and of the window are done
@@ -616,11 +684,13 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
 
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.ls_hi <= b.ls_lo) return;
-  const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + sizeof(SpecWindow);
-  static bool configured = false;
-  if (!configured) {
+  const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
+                      ((sizeof(SpecWindow) + 15) & ~size_t(15)) + (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t) +
+                      lut_smem_bytes(b);
+  static size_t configured = 0;
+  if (smem > configured) {
     cudaFuncSetAttribute(k_huff_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    configured = smem;
   }
   k_huff_spec<<<b.ls_hi - b.ls_lo, SPEC_THREADS, smem, s>>>(b);
 }

@@ -27,6 +27,7 @@ struct DecodeBatchDev {
   const uint32_t *list_restart;   // images decoded per restart interval
   int n_restart;
   uint32_t max_segments;          // max nseg_expected over list_restart
+  uint32_t max_pairs;             // max (dc, ac) table pairs any image uses (sizes the LUT shared memory)
   const uint32_t *list_spec;      // images decoded speculatively (no restart markers)
   int n_spec;
   uint32_t max_idct_tiles;        // max over images of tiles_per_row * mcus_high
