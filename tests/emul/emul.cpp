@@ -4,7 +4,10 @@
 // Nothing in the product links or calls this file.
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "hcj_device.cuh"
@@ -16,11 +19,17 @@ namespace {
 
 struct HostTables {
   std::vector<hcj::HuffLut> luts;  // [comp][dc/ac]
-  std::vector<uint16_t> lut;       // all primary tables back to back (what the kernels keep in shared memory)
+  // what the kernels keep in shared memory (table index = comp * 2 + (0 = dc, 1 = ac))
+  std::vector<uint32_t> fast;
+  std::vector<uint32_t> sub;
+  uint32_t max_bits[HCJ_MAX_COMP * 2];
+  const uint16_t *full[HCJ_MAX_COMP * 2];
+  BlkInfo blkinfo[HCJ_MAX_BPM + 2];
   Tables tab[HCJ_MAX_COMP];
   int32_t quant[HCJ_MAX_COMP * 128];
   uint8_t blk_comp[HCJ_MAX_BPM + 2];
-  Local local() const { return Local{lut.data(), quant, blk_comp}; }
+  FastTables fast_tables() const { return FastTables{fast.data(), sub.data(), max_bits, full, blkinfo, quant}; }
+  Local local() const { return Local{fast_tables(), quant, blk_comp}; }
 };
 
 int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj::ImagePlan *plan, HostTables *ht) {
@@ -40,19 +49,149 @@ int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj:
       ht->quant[c * 128 + e] = h->quant_tables[plan->qt_index[c]].elements[e];
       ht->quant[c * 128 + 64 + e] = HCJ_QD(e, h->quant_tables[plan->qt_index[c]].elements[e] & 0xff);
     }
+  ht->fast.assign((size_t)plan->info.ncomp * 2 * HCJ_LUT_SIZE, 0);
+  ht->sub.assign((size_t)plan->info.ncomp * 2 * HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE, 0);
   for (int c = 0; c < plan->info.ncomp; c++) {
+    for (int k = 0; k < 2; k++) {  // the kernels' table loader (load_tables in hcj_kernels.cu)
+      const hcj::HuffLut &l = ht->luts[c * 2 + k];
+      const int ti = c * 2 + k;
+      ht->max_bits[ti] = (uint32_t)l.max_bits;
+      ht->full[ti] = l.full.data();
+      for (int i = 0; i < HCJ_LUT_SIZE; i++)
+        ht->fast[(size_t)ti * HCJ_LUT_SIZE + i] = fast_entry_from_primary(l.primary[i], (uint32_t)l.max_bits, k == 0);
+      for (int i = 0; i < HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE; i++)
+        ht->sub[(size_t)ti * HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE + i] = fast_entry_or_none(l.primary[HCJ_LUT_SIZE + i], k == 0);
+    }
     Tables &t = ht->tab[c];
-    t.dc_off = (uint32_t)ht->lut.size();
-    ht->lut.insert(ht->lut.end(), ht->luts[c * 2].primary.begin(), ht->luts[c * 2].primary.end());
-    t.dc_full = ht->luts[c * 2].full.data();
+    t.dc_off = (uint32_t)(c * 2) * HCJ_LUT_SIZE;
+    t.ac_off = (uint32_t)(c * 2 + 1) * HCJ_LUT_SIZE;
     t.dc_max_bits = ht->luts[c * 2].max_bits;
-    t.ac_off = (uint32_t)ht->lut.size();
-    ht->lut.insert(ht->lut.end(), ht->luts[c * 2 + 1].primary.begin(), ht->luts[c * 2 + 1].primary.end());
-    t.ac_full = ht->luts[c * 2 + 1].full.data();
     t.ac_max_bits = ht->luts[c * 2 + 1].max_bits;
   }
-  for (int k = 0; k < plan->info.blocks_per_mcu; k++) ht->blk_comp[k] = (uint8_t)plan->blk_comp[k];
+  for (int k = 0; k < plan->info.blocks_per_mcu; k++) {
+    const int c = plan->blk_comp[k];
+    ht->blk_comp[k] = (uint8_t)c;
+    uint32_t qmax = 0;
+    for (int e = 1; e < 64; e++) qmax = std::max(qmax, (uint32_t)ht->quant[c * 128 + e]);
+    ht->blkinfo[k] = BlkInfo{ht->tab[c].dc_off, ht->tab[c].ac_off, (uint32_t)c * 128u, (uint32_t)c | (qmax << 8)};
+  }
   return 0;
+}
+
+// ---- single-lane stand-ins for the warp-synchronous fast passes of hcj_kernels.cu (warp_exact_fast,
+// warp_sync_fast): the same step functions in the same order, with the warp votes removed.  A lane runs
+// the fast steps until it has to leave, then hands its state to the literal loop.
+struct ExactState {
+  uint32_t p, cz, share;
+  int64_t blk;
+  int32_t pred[HCJ_MAX_COMP];
+};
+
+void store_sparse(const int16_t *row, int16_t *blk) {
+  for (int i = 0; i < 64; i++)
+    if (row[i]) blk[i] = row[i];
+}
+
+// Returns 0, or the status the fast pass itself reports (a run past coefficient 63), with *err_pos set.
+int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t end_bits, int64_t nblocks_end,
+                    int16_t *coefs, int64_t prezeroed_blk, ExactState &st, uint32_t *err_pos) {
+  const uint32_t lim = std::min(hi, end_bits >= 32u ? end_bits - 32u : 0u);
+  ExactLane s;
+  s.br.init(sc.words, st.p);
+  s.c = st.cz >> 8;
+  s.z = st.cz & 0xffu;
+  s.blk = (int32_t)st.blk;
+  s.p0 = st.pred[0], s.p1 = st.pred[1], s.p2 = st.pred[2], s.p3 = st.pred[3];
+  s.share = st.share;
+  s.sumabs = 0;
+  exact_bind_block(s, T);
+  bool leading = s.z != 0u;
+  if (leading && st.blk >= nblocks_end) return 0;
+  int16_t row[64];
+  memset(row, 0, sizeof(row));
+  for (;;) {
+    if (s.z == 0u) {
+      if (s.blk + 1 >= nblocks_end || s.br.pos >= lim) break;
+      if (!exact_dc_step(s, T, row)) break;
+    } else {
+      if (s.br.pos >= lim) break;
+      exact_ac_step(s, T, row);
+      if (z_block_done(s.z)) {
+        if (z_no_code(s.z)) {
+          exact_ac_undo_no_code(s);
+          break;
+        }
+        if (z_overrun(s.z)) {
+          *err_pos = s.br.pos;
+          return HCJ_DEV_COEF_INDEX;
+        }
+        if (exact_share_may_be_wide(s) && exact_share(s, T, row) >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, s.blk);
+        if (leading) store_sparse(row, coefs + (int64_t)s.blk * 64);
+        else memcpy(coefs + (int64_t)s.blk * 64, row, sizeof(row));
+        memset(row, 0, sizeof(row));
+        leading = false;
+        exact_next_block(s, T, sc.bpm);
+      }
+    }
+  }
+  if (s.z != 0u) {  // the literal loop stores straight to memory (in the kernel the block stays staged)
+    s.share = exact_share(s, T, row);
+    if (!leading && s.blk != prezeroed_blk) zero_block(coefs + (int64_t)s.blk * 64);
+    store_sparse(row, coefs + (int64_t)s.blk * 64);
+  }
+  exact_save_pred(s);
+  st.p = s.br.pos;
+  st.cz = (s.c << 8) | s.z;
+  st.share = s.share;
+  st.blk = s.blk;
+  st.pred[0] = s.p0, st.pred[1] = s.p1, st.pred[2] = s.p2, st.pred[3] = s.p3;
+  return 0;
+}
+
+// subseq_sync with the fast steps in front
+void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
+  const uint32_t lim = std::min(hi, sc.total_bits >= 32u ? sc.total_bits - 32u : 0u);
+  SyncLane s;
+  s.br.init(sc.words, p);
+  s.c = cz >> 8;
+  s.z = cz & 0xffu;
+  s.nstart = 0;
+  s.d0 = s.d1 = s.d2 = s.d3 = 0;
+  sync_bind_block(s, L.ft);
+  for (;;) {
+    if (s.br.pos >= lim) break;
+    if (s.z == 0u) {
+      if (!sync_dc_step(s, L.ft)) break;
+    } else {
+      sync_ac_step(s, L.ft);
+      if (z_no_code(s.z)) {
+        sync_ac_undo_no_code(s);
+        break;
+      }
+      if (z_block_done(s.z)) sync_next_block(s, L.ft, sc.bpm);
+    }
+  }
+  subseq_sync(sc, L, s.br.pos, (s.c << 8) | s.z, hi, r);
+  r.nstart += s.nstart;
+  r.dcsum[0] += s.d0;
+  r.dcsum[1] += s.d1;
+  r.dcsum[2] += s.d2;
+  r.dcsum[3] += s.d3;
+}
+
+// subseq_write with the fast steps in front
+int fast_subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
+                      int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *coefs, int64_t prezeroed_blk, uint32_t *err_pos) {
+  ExactState st;
+  st.p = p;
+  st.cz = cz;
+  st.share = 0;
+  st.blk = blk;
+  for (int k = 0; k < HCJ_MAX_COMP; k++) st.pred[k] = pred[k];
+  // the fast lane stops at `hi` exactly like the literal loop; with hi = 0xffffffff it runs to the end of the data
+  int err = fast_exact_lane(sc, L.ft, hi, end_bits, nblocks, coefs, prezeroed_blk, st, err_pos);
+  if (err) return err;
+  return subseq_write(sc, L, st.p, st.cz, hi, end_bits, st.blk, st.pred, nblocks, coefs, prezeroed_blk, err_pos, st.share);
 }
 
 }  // namespace
@@ -107,8 +246,8 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
     uint32_t err_pos = 0;
     if (seg_bits > 16) {
       int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-      err = subseq_write(sc, L, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
-                         (int64_t)mcu1 * bpm, coefs, -2, &err_pos);
+      err = fast_subseq_write(sc, L, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
+                              (int64_t)mcu1 * bpm, coefs, -2, &err_pos);
     } else {
       BitReader br;
       br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
@@ -183,7 +322,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       hi[t] = lo + S < L ? lo + S : L;
       sp[t] = t == 0 ? carry.p : lo;
       scz[t] = t == 0 ? carry.cz : 0;
-      subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t]);
+      fast_subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t]);
       endp[t] = r[t].p;
       endcz[t] = r[t].cz;
     }
@@ -192,12 +331,14 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
     for (;;) {
       std::vector<uint32_t> np(endp), ncz(endcz);
       bool any = false;
+      int redo_cnt = 0;
       for (int t = 0; t < nact; t++) {
         uint32_t nsp = t == 0 ? carry.p : endp[t - 1], nscz = t == 0 ? carry.cz : endcz[t - 1];
         if (nsp != sp[t] || nscz != scz[t]) {
           sp[t] = nsp;
           scz[t] = nscz;
-          subseq_sync(sc, LT, nsp, nscz, hi[t], r[t]);
+          redo_cnt++;
+          fast_subseq_sync(sc, LT, nsp, nscz, hi[t], r[t]);
           if (r[t].p != endp[t] || r[t].cz != endcz[t]) {
             any = true;
             np[t] = r[t].p;
@@ -208,6 +349,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       endp = np;
       endcz = ncz;
       rounds++;
+      if (getenv("EMU_STATS")) fprintf(stderr, "round %d redo %d of %d\n", rounds, redo_cnt, nact);
       if (!any) break;
     }
     if (rounds > max_rounds) max_rounds = rounds;
@@ -246,7 +388,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       bool last = base + t == nsub - 1;
       uint32_t err_pos = 0;
       const int64_t trailing = r[t].nstart > 0 ? blk + (int64_t)r[t].nstart : -2;
-      int err = subseq_write(sc, LT, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, trailing, &err_pos);
+      int err = fast_subseq_write(sc, LT, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, trailing, &err_pos);
       unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
       if (err && key < err_key) err_key = key;  // the kernel's atomicMin
     }

@@ -369,7 +369,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_lr, 4 * std::max<size_t>(list_restart.size(), 1));
   if (st == HCJ_OK) st = batch_alloc(c, b, (void **)&d_ls, 4 * std::max<size_t>(list_spec.size(), 1));
   BALLOC(states, HcjImageState *, sizeof(HcjImageState) * std::max(n, 1));
-  BALLOC(entropy, uint8_t *, ent_bytes + 16);
+  BALLOC(entropy, uint8_t *, ent_bytes + 64);  // + slack: the fast readers prefetch up to 16 bytes past the data
   BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
   b->coef_bytes = (size_t)total_blocks * 128;
   BALLOC(coefs, int16_t *, b->coef_bytes + 16);

@@ -91,10 +91,96 @@ struct BitReader {
   }
 };
 
-// Huffman tables of one scan component as the decode loops see them.
+// ------------------------------------------------------------------------------------------------
+// Huffman tables as the kernels see them: one 32-bit "fast" entry per HCJ_LUT_BITS-bit prefix, byte
+// aligned so that each field is one PRMT away:
+//   [7:0] code length + magnitude bits, [15:8] code length, [23:16] 32 - size,
+//   [31:24] zig-zag advance: run + 1 (1..16); HCJ_ZADV_EOB for end-of-block; 1 for a DC symbol;
+//   bit 31 = not resolved by the prefix: a longer code (sub-table in shared memory, or the model's full
+//   2^max_bits table in global memory for pathological tables); HCJ_FAST_NONE = no such code.
+// Adding the advance to the zig-zag index z (1..63) classifies the symbol with no further test:
+//   < 64 more coefficients follow; == 64 coefficient 63 was the last; 65..79 the run went past
+//   coefficient 63 (the model raises); [HCJ_ZADV_EOB + 1, HCJ_ZADV_EOB + 63] end of block; >= 256 no code.
+// ------------------------------------------------------------------------------------------------
+#define HCJ_FAST_SLOW 0x80000000u
+#define HCJ_FAST_SUB (1u << 8)   // slow entry: look in sub-table (entry & 7)
+#define HCJ_FAST_FULL (2u << 8)  // slow entry: look in the full table (global memory)
+#define HCJ_ZADV_EOB 96u
+#define HCJ_FAST_NONE 0xff200000u  // advance 255, size 0, consumes no bits
+
+// (length << 8 | data) of Tables.Lut -> fast entry.
+HCJ_HD uint32_t fast_entry(uint32_t e16, bool isdc) {
+  const uint32_t len = e16 >> 8, data = e16 & 0xffu;
+  const uint32_t size = isdc ? data : data & 15u;
+  const uint32_t zadv = isdc ? 1u : (data == 0u ? HCJ_ZADV_EOB : (data >> 4) + 1u);
+  return (len + size) | (len << 8) | ((32u - size) << 16) | (zadv << 24);
+}
+// Primary-table entry (hcj_common.h) -> fast entry.
+HCJ_HD uint32_t fast_entry_from_primary(uint32_t p16, uint32_t max_bits, bool isdc) {
+  if (p16 & 0x8000u) return HCJ_FAST_SLOW | HCJ_FAST_SUB | (p16 & (HCJ_LUT_NSUB - 1));
+  if (p16 == 0u) return max_bits > HCJ_LUT_BITS ? (HCJ_FAST_SLOW | HCJ_FAST_FULL) : HCJ_FAST_NONE;
+  return fast_entry(p16, isdc);
+}
+// Sub-table / full-table entry -> fast entry.
+HCJ_HD uint32_t fast_entry_or_none(uint32_t e16, bool isdc) { return e16 ? fast_entry(e16, isdc) : HCJ_FAST_NONE; }
+
+HCJ_HD uint32_t shr_clamp(uint32_t x, uint32_t n) {  // x >> n with n in [0, 32]
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
+#else
+  return n >= 32u ? 0u : x >> n;
+#endif
+}
+HCJ_HD uint32_t byte_of(uint32_t x, int k) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x4440 | k);
+#else
+  return (x >> (8 * k)) & 0xffu;
+#endif
+}
+
+// The tables of the CTA's image as the fast loops see them (pointers into shared memory in the kernels;
+// built in the kernel body and passed by value so that the loads compile to LDS).  A table is named by
+// the offset of its fast entries: toff = (pair * 2 + (0 = dc, 1 = ac)) * HCJ_LUT_SIZE.
+struct alignas(16) BlkInfo {
+  uint32_t tdc, tac, qoff;  // dc toff, ac toff, quant offset (entries)
+  uint32_t comp_qmax;       // scan component | largest AC quant entry << 8
+};
+struct FastTables {
+  const uint32_t *fast;         // [table][HCJ_LUT_SIZE]
+  const uint32_t *sub;          // [table][HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE], fast entries
+  const uint32_t *max_bits;     // [table]
+  const uint16_t *const *full;  // [table] -> global memory, (length << 8) | data
+  const BlkInfo *blkinfo;       // [block-in-MCU]
+  const int32_t *quant;         // [scan component][128]
+};
+
+// `e` has HCJ_FAST_SLOW set.  Returns a resolved entry or HCJ_FAST_NONE.
+HCJ_HD uint32_t fast_lookup_slow(const FastTables &T, uint32_t toff, uint32_t e, uint32_t win, bool isdc) {
+  if (e == HCJ_FAST_NONE) return e;
+  const uint32_t ti = toff >> HCJ_LUT_BITS, mb = T.max_bits[ti];
+  if (e & HCJ_FAST_SUB)
+    return T.sub[ti * (HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE) + (e & (HCJ_LUT_NSUB - 1)) * HCJ_LUT_SUB_SIZE +
+                 ((win >> (32u - mb)) & ((1u << (mb - HCJ_LUT_BITS)) - 1u))];
+  return fast_entry_or_none(T.full[ti][win >> (32u - mb)], isdc);
+}
+HCJ_HD uint32_t fast_lookup(const FastTables &T, uint32_t toff, uint32_t win, bool isdc) {
+  uint32_t e = T.fast[toff + (win >> (32 - HCJ_LUT_BITS))];
+  if (e & HCJ_FAST_SLOW) e = fast_lookup_slow(T, toff, e, win, isdc);
+  return e;
+}
+
+// fast entry -> (length << 8) | data of Tables.Lut (decoder.ml:89-105); lossless
+HCJ_HD uint32_t fast_to_e16(uint32_t e, bool isdc) {
+  const uint32_t len = (e >> 8) & 0xffu, size = 32u - ((e >> 16) & 0xffu), zadv = e >> 24;
+  return (len << 8) | (isdc ? size : zadv == HCJ_ZADV_EOB ? 0u : ((zadv - 1u) << 4) | size);
+}
+
+// Huffman tables of one scan component as the literal decode loops see them.
 struct Tables {
-  uint32_t dc_off, ac_off;            // offsets (entries) of the table's HCJ_LUT_ENTRIES in Local::lut
-  const uint16_t *dc_full, *ac_full;  // 2^max_bits entries (global memory)
+  uint32_t dc_off, ac_off;  // toff of the component's tables in FastTables
   uint32_t dc_max_bits, ac_max_bits;
 };
 
@@ -102,22 +188,15 @@ struct Tables {
 // struct is built in the kernel body and passed by value, so that after inlining the compiler knows
 // the address space and emits LDS (a generic load costs a long-scoreboard round trip per symbol).
 struct Local {
-  const uint16_t *lut;      // [pair][dc/ac][HCJ_LUT_ENTRIES]
+  FastTables ft;
   const int32_t *quant;     // [scan component][128]: 64 plain entries + 64 in dp2a form
   const uint8_t *blk_comp;  // [bpm] block-in-MCU -> scan component
 };
 
 // Tables.Lut lookup (decoder.ml:89-105): (length << 8) | data, 0 = None.
-HCJ_HD uint32_t lut_lookup(const uint16_t *lut, uint32_t off, const uint16_t *full, uint32_t max_bits, uint32_t win) {
-  const uint16_t *primary = lut + off;
-  uint32_t e = primary[win >> (32 - HCJ_LUT_BITS)];
-  if (e & 0x8000u) {  // longer code: sub-table indexed by the bits that follow the prefix
-    const uint32_t sub = (win >> (32u - max_bits)) & ((1u << (max_bits - HCJ_LUT_BITS)) - 1u);
-    e = primary[HCJ_LUT_SIZE + (e & (HCJ_LUT_NSUB - 1)) * HCJ_LUT_SUB_SIZE + sub];
-  } else if (e == 0u && max_bits > HCJ_LUT_BITS) {
-    e = full[win >> (32u - max_bits)];
-  }
-  return e;
+HCJ_HD uint32_t lut_lookup(const Local &L, uint32_t toff, bool isdc, uint32_t win) {
+  const uint32_t e = fast_lookup(L.ft, toff, win, isdc);
+  return (e & HCJ_FAST_SLOW) ? 0u : fast_to_e16(e, isdc);
 }
 
 // Decoder.mag' (decoder.ml:73-79) for cat >= 1 on the cat bits that follow the code.
@@ -153,7 +232,7 @@ HCJ_HD int decode_block_exact(BitReader &br, const Local L, const Tables &t, uin
   const bool careful = seg_bits <= 16u;
   if (careful && t.dc_max_bits >= seg_bits) return HCJ_DEV_BITS_OOB;
   uint32_t win = br.window();
-  uint32_t e = lut_lookup(L.lut, t.dc_off, t.dc_full, t.dc_max_bits, win);
+  uint32_t e = lut_lookup(L, t.dc_off, true, win);
   if (e == 0u) return HCJ_DEV_NO_DC_CODE;
   uint32_t len = e >> 8, cat = e & 0xffu;
   int32_t diff = 0;
@@ -169,7 +248,7 @@ HCJ_HD int decode_block_exact(BitReader &br, const Local L, const Tables &t, uin
   while (k < 64u) {
     if (careful && t.ac_max_bits >= seg_bits) return HCJ_DEV_BITS_OOB;
     win = br.window();
-    e = lut_lookup(L.lut, t.ac_off, t.ac_full, t.ac_max_bits, win);
+    e = lut_lookup(L, t.ac_off, false, win);
     if (e == 0u) return HCJ_DEV_NO_AC_CODE;
     len = e >> 8;
     uint32_t rs = e & 0xffu, size = rs & 15u;
@@ -239,8 +318,7 @@ struct Symbol {
 HCJ_HD Symbol read_symbol(const BitReader &br, const Local L, const Tables &t, bool isdc) {
   Symbol s;
   const uint32_t win = br.window();
-  const uint32_t e = lut_lookup(L.lut, isdc ? t.dc_off : t.ac_off, isdc ? t.dc_full : t.ac_full,
-                                isdc ? t.dc_max_bits : t.ac_max_bits, win);
+  const uint32_t e = lut_lookup(L, isdc ? t.dc_off : t.ac_off, isdc, win);
   const uint32_t len = e >> 8, rs = e & 0xffu;
   s.e = e;
   s.size = isdc ? rs : rs & 15u;
@@ -303,7 +381,7 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
 // that other thread's pass starts (the speculative kernel does so in a separate step); pass -2 if none.
 HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
                         int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, int64_t prezeroed_blk,
-                        uint32_t *err_pos) {
+                        uint32_t *err_pos, uint32_t share0 = 0) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   BitReader br;
   br.init(sc.words, p, end_bits);
@@ -313,7 +391,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   int32_t p0 = pred[0], p1 = pred[1], p2 = pred[2], p3 = pred[3];
   if (z != 0u && blk >= nblocks) return HCJ_DEV_OK;
   int16_t *out = coefs + blk * 64;
-  uint32_t share = 0;  // this thread's part of the block's sum(|dequantised coefficient|)
+  uint32_t share = share0;  // this thread's part of the block's sum(|dequantised coefficient|)
   int err = HCJ_DEV_OK;
   while (br.pos < hi) {
     const bool isdc = z == 0u;
@@ -364,6 +442,215 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
   if (err) *err_pos = br.pos;
   return err;
+}
+
+// ================================================================================================
+// Fast symbol loops (shared by K2 and K3).
+//
+// The loops above are the literal ones: every model exception, the zero-extending reader and the `show`
+// bound are in them, and their many data-dependent branches leave less than half of a warp's lanes
+// active.  The fast steps below decode the same symbols with straight-line code:
+//   * one 32-bit table entry per symbol carries everything the step needs (FastTables above);
+//   * the reader keeps four words in registers (two of them still raw: their loads were issued two
+//     refills ago) and never masks: a lane leaves the fast loop 32 bits before the end of its data;
+//   * a step tests nothing: what happened is read off the zig-zag index afterwards (see the table
+//     format), by the code that runs once per block, not once per symbol;
+//   * errors are not decided here: a lane that meets an undefined code or a DC out of int16 stops BEFORE
+//     that symbol with its state intact and the literal loop carries on from there and raises what the
+//     model raises; a run past coefficient 63 is the one error reported directly (same status and
+//     position as the literal loop: it too has consumed the symbol when it raises).
+// ================================================================================================
+// Unmasked reader: words pos/32 .. pos/32 + 3 in registers.  Only valid while pos + 32 <= end of data.
+struct FastReader {
+  const uint32_t *words;
+  uint32_t pos, w0, w1, r0, r1;
+  HCJ_HD static uint32_t ld(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+  }
+  HCJ_HD void init(const uint32_t *words_, uint32_t pos_) {
+    words = words_;
+    pos = pos_;
+    const uint32_t i = pos_ >> 5;
+    w0 = bswap32(ld(words + i));
+    w1 = bswap32(ld(words + i + 1));
+    r0 = ld(words + i + 2);
+    r1 = ld(words + i + 3);
+  }
+  HCJ_HD uint32_t window() const {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(w1, w0, pos);
+#else
+    uint32_t s = pos & 31u;
+    return s ? (w0 << s) | (w1 >> (32u - s)) : w0;
+#endif
+  }
+  HCJ_HD void consume(uint32_t n) {  // n < 32
+    const uint32_t np = pos + n;
+    const uint32_t cross = (np ^ pos) & 32u;
+    pos = np;
+    if (cross) {
+      w0 = w1;
+      w1 = bswap32(r0);
+      r0 = r1;
+    }
+#if defined(__CUDA_ARCH__)
+    // The load writes r1 in place (no temporary + move, which would wait for the data right here): its
+    // value is first looked at two refills from now.
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+        : "+r"(r1)
+        : "l"(words + (np >> 5) + 3), "r"(cross));
+#else
+    if (cross) r1 = ld(words + (np >> 5) + 3);
+#endif
+  }
+};
+
+// value of the `size` magnitude bits that follow a code of `len` bits (Decoder.mag', decoder.ml:73-79);
+// sh = 32 - size; 0 when size == 0
+HCJ_HD int32_t fast_value(uint32_t win, uint32_t len, uint32_t sh) {
+  const uint32_t t = win << len;
+  const uint32_t m = shr_clamp(t, sh), mask = shr_clamp(0xffffffffu, sh);
+  return (int32_t)m - (int32_t)(mask & ~(uint32_t)((int32_t)t >> 31));
+}
+
+// What a zig-zag index says after an AC step (z was 1..63 before it).
+HCJ_HD bool z_block_done(uint32_t z) { return z >= 64u; }
+HCJ_HD bool z_overrun(uint32_t z) { return z > 64u && z <= HCJ_ZADV_EOB; }  // run past coefficient 63
+HCJ_HD bool z_no_code(uint32_t z) { return z >= 256u; }
+
+// ---- exact pass -------------------------------------------------------------------------------
+struct ExactLane {
+  FastReader br;
+  uint32_t c, z;            // block-in-MCU; next zig-zag index (0 = at a block boundary)
+  uint32_t tdc, tac, qoff;  // tables of the current scan component
+  uint32_t comp;
+  int32_t blk;              // block in progress (at a boundary: the last one begun)
+  int32_t pcur, p0, p1, p2, p3;
+  // Wide-block guard (HCJ_WIDE_SHARE): `share` = exact sum(|coef| * q) of what the lane knows exactly (the
+  // DC it decoded, what a previous pass handed over); the AC symbols of the fast steps only add |coef| to
+  // `sumabs` (no table load per symbol): share + sumabs * qmax bounds the lane's share from above, and only
+  // when that bound reaches the limit is the exact value formed from the staged row (exact_share).
+  uint32_t share, sumabs, qmax;
+};
+
+HCJ_HD void exact_bind_block(ExactLane &s, const FastTables T) {  // tables and predictor of block-in-MCU s.c
+  const BlkInfo bi = T.blkinfo[s.c];
+  s.tdc = bi.tdc;
+  s.tac = bi.tac;
+  s.qoff = bi.qoff;
+  s.comp = bi.comp_qmax & 0xffu;
+  s.qmax = bi.comp_qmax >> 8;
+  s.pcur = s.comp == 0u ? s.p0 : s.comp == 1u ? s.p1 : s.comp == 2u ? s.p2 : s.p3;
+}
+HCJ_HD void exact_save_pred(ExactLane &s) {
+  s.p0 = s.comp == 0u ? s.pcur : s.p0;
+  s.p1 = s.comp == 1u ? s.pcur : s.p1;
+  s.p2 = s.comp == 2u ? s.pcur : s.p2;
+  s.p3 = s.comp == 3u ? s.pcur : s.p3;
+}
+// after a completed block: on to the next block-in-MCU
+HCJ_HD void exact_next_block(ExactLane &s, const FastTables T, uint32_t bpm) {
+  exact_save_pred(s);
+  s.c = s.c + 1u == bpm ? 0u : s.c + 1u;
+  s.z = 0u;
+  s.share = 0u;
+  s.sumabs = 0u;
+  exact_bind_block(s, T);
+}
+// The lane's exact share of the block in progress; `row` holds the AC coefficients behind `sumabs`.
+HCJ_HD bool exact_share_may_be_wide(const ExactLane &s) {
+  return s.sumabs >= 0x10000u || (uint64_t)s.share + (uint64_t)s.sumabs * s.qmax >= (uint64_t)HCJ_WIDE_SHARE;
+}
+HCJ_HD uint32_t exact_share(const ExactLane &s, const FastTables T, const int16_t *row) {
+  uint64_t a = s.share;
+  for (int zi = 1; zi < 64; zi++) {
+    const int32_t v = row[zi];
+    a += (uint64_t)(uint32_t)(v < 0 ? -v : v) * (uint32_t)T.quant[s.qoff + zi];
+  }
+  return a > 0xffffffffull ? 0xffffffffu : (uint32_t)a;
+}
+
+// One AC symbol of the block in progress (s.z in 1..63); `row` = the lane's staged block (64 int16,
+// zig-zag).  Afterwards s.z tells what happened (z_block_done / z_overrun / z_no_code); an undefined code
+// consumes nothing and stores nothing.
+HCJ_HD void exact_ac_step(ExactLane &s, const FastTables T, int16_t *row) {
+  const uint32_t win = s.br.window();
+  const uint32_t e = fast_lookup(T, s.tac, win, false);
+  const uint32_t znext = s.z + (e >> 24);
+  const uint32_t sh = byte_of(e, 2);
+  const int32_t v = fast_value(win, byte_of(e, 1), sh);
+  if (sh != 32u && znext <= 64u) {
+    row[znext - 1u] = (int16_t)v;
+    s.sumabs += (uint32_t)(v < 0 ? -v : v);
+  }
+  s.br.consume(byte_of(e, 0));
+  s.z = znext;
+}
+// undo the only effect of a step that met an undefined code
+HCJ_HD void exact_ac_undo_no_code(ExactLane &s) { s.z -= 255u; }
+
+// The DC symbol that begins the next block (s.z == 0, tables bound).  Returns false, with the state
+// untouched, if the literal loop has to look at it (undefined code, predictor out of int16).
+HCJ_HD bool exact_dc_step(ExactLane &s, const FastTables T, int16_t *row) {
+  const uint32_t win = s.br.window();
+  const uint32_t e = fast_lookup(T, s.tdc, win, true);
+  const int32_t pc = s.pcur + fast_value(win, byte_of(e, 1), byte_of(e, 2));
+  if (e == HCJ_FAST_NONE || pc < -32768 || pc > 32767) return false;
+  s.pcur = pc;
+  s.blk++;
+  row[0] = (int16_t)pc;
+  s.share = (uint32_t)(pc < 0 ? -pc : pc) * (uint32_t)T.quant[s.qoff];
+  s.sumabs = 0u;
+  s.br.consume(byte_of(e, 0));
+  s.z = 1u;
+  return true;
+}
+
+// ---- synchronisation pass (no coefficients): same symbols, only the state and the prefix-sum inputs
+struct SyncLane {
+  FastReader br;
+  uint32_t c, z;
+  uint32_t tdc, tac, comp;
+  uint32_t nstart;
+  int32_t d0, d1, d2, d3;
+};
+HCJ_HD void sync_bind_block(SyncLane &s, const FastTables T) {
+  const BlkInfo bi = T.blkinfo[s.c];
+  s.tdc = bi.tdc;
+  s.tac = bi.tac;
+  s.comp = bi.comp_qmax & 0xffu;
+}
+HCJ_HD void sync_next_block(SyncLane &s, const FastTables T, uint32_t bpm) {
+  s.c = s.c + 1u == bpm ? 0u : s.c + 1u;
+  s.z = 0u;
+  sync_bind_block(s, T);
+}
+// One AC symbol.  Afterwards: s.z >= 256 = undefined code (nothing consumed; the literal loop skips one
+// bit); any other s.z >= 64 closes the block, overlong runs included, exactly as subseq_sync does.
+HCJ_HD void sync_ac_step(SyncLane &s, const FastTables T) {
+  const uint32_t e = fast_lookup(T, s.tac, s.br.window(), false);
+  s.br.consume(byte_of(e, 0));
+  s.z += e >> 24;
+}
+HCJ_HD void sync_ac_undo_no_code(SyncLane &s) { s.z -= 255u; }
+HCJ_HD bool sync_dc_step(SyncLane &s, const FastTables T) {
+  const uint32_t win = s.br.window();
+  const uint32_t e = fast_lookup(T, s.tdc, win, true);
+  if (e == HCJ_FAST_NONE) return false;
+  const int32_t v = fast_value(win, byte_of(e, 1), byte_of(e, 2));
+  s.d0 += s.comp == 0u ? v : 0;
+  s.d1 += s.comp == 1u ? v : 0;
+  s.d2 += s.comp == 2u ? v : 0;
+  s.d3 += s.comp == 3u ? v : 0;
+  s.nstart++;
+  s.br.consume(byte_of(e, 0));
+  s.z = 1u;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------

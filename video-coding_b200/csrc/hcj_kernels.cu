@@ -173,41 +173,73 @@ void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
 }
 
 // ================================================================================================
-// Huffman tables in shared memory, shared by K2 and K3.
+// Huffman tables in shared memory, shared by K2 and K3: per table HCJ_LUT_SIZE fast entries (32 bit,
+// converted here from the host-built 16-bit primary table) + the second-level sub-tables.
 // ================================================================================================
 struct SmemTables {
-  uint16_t *primary;  // [pair][dc/ac][primary + sub-tables]: lives right behind the kernel's other dynamic shared memory
   uint32_t max_bits[HCJ_MAX_COMP * 2];
   const uint16_t *full[HCJ_MAX_COMP * 2];
   uint8_t comp_pair[HCJ_MAX_COMP];
   uint8_t blk_comp[HCJ_MAX_BPM + 2];
+  BlkInfo blkinfo[HCJ_MAX_BPM + 2];
   int32_t quant[HCJ_MAX_COMP * 128];  // per scan component: 64 plain entries + 64 in dp2a form
 };
+constexpr int LUT_SUB_ENTRIES = HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE;
 
-__device__ __forceinline__ void load_tables(SmemTables &st, uint16_t *lut_smem, const DecodeBatchDev &b, const HcjImageDesc &d) {
+// Bytes of shared memory behind a kernel's other dynamic shared memory: fast entries, then sub-tables.
+static inline size_t lut_smem_bytes(const DecodeBatchDev &b) {
+  return (size_t)b.max_pairs * 2 * (HCJ_LUT_SIZE + LUT_SUB_ENTRIES) * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ FastTables load_tables(SmemTables &st, void *lut_smem, const DecodeBatchDev &b, const HcjImageDesc &d) {
   const HcjTableSet &ts = b.table_sets[d.table_set];
-  if (threadIdx.x == 0) st.primary = lut_smem;
-  const uint32_t n = ts.npairs * 2 * HCJ_LUT_ENTRIES;
-  const uint4 *src = reinterpret_cast<const uint4 *>(b.lut_primary + ts.primary_off);
-  uint4 *dst = reinterpret_cast<uint4 *>(lut_smem);
-  for (uint32_t i = threadIdx.x; i < n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+  uint32_t *fast = reinterpret_cast<uint32_t *>(lut_smem);
+  uint32_t *sub = fast + (size_t)b.max_pairs * 2 * HCJ_LUT_SIZE;
+  const uint16_t *src = b.lut_primary + ts.primary_off;
+  const uint32_t ntab = ts.npairs * 2;
+  for (uint32_t i = threadIdx.x; i < ntab * HCJ_LUT_SIZE; i += blockDim.x) {
+    const uint32_t ti = i >> HCJ_LUT_BITS, k = i & (HCJ_LUT_SIZE - 1);
+    fast[i] = fast_entry_from_primary(__ldg(src + ti * HCJ_LUT_ENTRIES + k), ts.meta[ti >> 1][ti & 1].max_bits, (ti & 1u) == 0u);
+  }
+  for (uint32_t i = threadIdx.x; i < ntab * LUT_SUB_ENTRIES; i += blockDim.x) {
+    const uint32_t ti = i / LUT_SUB_ENTRIES, k = i - ti * LUT_SUB_ENTRIES;
+    sub[i] = fast_entry_or_none(__ldg(src + ti * HCJ_LUT_ENTRIES + HCJ_LUT_SIZE + k), (ti & 1u) == 0u);
+  }
   if (threadIdx.x < HCJ_MAX_COMP * 2) {
     const HcjTableMeta &m = ts.meta[threadIdx.x >> 1][threadIdx.x & 1];
     st.max_bits[threadIdx.x] = m.max_bits;
     st.full[threadIdx.x] = b.lut_full + m.full_off;
   }
   if (threadIdx.x < HCJ_MAX_COMP) st.comp_pair[threadIdx.x] = (uint8_t)d.comp[threadIdx.x].pair;
-  if (threadIdx.x < HCJ_MAX_BPM) st.blk_comp[threadIdx.x] = d.blk_comp[threadIdx.x];
+  if (threadIdx.x < HCJ_MAX_BPM) {
+    const uint32_t comp = d.blk_comp[threadIdx.x], pr = (uint32_t)d.comp[comp < HCJ_MAX_COMP ? comp : 0].pair;
+    st.blk_comp[threadIdx.x] = (uint8_t)comp;
+    uint32_t qmax = 0;
+    if (threadIdx.x < (uint32_t)d.bpm)
+      for (int e = 1; e < 64; e++) qmax = max(qmax, (uint32_t)__ldg(b.qtables + d.qt_off + comp * 128u + e));
+    BlkInfo bi;
+    bi.tdc = (pr * 2 + 0) * HCJ_LUT_SIZE;
+    bi.tac = (pr * 2 + 1) * HCJ_LUT_SIZE;
+    bi.qoff = comp * 128u;
+    bi.comp_qmax = comp | (qmax << 8);
+    st.blkinfo[threadIdx.x] = bi;
+  }
   for (uint32_t i = threadIdx.x; i < (uint32_t)d.ncomp * 128; i += blockDim.x) st.quant[i] = __ldg(b.qtables + d.qt_off + i);
+  FastTables T;
+  T.fast = fast;
+  T.sub = sub;
+  T.max_bits = st.max_bits;
+  T.full = st.full;
+  T.blkinfo = st.blkinfo;
+  T.quant = st.quant;
+  return T;
 }
 
 __device__ __forceinline__ Tables tables_of(const SmemTables &st, uint32_t comp) {
   uint32_t pr = st.comp_pair[comp];
   Tables t;
-  t.dc_off = (pr * 2 + 0) * HCJ_LUT_ENTRIES;
-  t.ac_off = (pr * 2 + 1) * HCJ_LUT_ENTRIES;
-  t.dc_full = st.full[pr * 2 + 0];
-  t.ac_full = st.full[pr * 2 + 1];
+  t.dc_off = (pr * 2 + 0) * HCJ_LUT_SIZE;
+  t.ac_off = (pr * 2 + 1) * HCJ_LUT_SIZE;
   t.dc_max_bits = st.max_bits[pr * 2 + 0];
   t.ac_max_bits = st.max_bits[pr * 2 + 1];
   return t;
@@ -226,9 +258,6 @@ __device__ __forceinline__ void fill_scan_ctx(ScanCtx &sc, const SmemTables &st,
   if (threadIdx.x < (uint32_t)d.ncomp) sc.tab[threadIdx.x] = tables_of(st, threadIdx.x);
 }
 
-// Shared memory for the LUTs of one image: as many (dc, ac) pairs as any image of the batch uses.
-static inline size_t lut_smem_bytes(const DecodeBatchDev &b) { return (size_t)b.max_pairs * 2 * HCJ_LUT_ENTRIES * sizeof(uint16_t); }
-
 __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32_t bit_pos) {
   atomicMin(&st->err_key, ((unsigned long long)bit_pos << 8) | (unsigned long long)(-code));
 }
@@ -237,7 +266,8 @@ __device__ __forceinline__ void raise_status(HcjImageState *st, int code, uint32
 // K2: one thread per restart interval.  Intervals are byte aligned and start with every DC predictor
 // at 0, so a thread owns its MCUs outright and writes resolved coefficients straight to HBM.
 // ================================================================================================
-constexpr int HR_STAGE_WORDS = 32 * 33;  // per warp: 32 lanes x (32 words + 1 pad)
+constexpr int HR_ROW_WORDS = 36;  // a lane's staged block: 32 words + pad to 144 bytes (16-byte aligned rows, conflict-free 16-byte reads)
+constexpr int HR_STAGE_WORDS = 32 * HR_ROW_WORDS;  // per warp
 
 // ------------------------------------------------------------------------------------------------
 // Warp-synchronous exact pass (the symbol semantics of subseq_write), shared by K2 and K3.
@@ -256,21 +286,157 @@ struct PassIn {
   int32_t blk;          // index of the block in progress (start of a block: the previous one)
   int32_t pred[HCJ_MAX_COMP];
   int32_t nblocks_end;  // blocks >= this are not decoded
+  uint32_t share;       // the lane's share of the block in progress (wide-block guard) so far
+  bool own_staged;      // the block in progress was begun by this lane: its first part is in the lane's stage row
   bool valid;
 };
+
+// Lanes waiting at a block boundary are served once (waiting << thr) >= running lanes: thr = 2 is "a
+// quarter of the lanes"; HCJ_DEBUG bits 4..6 override it for experiments.
+__device__ __forceinline__ int fast_threshold(const ScanCtx &sc) { return (sc.debug & 0x70) ? ((sc.debug >> 4) & 7) - 1 : 2; }
+
+// Blocks shared with a neighbouring thread (cleared in global memory before the pass): the warp hands over
+// the non-zero coefficients staged in the rows of the lanes in `mask`, as 2-byte stores, and zeroes the rows.
+__device__ __forceinline__ void warp_store_sparse(uint32_t mask, int32_t blk, uint32_t stage_sa, int lane, int16_t *coefs) {
+  while (mask) {
+    const int l = __ffs((int)mask) - 1;
+    mask &= mask - 1u;
+    const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
+    const uint32_t sa = stage_sa + ((uint32_t)l * HR_ROW_WORDS + (uint32_t)lane) * 4u;
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sa) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(0u) : "memory");
+    if (w & 0xffffu) coefs[(size_t)bidx * 64 + 2 * lane] = (int16_t)(w & 0xffffu);
+    if (w >> 16) coefs[(size_t)bidx * 64 + 2 * lane + 1] = (int16_t)(w >> 16);
+  }
+}
+
+// Finished blocks staged in the rows of the lanes in `mask`: the warp writes them out four at a time, a
+// quarter-warp per block (8 lanes x 16 bytes = the 128-byte line), and zeroes the rows.  Per block that is
+// one shared-memory load, one shared-memory store and one global store wavefront, the same as a fully
+// coalesced copy, for a quarter of the instructions of a block-at-a-time loop.
+__device__ __forceinline__ void warp_store_full(uint32_t mask, int32_t blk, uint32_t *stage, int lane, int16_t *coefs) {
+  const int quarter = lane >> 3, sub = lane & 7;
+  while (mask) {
+    const uint32_t m1 = mask & (mask - 1u), m2 = m1 & (m1 - 1u), m3 = m2 & (m2 - 1u);
+    const uint32_t mine = quarter == 0 ? mask : quarter == 1 ? m1 : quarter == 2 ? m2 : m3;
+    const int l = mine ? __ffs((int)mine) - 1 : 0;
+    const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
+    if (mine) {
+      uint4 *src = reinterpret_cast<uint4 *>(stage + l * HR_ROW_WORDS) + sub;
+      const uint4 v = *src;
+      *src = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4 *>(coefs + (size_t)bidx * 64)[sub] = v;
+    }
+    mask = m3 & (m3 - 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast exact pass: the straight-line steps of hcj_device.cuh, warp-synchronous.  Lanes in the middle of
+// a block decode one AC symbol per iteration; lanes at a block boundary wait until a quarter of the
+// running lanes are there (or nobody is mid-block); then, in one go, each of them writes its finished
+// block out (eight 16-byte stores from its own row), moves to the next block-in-MCU and decodes its DC
+// symbol.  Batching the per-block work keeps it out of the per-symbol instruction stream.  On return `in`
+// holds the state of every lane at the point where it left (end of its range, 32 bits before the end of
+// its data, or the symbol the literal loop has to look at); warp_exact_pass carries on from there.
+// Returns HCJ_DEV_COEF_INDEX (and the position) for a lane whose run went past coefficient 63.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_exact_fast(const ScanCtx &sc, const FastTables T, uint32_t *stage, int lane, PassIn &in,
+                                               int16_t *coefs, uint32_t *err_pos) {
+  const uint32_t bpm = sc.bpm;
+  const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+  int16_t *row = reinterpret_cast<int16_t *>(stage + lane * HR_ROW_WORDS);
+  const uint32_t lim = min(in.hi, in.end_bits >= 32u ? in.end_bits - 32u : 0u);
+  const int thr = fast_threshold(sc);
+  ExactLane s;
+  s.c = in.cz >> 8;
+  s.z = in.cz & 0xffu;
+  s.blk = in.blk;
+  s.p0 = in.pred[0], s.p1 = in.pred[1], s.p2 = in.pred[2], s.p3 = in.pred[3];
+  s.share = in.share;
+  s.sumabs = 0u;
+  const bool entered = in.valid && !(s.z != 0u && in.blk >= in.nblocks_end) && in.p < lim;
+  s.br.init(sc.words, entered ? in.p : 0u);
+  exact_bind_block(s, T);
+  bool leading = s.z != 0u && !in.own_staged;  // the block in progress was begun by another thread
+  int st = !entered ? 2 : s.z != 0u ? 0 : 1;   // 0 = mid-block, 1 = at a block boundary, 2 = left, 3 = left with an error
+  int err = HCJ_DEV_OK;
+
+  for (;;) {
+    if (st == 0) {
+      if (s.br.pos >= lim) {
+        st = 2;
+      } else {
+        exact_ac_step(s, T, row);
+        st = z_block_done(s.z) ? 1 : 0;
+      }
+    }
+    const uint32_t wmask = __ballot_sync(0xffffffffu, st == 1);
+    const uint32_t smask = __ballot_sync(0xffffffffu, st == 0);
+    if ((wmask | smask) == 0u) break;
+    if (wmask != 0u && (smask == 0u || (__popc(wmask) << thr) >= __popc(wmask | smask))) {
+      if (st == 1 && s.z > 64u) {  // what ended the block?
+        if (z_no_code(s.z)) {
+          exact_ac_undo_no_code(s);
+          st = 2;
+        } else if (z_overrun(s.z)) {
+          err = HCJ_DEV_COEF_INDEX;
+          *err_pos = s.br.pos;
+          st = 3;
+        }
+      }
+      const bool have = st == 1 && s.z != 0u;  // a finished block in the lane's row
+      if (have && exact_share_may_be_wide(s) && exact_share(s, T, row) >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, s.blk);
+      const uint32_t pmask = __ballot_sync(0xffffffffu, have && leading);
+      if (pmask) warp_store_sparse(pmask, s.blk, stage_sa, lane, coefs);
+      warp_store_full(__ballot_sync(0xffffffffu, have && !leading), s.blk, stage, lane, coefs);
+      if (have) {
+        leading = false;
+        exact_next_block(s, T, bpm);
+      }
+      if (st == 1) {
+        if (s.blk + 1 >= in.nblocks_end || s.br.pos >= lim) st = 2;
+        else st = exact_dc_step(s, T, row) ? 0 : 2;
+      }
+    }
+  }
+  // the literal loop keeps the exact share of the block in progress
+  if (entered && st == 2 && s.z != 0u) s.share = exact_share(s, T, row);
+  // a partly decoded block begun by another thread: hand its coefficients over now, the literal loop
+  // stores the rest of it straight to global memory
+  const uint32_t pmask = __ballot_sync(0xffffffffu, entered && st == 2 && s.z != 0u && leading);
+  if (pmask) warp_store_sparse(pmask, s.blk, stage_sa, lane, coefs);
+  if (entered) {
+    exact_save_pred(s);
+    in.p = s.br.pos;
+    in.cz = (s.c << 8) | s.z;
+    in.blk = s.blk;
+    in.pred[0] = s.p0, in.pred[1] = s.p1, in.pred[2] = s.p2, in.pred[3] = s.p3;
+    in.share = s.share;
+    in.own_staged = s.z != 0u && !leading;
+    if (err) {  // the lane is done: leave its row clean for the next pass of this warp
+      in.valid = false;
+      uint4 *src = reinterpret_cast<uint4 *>(row);
+#pragma unroll
+      for (int j = 0; j < 8; j++) src[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  return err;
+}
 
 __device__ __forceinline__ int warp_exact_pass(const ScanCtx &sc, const SmemTables &st, const Local L, uint32_t *stage,
                                                int lane, const PassIn &in, int16_t *coefs, uint32_t *err_pos) {
   uint32_t *coefs32 = reinterpret_cast<uint32_t *>(coefs);
   const uint32_t bpm = sc.bpm;
-  uint32_t c = in.cz >> 8, z = in.cz & 0xffu, share = 0;
+  uint32_t c = in.cz >> 8, z = in.cz & 0xffu, share = in.share;
   int32_t blk = in.blk;
   bool active = in.valid && !(z != 0u && blk >= in.nblocks_end);
-  bool leading = z != 0u;  // the block in progress was begun by another thread
+  bool leading = z != 0u && !in.own_staged;  // the block in progress was begun by another thread
   uint32_t comp = st.blk_comp[c];
   Tables t = sc.tab[comp];
   const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
-  const uint32_t mine_sa = stage_sa + (uint32_t)lane * 33u * 4u;
+  const uint32_t mine_sa = stage_sa + (uint32_t)lane * HR_ROW_WORDS * 4u;
   const uint32_t quant_sa = (uint32_t)__cvta_generic_to_shared(st.quant);
   uint32_t q_sa = quant_sa + comp * 512u;
   int32_t p0 = in.pred[0], p1 = in.pred[1], p2 = in.pred[2], p3 = in.pred[3];
@@ -339,7 +505,7 @@ __device__ __forceinline__ int warp_exact_pass(const ScanCtx &sc, const SmemTabl
       const int l = __ffs((int)mask) - 1;
       mask &= mask - 1u;
       const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
-      const uint32_t sa = stage_sa + ((uint32_t)l * 33u + (uint32_t)lane) * 4u;
+      const uint32_t sa = stage_sa + ((uint32_t)l * HR_ROW_WORDS + (uint32_t)lane) * 4u;
       uint32_t w;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sa) : "memory");
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(0u) : "memory");
@@ -384,13 +550,12 @@ __global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
   for (int j = lane; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
-  uint16_t *lut_smem = reinterpret_cast<uint16_t *>(s_stage + (HR_THREADS / 32) * HR_STAGE_WORDS);
-  load_tables(st, lut_smem, b, d);
+  const FastTables T = load_tables(st, s_stage + (HR_THREADS / 32) * HR_STAGE_WORDS, b, d);
   __syncthreads();
   fill_scan_ctx(sc, st, b, d, 0);
   __syncthreads();
   HcjImageState *state = b.states + img;
-  const Local L{lut_smem, st.quant, st.blk_comp};
+  const Local L{T, st.quant, st.blk_comp};
   const bool valid = seg < d.nseg_expected && state->status == 0;
 
   const uint32_t *segs = b.seg_offs + d.seg_off;
@@ -437,8 +602,12 @@ __global__ void __launch_bounds__(HR_THREADS, 2) k_huff_restart(DecodeBatchDev b
   in.blk = (int32_t)(mcu0 * bpm) - 1;
   in.pred[0] = in.pred[1] = in.pred[2] = in.pred[3] = 0;
   in.nblocks_end = (int32_t)(mcu1 * bpm);
+  in.share = 0;
+  in.own_staged = false;
   uint32_t err_pos = 0;
-  int err = warp_exact_pass(sc, st, L, stage, lane, in, coefs, &err_pos);
+  int err = warp_exact_fast(sc, T, stage, lane, in, coefs, &err_pos);
+  if (err) raise_status(state, err, err_pos);
+  err = warp_exact_pass(sc, st, L, stage, lane, in, coefs, &err_pos);
   if (err) raise_status(state, err, err_pos);
 }
 
@@ -474,7 +643,7 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 // Undefined codes / overlong runs met while speculating are skipped deterministically; only the exact
 // pass reports them.
 // ================================================================================================
-constexpr int SPEC_THREADS = 512;
+constexpr int SPEC_THREADS = 256;
 constexpr uint32_t SPEC_BITS = 1024;
 constexpr int SPEC_PER_THREAD = 2;
 constexpr int SPEC_WINDOW = SPEC_THREADS * SPEC_PER_THREAD;
@@ -541,6 +710,65 @@ __device__ __forceinline__ void window_scan(int32_t *a, int n, int32_t *s_warp) 
   if (threadIdx.x == 0) a[n] = total;
 }
 
+// Synchronisation decode of one subsequence per lane (the semantics of subseq_sync): the fast steps run
+// warp-synchronously with the per-block work batched as in warp_exact_fast; the literal loop finishes
+// what is left (the last 32 bits of the scan, undefined codes met while speculating).
+__device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local L, bool valid, uint32_t p, uint32_t cz,
+                                                 uint32_t hi, SubResult &r) {
+  const FastTables T = L.ft;
+  const uint32_t bpm = sc.bpm;
+  const uint32_t lim = min(hi, sc.total_bits >= 32u ? sc.total_bits - 32u : 0u);
+  const int thr = fast_threshold(sc);
+  SyncLane s;
+  s.c = cz >> 8;
+  s.z = cz & 0xffu;
+  s.nstart = 0;
+  s.d0 = s.d1 = s.d2 = s.d3 = 0;
+  const bool entered = valid && p < lim;
+  s.br.init(sc.words, entered ? p : 0u);
+  s.br.pos = p;
+  sync_bind_block(s, T);
+  int st = !entered ? 2 : s.z != 0u ? 0 : 1;  // 0 = mid-block, 1 = at a block boundary, 2 = left
+  for (;;) {
+    if (st == 0) {
+      if (s.br.pos >= lim) {
+        st = 2;
+      } else {
+        sync_ac_step(s, T);
+        st = z_block_done(s.z) ? 1 : 0;
+      }
+    }
+    const uint32_t wmask = __ballot_sync(0xffffffffu, st == 1);
+    const uint32_t smask = __ballot_sync(0xffffffffu, st == 0);
+    if ((wmask | smask) == 0u) break;
+    if (wmask != 0u && (smask == 0u || (__popc(wmask) << thr) >= __popc(wmask | smask))) {
+      if (st == 1) {
+        if (z_no_code(s.z)) {
+          sync_ac_undo_no_code(s);
+          st = 2;
+        } else {
+          if (s.z != 0u) sync_next_block(s, T, bpm);
+          if (s.br.pos >= lim) st = 2;
+          else st = sync_dc_step(s, T) ? 0 : 2;
+        }
+      }
+    }
+  }
+  r.p = s.br.pos;
+  r.cz = (s.c << 8) | s.z;
+  r.nstart = s.nstart;
+  r.dcsum[0] = s.d0, r.dcsum[1] = s.d1, r.dcsum[2] = s.d2, r.dcsum[3] = s.d3;
+  if (valid && s.br.pos < hi) {
+    SubResult r2;
+    subseq_sync(sc, L, s.br.pos, r.cz, hi, r2);
+    r.p = r2.p;
+    r.cz = r2.cz;
+    r.nstart += r2.nstart;
+#pragma unroll
+    for (int k = 0; k < HCJ_MAX_COMP; k++) r.dcsum[k] += r2.dcsum[k];
+  }
+}
+
 __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   extern __shared__ uint4 s_dyn4[];
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
@@ -549,8 +777,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   uint32_t *stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15))) +
                     (threadIdx.x >> 5) * HR_STAGE_WORDS;
   for (int j = threadIdx.x & 31; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
-  uint16_t *lut_smem = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15)) +
-                                                    (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t));
+  void *lut_smem = reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15)) +
+                   (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
   __shared__ int32_t s_scan[SPEC_THREADS / 32];
   __shared__ SpecCarry carry;
 
@@ -558,7 +786,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[img];
   HcjImageState *state = b.states + img;
   const int t = threadIdx.x;
-  load_tables(st, lut_smem, b, d);
+  const FastTables T = load_tables(st, lut_smem, b, d);
   __syncthreads();
   fill_scan_ctx(sc, st, b, d, state->ent_len * 8u);
   if (t == 0) {
@@ -569,7 +797,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
   }
   __syncthreads();
   if (state->status != 0) return;
-  const Local LT{lut_smem, st.quant, st.blk_comp};
+  const Local LT{T, st.quant, st.blk_comp};
 
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = d.nblocks;
@@ -599,44 +827,52 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
     const int n = (int)min(nsub - wbase, (uint32_t)SPEC_WINDOW);
 
     // ---- A: speculative first pass
-    for (int j = t; j < n; j += SPEC_THREADS) {
-      const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {  // warp-uniform trip count
+      const int j = j0 + t;
+      const bool valid = j < n;
+      const uint32_t lo = (wbase + (valid ? j : 0)) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
       uint32_t p = lo, cz = 0;
       if (j == 0) {
         p = carry.p;
         cz = carry.cz;
       }
       SubResult r;
-      subseq_sync(sc, LT, p, cz, hi, r);
-      win.start[j] = (uint16_t)spec_pack(p, lo, cz);
-      win.end[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
-      win.nstart[j] = (int32_t)r.nstart;
+      warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
+      if (valid) {
+        win.start[j] = (uint16_t)spec_pack(p, lo, cz);
+        win.end[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
+        win.nstart[j] = (int32_t)r.nstart;
 #pragma unroll
-      for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+        for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+      }
     }
     __syncthreads();
 
     // ---- B: fix-point over the window
     for (;;) {
       int changed = 0;
-      for (int j = t; j < n; j += SPEC_THREADS) {
-        if (j == 0) continue;  // exact by construction
-        const uint32_t ns = win.end[j - 1];
-        if (ns == win.start[j]) continue;
-        const uint32_t lo = (wbase + j) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
+      for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
+        const int j = j0 + t;
+        bool valid = j < n && j > 0;  // subsequence 0 is exact by construction
+        const uint32_t ns = valid ? win.end[j - 1] : 0u;
+        valid = valid && ns != win.start[j];
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const uint32_t lo = (wbase + (valid ? j : 0)) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
         uint32_t p, cz;
         spec_unpack(ns, lo, p, cz);
         SubResult r;
-        subseq_sync(sc, LT, p, cz, hi, r);
-        win.start[j] = (uint16_t)ns;
-        const uint32_t ne = spec_pack(r.p, hi, r.cz);
-        if (ne != win.end[j]) {
-          win.end[j] = (uint16_t)ne;
-          changed = 1;
-        }
-        win.nstart[j] = (int32_t)r.nstart;
+        warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
+        if (valid) {
+          win.start[j] = (uint16_t)ns;
+          const uint32_t ne = spec_pack(r.p, hi, r.cz);
+          if (ne != win.end[j]) {
+            win.end[j] = (uint16_t)ne;
+            changed = 1;
+          }
+          win.nstart[j] = (int32_t)r.nstart;
 #pragma unroll
-        for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+          for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+        }
       }
       if (!__syncthreads_or(changed)) break;
     }
@@ -667,8 +903,12 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
       in.hi = last ? 0xffffffffu : hi;
       in.end_bits = L;
       in.nblocks_end = (int32_t)nblocks;
+      in.share = 0;
+      in.own_staged = false;
       uint32_t err_pos = 0;
-      int err = warp_exact_pass(sc, st, LT, stage, t & 31, in, coefs, &err_pos);
+      int err = warp_exact_fast(sc, T, stage, t & 31, in, coefs, &err_pos);
+      if (err) raise_status(state, err, err_pos);
+      err = warp_exact_pass(sc, st, LT, stage, t & 31, in, coefs, &err_pos);
       if (err) raise_status(state, err, err_pos);
     }
     __syncthreads();  // all reads of carry and of the window are done
