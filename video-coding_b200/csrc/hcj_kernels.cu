@@ -291,10 +291,6 @@ struct PassIn {
   bool valid;
 };
 
-// Lanes waiting at a block boundary are served once (waiting << thr) >= running lanes: thr = 2 is "a
-// quarter of the lanes"; HCJ_DEBUG bits 4..6 override it for experiments.
-__device__ __forceinline__ int fast_threshold(const ScanCtx &sc) { return (sc.debug & 0x70) ? ((sc.debug >> 4) & 7) - 1 : 2; }
-
 // Blocks shared with a neighbouring thread (cleared in global memory before the pass): the warp hands over
 // the non-zero coefficients staged in the rows of the lanes in `mask`, as 2-byte stores, and zeroes the rows.
 __device__ __forceinline__ void warp_store_sparse(uint32_t mask, int32_t blk, uint32_t stage_sa, int lane, int16_t *coefs) {
@@ -314,30 +310,29 @@ __device__ __forceinline__ void warp_store_sparse(uint32_t mask, int32_t blk, ui
 // Finished blocks staged in the rows of the lanes in `mask`: the warp writes them out four at a time, a
 // quarter-warp per block (8 lanes x 16 bytes = the 128-byte line), and zeroes the rows.  Per block that is
 // one shared-memory load, one shared-memory store and one global store wavefront, the same as a fully
-// coalesced copy, for a quarter of the instructions of a block-at-a-time loop.
+// coalesced copy, for a fraction of the instructions of a block-at-a-time loop.
 __device__ __forceinline__ void warp_store_full(uint32_t mask, int32_t blk, uint32_t *stage, int lane, int16_t *coefs) {
   const int quarter = lane >> 3, sub = lane & 7;
-  while (mask) {
-    const uint32_t m1 = mask & (mask - 1u), m2 = m1 & (m1 - 1u), m3 = m2 & (m2 - 1u);
-    const uint32_t mine = quarter == 0 ? mask : quarter == 1 ? m1 : quarter == 2 ? m2 : m3;
-    const int l = mine ? __ffs((int)mine) - 1 : 0;
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    if (((mask >> (4 * p)) & 0xfu) == 0u) continue;  // warp-uniform
+    const int l = 4 * p + quarter;
     const int32_t bidx = __shfl_sync(0xffffffffu, blk, l);
-    if (mine) {
+    if ((mask >> l) & 1u) {
       uint4 *src = reinterpret_cast<uint4 *>(stage + l * HR_ROW_WORDS) + sub;
       const uint4 v = *src;
       *src = make_uint4(0u, 0u, 0u, 0u);
       reinterpret_cast<uint4 *>(coefs + (size_t)bidx * 64)[sub] = v;
     }
-    mask = m3 & (m3 - 1u);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Fast exact pass: the straight-line steps of hcj_device.cuh, warp-synchronous.  Lanes in the middle of
-// a block decode one AC symbol per iteration; lanes at a block boundary wait until a quarter of the
-// running lanes are there (or nobody is mid-block); then, in one go, each of them writes its finished
-// block out (eight 16-byte stores from its own row), moves to the next block-in-MCU and decodes its DC
-// symbol.  Batching the per-block work keeps it out of the per-symbol instruction stream.  On return `in`
+// a block decode AC symbols; lanes at a block boundary wait until every lane is there; then, in one go,
+// the warp writes the finished blocks out (warp_store_full), and every lane moves to its next
+// block-in-MCU and decodes its DC symbol.  Batching the per-block work keeps it out of the per-symbol
+// instruction stream and runs it with all lanes active.  On return `in`
 // holds the state of every lane at the point where it left (end of its range, 32 bits before the end of
 // its data, or the symbol the literal loop has to look at); warp_exact_pass carries on from there.
 // Returns HCJ_DEV_COEF_INDEX (and the position) for a lane whose run went past coefficient 63.
@@ -348,7 +343,6 @@ __device__ __forceinline__ int warp_exact_fast(const ScanCtx &sc, const FastTabl
   const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
   int16_t *row = reinterpret_cast<int16_t *>(stage + lane * HR_ROW_WORDS);
   const uint32_t lim = min(in.hi, in.end_bits >= 32u ? in.end_bits - 32u : 0u);
-  const int thr = fast_threshold(sc);
   ExactLane s;
   s.c = in.cz >> 8;
   s.z = in.cz & 0xffu;
@@ -364,18 +358,24 @@ __device__ __forceinline__ int warp_exact_fast(const ScanCtx &sc, const FastTabl
   int err = HCJ_DEV_OK;
 
   for (;;) {
-    if (st == 0) {
-      if (s.br.pos >= lim) {
-        st = 2;
-      } else {
-        exact_ac_step(s, T, row);
-        st = z_block_done(s.z) ? 1 : 0;
+    // every lane that is mid-block decodes AC symbols until its block ends; the warp moves on when the last
+    // one is there.  (Serving boundary lanes earlier, in smaller groups, costs more instructions in the
+    // per-block code than the waiting costs here: measured.)
+    while (__any_sync(0xffffffffu, st == 0)) {
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (st == 0) {
+          if (s.br.pos >= lim) {
+            st = 2;
+          } else {
+            exact_ac_step(s, T, row);
+            st = z_block_done(s.z) ? 1 : 0;
+          }
+        }
       }
     }
-    const uint32_t wmask = __ballot_sync(0xffffffffu, st == 1);
-    const uint32_t smask = __ballot_sync(0xffffffffu, st == 0);
-    if ((wmask | smask) == 0u) break;
-    if (wmask != 0u && (smask == 0u || (__popc(wmask) << thr) >= __popc(wmask | smask))) {
+    if (!__any_sync(0xffffffffu, st == 1)) break;
+    {
       if (st == 1 && s.z > 64u) {  // what ended the block?
         if (z_no_code(s.z)) {
           exact_ac_undo_no_code(s);
@@ -718,7 +718,6 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   const FastTables T = L.ft;
   const uint32_t bpm = sc.bpm;
   const uint32_t lim = min(hi, sc.total_bits >= 32u ? sc.total_bits - 32u : 0u);
-  const int thr = fast_threshold(sc);
   SyncLane s;
   s.c = cz >> 8;
   s.z = cz & 0xffu;
@@ -730,27 +729,28 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   sync_bind_block(s, T);
   int st = !entered ? 2 : s.z != 0u ? 0 : 1;  // 0 = mid-block, 1 = at a block boundary, 2 = left
   for (;;) {
-    if (st == 0) {
-      if (s.br.pos >= lim) {
-        st = 2;
-      } else {
-        sync_ac_step(s, T);
-        st = z_block_done(s.z) ? 1 : 0;
+    while (__any_sync(0xffffffffu, st == 0)) {  // as in warp_exact_fast: AC symbols until every block in progress has ended
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (st == 0) {
+          if (s.br.pos >= lim) {
+            st = 2;
+          } else {
+            sync_ac_step(s, T);
+            st = z_block_done(s.z) ? 1 : 0;
+          }
+        }
       }
     }
-    const uint32_t wmask = __ballot_sync(0xffffffffu, st == 1);
-    const uint32_t smask = __ballot_sync(0xffffffffu, st == 0);
-    if ((wmask | smask) == 0u) break;
-    if (wmask != 0u && (smask == 0u || (__popc(wmask) << thr) >= __popc(wmask | smask))) {
-      if (st == 1) {
-        if (z_no_code(s.z)) {
-          sync_ac_undo_no_code(s);
-          st = 2;
-        } else {
-          if (s.z != 0u) sync_next_block(s, T, bpm);
-          if (s.br.pos >= lim) st = 2;
-          else st = sync_dc_step(s, T) ? 0 : 2;
-        }
+    if (!__any_sync(0xffffffffu, st == 1)) break;
+    if (st == 1) {
+      if (z_no_code(s.z)) {
+        sync_ac_undo_no_code(s);
+        st = 2;
+      } else {
+        if (s.z != 0u) sync_next_block(s, T, bpm);
+        if (s.br.pos >= lim) st = 2;
+        else st = sync_dc_step(s, T) ? 0 : 2;
       }
     }
   }
@@ -769,7 +769,7 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   }
 }
 
-__global__ void __launch_bounds__(SPEC_THREADS) k_huff_spec(DecodeBatchDev b) {
+__global__ void __launch_bounds__(SPEC_THREADS, 3) k_huff_spec(DecodeBatchDev b) {
   extern __shared__ uint4 s_dyn4[];
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
