@@ -499,9 +499,10 @@ struct FastReader {
     }
 #if defined(__CUDA_ARCH__)
     // The load writes r1 in place (no temporary + move, which would wait for the data right here): its
-    // value is first looked at two refills from now.
+    // value is first looked at two refills from now.  (Scoreboards are per warp, so the lane that refills in
+    // the next step does wait for this load: L2::128B makes that an L2 hit for 31 words out of 32.)
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.L2::128B.u32 %0, [%1];\n\t}"
         : "+r"(r1)
         : "l"(words + (np >> 5) + 3), "r"(cross));
 #else
