@@ -195,7 +195,10 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   std::vector<uint32_t> list_restart, list_spec;
   size_t file_bytes = 0, ent_bytes = 0, nsegs = 0, out_total = 0, plane_total = 0;
   uint64_t total_blocks = 0;
-  uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0;
+  uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0, max_sub_chunks = 0;
+  size_t total_sub = 0;
+  uint32_t sub_log2 = 11;
+  if (const char *e = getenv("HCJ_SUB_LOG2")) sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));  // experiments
   const int tile_mcus = 42;  // upper bound on MCUs per IDCT tile (256 threads / 6 blocks for 4:2:0)
   hcj_header *h = new (std::nothrow) hcj_header;
   if (!h) {
@@ -334,6 +337,13 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       max_segments = std::max(max_segments, d.nseg_expected);
     } else {
       list_spec.push_back((uint32_t)i);
+      // subsequences of 2^sub_log2 bits: long enough for the decoder to resynchronise inside one almost always
+      // (a couple of MCUs), short enough for one thread each to fill the GPU
+      d.sub_log2 = sub_log2;
+      d.sub_off = (uint32_t)total_sub;
+      const size_t nsub_max = (((size_t)d.ent_cap * 8) >> sub_log2) + 2;
+      total_sub += nsub_max + 1;
+      max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max + 255) / 256));
     }
     int tm_max = std::max(1, std::min(tile_mcus, 256 / d.bpm));
     uint32_t tiles = (uint32_t)((d.mcus_wide + tm_max - 1) / tm_max) * (uint32_t)d.mcus_high;
@@ -371,6 +381,14 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   BALLOC(states, HcjImageState *, sizeof(HcjImageState) * std::max(n, 1));
   BALLOC(entropy, uint8_t *, ent_bytes + 64);  // + slack: the fast readers prefetch up to 16 bytes past the data
   BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
+  if (!list_spec.empty()) {
+    BALLOC(sub_start, uint16_t *, 2 * total_sub + 16);
+    BALLOC(sub_end, uint16_t *, 2 * total_sub + 16);
+    BALLOC(sub_end2, uint16_t *, 2 * total_sub + 16);
+    BALLOC(sub_nstart, int32_t *, 4 * total_sub + 16);
+    BALLOC(sub_dc, int4 *, 16 * total_sub + 16);
+    BALLOC(sub_list, uint32_t *, 4 * total_sub + 16);
+  }
   b->coef_bytes = (size_t)total_blocks * 128;
   BALLOC(coefs, int16_t *, b->coef_bytes + 16);
   BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4 + 64);  // + slack: k_idct stages 48 bytes per tile
@@ -395,6 +413,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   for (const HcjTableSet &ts : table_sets) dv.max_pairs = std::max(dv.max_pairs, ts.npairs);
   dv.list_spec = d_ls;
   dv.n_spec = (int)list_spec.size();
+  dv.max_sub_chunks = max_sub_chunks;
   dv.max_idct_tiles = max_tiles;
   dv.tile_mcus = tile_mcus;
   dv.max_rgb_rows = max_rows;
@@ -412,7 +431,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     const char *e = getenv("HCJ_DEBUG");
     dv.debug = e ? atoi(e) : 0;
   }
-  b->kernels = 1 + (dv.n_restart ? 1 : 0) + (dv.n_spec ? 1 : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
+  b->kernels = 1 + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;

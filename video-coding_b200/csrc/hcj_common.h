@@ -87,7 +87,9 @@ struct HcjImageDesc {
   uint64_t out_bytes;
   int32_t chroma;        // 420 / 422 / 444 / 0
   int32_t width, height;
-  int32_t pad2_;
+  uint32_t sub_log2;     // scans without restart markers: log2 of the subsequence length in bits
+  uint32_t sub_off;      // index of the image's first subsequence record in the batch arrays
+  uint32_t pad2_;
 };
 
 // Written by the destuff kernel, read by the decode kernels and fetched for debugging.

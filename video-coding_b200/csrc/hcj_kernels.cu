@@ -625,41 +625,26 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 }
 
 // ================================================================================================
-// K3: scans without restart markers.  One CTA per image; subsequences of SPEC_BITS bits; windows of up to
-// SPEC_WINDOW subsequences whose decoder states live in shared memory (16 bits each: position relative to
-// the subsequence boundary, block-in-MCU, zig-zag index).  Per window:
-//   A  every subsequence is decoded from a guessed state (block 0 of an MCU, DC next), the first one
-//      from the exact state carried over from the previous window;
-//   B  fix-point over the whole window: a subsequence whose left neighbour's end state differs from the
-//      start state it last used is decoded again; rounds repeat until nothing changes.  Reads of the
-//      neighbour's state are unsynchronised within a round (chaotic relaxation): the fix-point is unique
-//      because subsequence 0 is exact, so the order of updates does not matter, and after k rounds the
-//      first k+1 subsequences are exact, so it terminates.  JPEG streams self-synchronise within a few
-//      hundred bits, but the block-in-MCU phase can take several subsequences to lock: doing the rounds
-//      over the whole window (not per 512-thread chunk) keeps their number at the length of the
-//      longest unsynchronised run instead of the sum over chunks;
-//   C  exclusive scans over the window of (blocks begun, DC sums per component) give every subsequence
-//      its first block index and DC predictors; the exact pass stores the coefficients.
-// Undefined codes / overlong runs met while speculating are skipped deterministically; only the exact
-// pass reports them.
+// K3: scans without restart markers (the reference encoder's own format): self-synchronising speculative
+// decode.  The scan of every image is cut into subsequences of 2^sub_log2 bits; a decoder state between
+// symbols is (bit position, block-in-MCU, zig-zag index), 16 bits packed relative to the subsequence
+// boundary.  Four kernels, the first, second and last of them over ALL subsequences of the batch at once
+// (one thread each, so the grid is full whatever the number of images):
+//   k_spec_sync pass 0  decodes every subsequence from a guessed state (block 0 of an MCU, DC next);
+//   k_spec_sync pass 1  decodes it again from the end state its left neighbour found in pass 0;
+//   k_spec_fix          one CTA per image: fix-point rounds over the subsequences whose left neighbour's end
+//                       state differs from the start state they last used (a compacted list, a few per cent
+//                       after pass 1: JPEG streams resynchronise within a couple of MCUs); subsequence 0 is
+//                       exact, so after k rounds the first k + 1 are and it terminates for any input.  Then
+//                       exclusive scans of (blocks begun, DC sums per component) over the image give every
+//                       subsequence its first block index and DC predictors, and the blocks shared by two
+//                       threads are cleared;
+//   k_spec_write        the exact pass: stores the coefficients (warp_exact_fast + warp_exact_pass).
+// Undefined codes / overlong runs met while speculating are skipped deterministically (subseq_sync); only
+// the exact pass reports them.  Scans of <= 16 bits, where the model's `show` bound is observable, are
+// decoded serially with the literal per-block routine (k_spec_fix).
 // ================================================================================================
 constexpr int SPEC_THREADS = 256;
-constexpr uint32_t SPEC_BITS = 1024;
-constexpr int SPEC_PER_THREAD = 2;
-constexpr int SPEC_WINDOW = SPEC_THREADS * SPEC_PER_THREAD;
-
-struct SpecCarry {
-  uint32_t p, cz;
-  int64_t nstart;
-  int32_t dc[HCJ_MAX_COMP];
-};
-
-struct SpecWindow {
-  uint16_t start[SPEC_WINDOW];       // packed state the subsequence was last decoded from
-  uint16_t end[SPEC_WINDOW];         // packed state at its end (relative to the next boundary)
-  int32_t nstart[SPEC_WINDOW + 1];   // blocks begun; after the scan: exclusive prefix (entry n = total)
-  int32_t dc[HCJ_MAX_COMP][SPEC_WINDOW + 1];
-};
 
 __device__ __forceinline__ uint32_t spec_pack(uint32_t p, uint32_t base, uint32_t cz) {
   return ((p - base) << 10) | ((cz >> 8) << 6) | (cz & 63u);
@@ -689,25 +674,6 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t *s_warp, i
     total += t;
   }
   return base + incl - v;
-}
-
-// In-place exclusive scan of a[0..n) (n <= SPEC_WINDOW), a[n] = total; every thread owns SPEC_PER_THREAD consecutive entries.
-__device__ __forceinline__ void window_scan(int32_t *a, int n, int32_t *s_warp) {
-  const int i0 = threadIdx.x * SPEC_PER_THREAD;
-  int32_t v[SPEC_PER_THREAD], sum = 0;
-#pragma unroll
-  for (int k = 0; k < SPEC_PER_THREAD; k++) {
-    v[k] = i0 + k < n ? a[i0 + k] : 0;
-    sum += v[k];
-  }
-  int32_t total;
-  int32_t run = block_excl_scan(sum, s_warp, total);
-#pragma unroll
-  for (int k = 0; k < SPEC_PER_THREAD; k++) {
-    if (i0 + k < n) a[i0 + k] = run;
-    run += v[k];
-  }
-  if (threadIdx.x == 0) a[n] = total;
 }
 
 // Synchronisation decode of one subsequence per lane (the semantics of subseq_sync): the fast steps run
@@ -769,52 +735,102 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   }
 }
 
-__global__ void __launch_bounds__(SPEC_THREADS, 3) k_huff_spec(DecodeBatchDev b) {
+// What every K3 kernel needs about its image.  Returns false if there is nothing to do for this CTA.
+struct SpecImage {
+  const HcjImageDesc *d;
+  HcjImageState *state;
+  uint32_t L, S, nsub;
+  uint16_t *start, *end, *end2;
+  int32_t *nstart;
+  int4 *dc;
+};
+__device__ __forceinline__ bool spec_image(const DecodeBatchDev &b, uint32_t list_index, SpecImage &si) {
+  const uint32_t img = b.list_spec[list_index + b.ls_lo];
+  si.d = &b.descs[img];
+  si.state = b.states + img;
+  if (si.state->status != 0) return false;
+  si.L = si.state->ent_len * 8u;
+  si.S = 1u << si.d->sub_log2;
+  si.nsub = (si.L + si.S - 1u) >> si.d->sub_log2;
+  si.start = b.sub_start + si.d->sub_off;
+  si.end = b.sub_end + si.d->sub_off;
+  si.end2 = b.sub_end2 + si.d->sub_off;
+  si.nstart = b.sub_nstart + si.d->sub_off;
+  si.dc = b.sub_dc + si.d->sub_off;
+  return true;
+}
+
+// Shared memory of the K3 kernels that only synchronise: [SmemTables][ScanCtx][tables]
+__global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_sync(DecodeBatchDev b, int pass) {
   extern __shared__ uint4 s_dyn4[];
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
-  SpecWindow &win = *reinterpret_cast<SpecWindow *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
-  uint32_t *stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15))) +
-                    (threadIdx.x >> 5) * HR_STAGE_WORDS;
-  for (int j = threadIdx.x & 31; j < HR_STAGE_WORDS; j += 32) stage[j] = 0u;
-  void *lut_smem = reinterpret_cast<char *>(&win) + ((sizeof(SpecWindow) + 15) & ~size_t(15)) +
-                   (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
-  __shared__ int32_t s_scan[SPEC_THREADS / 32];
-  __shared__ SpecCarry carry;
-
-  const uint32_t img = b.list_spec[blockIdx.x + b.ls_lo];
-  const HcjImageDesc &d = b.descs[img];
-  HcjImageState *state = b.states + img;
-  const int t = threadIdx.x;
-  const FastTables T = load_tables(st, lut_smem, b, d);
+  void *lut_smem = reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15));
+  SpecImage si;
+  if (!spec_image(b, blockIdx.y, si)) return;
+  if (si.L <= 16u || blockIdx.x * SPEC_THREADS >= si.nsub) return;
+  const FastTables T = load_tables(st, lut_smem, b, *si.d);
   __syncthreads();
-  fill_scan_ctx(sc, st, b, d, state->ent_len * 8u);
-  if (t == 0) {
-    carry.p = 0;
-    carry.cz = 0;
-    carry.nstart = 0;
-    for (int k = 0; k < HCJ_MAX_COMP; k++) carry.dc[k] = 0;
-  }
+  fill_scan_ctx(sc, st, b, *si.d, si.L);
   __syncthreads();
-  if (state->status != 0) return;
   const Local LT{T, st.quant, st.blk_comp};
 
-  const uint32_t L = sc.total_bits;
+  const uint32_t j = blockIdx.x * SPEC_THREADS + threadIdx.x;
+  bool valid = j < si.nsub;
+  const uint32_t lo = (valid ? j : 0u) << si.d->sub_log2, hi = min(lo + si.S, si.L);
+  uint32_t p = lo, cz = 0, ns = 0;
+  if (pass == 1) {
+    if (j == 0) si.end2[0] = si.end[0];  // exact by construction
+    valid = valid && j > 0;
+    ns = valid ? si.end[j - 1] : 0u;
+    // a neighbour that ended in the guessed state: pass 0 already decoded from it
+    if (valid && ns == si.start[j]) {
+      si.end2[j] = si.end[j];
+      valid = false;
+    }
+    spec_unpack(ns, lo, p, cz);
+  }
+  SubResult r;
+  warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
+  if (valid) {
+    si.start[j] = (uint16_t)(pass == 0 ? spec_pack(p, lo, cz) : ns);
+    (pass == 0 ? si.end : si.end2)[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
+    si.nstart[j] = (int32_t)r.nstart;
+    si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
+  }
+}
+
+__global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_fix(DecodeBatchDev b) {
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  void *lut_smem = reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15));
+  __shared__ int32_t s_scan[SPEC_THREADS / 32];
+  __shared__ uint32_t s_count;
+  SpecImage si;
+  if (!spec_image(b, blockIdx.x, si)) return;
+  const HcjImageDesc &d = *si.d;
+  const int t = threadIdx.x, lane = t & 31;
+  const FastTables T = load_tables(st, lut_smem, b, d);
+  __syncthreads();
+  fill_scan_ctx(sc, st, b, d, si.L);
+  __syncthreads();
+  const Local LT{T, st.quant, st.blk_comp};
   const int64_t nblocks = d.nblocks;
   int16_t *coefs = b.coefs + d.coef_off * 64;
 
-  if (L <= 16u) {
+  if (si.L <= 16u) {
     // Degenerate scans: the model's `show` bound (bitstream_reader.ml:32) is in play; decode serially.
     if (t == 0) {
       BitReader br;
-      br.init(sc.words, 0, L);
+      br.init(sc.words, 0, si.L);
       int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
       for (int64_t blk = 0; blk < nblocks; blk++) {
         uint32_t comp = st.blk_comp[blk % d.bpm];
-        int err = decode_block_exact(br, LT, sc.tab[comp], L, pred[comp], coefs + blk * 64);
+        int err = decode_block_exact(br, LT, sc.tab[comp], si.L, pred[comp], coefs + blk * 64);
         flag_wide_block(sc, blk);
         if (err) {
-          raise_status(state, err, br.pos);
+          raise_status(si.state, err, br.pos);
           break;
         }
       }
@@ -822,118 +838,140 @@ __global__ void __launch_bounds__(SPEC_THREADS, 3) k_huff_spec(DecodeBatchDev b)
     return;
   }
 
-  const uint32_t nsub = (L + SPEC_BITS - 1) / SPEC_BITS;
-  for (uint32_t wbase = 0; wbase < nsub; wbase += SPEC_WINDOW) {
-    const int n = (int)min(nsub - wbase, (uint32_t)SPEC_WINDOW);
-
-    // ---- A: speculative first pass
-    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {  // warp-uniform trip count
+  // ---- fix-point rounds over a compacted list of the subsequences that have to be decoded again
+  const int n = (int)si.nsub;
+  uint32_t *list = b.sub_list + d.sub_off;
+  for (;;) {
+    if (t == 0) s_count = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
       const int j = j0 + t;
-      const bool valid = j < n;
-      const uint32_t lo = (wbase + (valid ? j : 0)) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
-      uint32_t p = lo, cz = 0;
-      if (j == 0) {
-        p = carry.p;
-        cz = carry.cz;
+      const bool need = j >= 1 && j < n && si.end2[j - 1] != si.start[j];
+      const uint32_t mask = __ballot_sync(0xffffffffu, need);
+      if (mask) {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&s_count, (uint32_t)__popc(mask));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (need) list[at + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)j;
       }
+    }
+    __syncthreads();
+    const int nredo = (int)s_count;
+    if (nredo == 0) break;
+    for (int k0 = 0; k0 < nredo; k0 += SPEC_THREADS) {
+      const int k = k0 + t;
+      const bool valid = k < nredo;
+      const uint32_t j = valid ? list[k] : 1u;
+      const uint32_t ns = si.end2[j - 1];  // reads within a round are unsynchronised (chaotic relaxation): the fix-point is unique
+      const uint32_t lo = j << d.sub_log2, hi = min(lo + si.S, si.L);
+      uint32_t p, cz;
+      spec_unpack(ns, lo, p, cz);
       SubResult r;
       warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
       if (valid) {
-        win.start[j] = (uint16_t)spec_pack(p, lo, cz);
-        win.end[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
-        win.nstart[j] = (int32_t)r.nstart;
-#pragma unroll
-        for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
+        si.start[j] = (uint16_t)ns;
+        si.end2[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
+        si.nstart[j] = (int32_t)r.nstart;
+        si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
       }
-    }
-    __syncthreads();
-
-    // ---- B: fix-point over the window
-    for (;;) {
-      int changed = 0;
-      for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
-        const int j = j0 + t;
-        bool valid = j < n && j > 0;  // subsequence 0 is exact by construction
-        const uint32_t ns = valid ? win.end[j - 1] : 0u;
-        valid = valid && ns != win.start[j];
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        const uint32_t lo = (wbase + (valid ? j : 0)) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
-        uint32_t p, cz;
-        spec_unpack(ns, lo, p, cz);
-        SubResult r;
-        warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
-        if (valid) {
-          win.start[j] = (uint16_t)ns;
-          const uint32_t ne = spec_pack(r.p, hi, r.cz);
-          if (ne != win.end[j]) {
-            win.end[j] = (uint16_t)ne;
-            changed = 1;
-          }
-          win.nstart[j] = (int32_t)r.nstart;
-#pragma unroll
-          for (int k = 0; k < HCJ_MAX_COMP; k++) win.dc[k][j] = r.dcsum[k];
-        }
-      }
-      if (!__syncthreads_or(changed)) break;
-    }
-
-    // ---- C: prefix sums over the window, then the exact pass that stores coefficients
-    window_scan(win.nstart, n, s_scan);
-    for (int k = 0; k < d.ncomp; k++) window_scan(win.dc[k], n, s_scan);
-    __syncthreads();
-    // The last block a subsequence begins is finished by its right neighbour, whose pass may reach it
-    // first: clear it now, before anybody stores into it.
-    for (int j = t; j < n; j += SPEC_THREADS) {
-      const int32_t begun = win.nstart[j + 1] - win.nstart[j];
-      const int64_t trailing = carry.nstart + win.nstart[j] - 1 + begun;
-      if (begun > 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
-    }
-    __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {  // warp-uniform trip count
-      const int j = j0 + t;
-      PassIn in;
-      in.valid = j < n;
-      const int jj = in.valid ? j : 0;
-      const uint32_t lo = (wbase + jj) * SPEC_BITS, hi = min(lo + SPEC_BITS, L);
-      const bool last = wbase + jj == nsub - 1;
-      spec_unpack(win.start[jj], lo, in.p, in.cz);
-#pragma unroll
-      for (int k = 0; k < HCJ_MAX_COMP; k++) in.pred[k] = carry.dc[k] + (k < d.ncomp ? win.dc[k][jj] : 0);
-      in.blk = (int32_t)(carry.nstart + win.nstart[jj] - 1);
-      in.hi = last ? 0xffffffffu : hi;
-      in.end_bits = L;
-      in.nblocks_end = (int32_t)nblocks;
-      in.share = 0;
-      in.own_staged = false;
-      uint32_t err_pos = 0;
-      int err = warp_exact_fast(sc, T, stage, t & 31, in, coefs, &err_pos);
-      if (err) raise_status(state, err, err_pos);
-      err = warp_exact_pass(sc, st, LT, stage, t & 31, in, coefs, &err_pos);
-      if (err) raise_status(state, err, err_pos);
-    }
-    __syncthreads();  // all reads of carry and of the window are done
-    if (t == 0) {
-      const uint32_t hi = min((wbase + n) * SPEC_BITS, L);
-      spec_unpack(win.end[n - 1], hi, carry.p, carry.cz);
-      carry.nstart += win.nstart[n];
-      for (int k = 0; k < d.ncomp; k++) carry.dc[k] += win.dc[k][n];
     }
     __syncthreads();
   }
+
+  // ---- exclusive scans over the image (entry n = totals), in place
+  {
+    int32_t carry = 0;
+    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
+      const int j = j0 + t;
+      const int32_t v = j < n ? si.nstart[j] : 0;
+      int32_t total;
+      const int32_t ex = block_excl_scan(v, s_scan, total);
+      if (j < n) si.nstart[j] = carry + ex;
+      carry += total;
+    }
+    if (t == 0) si.nstart[n] = carry;
+    int32_t *dc32 = reinterpret_cast<int32_t *>(si.dc);
+    for (int c = 0; c < d.ncomp; c++) {
+      carry = 0;
+      for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
+        const int j = j0 + t;
+        const int32_t v = j < n ? dc32[j * 4 + c] : 0;
+        int32_t total;
+        const int32_t ex = block_excl_scan(v, s_scan, total);
+        if (j < n) dc32[j * 4 + c] = carry + ex;
+        carry += total;
+      }
+    }
+  }
+  __syncthreads();
+  // The last block a subsequence begins is finished by its right neighbour, whose pass may reach it
+  // first: clear it now, before anybody stores into it.
+  for (int j = t; j < n; j += SPEC_THREADS) {
+    const int32_t begun = si.nstart[j + 1] - si.nstart[j];
+    const int64_t trailing = (int64_t)si.nstart[j] - 1 + begun;
+    if (begun > 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
+  }
+}
+
+// Shared memory: [SmemTables][ScanCtx][stage rows][tables]
+__global__ void __launch_bounds__(SPEC_THREADS, 3) k_spec_write(DecodeBatchDev b) {
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
+  SpecImage si;
+  if (!spec_image(b, blockIdx.y, si)) return;
+  if (si.L <= 16u || blockIdx.x * SPEC_THREADS >= si.nsub) return;
+  const HcjImageDesc &d = *si.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
+  for (int k = lane; k < HR_STAGE_WORDS; k += 32) stage[k] = 0u;
+  const FastTables T = load_tables(st, s_stage + (SPEC_THREADS / 32) * HR_STAGE_WORDS, b, d);
+  __syncthreads();
+  fill_scan_ctx(sc, st, b, d, si.L);
+  __syncthreads();
+  const Local LT{T, st.quant, st.blk_comp};
+  int16_t *coefs = b.coefs + d.coef_off * 64;
+
+  const uint32_t j = blockIdx.x * SPEC_THREADS + threadIdx.x;
+  PassIn in;
+  in.valid = j < si.nsub;
+  const uint32_t jj = in.valid ? j : 0u;
+  const uint32_t lo = jj << d.sub_log2, hi = min(lo + si.S, si.L);
+  spec_unpack(si.start[jj], lo, in.p, in.cz);
+  const int4 dc = si.dc[jj];
+  in.pred[0] = dc.x, in.pred[1] = dc.y, in.pred[2] = dc.z, in.pred[3] = dc.w;
+  in.blk = si.nstart[jj] - 1;
+  in.hi = jj == si.nsub - 1 ? 0xffffffffu : hi;
+  in.end_bits = si.L;
+  in.nblocks_end = (int32_t)d.nblocks;
+  in.share = 0;
+  in.own_staged = false;
+  uint32_t err_pos = 0;
+  int err = warp_exact_fast(sc, T, stage, lane, in, coefs, &err_pos);
+  if (err) raise_status(si.state, err, err_pos);
+  err = warp_exact_pass(sc, st, LT, stage, lane, in, coefs, &err_pos);
+  if (err) raise_status(si.state, err, err_pos);
 }
 
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.ls_hi <= b.ls_lo) return;
-  const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
-                      ((sizeof(SpecWindow) + 15) & ~size_t(15)) + (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t) +
-                      lut_smem_bytes(b);
+  if (b.ls_hi <= b.ls_lo || b.max_sub_chunks == 0) return;
+  const size_t base = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + lut_smem_bytes(b);
+  const size_t smem_write = base + (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
   static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_huff_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  if (smem_write > configured) {
+    cudaFuncSetAttribute(k_spec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    cudaFuncSetAttribute(k_spec_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    cudaFuncSetAttribute(k_spec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write);
+    configured = smem_write;
   }
-  k_huff_spec<<<b.ls_hi - b.ls_lo, SPEC_THREADS, smem, s>>>(b);
+  const dim3 grid(b.max_sub_chunks, b.ls_hi - b.ls_lo);
+  k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 0);
+  k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 1);
+  k_spec_fix<<<b.ls_hi - b.ls_lo, SPEC_THREADS, base, s>>>(b);
+  k_spec_write<<<grid, SPEC_THREADS, smem_write, s>>>(b);
 }
+int huff_spec_kernel_count() { return 4; }
 
 // ================================================================================================
 // K5: fused dequantise + inverse zig-zag + Chen IDCT + clip/level shift + store (+ crop).

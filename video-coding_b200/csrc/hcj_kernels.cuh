@@ -30,6 +30,14 @@ struct DecodeBatchDev {
   uint32_t max_pairs;             // max (dc, ac) table pairs any image uses (sizes the LUT shared memory)
   const uint32_t *list_spec;      // images decoded speculatively (no restart markers)
   int n_spec;
+  // per subsequence of those images (index = HcjImageDesc::sub_off + subsequence):
+  uint16_t *sub_start;            // packed decoder state the subsequence was last decoded from
+  uint16_t *sub_end;              // packed state at its end after the first pass
+  uint16_t *sub_end2;             // ... after the later passes (the current one)
+  int32_t *sub_nstart;            // blocks begun; after the scan: exclusive prefix within the image
+  int4 *sub_dc;                   // DC differential sums per scan component; after the scan: exclusive prefix
+  uint32_t *sub_list;             // scratch: subsequences to decode again in the current fix-point round
+  uint32_t max_sub_chunks;        // max over list_spec of ceil(subsequences / 256)
   uint32_t max_idct_tiles;        // max over images of tiles_per_row * mcus_high
   int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
   uint32_t max_rgb_rows;          // max image height (RGB mode)
@@ -45,6 +53,7 @@ struct DecodeBatchDev {
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
+int huff_spec_kernel_count();
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s);
 void launch_rgb(const DecodeBatchDev &b, cudaStream_t s);
 void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
