@@ -193,6 +193,9 @@ int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t 
  * ms[0..*nstages) in launch order and synchronises.  Stage names: hcj_decode_stage_name(i). */
 int hcj_batch_decode_stages(hcj_ctx *ctx, hcj_batch *b, float *ms, int capacity, int *nstages);
 const char *hcj_decode_stage_name(int i);
+/* Device time of the latest hcj_encode_batch on this context: from the first kernel (frames already in HBM)
+ * to the last one (files complete in HBM), including the one host round trip that sizes the byte buffers. */
+int hcj_encode_last_device_ms(hcj_ctx *ctx, float *ms);
 /* ms between two points on the context's stream */
 int hcj_timer_start(hcj_ctx *ctx);
 int hcj_timer_stop(hcj_ctx *ctx, float *ms); /* synchronises */

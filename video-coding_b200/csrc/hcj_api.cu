@@ -105,6 +105,8 @@ int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out) {
   }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  cudaEventCreate(&c->enc0);
+  cudaEventCreate(&c->enc1);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   *out = c;
   return HCJ_OK;
@@ -117,6 +119,8 @@ void hcj_ctx_destroy(hcj_ctx *c) {
   for (auto &f : c->pool) cudaFree(f.p);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->enc0) cudaEventDestroy(c->enc0);
+  if (c->enc1) cudaEventDestroy(c->enc1);
   for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -243,34 +243,57 @@ __device__ __forceinline__ void seg_raw_range(const EncodeBatchDev &e, const uin
   nbytes = (P[next] - P[first] + 7u) >> 3;
 }
 
+// A unit = one warp's share of a segment: the whole segment when restart intervals keep segments short,
+// STUFF_CHUNK raw bytes of it otherwise (a scan without restart markers is one segment per frame).
+constexpr uint32_t STUFF_CHUNK = 1024;
+__device__ __forceinline__ void unit_raw_range(const EncodeBatchDev &e, const uint32_t *P, uint32_t unit, uint32_t &seg,
+                                               uint32_t &byte0, uint32_t &nbytes, bool &last_of_seg) {
+  seg = unit / e.seg_chunks;
+  const uint32_t chunk = unit - seg * e.seg_chunks;
+  uint32_t b0, n;
+  seg_raw_range(e, P, seg, b0, n);
+  last_of_seg = chunk + 1 == e.seg_chunks;
+  if (e.seg_chunks > 1) {
+    const uint32_t lo = min(chunk * STUFF_CHUNK, n), hi = min(lo + STUFF_CHUNK, n);
+    byte0 = b0 + lo;
+    nbytes = hi - lo;
+  } else {
+    byte0 = b0;
+    nbytes = n;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_seg_count(EncodeBatchDev e) {
-  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31;
-  if (seg >= e.nseg) return;
+  if (unit >= e.nseg * e.seg_chunks) return;
   const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
-  uint32_t byte0, nbytes;
-  seg_raw_range(e, P, seg, byte0, nbytes);
+  uint32_t seg, byte0, nbytes;
+  bool last;
+  unit_raw_range(e, P, unit, seg, byte0, nbytes, last);
   const uint8_t *raw = e.raw + (uint64_t)frame * e.raw_stride + byte0;
   uint32_t ff = 0;
   for (uint32_t i = lane; i < nbytes; i += 32) ff += raw[i] == 0xffu;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) ff += __shfl_xor_sync(0xffffffffu, ff, s);
-  if (lane == 0) e.seg_bytes[(uint64_t)frame * (e.nseg + 1) + seg] = nbytes + ff;
+  if (lane == 0) e.seg_bytes[(uint64_t)frame * (e.nseg * e.seg_chunks + 1) + unit] = nbytes + ff;
 }
 
-// ---- K8b: per frame, exclusive scan of segment sizes (+2 bytes of RSTn after each but the last),
+// ---- K8b: per frame, exclusive scan of the unit sizes (+2 bytes of RSTn after each segment but the last),
 //      starting after the header; copies the header; writes the frame's total length -------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_seg_scan(EncodeBatchDev e) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t frame = blockIdx.x;
-  uint32_t *sb = e.seg_bytes + (uint64_t)frame * (e.nseg + 1);
+  const uint32_t nunits = e.nseg * e.seg_chunks;
+  uint32_t *sb = e.seg_bytes + (uint64_t)frame * (nunits + 1);
   uint8_t *out = e.out + (uint64_t)frame * e.out_stride;
   for (uint32_t i = threadIdx.x; i < e.header_len; i += SCAN_THREADS) out[i] = e.header[i];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t carry = e.header_len;
-  for (uint32_t base = 0; base < e.nseg; base += SCAN_THREADS) {
+  for (uint32_t base = 0; base < nunits; base += SCAN_THREADS) {
     uint32_t i = base + threadIdx.x;
-    uint32_t v = i < e.nseg ? sb[i] + (i + 1 < e.nseg ? 2u : 0u) : 0;
+    const bool rst = i < nunits && (i + 1) % e.seg_chunks == 0 && (i + 1) / e.seg_chunks < e.nseg;
+    uint32_t v = i < nunits ? sb[i] + (rst ? 2u : 0u) : 0;
     uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -286,30 +309,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seg_scan(EncodeBatchDev e) {
       if (k < warp) wbase += t;
       total += t;
     }
-    if (i < e.nseg) sb[i] = carry + wbase + incl - v;
+    if (i < nunits) sb[i] = carry + wbase + incl - v;
     carry += total;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    sb[e.nseg] = carry;
+    sb[nunits] = carry;
     out[carry] = 0xff;  // complete_and_write_eoi (encoder.ml:507-510)
     out[carry + 1] = 0xd9;
     e.out_len[frame] = carry + 2;
   }
 }
 
-// ---- K8c: copy with byte stuffing; one warp per segment ---------------------------------------------
+// ---- K8c: copy with byte stuffing; one warp per unit ------------------------------------------------
 __global__ void __launch_bounds__(128) k_stuff(EncodeBatchDev e) {
-  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31;
-  if (seg >= e.nseg) return;
+  const uint32_t nunits = e.nseg * e.seg_chunks;
+  if (unit >= nunits) return;
   const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
-  const uint32_t *sb = e.seg_bytes + (uint64_t)frame * (e.nseg + 1);
-  uint32_t byte0, nbytes;
-  seg_raw_range(e, P, seg, byte0, nbytes);
+  const uint32_t *sb = e.seg_bytes + (uint64_t)frame * (nunits + 1);
+  uint32_t seg, byte0, nbytes;
+  bool last;
+  unit_raw_range(e, P, unit, seg, byte0, nbytes, last);
   const uint8_t *raw = e.raw + (uint64_t)frame * e.raw_stride + byte0;
   uint8_t *out = e.out + (uint64_t)frame * e.out_stride;
-  uint32_t opos = sb[seg];
+  uint32_t opos = sb[unit];
   for (uint32_t base = 0; base < nbytes; base += 32 * 8) {  // 8 bytes per lane per round
     uint32_t i0 = base + lane * 8;
     uint8_t v[8];
@@ -337,7 +362,7 @@ __global__ void __launch_bounds__(128) k_stuff(EncodeBatchDev e) {
       }
     opos += total;
   }
-  if (lane == 0 && seg + 1 < e.nseg) {  // stated extension: RSTn, n = segment index mod 8
+  if (lane == 0 && last && seg + 1 < e.nseg) {  // stated extension: RSTn, n = segment index mod 8
     out[opos] = 0xff;
     out[opos + 1] = (uint8_t)(0xd0 + (seg & 7u));
   }
@@ -367,7 +392,7 @@ static void launch_bit_lengths(const EncodeBatchDev &e, int *d_status, uint32_t 
 static void launch_entropy(const EncodeBatchDev &e, cudaStream_t s) {
   dim3 gb((e.nblocks + 127) / 128, e.n);
   k_pack<<<gb, 128, 0, s>>>(e);
-  dim3 gs((e.nseg + 3) / 4, e.n);
+  dim3 gs((e.nseg * e.seg_chunks + 3) / 4, e.n);
   k_seg_count<<<gs, 128, 0, s>>>(e);
   k_seg_scan<<<e.n, SCAN_THREADS, 0, s>>>(e);
   k_stuff<<<gs, 128, 0, s>>>(e);
@@ -448,7 +473,6 @@ int setup_encode(hcj_ctx *c, int n, int width, int height, int chroma, int quali
   alloc((void **)&S->d_status, 4 * (size_t)std::max(n, 1));
   if (entropy) {
     alloc((void **)&e.blk_bits, (uint64_t)n * (e.nblocks + 1) * 4);
-    alloc((void **)&e.seg_bytes, (uint64_t)n * (e.nseg + 1) * 4);
     alloc((void **)&e.out_len, 4 * (size_t)std::max(n, 1));
   }
   if (st != HCJ_OK) return st;
@@ -513,8 +537,10 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
                           cudaMemcpyHostToDevice, s);
   std::vector<uint32_t> lens(std::max(n, 1));
   std::vector<int> dev_status(std::max(n, 1), 0);
+  c->enc_timed = false;
   if (err == cudaSuccess && n > 0) {
     // phase 1: coefficients and the bit length of every block; the totals size the byte buffers
+    cudaEventRecord(c->enc0, s);
     hcjk::launch_encode(e, s);
     hcjk::launch_bit_lengths(e, S.d_status, e.out_len, s);
     err = cudaGetLastError();
@@ -524,9 +550,12 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
     for (int i = 0; i < n; i++) max_bits = std::max<uint64_t>(max_bits, lens[i]);
     e.raw_stride = hcj::align_up(max_bits / 8 + e.nseg + 64, 256);
     e.out_stride = hcj::align_up(e.header_len + 2 * e.raw_stride + 2ull * e.nseg + 16, 256);  // every byte stuffed
+    e.seg_chunks = e.nseg == 1 ? (uint32_t)((e.raw_stride + hcjk::STUFF_CHUNK - 1) / hcjk::STUFF_CHUNK) : 1u;
     if (err == cudaSuccess) {
       st = c->alloc((void **)&e.raw, (uint64_t)n * e.raw_stride);
       if (st == HCJ_OK) S.owned.push_back(e.raw);
+      if (st == HCJ_OK) st = c->alloc((void **)&e.seg_bytes, (uint64_t)n * ((uint64_t)e.nseg * e.seg_chunks + 1) * 4);
+      if (st == HCJ_OK) S.owned.push_back(e.seg_bytes);
       if (st == HCJ_OK) st = c->alloc((void **)&e.out, (uint64_t)n * e.out_stride);
       if (st == HCJ_OK) S.owned.push_back(e.out);
     }
@@ -539,6 +568,8 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
     if (err == cudaSuccess) {
       hcjk::launch_entropy(e, s);
       err = cudaGetLastError();
+      cudaEventRecord(c->enc1, s);
+      c->enc_timed = err == cudaSuccess;
     }
     if (err == cudaSuccess) err = cudaMemcpyAsync(lens.data(), e.out_len, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
     if (err == cudaSuccess) err = cudaMemcpyAsync(dev_status.data(), S.d_status, 4 * (size_t)n, cudaMemcpyDeviceToHost, s);
@@ -555,6 +586,14 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
   }
   teardown_encode(c, &S);
   return err == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)err;
+}
+
+int hcj_encode_last_device_ms(hcj_ctx *c, float *ms) {
+  if (!c || !ms) return HCJ_ERR_INVALID_ARG;
+  if (!c->enc_timed) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaEventSynchronize(c->enc1));
+  CU_TRY(cudaEventElapsedTime(ms, c->enc0, c->enc1));
+  return HCJ_OK;
 }
 
 int hcj_encode_quantized(hcj_ctx *c, const uint8_t *yuv, int width, int height, int chroma, int quality, int16_t *quant,

@@ -27,6 +27,8 @@ struct hcj_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t enc0 = nullptr, enc1 = nullptr;  // around the device work of the latest hcj_encode_batch
+  bool enc_timed = false;
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the kernels of the next chunk
   std::vector<cudaEvent_t> chunk_events;
   std::vector<hcj::FreeBlock> pool;  // device memory recycled between batches (grow-only)

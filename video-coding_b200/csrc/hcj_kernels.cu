@@ -694,29 +694,35 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   s.br.pos = p;
   sync_bind_block(s, T);
   int st = !entered ? 2 : s.z != 0u ? 0 : 1;  // 0 = mid-block, 1 = at a block boundary, 2 = left
+  // Unlike the exact pass, the per-block code is light here (no write-out), and when decoding from a
+  // guessed state the "blocks" of the lanes are of wildly different lengths: lanes at a block boundary are
+  // served as soon as a quarter of the running lanes are waiting (HCJ_DEBUG bits 4..6 change the fraction).
+  const int thr = (sc.debug & 0x70) ? ((sc.debug >> 4) & 7) - 1 : 2;
   for (;;) {
-    while (__any_sync(0xffffffffu, st == 0)) {  // as in warp_exact_fast: AC symbols until every block in progress has ended
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (st == 0) {
-          if (s.br.pos >= lim) {
-            st = 2;
-          } else {
-            sync_ac_step(s, T);
-            st = z_block_done(s.z) ? 1 : 0;
-          }
+    for (int u = 0; u < 2; u++) {
+      if (st == 0) {
+        if (s.br.pos >= lim) {
+          st = 2;
+        } else {
+          sync_ac_step(s, T);
+          st = z_block_done(s.z) ? 1 : 0;
         }
       }
     }
-    if (!__any_sync(0xffffffffu, st == 1)) break;
-    if (st == 1) {
-      if (z_no_code(s.z)) {
-        sync_ac_undo_no_code(s);
-        st = 2;
-      } else {
-        if (s.z != 0u) sync_next_block(s, T, bpm);
-        if (s.br.pos >= lim) st = 2;
-        else st = sync_dc_step(s, T) ? 0 : 2;
+    const uint32_t wmask = __ballot_sync(0xffffffffu, st == 1);
+    const uint32_t smask = __ballot_sync(0xffffffffu, st == 0);
+    if ((wmask | smask) == 0u) break;
+    if (wmask != 0u && (smask == 0u || (__popc(wmask) << thr) >= __popc(wmask | smask))) {
+      if (st == 1) {
+        if (z_no_code(s.z)) {
+          sync_ac_undo_no_code(s);
+          st = 2;
+        } else {
+          if (s.z != 0u) sync_next_block(s, T, bpm);
+          if (s.br.pos >= lim) st = 2;
+          else st = sync_dc_step(s, T) ? 0 : 2;
+        }
       }
     }
   }

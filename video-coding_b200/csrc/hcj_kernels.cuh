@@ -74,6 +74,7 @@ struct EncodeBatchDev {
   uint32_t nblocks;           // per frame
   uint32_t restart_interval;  // 0 = none
   uint32_t nseg;              // segments per frame (1 if no restart)
+  uint32_t seg_chunks;        // byte-stuffing work units per segment (a lone segment is cut into 1 KiB chunks)
   uint8_t blk_comp[HCJ_MAX_BPM + 2], blk_bx[HCJ_MAX_BPM + 2], blk_by[HCJ_MAX_BPM + 2];
   const uint8_t *src;         // [n] frames
   const uint16_t *qt;         // [2][64] zig-zag
@@ -82,7 +83,7 @@ struct EncodeBatchDev {
   const uint32_t *ac_codes;   // [2][256]
   int16_t *quant;             // [n][nblocks][64] zig-zag, DC absolute
   uint32_t *blk_bits;         // [n][nblocks] bit length of each block's code, later exclusive offsets per segment
-  uint32_t *seg_bytes;        // [n][nseg] stuffed byte length of every segment
+  uint32_t *seg_bytes;        // [n][nseg * seg_chunks + 1] stuffed byte length of every unit, later exclusive offsets
   uint8_t *raw;               // [n][raw_stride] unstuffed packed bits, segments byte-aligned
   uint64_t raw_stride;
   uint8_t *out;               // [n][out_stride] finished files

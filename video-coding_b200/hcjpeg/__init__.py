@@ -169,6 +169,7 @@ _SIGS = {
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
     "hcj_batch_decode_stages": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
     "hcj_decode_stage_name": (C.c_char_p, [C.c_int]),
+    "hcj_encode_last_device_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "hcj_timer_start": (C.c_int, [C.c_void_p]),
     "hcj_timer_stop": (C.c_int, [C.c_void_p, _P(C.c_float)]),
 }
