@@ -108,6 +108,7 @@ int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out) {
   cudaEventCreate(&c->enc0);
   cudaEventCreate(&c->enc1);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
   *out = c;
   return HCJ_OK;
 }
@@ -123,6 +124,8 @@ void hcj_ctx_destroy(hcj_ctx *c) {
   if (c->enc1) cudaEventDestroy(c->enc1);
   for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -177,8 +180,31 @@ void hcj_batch_destroy(hcj_ctx *c, hcj_batch *b) {
   delete b;
 }
 
-int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
-                     int *status, hcj_batch **out) {
+// Copies the compressed files of images [lo, hi) to the device on `s`, merging images that are adjacent in
+// host memory with matching padding into one copy.
+static cudaError_t upload_files(const hcj_batch *b, const uint8_t *const *jpeg, const size_t *len, int lo, int hi,
+                                cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  uint8_t *d_files = const_cast<uint8_t *>(b->dev.files);
+  for (int i = lo; i < hi && e == cudaSuccess;) {
+    if (!b->descs[i].valid) {
+      i++;
+      continue;
+    }
+    int j = i;
+    size_t bytes = len[i];
+    while (j + 1 < hi && b->descs[j + 1].valid && jpeg[j + 1] == jpeg[i] + (b->descs[j + 1].file_off - b->descs[i].file_off)) {
+      j++;
+      bytes = (size_t)(b->descs[j].file_off - b->descs[i].file_off) + len[j];
+    }
+    e = cudaMemcpyAsync(d_files + b->descs[i].file_off, jpeg[i], bytes, cudaMemcpyHostToDevice, s);
+    i = j + 1;
+  }
+  return e;
+}
+
+static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                        int *status, hcj_batch **out, bool with_files) {
   if (!c || !out || n < 0 || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > 2) return HCJ_ERR_INVALID_ARG;
   *out = nullptr;
   CU_TRY(cudaSetDevice(c->device));
@@ -200,7 +226,8 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   size_t file_bytes = 0, ent_bytes = 0, nsegs = 0, out_total = 0, plane_total = 0;
   uint64_t total_blocks = 0;
   uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0, max_sub_chunks = 0;
-  size_t total_sub = 0;
+  size_t total_sub = 0, total_ds_tiles = 0;
+  uint32_t max_ds_tiles = 0;
   uint32_t sub_log2 = 11;
   if (const char *e = getenv("HCJ_SUB_LOG2")) sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));  // experiments
   const int tile_mcus = 42;  // upper bound on MCUs per IDCT tile (256 threads / 6 blocks for 4:2:0)
@@ -280,6 +307,13 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     d.scan_start = (uint32_t)h->scan_byte_pos;
     if (d.scan_start > d.file_len) d.scan_start = d.file_len;
     file_bytes += align_up(len[i] + 16, 16);
+    d.ds_off = (uint32_t)total_ds_tiles;
+    {
+      const uint32_t base0 = d.scan_start & ~15u;
+      const uint32_t nt = d.file_len > base0 ? (d.file_len - base0 + 4095) / 4096 : 0;
+      total_ds_tiles += nt;
+      max_ds_tiles = std::max(max_ds_tiles, nt);
+    }
     d.ent_off = ent_bytes;
     d.ent_cap = (uint32_t)align_up(len[i] - d.scan_start + 32, 16);
     ent_bytes += d.ent_cap;
@@ -385,6 +419,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   BALLOC(states, HcjImageState *, sizeof(HcjImageState) * std::max(n, 1));
   BALLOC(entropy, uint8_t *, ent_bytes + 64);  // + slack: the fast readers prefetch up to 16 bytes past the data
   BALLOC(seg_offs, uint32_t *, 4 * (nsegs + 1));
+  BALLOC(ds_tiles, hcjk::DsTile *, 8 * (total_ds_tiles + 1));
   if (!list_spec.empty()) {
     BALLOC(sub_start, uint16_t *, 2 * total_sub + 16);
     BALLOC(sub_end, uint16_t *, 2 * total_sub + 16);
@@ -418,6 +453,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   dv.list_spec = d_ls;
   dv.n_spec = (int)list_spec.size();
   dv.max_sub_chunks = max_sub_chunks;
+  dv.max_ds_tiles = max_ds_tiles;
   dv.max_idct_tiles = max_tiles;
   dv.tile_mcus = tile_mcus;
   dv.max_rgb_rows = max_rows;
@@ -435,7 +471,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     const char *e = getenv("HCJ_DEBUG");
     dv.debug = e ? atoi(e) : 0;
   }
-  b->kernels = 1 + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;
@@ -450,21 +486,7 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   up(d_qt, qt_pool.data(), 4 * qt_pool.size());
   up(d_lr, list_restart.data(), 4 * list_restart.size());
   up(d_ls, list_spec.data(), 4 * list_spec.size());
-  // compressed files: merge copies of images that are adjacent in host memory with matching padding
-  for (int i = 0; i < n && e == cudaSuccess;) {
-    if (!b->descs[i].valid) {
-      i++;
-      continue;
-    }
-    int j = i;
-    size_t bytes = len[i];
-    while (j + 1 < n && b->descs[j + 1].valid && jpeg[j + 1] == jpeg[i] + (b->descs[j + 1].file_off - b->descs[i].file_off)) {
-      j++;
-      bytes = (size_t)(b->descs[j].file_off - b->descs[i].file_off) + len[j];
-    }
-    up(d_files + b->descs[i].file_off, jpeg[i], bytes);
-    i = j + 1;
-  }
+  if (e == cudaSuccess && with_files) e = upload_files(b, jpeg, len, 0, n, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // host staging vectors go out of scope
   if (e != cudaSuccess) {
     hcj_batch_destroy(c, b);
@@ -472,6 +494,11 @@ int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   }
   *out = b;
   return HCJ_OK;
+}
+
+int hcj_batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
+                     int *status, hcj_batch **out) {
+  return batch_create(c, jpeg, len, n, mode, flags, status, out, true);
 }
 
 int hcj_batch_count_kernels(const hcj_batch *b) { return b ? b->kernels : 0; }
@@ -574,14 +601,16 @@ int hcj_batch_device_output(hcj_batch *b, int i, void **dptr, size_t *bytes) {
 // end-to-end time: 3 MB out per 0.4 MB in for 1080p 4:2:0).
 int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      uint8_t *const *out, const size_t *out_capacity, int *status) {
+  // Three streams: the files of chunk k + 1 go up while the kernels of chunk k run and the frames of chunk
+  // k - 1 come down; PCIe is full duplex and the kernels are a small fraction of either transfer.
   hcj_batch *b = nullptr;
-  int st = hcj_batch_create(c, jpeg, len, n, mode, flags, status, &b);
+  int st = batch_create(c, jpeg, len, n, mode, flags, status, &b, false);
   if (st != HCJ_OK) return st;
   if (n > 0 && (!out || !out_capacity)) {
     hcj_batch_destroy(c, b);
     return HCJ_ERR_INVALID_ARG;
   }
-  cudaStream_t s = c->stream, cs = c->copy_stream;
+  cudaStream_t s = c->stream, cs = c->copy_stream, us = c->up_stream;
   cudaError_t e = cudaSuccess;
   const int chunk = std::max(16, std::min(128, (n + 7) / 8));
   const int nchunks = n ? (n + chunk - 1) / chunk : 0;
@@ -590,8 +619,17 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
     c->chunk_events.push_back(ev);
   }
+  while ((int)c->up_events.size() < nchunks + 1) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
+    c->up_events.push_back(ev);
+  }
   std::vector<int> host_st(b->host_status);
-  if (n > 0 && (int)c->chunk_events.size() >= nchunks + 1) {
+  if (n > 0 && (int)c->chunk_events.size() >= nchunks + 1 && (int)c->up_events.size() >= nchunks + 1) {
+    for (int k = 0; k < nchunks && e == cudaSuccess; k++) {
+      e = upload_files(b, jpeg, len, k * chunk, std::min(n, (k + 1) * chunk), us);
+      if (e == cudaSuccess) e = cudaEventRecord(c->up_events[k], us);
+    }
     e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * n, s);
     const int kmode = mode == HCJ_OUT_YUV ? 0 : mode == HCJ_OUT_PLANES ? 1 : 2;
@@ -606,6 +644,8 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       dv.ls_lo = (uint32_t)ls;
       while (ls < b->list_spec.size() && b->list_spec[ls] < dv.img_hi) ls++;
       dv.ls_hi = (uint32_t)ls;
+      e = cudaStreamWaitEvent(s, c->up_events[k], 0);
+      if (e != cudaSuccess) break;
       hcjk::launch_destuff(dv, s);
       hcjk::launch_huff_restart(dv, s);
       hcjk::launch_huff_spec(dv, s);
@@ -614,13 +654,24 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       e = cudaGetLastError();
       if (e == cudaSuccess) e = cudaEventRecord(c->chunk_events[k], s);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, c->chunk_events[k], 0);
-      for (uint32_t i = dv.img_lo; i < dv.img_hi && e == cudaSuccess; i++) {
-        if (host_st[i] != HCJ_OK) continue;
-        if (!out[i] || out_capacity[i] < b->out_bytes[i]) {
-          host_st[i] = HCJ_ERR_BUFFER_TOO_SMALL;
+      for (uint32_t i = dv.img_lo; i < dv.img_hi; i++)
+        if (host_st[i] == HCJ_OK && (!out[i] || out_capacity[i] < b->out_bytes[i])) host_st[i] = HCJ_ERR_BUFFER_TOO_SMALL;
+      for (uint32_t i = dv.img_lo; i < dv.img_hi && e == cudaSuccess;) {
+        if (host_st[i] != HCJ_OK) {
+          i++;
           continue;
         }
-        e = cudaMemcpyAsync(out[i], b->dev.out + b->descs[i].out_off, b->out_bytes[i], cudaMemcpyDeviceToHost, cs);
+        // frames that are laid out in the caller's memory like in the device buffer leave in one copy
+        uint32_t j = i;
+        size_t bytes = b->out_bytes[i];
+        while (j + 1 < dv.img_hi && host_st[j + 1] == HCJ_OK &&
+               out[j + 1] == out[i] + (b->descs[j + 1].out_off - b->descs[i].out_off) &&
+               out_capacity[j] >= (size_t)(b->descs[j + 1].out_off - b->descs[j].out_off)) {
+          j++;
+          bytes = (size_t)(b->descs[j].out_off - b->descs[i].out_off) + b->out_bytes[j];
+        }
+        e = cudaMemcpyAsync(out[i], b->dev.out + b->descs[i].out_off, bytes, cudaMemcpyDeviceToHost, cs);
+        i = j + 1;
       }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(cs);

@@ -89,7 +89,7 @@ struct HcjImageDesc {
   int32_t width, height;
   uint32_t sub_log2;     // scans without restart markers: log2 of the subsequence length in bits
   uint32_t sub_off;      // index of the image's first subsequence record in the batch arrays
-  uint32_t pad2_;
+  uint32_t ds_off;       // index of the image's first destuff tile record
 };
 
 // Written by the destuff kernel, read by the decode kernels and fetched for debugging.

@@ -22,11 +22,19 @@ namespace hcjk {
 using namespace hcjdev;
 
 // ================================================================================================
-// K1: destuff + marker scan.  One CTA per image walks the scan in 4 KiB tiles; within a tile every
-// thread classifies 16 bytes from (previous byte, byte) pairs exactly as the model's recursive
-// search_for_marker does, a block scan turns the keep flags into output offsets.
+// K1: destuff + marker scan (extract_entropy_coded_bits, decoder.ml:261-281, + RSTn splitting).
+// The scan of every image is cut into 4 KiB tiles; a byte's fate depends only on itself and its
+// predecessor, exactly as in the model's recursive search_for_marker, so tiles are independent:
+//   k_destuff_count  per tile: bytes kept, restart markers, position of the first terminating marker
+//   k_destuff_scan   per image: the first tile with a terminator ends the scan; exclusive scan of the
+//                    counts before it -> every tile's output offset and first interval index; image state
+//   k_destuff_write  per tile: compacts its bytes (block scan), stages them in shared memory at the same
+//                    16-byte phase as their destination and writes aligned 16-byte words (+ the partial
+//                    words at both ends byte by byte); interval start offsets go to seg_offs
+// All three run over (tile, image) grids, so one large image fills the GPU as well as many small ones.
 // ================================================================================================
 constexpr int DS_THREADS = 256;
+constexpr uint32_t DS_TILE = DS_THREADS * 16;
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -37,140 +45,246 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
+// The 16 bytes of one thread classified: bit i of `emit` = byte i is kept (an FF 00 pair keeps its FF at
+// the 00), of `mark` = byte i is the second byte of a restart marker, of `term` = of any other marker.
+struct DsClass {
+  uint32_t w[4];
+  uint32_t emit, mark, term, ffmask;
+};
+__device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off, uint32_t start, uint32_t flen, bool restart,
+                                               uint8_t *s_last, int tid) {
+  DsClass c;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (off < flen) v = __ldg(reinterpret_cast<const uint4 *>(file + off));
+  c.w[0] = v.x, c.w[1] = v.y, c.w[2] = v.z, c.w[3] = v.w;
+  s_last[tid] = (uint8_t)(v.w >> 24);
+  __syncthreads();
+  uint32_t prev = tid == 0 ? (off > start && off - 1 < flen ? (uint32_t)__ldg(file + off - 1) : 0u) : s_last[tid - 1];
+  c.emit = c.mark = c.term = c.ffmask = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    uint32_t ch = (c.w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+    uint32_t pos = off + i;
+    uint32_t p = pos == start ? 0u : prev;  // the model starts with prev = '\x00' (decoder.ml:279)
+    bool in = pos >= start && pos < flen;
+    if (in) {
+      if (p == 0xffu) {
+        if (ch == 0u) {
+          c.emit |= 1u << i;
+          c.ffmask |= 1u << i;  // this slot emits the deferred FF
+        } else if (restart && (ch & 0xf8u) == 0xd0u) {
+          c.mark |= 1u << i;
+        } else {
+          c.term |= 1u << i;
+        }
+      } else if (ch != 0xffu) {
+        c.emit |= 1u << i;
+      }
+    }
+    prev = ch;
+  }
+  return c;
+}
+// first terminator of the tile (block-wide min), 0xffffffff if none; drops everything at or after it
+__device__ __forceinline__ uint32_t ds_cut_at_terminator(DsClass &c, uint32_t off, uint32_t *s_min, int lane, int warp) {
+  uint32_t tpos = c.term ? off + (uint32_t)__ffs((int)c.term) - 1u : 0xffffffffu;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) tpos = min(tpos, __shfl_xor_sync(0xffffffffu, tpos, s));
+  if (lane == 0) s_min[warp] = tpos;
+  __syncthreads();
+  uint32_t tmin = s_min[0];
+#pragma unroll
+  for (int k = 1; k < DS_THREADS / 32; k++) tmin = min(tmin, s_min[k]);
+  if (tmin != 0xffffffffu && off + 16 > tmin) {
+    uint32_t keep = tmin > off ? (1u << (tmin - off)) - 1u : 0u;
+    c.emit &= keep;
+    c.mark &= keep;
+  }
+  return tmin;
+}
+
+struct DsTile {
+  uint32_t counts;  // after k_destuff_count: kept bytes | markers << 16; after k_destuff_scan: output offset (0xffffffff = dropped)
+  uint32_t term;    // after k_destuff_count: first terminator or 0xffffffff; after k_destuff_scan: first interval index
+};
+
+__device__ __forceinline__ bool ds_tile_setup(const DecodeBatchDev &b, const HcjImageDesc *&d, uint32_t &off) {
+  d = &b.descs[blockIdx.y + b.img_lo];
+  if (!d->valid) return false;
+  const uint32_t base0 = d->scan_start & ~15u;
+  if (base0 + (uint64_t)blockIdx.x * DS_TILE >= d->file_len) return false;
+  off = base0 + blockIdx.x * DS_TILE + threadIdx.x * 16;
+  return true;
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_destuff_count(DecodeBatchDev b) {
+  __shared__ uint8_t s_last[DS_THREADS];
+  __shared__ uint32_t s_min[DS_THREADS / 32];
+  __shared__ uint32_t s_cnt[DS_THREADS / 32];
+  const HcjImageDesc *d;
+  uint32_t off;
+  if (!ds_tile_setup(b, d, off)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  const uint32_t tmin = ds_cut_at_terminator(c, off, s_min, lane, warp);
+  uint32_t cnt = ((uint32_t)__popc(c.mark) << 16) | (uint32_t)__popc(c.emit);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < DS_THREADS / 32; k++) total += s_cnt[k];
+    DsTile t;
+    t.counts = total;
+    t.term = tmin;
+    b.ds_tiles[d->ds_off + blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_destuff_scan(DecodeBatchDev b) {
+  __shared__ uint32_t s_warp[DS_THREADS / 32];
+  __shared__ uint32_t s_first;
   const int img = blockIdx.x + b.img_lo;
   const HcjImageDesc &d = b.descs[img];
   if (!d.valid) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint8_t *file = b.files + d.file_off;
-  uint8_t *ent = b.entropy + d.ent_off;
-  uint32_t *segs = b.seg_offs + d.seg_off;
-  const bool restart = d.ri > 0;
-  const uint32_t start = d.scan_start, flen = d.file_len, nseg_expected = d.nseg_expected;
-
-  __shared__ uint8_t s_last[DS_THREADS];
-  __shared__ uint32_t s_warp[DS_THREADS / 32];
-  __shared__ uint32_t s_min[DS_THREADS / 32];
-  // Compacted bytes of the tile, placed at the same 16-byte phase as their destination so that they
-  // leave as aligned 16-byte words; [0, phase) holds the not yet written tail of the previous tile.
-  __shared__ __align__(16) uint8_t s_out[DS_THREADS * 16 + 32];
-
-  uint32_t carry_out = 0, carry_mark = 0;
-  uint32_t prev_tile_last = 0;
-  bool found = false;
-
-  for (uint32_t base = start & ~15u; base < flen && !found; base += DS_THREADS * 16) {
-    const uint32_t off = base + tid * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (off < flen) v = __ldg(reinterpret_cast<const uint4 *>(file + off));
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    s_last[tid] = (uint8_t)(v.w >> 24);
+  const uint32_t base0 = d.scan_start & ~15u;
+  const uint32_t ntiles = d.file_len > base0 ? (d.file_len - base0 + DS_TILE - 1) / DS_TILE : 0;
+  DsTile *tiles = b.ds_tiles + d.ds_off;
+  // the first tile that holds a terminator ends the scan
+  if (tid == 0) s_first = 0xffffffffu;
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < ntiles; t0 += DS_THREADS) {
+    const uint32_t t = t0 + tid;
+    const bool has = t < ntiles && tiles[t].term != 0xffffffffu;
+    const uint32_t m = __ballot_sync(0xffffffffu, has);
+    if (m && lane == 0) atomicMin(&s_first, t0 + warp * 32 + (uint32_t)__ffs((int)m) - 1u);
     __syncthreads();
-    uint32_t prev = tid == 0 ? prev_tile_last : s_last[tid - 1];
-
-    uint32_t emit = 0, mark = 0, term = 0, ffmask = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-      uint32_t pos = off + i;
-      uint32_t p = pos == start ? 0u : prev;  // the model starts with prev = '\x00' (decoder.ml:279)
-      bool in = pos >= start && pos < flen;
-      if (in) {
-        if (p == 0xffu) {
-          if (c == 0u) {
-            emit |= 1u << i;
-            ffmask |= 1u << i;  // this slot emits the deferred FF
-          } else if (restart && (c & 0xf8u) == 0xd0u) {
-            mark |= 1u << i;
-          } else {
-            term |= 1u << i;
-          }
-        } else if (c != 0xffu) {
-          emit |= 1u << i;
-        }
-      }
-      prev = c;
-    }
-    // first terminator of the tile
-    uint32_t tpos = term ? off + (uint32_t)__ffs((int)term) - 1u : 0xffffffffu;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) tpos = min(tpos, __shfl_xor_sync(0xffffffffu, tpos, s));
-    if (lane == 0) s_min[warp] = tpos;
+    if (s_first != 0xffffffffu) break;
+  }
+  const uint32_t first = s_first;
+  const bool found = first != 0xffffffffu;
+  const uint32_t nlive = found ? first + 1 : ntiles;
+  uint32_t carry = 0;  // kept bytes | markers << 16 (a scan has far fewer than 2^16 restart intervals... checked on the host)
+  uint32_t carry_mark = 0;
+  for (uint32_t t0 = 0; t0 < ntiles; t0 += DS_THREADS) {
+    const uint32_t t = t0 + tid;
+    const uint32_t v = t < nlive ? tiles[t].counts : 0u;
+    const uint32_t ve = v & 0xffffu, vm = v >> 16;
+    // two scans in one: bytes in the low half would overflow 16 bits, so scan them separately
+    uint32_t ie = warp_incl_scan(ve, lane), im = warp_incl_scan(vm, lane);
     __syncthreads();
-    uint32_t tmin = s_min[0];
-#pragma unroll
-    for (int k = 1; k < DS_THREADS / 32; k++) tmin = min(tmin, s_min[k]);
-    if (tmin != 0xffffffffu) {
-      found = true;
-      // drop everything at or after the terminator
-      if (off + 16 > tmin) {
-        uint32_t keep = tmin > off ? (1u << (tmin - off)) - 1u : 0u;
-        emit &= keep;
-        mark &= keep;
-      }
-    }
-    // block exclusive scan of (markers << 16 | emitted bytes)
-    uint32_t cnt = ((uint32_t)__popc(mark) << 16) | (uint32_t)__popc(emit);
-    uint32_t incl = warp_incl_scan(cnt, lane);
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[warp] = ie;
     __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    uint32_t be = 0, te = 0;
 #pragma unroll
     for (int k = 0; k < DS_THREADS / 32; k++) {
-      uint32_t t = s_warp[k];
-      if (k < warp) wbase += t;
-      total += t;
+      const uint32_t x = s_warp[k];
+      if (k < warp) be += x;
+      te += x;
     }
-    uint32_t excl = wbase + incl - cnt;
-    const uint32_t phase = carry_out & 15u;
-    uint32_t opos = carry_out + (excl & 0xffffu);
-    uint32_t so = phase + (excl & 0xffffu);
-    uint32_t mk = carry_mark + (excl >> 16);
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = im;
+    __syncthreads();
+    uint32_t bm = 0, tm = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      if (emit & (1u << i)) {
-        uint32_t c = (ffmask & (1u << i)) ? 0xffu : (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-        s_out[so++] = (uint8_t)c;
-        opos++;
-      } else if (mark & (1u << i)) {
-        mk++;
-        if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
-      }
+    for (int k = 0; k < DS_THREADS / 32; k++) {
+      const uint32_t x = s_warp[k];
+      if (k < warp) bm += x;
+      tm += x;
     }
-    __syncthreads();
-    const uint32_t avail = phase + (total & 0xffffu);  // bytes staged, including the carried tail
-    const uint32_t nfull = avail >> 4;
-    uint4 *dst = reinterpret_cast<uint4 *>(ent + (carry_out - phase));
-    for (uint32_t k = tid; k < nfull; k += DS_THREADS) dst[k] = reinterpret_cast<const uint4 *>(s_out)[k];
-    uint8_t tail = 0;
-    const uint32_t ntail = avail & 15u;
-    if ((uint32_t)tid < ntail) tail = s_out[nfull * 16 + tid];
-    __syncthreads();
-    if ((uint32_t)tid < ntail) s_out[tid] = tail;
-    carry_out += total & 0xffffu;
-    carry_mark += total >> 16;
-    prev_tile_last = s_last[DS_THREADS - 1];
-    __syncthreads();  // s_last / s_warp / s_min are rewritten by the next tile
+    if (t < ntiles) {
+      DsTile o;
+      o.counts = t < nlive ? carry + be + ie - ve : 0xffffffffu;
+      o.term = carry_mark + bm + im - vm;
+      tiles[t] = o;
+    }
+    carry += te;
+    carry_mark += tm;
   }
-  if ((uint32_t)tid < (carry_out & 15u)) ent[(carry_out & ~15u) + tid] = s_out[tid];  // last partial word
   if (tid == 0) {
+    uint32_t *segs = b.seg_offs + d.seg_off;
     HcjImageState st;
-    st.ent_len = carry_out;
+    st.ent_len = carry;
     st.nseg_found = carry_mark + 1;
     st.status = HCJ_DEV_OK;
     st.pad_ = 0;
     st.err_key = HCJ_NO_ERR_KEY;
     if (!found) st.status = HCJ_DEV_NO_TERMINATOR;
-    else if (restart && st.nseg_found != nseg_expected) st.status = HCJ_DEV_RESTART_COUNT;
+    else if (d.ri > 0 && st.nseg_found != d.nseg_expected) st.status = HCJ_DEV_RESTART_COUNT;
     segs[0] = 0;
-    segs[nseg_expected] = carry_out;
+    segs[d.nseg_expected] = carry;
     b.states[img] = st;
   }
 }
 
-void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.img_hi > b.img_lo) k_destuff<<<b.img_hi - b.img_lo, DS_THREADS, 0, s>>>(b);
+__global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) {
+  __shared__ uint8_t s_last[DS_THREADS];
+  __shared__ uint32_t s_warp[DS_THREADS / 32];
+  __shared__ uint32_t s_min[DS_THREADS / 32];
+  // Compacted bytes of the tile, placed at the same 16-byte phase as their destination
+  __shared__ __align__(16) uint8_t s_out[DS_TILE + 32];
+  const HcjImageDesc *d;
+  uint32_t off;
+  if (!ds_tile_setup(b, d, off)) return;
+  const DsTile tile = b.ds_tiles[d->ds_off + blockIdx.x];
+  if (tile.counts == 0xffffffffu) return;  // behind the terminator
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t *ent = b.entropy + d->ent_off;
+  uint32_t *segs = b.seg_offs + d->seg_off;
+  const uint32_t nseg_expected = d->nseg_expected;
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  ds_cut_at_terminator(c, off, s_min, lane, warp);
+  // block exclusive scan of (markers << 16 | kept bytes): at most 4096 bytes and 2048 markers per tile
+  const uint32_t cnt = ((uint32_t)__popc(c.mark) << 16) | (uint32_t)__popc(c.emit);
+  const uint32_t incl = warp_incl_scan(cnt, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < DS_THREADS / 32; k++) {
+    const uint32_t t = s_warp[k];
+    if (k < warp) wbase += t;
+    total += t;
+  }
+  const uint32_t excl = wbase + incl - cnt;
+  const uint32_t out0 = tile.counts, phase = out0 & 15u;
+  uint32_t opos = out0 + (excl & 0xffffu);
+  uint32_t so = phase + (excl & 0xffffu);
+  uint32_t mk = tile.term + (excl >> 16);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (c.emit & (1u << i)) {
+      const uint32_t ch = (c.ffmask & (1u << i)) ? 0xffu : (c.w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+      s_out[so++] = (uint8_t)ch;
+      opos++;
+    } else if (c.mark & (1u << i)) {
+      mk++;
+      if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+    }
+  }
+  __syncthreads();
+  const uint32_t nbytes = total & 0xffffu, avail = phase + nbytes;
+  uint8_t *dst0 = ent + (out0 - phase);  // 16-byte aligned
+  const uint32_t w_lo = phase ? 1u : 0u, w_hi = avail >> 4;  // words [w_lo, w_hi) are wholly this tile's
+  for (uint32_t k = w_lo + tid; k < w_hi; k += DS_THREADS)
+    reinterpret_cast<uint4 *>(dst0)[k] = reinterpret_cast<const uint4 *>(s_out)[k];
+  // partial words at both ends (shared with the neighbouring tiles): byte by byte
+  if (phase && (uint32_t)tid < 16u - phase && phase + tid < avail) dst0[phase + tid] = s_out[phase + tid];
+  const uint32_t tail0 = max(w_hi << 4, w_lo << 4);
+  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_out[tail0 + tid];
 }
+
+void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
+  if (b.img_hi <= b.img_lo || b.max_ds_tiles == 0) return;
+  const dim3 grid(b.max_ds_tiles, b.img_hi - b.img_lo);
+  k_destuff_count<<<grid, DS_THREADS, 0, s>>>(b);
+  k_destuff_scan<<<b.img_hi - b.img_lo, DS_THREADS, 0, s>>>(b);
+  k_destuff_write<<<grid, DS_THREADS, 0, s>>>(b);
+}
+int destuff_kernel_count() { return 3; }
 
 // ================================================================================================
 // Huffman tables in shared memory, shared by K2 and K3: per table HCJ_LUT_SIZE fast entries (32 bit,

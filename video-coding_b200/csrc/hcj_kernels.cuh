@@ -7,6 +7,8 @@
 
 namespace hcjk {
 
+struct DsTile;
+
 // Everything the decode kernels need about one batch resident in HBM.
 struct DecodeBatchDev {
   int n;                          // images
@@ -15,6 +17,8 @@ struct DecodeBatchDev {
   const uint8_t *files;           // compressed files, each starting at a 16-byte boundary
   uint8_t *entropy;               // destuffed entropy-coded bytes per image
   uint32_t *seg_offs;             // per image: nseg_expected + 1 byte offsets into its entropy bytes
+  struct DsTile *ds_tiles;        // per 4 KiB tile of every scan: counts, then offsets (k_destuff_*)
+  uint32_t max_ds_tiles;          // max tiles of any image
   const HcjTableSet *table_sets;
   const uint16_t *lut_primary;    // primary LUT pool
   const uint16_t *lut_full;       // full LUT pool
@@ -51,6 +55,7 @@ struct DecodeBatchDev {
 };
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
+int destuff_kernel_count();
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
 int huff_spec_kernel_count();
