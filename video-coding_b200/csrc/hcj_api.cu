@@ -230,7 +230,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t max_ds_tiles = 0;
   uint32_t sub_log2 = 11;
   if (const char *e = getenv("HCJ_SUB_LOG2")) sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));  // experiments
-  const int tile_mcus = 42;  // upper bound on MCUs per IDCT tile (256 threads / 6 blocks for 4:2:0)
+  const int tile_mcus = HCJ_IDCT_THREADS;  // upper bound on MCUs per IDCT tile (one thread per block)
   hcj_header *h = new (std::nothrow) hcj_header;
   if (!h) {
     delete b;
@@ -383,7 +383,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       total_sub += nsub_max + 1;
       max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max + 255) / 256));
     }
-    int tm_max = std::max(1, std::min(tile_mcus, 256 / d.bpm));
+    int tm_max = std::max(1, std::min(tile_mcus, HCJ_IDCT_THREADS / d.bpm));
     uint32_t tiles = (uint32_t)((d.mcus_wide + tm_max - 1) / tm_max) * (uint32_t)d.mcus_high;
     max_tiles = std::max(max_tiles, tiles);
     max_rows = std::max(max_rows, (uint32_t)f.height);

@@ -14,6 +14,10 @@
 #define HCJ_LUT_ENTRIES (HCJ_LUT_SIZE + HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE)  // per table, uint16 each
 #define HCJ_MAX_BPM 10                     // blocks per MCU (T.81 limit)
 #define HCJ_MAX_COMP 4
+#ifndef HCJ_IDCT_THREADS
+#define HCJ_IDCT_THREADS 128              // threads (= blocks) per IDCT tile
+#endif
+#define HCJ_IDCT_CTAS_PER_SM (512 / HCJ_IDCT_THREADS)
 
 // Internal status values produced on the device (same numbering as include/hcjpeg.h).
 #define HCJ_DEV_OK 0

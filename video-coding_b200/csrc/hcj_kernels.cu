@@ -1103,7 +1103,7 @@ int huff_spec_kernel_count() { return 4; }
 // (component, block row, MCU, block column) so that a warp stores 32 horizontally adjacent blocks:
 // every store instruction writes 256 contiguous bytes of one image row.
 // ================================================================================================
-constexpr int IDCT_MAX_THREADS = 256;
+constexpr int IDCT_MAX_THREADS = HCJ_IDCT_THREADS;
 constexpr int IDCT_ROW_U4 = 9;  // 144 bytes per staged block
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -1180,20 +1180,87 @@ struct IdctStage {  // one pipeline stage in shared memory
   uint4 flags[IDCT_FLAG_U4 + 1];
 };
 
-__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, uint32_t tile_id, IdctStage &st, int tid) {
-  const IdctTile t = idct_tile(b, tile_id);
-  if (t.d) {
-    const HcjImageDesc &d = *t.d;
-    const uint64_t blk0 = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm;
-    const int16_t *src = b.coefs + blk0 * 64;
-    for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&st.tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
-    if (tid < d.ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
-    if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (blk0 >> 7) + tid);
+// The CTA's walk over its range of tile ids (id = image * max_idct_tiles + tile within the image).  All the
+// divisions that turn an id into (image, MCU row, first MCU) are done once per image; from one tile to the
+// next the cursor only increments.  (Recomputing them per tile cost every thread some 400 instructions per
+// block, a third of the kernel: profiles/r02_idct_before_cursor.)
+struct IdctWork {  // one tile, everything the load and the transform need
+  const HcjImageDesc *d;
+  int my, m0, tm, nblk;
+  uint64_t blk0;  // first block of the tile in the batch coefficient buffer
+};
+struct TileCursor {
+  uint32_t id, end, tile;  // next tile id; end of the range; tile index within the image
+  uint32_t rel;            // image, relative to img_lo
+  const HcjImageDesc *d;
+  int tiles_per_row, tm_bal, ntiles, my, tx;
+  uint64_t blk;            // first block of the next tile
+
+  __device__ __forceinline__ void load_image(const DecodeBatchDev &b) {
+    d = &b.descs[rel + b.img_lo];
+    ntiles = 0;
+    if (d->valid) {
+      const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / d->bpm);
+      tiles_per_row = (d->mcus_wide + tm_max - 1) / tm_max;
+      tm_bal = (d->mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
+      ntiles = tiles_per_row * d->mcus_high;
+    }
   }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  __device__ __forceinline__ void init(const DecodeBatchDev &b, uint32_t begin, uint32_t end_) {
+    id = begin;
+    end = end_;
+    rel = begin / b.max_idct_tiles;
+    tile = begin - rel * b.max_idct_tiles;
+    load_image(b);
+    my = tx = 0;
+    blk = 0;
+    if ((int)tile < ntiles) {
+      my = (int)tile / tiles_per_row;
+      tx = (int)tile - my * tiles_per_row;
+      blk = d->coef_off + ((uint64_t)my * d->mcus_wide + (uint64_t)tx * tm_bal) * d->bpm;
+    }
+  }
+  // the next tile of the range, or false
+  __device__ __forceinline__ bool next(const DecodeBatchDev &b, IdctWork &w) {
+    while (id < end) {
+      if ((int)tile >= ntiles) {  // past the image's last tile (or an invalid image): on to the next image
+        id += b.max_idct_tiles - tile;
+        rel++;
+        tile = 0;
+        if (id >= end) return false;
+        load_image(b);
+        my = tx = 0;
+        blk = d->valid ? d->coef_off : 0;
+        continue;
+      }
+      w.d = d;
+      w.my = my;
+      w.m0 = tx * tm_bal;
+      w.tm = min(tm_bal, d->mcus_wide - w.m0);
+      w.nblk = w.tm * d->bpm;
+      w.blk0 = blk;
+      blk += (uint64_t)w.nblk;
+      id++;
+      tile++;
+      if (++tx == tiles_per_row) {
+        tx = 0;
+        my++;
+      }
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctWork &t, IdctStage &st, int tid) {
+  const HcjImageDesc &d = *t.d;
+  const int16_t *src = b.coefs + t.blk0 * 64;
+  for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&st.tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
+  if (tid < d.ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
+  if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (t.blk0 >> 7) + tid);
 }
 
-__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeBatchDev b, int mode) {
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct_persistent(DecodeBatchDev b, int mode) {
   extern __shared__ uint4 s_dyn[];
   IdctStage *stages = reinterpret_cast<IdctStage *>(s_dyn);
   const int tid = threadIdx.x;
@@ -1210,21 +1277,32 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeB
   int xoff = 0, yoff = 0;     // sample offset of the block inside the tile's MCU row
   int hs8 = 0, vs8 = 0;       // samples per MCU of this component
   int stride = 0, w_limit = 0, h_limit = 0;
-  uint64_t plane_off = 0;     // component plane offset inside the image's output / plane buffer
+  uint8_t *plane = nullptr;   // the component's plane in the image's output / plane buffer
+  bool img_wide = false;
 
-  idct_issue(b, begin, stages[0], tid);
-  int buf = 0;
-  for (uint32_t cur = begin; cur < end; cur++, buf ^= 1) {
+  // The cursor lives in shared memory and is advanced by thread 0 two tiles ahead of the transform, so that
+  // its state costs no registers in the threads that need them for the 64 values of a block.
+  __shared__ TileCursor s_cur;
+  __shared__ IdctWork s_work[4];
+  __shared__ int s_have[4];
+  if (tid == 0) {
+    s_cur.init(b, begin, end);
+    s_have[0] = s_cur.next(b, s_work[0]);
+    s_have[1] = s_have[0] && s_cur.next(b, s_work[1]);
+  }
+  __syncthreads();
+  if (s_have[0]) idct_issue(b, s_work[0], stages[0], tid);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int i = 0; s_have[i & 3]; i++) {
+    const int buf = i & 1;
     IdctStage &st = stages[buf];
-    if (cur + 1 < end) {
-      idct_issue(b, cur + 1, stages[buf ^ 1], tid);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
+    if (tid == 0) s_have[(i + 2) & 3] = s_have[(i + 1) & 3] && s_cur.next(b, s_work[(i + 2) & 3]);
+    if (s_have[(i + 1) & 3]) idct_issue(b, s_work[(i + 1) & 3], stages[buf ^ 1], tid);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
-    const IdctTile t = idct_tile(b, cur);
-    if (t.d) {
+    const IdctWork &t = s_work[i & 3];
+    {
       const HcjImageDesc &d = *t.d;
       if (t.d != map_img || t.tm != map_tm) {  // CTA-uniform: new image or a narrower last tile in the row
         map_img = t.d;
@@ -1248,12 +1326,13 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeB
         vs8 = g.vs * 8;
         xoff = m * hs8 + bx * 8;
         yoff = by * 8;
+        img_wide = d.wide_idct != 0;
         if (mode == 0) {
-          plane_off = g.out_off;
+          plane = b.out + d.out_off + g.out_off;
           stride = w_limit = g.actual_w;
           h_limit = g.actual_h;
         } else {
-          plane_off = g.plane_off;
+          plane = (mode == 2 ? b.planes : b.out + d.out_off) + g.plane_off;
           stride = w_limit = g.decoded_w;
           h_limit = g.decoded_h;
         }
@@ -1268,17 +1347,15 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeB
           cw[4 * j + 2] = u.z;
           cw[4 * j + 3] = u.w;
         }
-        const uint64_t blk0 = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm;
-        const uint32_t fbit = (uint32_t)(blk0 & 127u) + slot;  // bit index inside the staged flag chunks
-        const bool wide = d.wide_idct || ((reinterpret_cast<const uint32_t *>(st.flags)[fbit >> 5] >> (fbit & 31u)) & 1u);
-        uint8_t *base = (mode == 2 ? b.planes : b.out + d.out_off) + plane_off;
+        const uint32_t fbit = (uint32_t)(t.blk0 & 127u) + slot;  // bit index inside the staged flag chunks
+        const bool wide = img_wide || ((reinterpret_cast<const uint32_t *>(st.flags)[fbit >> 5] >> (fbit & 31u)) & 1u);
         const int x = t.m0 * hs8 + xoff, y = t.my * vs8 + yoff;
         const int32_t *q = st.q + qoff;
         uint32_t pix[16];
         if (wide || !reconstruct_fast<false>(cw, q + 64, pix))
-          wide_block_store(reinterpret_cast<const uint32_t *>(&st.tile[slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
+          wide_block_store(reinterpret_cast<const uint32_t *>(&st.tile[slot * IDCT_ROW_U4]), q, plane, stride, x, y, w_limit, h_limit);
         else
-          store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
+          store_block_rows(pix, plane, stride, x, y, w_limit, h_limit);
       }
     }
     __syncthreads();  // this stage is refilled by the next iteration's prefetch
@@ -1286,7 +1363,7 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct_persistent(DecodeB
 }
 
 // One tile per CTA: load (cp.async) -> transform -> store; latency is hidden by the other resident CTAs.
-__global__ void __launch_bounds__(IDCT_MAX_THREADS, 2) k_idct(DecodeBatchDev b, int mode) {
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct(DecodeBatchDev b, int mode) {
   extern __shared__ uint4 s_dyn[];
   uint4 *s_tile = s_dyn;
   int32_t *s_q = reinterpret_cast<int32_t *>(s_dyn + IDCT_MAX_THREADS * IDCT_ROW_U4);
@@ -1355,7 +1432,7 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(IdctStage)));
-    grid = 2 * sms;
+    grid = HCJ_IDCT_CTAS_PER_SM * sms;
     const char *e = getenv("HCJ_IDCT_PERSISTENT");
     persistent = !(e && e[0] == '0');  // default; HCJ_IDCT_PERSISTENT=0 selects the one-tile-per-CTA kernel
   }
