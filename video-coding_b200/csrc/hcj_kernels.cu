@@ -1252,12 +1252,19 @@ struct TileCursor {
   }
 };
 
+// Requests one tile: 16-byte chunk g of the run of blocks goes to row g / 8, column g % 8 of the padded stage;
+// thread tid takes chunks tid, tid + T, ...: eight copies whose addresses differ by constants.
 __device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctWork &t, IdctStage &st, int tid) {
-  const HcjImageDesc &d = *t.d;
-  const int16_t *src = b.coefs + t.blk0 * 64;
-  for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&st.tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
-  if (tid < d.ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
-  if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (t.blk0 >> 7) + tid);
+  const HcjImageDesc *d = t.d;
+  const int n8 = t.nblk * 8;
+  const uint64_t blk0 = t.blk0;
+  const int16_t *src = b.coefs + blk0 * 64 + tid * 8;
+  uint4 *dst = &st.tile[(tid >> 3) * IDCT_ROW_U4 + (tid & 7)];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (tid + k * IDCT_MAX_THREADS < n8) cp_async16(dst + k * (IDCT_MAX_THREADS / 8) * IDCT_ROW_U4, src + k * IDCT_MAX_THREADS * 8);
+  if (tid < d->ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d->qt_off + tid * 4);  // comp k uses table slot k
+  if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (blk0 >> 7) + tid);
 }
 
 __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct_persistent(DecodeBatchDev b, int mode) {
