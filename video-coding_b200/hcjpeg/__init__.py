@@ -177,13 +177,31 @@ _SIGS = {
 _lib = None
 
 
-def build(force=False):
-    """Compile libhcjpeg.so for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+def _source_digest():
+    import hashlib
+
     csrc = os.path.join(_ROOT, "csrc")
-    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(os.path.dirname(_ROOT), "include", "hcjpeg.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(csrc)) + [os.path.join(os.path.dirname(_ROOT), "include", "hcjpeg.h")]:
+        path = f if os.path.isabs(f) else os.path.join(csrc, f)
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(force=False):
+    """Compile libhcjpeg.so for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU).
+    The library is rebuilt when the sources differ from the ones it was built from (a content stamp next to
+    it: file times do not survive being copied to another machine)."""
+    csrc = os.path.join(_ROOT, "csrc")
+    stamp = LIB_PATH + ".stamp"
+    digest = _source_digest()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
-    subprocess.check_call(["make", "-s", "-C", csrc])
+    subprocess.check_call(["make", "-s", "-C", csrc, "-B"] if os.path.exists(LIB_PATH) else ["make", "-s", "-C", csrc])
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 
