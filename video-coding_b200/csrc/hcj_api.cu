@@ -8,9 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hcjpeg.h"
@@ -125,6 +127,7 @@ void hcj_ctx_destroy(hcj_ctx *c) {
   for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  free(c->hdr_buf);
   for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -231,18 +234,55 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t sub_log2 = 11;
   if (const char *e = getenv("HCJ_SUB_LOG2")) sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));  // experiments
   const int tile_mcus = HCJ_IDCT_THREADS;  // upper bound on MCUs per IDCT tile (one thread per block)
-  hcj_header *h = new (std::nothrow) hcj_header;
-  if (!h) {
+  // Decoder.Header.decode + the geometry of Decoder.init for every image: independent per image, so spread over
+  // a few host threads (it is the serial prologue of every batch: 6 ms single-threaded for 1024 files)
+  if (c->hdr_cap < (size_t)std::max(n, 1) * sizeof(hcj_header)) {
+    free(c->hdr_buf);
+    c->hdr_cap = (size_t)std::max(n, 1) * sizeof(hcj_header);
+    c->hdr_buf = malloc(c->hdr_cap);
+    if (!c->hdr_buf) {
+      c->hdr_cap = 0;
+      delete b;
+      return HCJ_ERR_OUT_OF_MEMORY;
+    }
+  }
+  hcj_header *hdrs = static_cast<hcj_header *>(c->hdr_buf);
+  std::vector<hcj::ImagePlan> plans;
+  std::vector<int> parse_st;
+  try {
+    plans.resize(std::max(n, 1));
+    parse_st.assign(std::max(n, 1), HCJ_OK);
+  } catch (const std::bad_alloc &) {
     delete b;
     return HCJ_ERR_OUT_OF_MEMORY;
   }
+  {
+    auto work = [&](int lo, int hi) {
+      for (int i = lo; i < hi; i++) {
+        int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i]) : HCJ_ERR_INVALID_ARG;
+        if (st == HCJ_OK) st = hcj::plan_image(hdrs[i], flags, &plans[i]);
+        parse_st[i] = st;
+      }
+    };
+    const int nthreads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n / 64}));
+    if (nthreads <= 1) {
+      work(0, n);
+    } else {
+      std::vector<std::thread> pool;
+      const int per = (n + nthreads - 1) / nthreads;
+      for (int t = 1; t < nthreads; t++) pool.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+      work(0, std::min(n, per));
+      for (auto &th : pool) th.join();
+    }
+  }
+  int prev_pairs = -1, prev_pair_dc[HCJ_MAX_COMPONENTS], prev_pair_ac[HCJ_MAX_COMPONENTS], prev_img = -1;
 
   for (int i = 0; i < n; i++) {
     HcjImageDesc &d = b->descs[i];
     memset(&d, 0, sizeof(d));
-    hcj::ImagePlan plan;
-    int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], h) : HCJ_ERR_INVALID_ARG;
-    if (st == HCJ_OK) st = hcj::plan_image(*h, flags, &plan);
+    const hcj_header *h = &hdrs[i];
+    const hcj::ImagePlan &plan = plans[i];
+    int st = parse_st[i];
     const hcj_frame_info &f = plan.info;
     // table set of this image: one (dc, ac) pair per distinct binding among its scan components
     int pair_of[HCJ_MAX_COMPONENTS] = {0, 0, 0, 0}, npairs = 0, pair_dc[HCJ_MAX_COMPONENTS], pair_ac[HCJ_MAX_COMPONENTS];
@@ -256,17 +296,26 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
           p = npairs++;
           pair_dc[p] = plan.dc_index[k];
           pair_ac[p] = plan.ac_index[k];
+        }
+        pair_of[k] = p;
+      }
+      // same tables as the previous image (the usual case in a batch): same table set, no key to build
+      bool same_as_prev = prev_img >= 0 && prev_pairs == npairs;
+      for (int p = 0; same_as_prev && p < npairs; p++)
+        same_as_prev = memcmp(&h->huffman_tables[pair_dc[p]], &hdrs[prev_img].huffman_tables[prev_pair_dc[p]], sizeof(hcj_dht)) == 0 &&
+                       memcmp(&h->huffman_tables[pair_ac[p]], &hdrs[prev_img].huffman_tables[prev_pair_ac[p]], sizeof(hcj_dht)) == 0;
+      if (!same_as_prev)
+        for (int p = 0; p < npairs; p++)
           for (int which = 0; which < 2; which++) {
             const hcj_dht &t = h->huffman_tables[which ? pair_ac[p] : pair_dc[p]];
             key.push_back((char)t.table_class);
             for (int q = 0; q < 16; q++) key.push_back((char)t.lengths[q]);
             key.append(reinterpret_cast<const char *>(t.values), (size_t)t.nvalues);
           }
-        }
-        pair_of[k] = p;
-      }
-      auto it = set_index.find(key);
-      if (it != set_index.end()) {
+      auto it = same_as_prev ? set_index.end() : set_index.find(key);
+      if (same_as_prev) {
+        d.table_set = b->descs[prev_img].table_set;
+      } else if (it != set_index.end()) {
         d.table_set = it->second;
       } else {
         HcjTableSet ts;
@@ -292,6 +341,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
           set_index[key] = d.table_set;
           table_sets.push_back(ts);
         }
+      }
+      if (st == HCJ_OK) {
+        prev_img = i;
+        prev_pairs = npairs;
+        for (int p = 0; p < npairs; p++) prev_pair_dc[p] = pair_dc[p], prev_pair_ac[p] = pair_ac[p];
       }
     }
     if (st == HCJ_OK && (mode == HCJ_OUT_YUV || mode == HCJ_OUT_RGB24)) {
@@ -389,7 +443,6 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     max_rows = std::max(max_rows, (uint32_t)f.height);
     max_width = std::max(max_width, (uint32_t)f.width);
   }
-  delete h;
   if (status)
     for (int i = 0; i < n; i++) status[i] = b->host_status[i];
 
@@ -603,8 +656,16 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
                      uint8_t *const *out, const size_t *out_capacity, int *status) {
   // Three streams: the files of chunk k + 1 go up while the kernels of chunk k run and the frames of chunk
   // k - 1 come down; PCIe is full duplex and the kernels are a small fraction of either transfer.
+  const bool trace = getenv("HCJ_TRACE") != nullptr;  // host-side milestones of one call, to stderr
+  const auto t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what) {
+    if (trace)
+      fprintf(stderr, "[hcj_decode_batch] %-28s %8.3f ms\n", what,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   hcj_batch *b = nullptr;
   int st = batch_create(c, jpeg, len, n, mode, flags, status, &b, false);
+  mark("headers parsed, tables up");
   if (st != HCJ_OK) return st;
   if (n > 0 && (!out || !out_capacity)) {
     hcj_batch_destroy(c, b);
@@ -674,7 +735,15 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
         i = j + 1;
       }
     }
+    mark("everything enqueued");
+    if (trace && e == cudaSuccess) {
+      e = cudaStreamSynchronize(us);
+      mark("files on the device");
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      mark("kernels done");
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    mark("frames on the host");
     std::vector<HcjImageState> states;
     if (e == cudaSuccess) {
       int r = fetch_states(c, b, &states);
@@ -691,6 +760,7 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   if (status)
     for (int i = 0; i < n; i++) status[i] = host_st[i];
   hcj_batch_destroy(c, b);
+  mark("batch released");
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
 }
 

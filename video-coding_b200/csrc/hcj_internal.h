@@ -32,6 +32,8 @@ struct hcj_ctx {
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the kernels of the next chunk
   cudaStream_t up_stream = nullptr;    // H2D of the next chunk's files overlaps both
   std::vector<cudaEvent_t> up_events;
+  void *hdr_buf = nullptr;  // parsed headers of the batch being created (39 KB each): kept between calls, never zero-filled
+  size_t hdr_cap = 0;
   std::vector<cudaEvent_t> chunk_events;
   std::vector<hcj::FreeBlock> pool;  // device memory recycled between batches (grow-only)
 
