@@ -759,6 +759,7 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 // decoded serially with the literal per-block routine (k_spec_fix).
 // ================================================================================================
 constexpr int SPEC_THREADS = 256;
+constexpr int SPEC_WRITE_THREADS = 512;  // the exact pass: same shape as K2 (2 CTAs of 16 warps per SM at 64 registers)
 
 __device__ __forceinline__ uint32_t spec_pack(uint32_t p, uint32_t base, uint32_t cz) {
   return ((p - base) << 10) | ((cz >> 8) << 6) | (cz & 63u);
@@ -1034,26 +1035,26 @@ __global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_fix(DecodeBatchDev b) 
 }
 
 // Shared memory: [SmemTables][ScanCtx][stage rows][tables]
-__global__ void __launch_bounds__(SPEC_THREADS, 3) k_spec_write(DecodeBatchDev b) {
+__global__ void __launch_bounds__(SPEC_WRITE_THREADS, 2) k_spec_write(DecodeBatchDev b) {
   extern __shared__ uint4 s_dyn4[];
   SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
   ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
   uint32_t *s_stage = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15)));
   SpecImage si;
   if (!spec_image(b, blockIdx.y, si)) return;
-  if (si.L <= 16u || blockIdx.x * SPEC_THREADS >= si.nsub) return;
+  if (si.L <= 16u || blockIdx.x * SPEC_WRITE_THREADS >= si.nsub) return;
   const HcjImageDesc &d = *si.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stage = s_stage + warp * HR_STAGE_WORDS;
   for (int k = lane; k < HR_STAGE_WORDS; k += 32) stage[k] = 0u;
-  const FastTables T = load_tables(st, s_stage + (SPEC_THREADS / 32) * HR_STAGE_WORDS, b, d);
+  const FastTables T = load_tables(st, s_stage + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS, b, d);
   __syncthreads();
   fill_scan_ctx(sc, st, b, d, si.L);
   __syncthreads();
   const Local LT{T, st.quant, st.blk_comp};
   int16_t *coefs = b.coefs + d.coef_off * 64;
 
-  const uint32_t j = blockIdx.x * SPEC_THREADS + threadIdx.x;
+  const uint32_t j = blockIdx.x * SPEC_WRITE_THREADS + threadIdx.x;
   PassIn in;
   in.valid = j < si.nsub;
   const uint32_t jj = in.valid ? j : 0u;
@@ -1077,7 +1078,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 3) k_spec_write(DecodeBatchDev b
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.ls_hi <= b.ls_lo || b.max_sub_chunks == 0) return;
   const size_t base = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + lut_smem_bytes(b);
-  const size_t smem_write = base + (SPEC_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
+  const size_t smem_write = base + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
   static size_t configured = 0;
   if (smem_write > configured) {
     cudaFuncSetAttribute(k_spec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
@@ -1089,7 +1090,8 @@ void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 0);
   k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 1);
   k_spec_fix<<<b.ls_hi - b.ls_lo, SPEC_THREADS, base, s>>>(b);
-  k_spec_write<<<grid, SPEC_THREADS, smem_write, s>>>(b);
+  const dim3 grid_w((b.max_sub_chunks * SPEC_THREADS + SPEC_WRITE_THREADS - 1) / SPEC_WRITE_THREADS, b.ls_hi - b.ls_lo);
+  k_spec_write<<<grid_w, SPEC_WRITE_THREADS, smem_write, s>>>(b);
 }
 int huff_spec_kernel_count() { return 4; }
 
