@@ -759,6 +759,7 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 // decoded serially with the literal per-block routine (k_spec_fix).
 // ================================================================================================
 constexpr int SPEC_THREADS = 256;
+constexpr uint32_t SPEC_GUESS_BITS = 2048;  // bits the guessed-state decode of pass 0 looks at
 constexpr int SPEC_WRITE_THREADS = 512;  // the exact pass: same shape as K2 (2 CTAs of 16 warps per SM at 64 registers)
 
 __device__ __forceinline__ uint32_t spec_pack(uint32_t p, uint32_t base, uint32_t cz) {
@@ -899,22 +900,21 @@ __global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_sync(DecodeBatchDev b,
   const uint32_t j = blockIdx.x * SPEC_THREADS + threadIdx.x;
   bool valid = j < si.nsub;
   const uint32_t lo = (valid ? j : 0u) << si.d->sub_log2, hi = min(lo + si.S, si.L);
-  uint32_t p = lo, cz = 0, ns = 0;
+  // Pass 0 only has to find the state at the END of the subsequence, and a decoder started from a guess is
+  // in step with the real one after a couple of MCUs: it decodes the last SPEC_GUESS_BITS bits only (the
+  // first subsequence, whose start is exact, in full).  Where that was not enough, pass 1 starts from a wrong
+  // state and k_spec_fix decodes the right neighbour again: cheaper than decoding everything twice.
+  uint32_t p = j == 0 ? lo : max(lo, hi > SPEC_GUESS_BITS ? hi - SPEC_GUESS_BITS : 0u), cz = 0, ns = 0;
   if (pass == 1) {
     if (j == 0) si.end2[0] = si.end[0];  // exact by construction
     valid = valid && j > 0;
     ns = valid ? si.end[j - 1] : 0u;
-    // a neighbour that ended in the guessed state: pass 0 already decoded from it
-    if (valid && ns == si.start[j]) {
-      si.end2[j] = si.end[j];
-      valid = false;
-    }
     spec_unpack(ns, lo, p, cz);
   }
   SubResult r;
   warp_subseq_sync(sc, LT, valid, p, cz, hi, r);
   if (valid) {
-    si.start[j] = (uint16_t)(pass == 0 ? spec_pack(p, lo, cz) : ns);
+    si.start[j] = (uint16_t)(pass == 0 ? 0u : ns);  // pass 0: only subsequence 0 keeps its entry (the exact start, packed 0)
     (pass == 0 ? si.end : si.end2)[j] = (uint16_t)spec_pack(r.p, hi, r.cz);
     si.nstart[j] = (int32_t)r.nstart;
     si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
