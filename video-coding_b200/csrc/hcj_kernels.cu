@@ -45,12 +45,19 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-// The 16 bytes of one thread classified: bit i of `emit` = byte i is kept (an FF 00 pair keeps its FF at
-// the 00), of `mark` = byte i is the second byte of a restart marker, of `term` = of any other marker.
+// The 16 bytes of one thread classified, four bytes at a time: every mask below is a word with 0x80 in the
+// bytes that have the property (SIMD within a register: no per-byte loop on the common path).
+//   emit  the byte is kept (for an FF 00 pair: the 00 position keeps the deferred FF, see ffz)
+//   mark  second byte of a restart marker        term  second byte of any other marker (ends the scan)
+//   ffz   00 that follows FF: emits FF            ff    the byte is FF
 struct DsClass {
   uint32_t w[4];
-  uint32_t emit, mark, term, ffmask;
+  uint32_t emit[4], mark[4], term[4], ffz[4];
+  uint32_t anyff;  // some byte of the 16 is FF, or the byte before them is: the bytes are not kept verbatim
 };
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {  // 0x80 in every byte of x that is 0 (exact)
+  return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
 __device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off, uint32_t start, uint32_t flen, bool restart,
                                                uint8_t *s_last, int tid) {
   DsClass c;
@@ -59,35 +66,67 @@ __device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off
   c.w[0] = v.x, c.w[1] = v.y, c.w[2] = v.z, c.w[3] = v.w;
   s_last[tid] = (uint8_t)(v.w >> 24);
   __syncthreads();
-  uint32_t prev = tid == 0 ? (off > start && off - 1 < flen ? (uint32_t)__ldg(file + off - 1) : 0u) : s_last[tid - 1];
-  c.emit = c.mark = c.term = c.ffmask = 0;
+  const uint32_t prev = tid == 0 ? (off > start && off - 1 < flen ? (uint32_t)__ldg(file + off - 1) : 0u) : s_last[tid - 1];
+  // the model starts with prev = '\x00' (decoder.ml:279): the byte before `start` does not count
+  uint32_t pff = (prev == 0xffu && off != start) ? 0x80u : 0u;  // "the previous byte is FF", for byte 0 of the word
+  c.anyff = pff;
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    uint32_t ch = (c.w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-    uint32_t pos = off + i;
-    uint32_t p = pos == start ? 0u : prev;  // the model starts with prev = '\x00' (decoder.ml:279)
-    bool in = pos >= start && pos < flen;
-    if (in) {
-      if (p == 0xffu) {
-        if (ch == 0u) {
-          c.emit |= 1u << i;
-          c.ffmask |= 1u << i;  // this slot emits the deferred FF
-        } else if (restart && (ch & 0xf8u) == 0xd0u) {
-          c.mark |= 1u << i;
-        } else {
-          c.term |= 1u << i;
-        }
-      } else if (ch != 0xffu) {
-        c.emit |= 1u << i;
+  for (int k = 0; k < 4; k++) {
+    const uint32_t w = c.w[k];
+    const uint32_t ff = zero_bytes(~w), zz = zero_bytes(w);
+    const uint32_t rst = restart ? zero_bytes((w & 0xf8f8f8f8u) ^ 0xd0d0d0d0u) : 0u;
+    const uint32_t p = (ff << 8) | pff;  // previous byte is FF
+    c.ffz[k] = p & zz;
+    c.emit[k] = (p & zz) | (~p & ~ff & 0x80808080u);
+    c.mark[k] = p & rst;
+    c.term[k] = p & ~zz & ~rst;
+    c.anyff |= ff;
+    pff = ff >> 24;
+  }
+  // bytes outside [start, flen) do not exist (first and last tile of the scan only)
+  if (off < start || off + 16u > flen) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t in = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t pos = off + 4 * k + i;
+        if (pos >= start && pos < flen) in |= 0x80u << (8 * i);
       }
+      // a marker / stuffed pair straddling `start` cannot happen (prev is forced to 0 there); mask everything
+      c.emit[k] &= in;
+      c.mark[k] &= in;
+      c.term[k] &= in;
+      c.ffz[k] &= in;
     }
-    prev = ch;
+    c.anyff |= 0x80u;  // take the byte-wise path
+    // the byte at `start` sees prev = 0 even if the byte before it is FF
+    if (start > off && start < off + 16u) {
+      const uint32_t k = (start - off) >> 2, i = (start - off) & 3u, bit = 0x80u << (8 * i);
+      const uint32_t ch = (c.w[k] >> (8 * i)) & 0xffu;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++)
+        if ((uint32_t)kk == k) {
+          c.mark[kk] &= ~bit;
+          c.term[kk] &= ~bit;
+          c.ffz[kk] &= ~bit;
+          c.emit[kk] = (c.emit[kk] & ~bit) | (ch != 0xffu ? bit : 0u);
+        }
+    }
   }
   return c;
 }
+__device__ __forceinline__ uint32_t ds_count(const uint32_t m[4]) {
+  return (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+}
 // first terminator of the tile (block-wide min), 0xffffffff if none; drops everything at or after it
 __device__ __forceinline__ uint32_t ds_cut_at_terminator(DsClass &c, uint32_t off, uint32_t *s_min, int lane, int warp) {
-  uint32_t tpos = c.term ? off + (uint32_t)__ffs((int)c.term) - 1u : 0xffffffffu;
+  uint32_t tpos = 0xffffffffu;
+  if (c.term[0] | c.term[1] | c.term[2] | c.term[3]) {
+#pragma unroll
+    for (int k = 3; k >= 0; k--)
+      if (c.term[k]) tpos = off + 4 * k + (((uint32_t)__ffs((int)c.term[k]) - 1u) >> 3);
+  }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) tpos = min(tpos, __shfl_xor_sync(0xffffffffu, tpos, s));
   if (lane == 0) s_min[warp] = tpos;
@@ -96,9 +135,17 @@ __device__ __forceinline__ uint32_t ds_cut_at_terminator(DsClass &c, uint32_t of
 #pragma unroll
   for (int k = 1; k < DS_THREADS / 32; k++) tmin = min(tmin, s_min[k]);
   if (tmin != 0xffffffffu && off + 16 > tmin) {
-    uint32_t keep = tmin > off ? (1u << (tmin - off)) - 1u : 0u;
-    c.emit &= keep;
-    c.mark &= keep;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t keep = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (off + 4 * k + i < tmin) keep |= 0x80u << (8 * i);
+      c.emit[k] &= keep;
+      c.mark[k] &= keep;
+      c.ffz[k] &= keep;
+    }
+    c.anyff |= 0x80u;
   }
   return tmin;
 }
@@ -127,7 +174,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_count(DecodeBatchDev b) 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
   const uint32_t tmin = ds_cut_at_terminator(c, off, s_min, lane, warp);
-  uint32_t cnt = ((uint32_t)__popc(c.mark) << 16) | (uint32_t)__popc(c.emit);
+  uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
   if (lane == 0) s_cnt[warp] = cnt;
@@ -224,24 +271,27 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
   __shared__ uint8_t s_last[DS_THREADS];
   __shared__ uint32_t s_warp[DS_THREADS / 32];
   __shared__ uint32_t s_min[DS_THREADS / 32];
-  // Compacted bytes of the tile, placed at the same 16-byte phase as their destination
-  __shared__ __align__(16) uint8_t s_out[DS_TILE + 32];
+  // Compacted bytes of the tile, placed at the same 16-byte phase as their destination.  Zeroed first:
+  // a thread ORs the words it shares with its neighbours and stores the ones that are wholly its own.
+  __shared__ __align__(16) uint32_t s_out[(DS_TILE + 32) / 4];
   const HcjImageDesc *d;
   uint32_t off;
   if (!ds_tile_setup(b, d, off)) return;
   const DsTile tile = b.ds_tiles[d->ds_off + blockIdx.x];
   if (tile.counts == 0xffffffffu) return;  // behind the terminator
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4 *>(s_out)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 2) reinterpret_cast<uint4 *>(s_out)[DS_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
   uint8_t *ent = b.entropy + d->ent_off;
   uint32_t *segs = b.seg_offs + d->seg_off;
   const uint32_t nseg_expected = d->nseg_expected;
   DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
   ds_cut_at_terminator(c, off, s_min, lane, warp);
   // block exclusive scan of (markers << 16 | kept bytes): at most 4096 bytes and 2048 markers per tile
-  const uint32_t cnt = ((uint32_t)__popc(c.mark) << 16) | (uint32_t)__popc(c.emit);
+  const uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
   const uint32_t incl = warp_incl_scan(cnt, lane);
   if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
+  __syncthreads();  // also orders the zeroing of s_out before the ORs below
   uint32_t wbase = 0, total = 0;
 #pragma unroll
   for (int k = 0; k < DS_THREADS / 32; k++) {
@@ -251,30 +301,49 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
   }
   const uint32_t excl = wbase + incl - cnt;
   const uint32_t out0 = tile.counts, phase = out0 & 15u;
-  uint32_t opos = out0 + (excl & 0xffffu);
-  uint32_t so = phase + (excl & 0xffffu);
-  uint32_t mk = tile.term + (excl >> 16);
+  const uint32_t so = phase + (excl & 0xffffu);
+  if (c.anyff == 0u) {
+    // all 16 bytes kept verbatim: shift them to the byte phase of their place and store word-wise
+    const uint32_t q = so >> 2, sh = (so & 3u) * 8u;
+    if (sh == 0u) {
+      s_out[q] = c.w[0], s_out[q + 1] = c.w[1], s_out[q + 2] = c.w[2], s_out[q + 3] = c.w[3];
+    } else {
+      atomicOr(&s_out[q], c.w[0] << sh);
+      s_out[q + 1] = __funnelshift_l(c.w[0], c.w[1], sh);
+      s_out[q + 2] = __funnelshift_l(c.w[1], c.w[2], sh);
+      s_out[q + 3] = __funnelshift_l(c.w[2], c.w[3], sh);
+      atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
+    }
+  } else {
+    uint32_t o = so, opos = out0 + (excl & 0xffffu), mk = tile.term + (excl >> 16);
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    if (c.emit & (1u << i)) {
-      const uint32_t ch = (c.ffmask & (1u << i)) ? 0xffu : (c.w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-      s_out[so++] = (uint8_t)ch;
-      opos++;
-    } else if (c.mark & (1u << i)) {
-      mk++;
-      if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t bit = 0x80u << (8 * i);
+        if (c.emit[k] & bit) {
+          const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
+          atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
+          o++;
+          opos++;
+        } else if (c.mark[k] & bit) {
+          mk++;
+          if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+        }
+      }
     }
   }
   __syncthreads();
+  const uint8_t *s_bytes = reinterpret_cast<const uint8_t *>(s_out);
   const uint32_t nbytes = total & 0xffffu, avail = phase + nbytes;
   uint8_t *dst0 = ent + (out0 - phase);  // 16-byte aligned
   const uint32_t w_lo = phase ? 1u : 0u, w_hi = avail >> 4;  // words [w_lo, w_hi) are wholly this tile's
   for (uint32_t k = w_lo + tid; k < w_hi; k += DS_THREADS)
     reinterpret_cast<uint4 *>(dst0)[k] = reinterpret_cast<const uint4 *>(s_out)[k];
   // partial words at both ends (shared with the neighbouring tiles): byte by byte
-  if (phase && (uint32_t)tid < 16u - phase && phase + tid < avail) dst0[phase + tid] = s_out[phase + tid];
+  if (phase && (uint32_t)tid < 16u - phase && phase + tid < avail) dst0[phase + tid] = s_bytes[phase + tid];
   const uint32_t tail0 = max(w_hi << 4, w_lo << 4);
-  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_out[tail0 + tid];
+  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_bytes[tail0 + tid];
 }
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
