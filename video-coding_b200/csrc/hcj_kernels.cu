@@ -315,20 +315,33 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
       atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
     }
   } else {
+    // some byte of the 16 is special: words that are still kept verbatim go as a unit, the others byte by byte
     uint32_t o = so, opos = out0 + (excl & 0xffffu), mk = tile.term + (excl >> 16);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
+      if (c.emit[k] == 0x80808080u && c.ffz[k] == 0u) {
+        const uint32_t sh = (o & 3u) * 8u;
+        if (sh == 0u) {
+          s_out[o >> 2] = c.w[k];
+        } else {
+          atomicOr(&s_out[o >> 2], c.w[k] << sh);
+          atomicOr(&s_out[(o >> 2) + 1], c.w[k] >> (32u - sh));
+        }
+        o += 4;
+        opos += 4;
+      } else if ((c.emit[k] | c.mark[k]) != 0u) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint32_t bit = 0x80u << (8 * i);
-        if (c.emit[k] & bit) {
-          const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
-          atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
-          o++;
-          opos++;
-        } else if (c.mark[k] & bit) {
-          mk++;
-          if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+        for (int i = 0; i < 4; i++) {
+          const uint32_t bit = 0x80u << (8 * i);
+          if (c.emit[k] & bit) {
+            const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
+            atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
+            o++;
+            opos++;
+          } else if (c.mark[k] & bit) {
+            mk++;
+            if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+          }
         }
       }
     }
