@@ -265,3 +265,79 @@ def test_4k_444_rgb_full_size(hcj, ctx, orc):
     assert st == [0, 0]
     want = oracle_rgb(orc, orc.decode(jpg)).tobytes()
     assert bytes(outs[0]) == want and bytes(outs[1]) == want
+
+
+# ---- the batch pipeline and the tile-parallel kernels at their seams ----------------------------------
+def test_entropy_tap_many_tiles(hcj, ctx, orc):
+    """A scan of hundreds of 4 KiB destuff tiles (stuffed FF 00 pairs and restart markers straddle tile and
+    16-byte boundaries): the destuffed bytes and the interval count must equal the model's."""
+    w, h = 1280, 720
+    for ri, q in ((0, 97), (4, 97)):
+        jpg = orc.encode(synth.frame(4242 + ri, w, h, 444), w, h, 444, q, restart_interval=ri)
+        assert len(jpg) > 600_000
+        hdr = orc.header_decode(jpg)
+        with ctx.batch([jpg], hcj.OUT_PLANES) as b:
+            b.decode()
+            got = bytes(b.entropy(0))
+            dec = orc.decode(jpg, want_blocks=True)
+            assert len(got) == dec.entropy_len
+            if ri == 0:  # the pure model's extract_entropy_coded_bits stops at the first marker: comparable without restarts
+                assert got == bytes(orc.extract_entropy_coded_bits(jpg, hdr.scan_bit_pos // 8))
+            assert np.array_equal(b.coefficients(0), dec.coefs_abs_dc().astype(np.int16))
+
+
+def test_decode_batch_pinned_contiguous(hcj, ctx, orc, data):
+    """hcj_decode_batch with caller buffers laid out back to back in pinned memory (the merged-copy path of the
+    three-stream pipeline), a mix of restart / no-restart / corrupt images, more than one chunk."""
+    import ctypes as C
+
+    L = hcj.lib()
+    w, h = 320, 176
+    jpgs = []
+    for i in range(40):
+        jpgs.append(orc.encode(synth.frame(900 + i, w, h, 420), w, h, 420, 75, restart_interval=(8 if i % 3 else 0)))
+    bad = bytearray(jpgs[7])
+    bad[len(bad) // 2] ^= 0x5A
+    jpgs[7] = bytes(bad)
+    jpgs[21] = data("Mouse480.jpg")
+    n = len(jpgs)
+    sizes = [hcj.out_size(hcj.frame_info(j), hcj.OUT_YUV) for j in jpgs]
+    in_bytes = sum((len(j) + 31) // 16 * 16 for j in jpgs)
+    out_bytes = sum((s + 255) // 256 * 256 for s in sizes)
+    pin_in, pin_out = L.hcj_host_alloc(in_bytes), L.hcj_host_alloc(out_bytes)
+    assert pin_in and pin_out
+    try:
+        jp, lens = (C.c_void_p * n)(), (C.c_size_t * n)()
+        op, caps, status = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        oi = oo = 0
+        for i, j in enumerate(jpgs):
+            C.memmove(pin_in + oi, j, len(j))
+            jp[i], lens[i] = pin_in + oi, len(j)
+            oi += (len(j) + 31) // 16 * 16
+            op[i], caps[i] = pin_out + oo, (sizes[i] + 255) // 256 * 256
+            oo += (sizes[i] + 255) // 256 * 256
+        C.memset(pin_out, 0xA5, out_bytes)
+        hcj._check(L.hcj_decode_batch(ctx._h, jp, lens, n, hcj.OUT_YUV, hcj.FLAG_DEFAULT, op, caps, status))
+        for i, j in enumerate(jpgs):
+            try:
+                want = orc.decode(j).yuv()
+            except orc.OracleError as e:
+                assert status[i] == e.status, i
+                continue
+            assert status[i] == 0, (i, status[i])
+            got = bytes(np.ctypeslib.as_array(C.cast(op[i], C.POINTER(C.c_uint8)), shape=(sizes[i],)))
+            assert got == want, i
+    finally:
+        L.hcj_host_free(pin_in)
+        L.hcj_host_free(pin_out)
+
+
+def test_speculative_many_subsequences_and_rounds(hcj, ctx, orc):
+    """Scans without restart markers long enough for several CTAs of subsequences per image, at a quality where
+    blocks are longer than the guess window of the first pass (the fix-point rounds have work to do)."""
+    cases = [(444, 98, 640, 480), (420, 12, 1024, 768), (422, 90, 800, 608)]
+    jpgs = [orc.encode(synth.frame(3100 + i, w, h, c), w, h, c, q) for i, (c, q, w, h) in enumerate(cases)]
+    outs, st = ctx.decode_batch(jpgs)
+    assert st == [0] * len(jpgs)
+    for j, o in zip(jpgs, outs):
+        assert bytes(o) == orc.decode(j).yuv()

@@ -113,3 +113,17 @@ def test_1080p_encode_full_size(hcj, ctx, orc, ri):
     assert st == [0, 0]
     for j, d in zip(want, dec):
         assert bytes(d) == orc.decode(j).yuv()
+
+
+def test_encode_device_time_and_long_single_segment(hcj, ctx, orc):
+    """A frame whose scan is one long segment (no restart markers): the byte stuffing is split into 1 KiB units;
+    the result must still be the model's bytes, and the device time of the call is reported."""
+    import ctypes as C
+
+    w, h = 1024, 768
+    frame = synth.frame(77, w, h, 444)
+    outs, st = ctx.encode_batch([frame], w, h, 444, 96)
+    assert st == [0] and outs[0] == orc.encode(frame, w, h, 444, 96)
+    ms = C.c_float()
+    hcj._check(hcj.lib().hcj_encode_last_device_ms(ctx._h, C.byref(ms)))
+    assert 0.0 < ms.value < 1000.0
