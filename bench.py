@@ -159,6 +159,31 @@ def measured_traffic(kernel, n_images):
         return None
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and so its pinned host buffers, first-touch) to the CPUs of the NUMA node the GPU hangs
+    off: with one process per GPU the PCIe copies of the end-to-end leg then stay on the GPU's own socket.
+    Best effort: returns the node or None."""
+    try:
+        bdf = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True).strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -227,6 +252,8 @@ def main():
             "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    config["numa_node"] = numa
     import torch
 
     torch.cuda.set_device(local)
