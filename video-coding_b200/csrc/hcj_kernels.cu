@@ -1593,44 +1593,70 @@ __device__ __forceinline__ int up_sample(const uint8_t *p, int stride, int w, in
   return (a + p[cy * stride + cx1] + p[cy1 * stride + cx] + p[cy1 * stride + cx1] + 2) >> 2;
 }
 
-__global__ void k_rgb(DecodeBatchDev b) {
+// The stated colour formula for one pixel, packed 0x00BBGGRR.
+__device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
+  Cb -= 128;
+  Cr -= 128;
+  const int r = Y + ((91881 * Cr + 32768) >> 16);
+  const int g = Y + ((-22554 * Cb - 46802 * Cr + 32768) >> 16);
+  const int bl = Y + ((116130 * Cb + 32768) >> 16);
+  return (uint32_t)min(255, max(0, r)) | ((uint32_t)min(255, max(0, g)) << 8) | ((uint32_t)min(255, max(0, bl)) << 16);
+}
+
+// Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16).  4:4:4 images whose rows keep
+// 16-byte alignment (width and padded width multiples of 16) take the vector path: one 16-byte load per
+// plane, three 16-byte stores; everything else goes pixel by pixel through up_sample.
+__global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
   if (!d.valid || d.chroma == 0) return;
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
   if (y >= d.height || x0 >= d.width) return;
-  const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
   const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off,
                 *pv = b.planes + d.comp[2].plane_off;
   uint8_t *dst = b.out + d.out_off + ((size_t)y * d.width + x0) * 3;
-  uint8_t rgb[12];
-  const int n = min(4, d.width - x0);
-  for (int i = 0; i < n; i++) {
-    int x = x0 + i;
-    int Y = py[y * d.comp[0].decoded_w + x];
-    int Cb = up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log) - 128;
-    int Cr = up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log) - 128;
-    int r = Y + ((91881 * Cr + 32768) >> 16);
-    int g = Y + ((-22554 * Cb - 46802 * Cr + 32768) >> 16);
-    int bl = Y + ((116130 * Cb + 32768) >> 16);
-    rgb[3 * i + 0] = (uint8_t)min(255, max(0, r));
-    rgb[3 * i + 1] = (uint8_t)min(255, max(0, g));
-    rgb[3 * i + 2] = (uint8_t)min(255, max(0, bl));
+  const int sy = d.comp[0].decoded_w;
+  const bool vec = d.chroma == 444 && ((d.width | sy | d.comp[1].decoded_w | d.comp[2].decoded_w) & 15) == 0 &&
+                   (((uintptr_t)py | (uintptr_t)pu | (uintptr_t)pv | (uintptr_t)(b.out + d.out_off)) & 15u) == 0;
+  if (vec) {
+    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
+    const uint4 vu = __ldg(reinterpret_cast<const uint4 *>(pu + (size_t)y * d.comp[1].decoded_w + x0));
+    const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pv + (size_t)y * d.comp[2].decoded_w + x0));
+    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w}, wv[4] = {vv.x, vv.y, vv.z, vv.w};
+    uint32_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
+      uint32_t px[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, (wu[k] >> (8 * i)) & 0xff, (wv[k] >> (8 * i)) & 0xff);
+      o[3 * k + 0] = px[0] | (px[1] << 24);
+      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    return;
   }
-  if (n == 4 && ((uintptr_t)dst & 3u) == 0) {
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(rgb);
-    d32[0] = s32[0];
-    d32[1] = s32[1];
-    d32[2] = s32[2];
-  } else {
-    for (int i = 0; i < 3 * n; i++) dst[i] = rgb[i];
+  const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
+  const int n = min(16, d.width - x0);
+  for (int i = 0; i < n; i++) {
+    const int x = x0 + i;
+    const int Y = py[(size_t)y * sy + x];
+    const int Cb = up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log);
+    const int Cr = up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
+    const uint32_t px = ycc_to_rgb(Y, Cb, Cr);
+    dst[3 * i + 0] = (uint8_t)px;
+    dst[3 * i + 1] = (uint8_t)(px >> 8);
+    dst[3 * i + 2] = (uint8_t)(px >> 16);
   }
 }
 
 void launch_rgb(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
   dim3 block(128);
-  dim3 grid((b.max_width / 4 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
+  dim3 grid((b.max_width / 16 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
   k_rgb<<<grid, block, 0, s>>>(b);
 }
 
