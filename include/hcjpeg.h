@@ -147,7 +147,9 @@ int hcj_decode_batch(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len
 
 /* The same in three steps, for pipelines that keep data resident in HBM. */
 typedef struct hcj_batch hcj_batch;
-/* Header.decode + init for every image, then upload (H2D) of the compressed bytes and tables. */
+/* Header.decode + init for every image, then upload (H2D) of the compressed bytes and tables.
+ * n <= HCJ_MAX_BATCH (the image index is a CUDA grid dimension); larger jobs are split by the caller. */
+#define HCJ_MAX_BATCH 65535
 int hcj_batch_create(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      int *status, hcj_batch **out);
 /* Decoder.decode for the whole batch: kernels only, asynchronous on the context's stream. */

@@ -208,7 +208,7 @@ static cudaError_t upload_files(const hcj_batch *b, const uint8_t *const *jpeg, 
 
 static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                         int *status, hcj_batch **out, bool with_files) {
-  if (!c || !out || n < 0 || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > 2) return HCJ_ERR_INVALID_ARG;
+  if (!c || !out || n < 0 || n > HCJ_MAX_BATCH || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > 2) return HCJ_ERR_INVALID_ARG;
   *out = nullptr;
   CU_TRY(cudaSetDevice(c->device));
   hcj_batch *b = new (std::nothrow) hcj_batch;

@@ -521,7 +521,7 @@ int hcj_write_headers(int width, int height, int chroma, int quality, int restar
 
 int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
                      int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len, int *status) {
-  if (!c || n < 0 || (n > 0 && (!yuv || !out || !out_capacity || !out_len))) return HCJ_ERR_INVALID_ARG;
+  if (!c || n < 0 || n > HCJ_MAX_BATCH || (n > 0 && (!yuv || !out || !out_capacity || !out_len))) return HCJ_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(c->device));
   EncodeSetup S;
   int st = setup_encode(c, n, width, height, chroma, quality, restart_interval, true, &S);
