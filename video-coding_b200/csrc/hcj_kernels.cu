@@ -1,15 +1,20 @@
 // hcj_kernels.cu — decode kernels for sm_100a.
 //
-//   k_destuff        D3  extract_entropy_coded_bits (decoder.ml:261-281) + restart-marker scan
-//   k_huff_restart   D6  huffman_decode per restart interval (stated extension), DC resolved in-thread
-//   k_huff_spec      D6  huffman_decode of a scan without restart markers: self-synchronising
-//                        speculative subsequence decode, block-wide fix-point, prefix sums for block
-//                        indices and DC predictors (decoder.ml:118-165,347-397)
-//   k_idct           D7-D11 dequantise + inverse zig-zag + Chen IDCT + clip + store (+ crop)
-//   k_rgb            D12/D13 Planar_444 up-sampling + stated YCbCr->RGB
+//   k_destuff_count / _scan / _write   D3  extract_entropy_coded_bits (decoder.ml:261-281) + restart-marker
+//                                          scan, tile-parallel
+//   k_huff_restart                     D6  huffman_decode per restart interval (stated extension), DC
+//                                          resolved in-thread: fast steps in lock step per block
+//   k_spec_sync x2 / _fix / _write     D6  huffman_decode of a scan without restart markers: self-synchronising
+//                                          speculative subsequence decode over the whole batch, per-image
+//                                          fix-point on a compacted list, prefix sums for block indices and
+//                                          DC predictors (decoder.ml:118-165,347-397), exact pass
+//   k_idct_persistent                  D7-D11 dequantise + inverse zig-zag + Chen IDCT + clip + store (+ crop)
+//   k_rgb                              D12/D13 Planar_444 up-sampling + stated YCbCr->RGB
+//   k_idct_blocks, k_compare           debug tap (Component.recon), Ocompare on the device
 //
-// None of this is GEMM-shaped: no tensor cores.  The entropy kernels are issue/latency bound, the
-// IDCT kernel is HBM bound (DESIGN.md has the byte counts).
+// None of this is GEMM-shaped: no tensor cores.  The entropy kernels are bound by instruction issue and
+// shared-memory table look-ups, the IDCT kernel by integer issue at 50 % of the HBM roofline (DESIGN.md has
+// the byte counts and the ncu numbers).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -1224,32 +1229,7 @@ __device__ __noinline__ void wide_block_store(const uint32_t *cw, const int32_t 
   store_block_rows(pix, dst, stride, x, y, w_limit, h_limit);
 }
 
-struct IdctTile {
-  const HcjImageDesc *d;  // nullptr: nothing to do
-  int my, m0, tm, nblk;
-};
-
-__device__ __forceinline__ IdctTile idct_tile(const DecodeBatchDev &b, uint32_t tile_id) {
-  IdctTile t;
-  t.d = nullptr;
-  t.my = t.m0 = t.tm = t.nblk = 0;
-  const uint32_t rel = tile_id / b.max_idct_tiles, tile = tile_id - rel * b.max_idct_tiles;
-  const HcjImageDesc &d = b.descs[rel + b.img_lo];
-  if (!d.valid) return t;
-  const int bpm = d.bpm;
-  const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / bpm);
-  const int tiles_per_row = (d.mcus_wide + tm_max - 1) / tm_max;
-  const int tm_bal = (d.mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
-  if (tile >= (uint32_t)(tiles_per_row * d.mcus_high)) return t;
-  t.my = tile / tiles_per_row;
-  t.m0 = (tile - t.my * tiles_per_row) * tm_bal;
-  t.tm = min(tm_bal, d.mcus_wide - t.m0);
-  t.nblk = t.tm * bpm;
-  t.d = &d;
-  return t;
-}
-
-// Persistent CTAs (2 per SM): each owns a contiguous range of the batch's tiles and keeps the coefficient
+// Persistent CTAs (HCJ_IDCT_CTAS_PER_SM per SM): each owns a contiguous range of the batch's tiles and keeps the coefficient
 // tile, the quant tables and the wide-block flags of tile i+1 in flight (cp.async) while tile i is being
 // transformed.  The thread -> block mapping depends only on (image geometry, tile width): it is computed
 // when either changes and kept in registers, so the per-tile overhead is a handful of instructions.
@@ -1453,86 +1433,18 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct
   }
 }
 
-// One tile per CTA: load (cp.async) -> transform -> store; latency is hidden by the other resident CTAs.
-__global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct(DecodeBatchDev b, int mode) {
-  extern __shared__ uint4 s_dyn[];
-  uint4 *s_tile = s_dyn;
-  int32_t *s_q = reinterpret_cast<int32_t *>(s_dyn + IDCT_MAX_THREADS * IDCT_ROW_U4);
-  const int tid = threadIdx.x;
-  const IdctTile t = idct_tile(b, blockIdx.y * b.max_idct_tiles + blockIdx.x);
-  if (!t.d) return;
-  const HcjImageDesc &d = *t.d;
-  const int16_t *src = b.coefs + (d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm) * 64;
-  for (int g = tid; g < t.nblk * 8; g += IDCT_MAX_THREADS) cp_async16(&s_tile[(g >> 3) * IDCT_ROW_U4 + (g & 7)], src + g * 8);
-  if (tid < d.ncomp * 32) cp_async16(s_q + tid * 4, b.qtables + d.qt_off + tid * 4);  // comp k uses table slot k
-  cp_async_wait_all();
-  __syncthreads();
-  if (tid >= t.nblk) return;
-  // thread -> (component, block row, MCU, block column)
-  int rem = tid, c = 0;
-  for (; c < d.ncomp - 1; c++) {
-    int n = t.tm * d.comp[c].hs * d.comp[c].vs;
-    if (rem < n) break;
-    rem -= n;
-  }
-  const HcjCompGeom &g = d.comp[c];
-  const int rowlen = t.tm * g.hs;
-  const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
-  const int r2 = rem - by * rowlen;
-  const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
-  const int bx = r2 - m * g.hs;
-  const int slot = m * d.bpm + g.first_blk + by * g.hs + bx;
-  uint32_t cw[32];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    uint4 u = s_tile[slot * IDCT_ROW_U4 + j];
-    cw[4 * j] = u.x;
-    cw[4 * j + 1] = u.y;
-    cw[4 * j + 2] = u.z;
-    cw[4 * j + 3] = u.w;
-  }
-  uint32_t pix[16];
-  const int32_t *q = s_q + c * 128;
-  const int x = ((t.m0 + m) * g.hs + bx) * 8, y = (t.my * g.vs + by) * 8;
-  uint8_t *base;
-  int stride, w_limit, h_limit;
-  if (mode == 0) {
-    base = b.out + d.out_off + g.out_off;
-    stride = w_limit = g.actual_w;
-    h_limit = g.actual_h;
-  } else {
-    base = (mode == 1 ? b.out + d.out_off : b.planes) + g.plane_off;
-    stride = w_limit = g.decoded_w;
-    h_limit = g.decoded_h;
-  }
-  const uint64_t gblk = d.coef_off + ((uint64_t)t.my * d.mcus_wide + t.m0) * d.bpm + slot;
-  const bool wide = d.wide_idct || ((__ldg(b.wide_flags + (gblk >> 5)) >> (gblk & 31u)) & 1u);
-  if (wide || !reconstruct_fast<false>(cw, q + 64, pix)) {
-    wide_block_store(reinterpret_cast<const uint32_t *>(&s_tile[slot * IDCT_ROW_U4]), q, base, stride, x, y, w_limit, h_limit);
-    return;
-  }
-  store_block_rows(pix, base, stride, x, y, w_limit, h_limit);
-}
-
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_idct_tiles == 0) return;
-  static int grid = 0, persistent = 0;
-  const size_t smem1 = (size_t)IDCT_MAX_THREADS * IDCT_ROW_U4 * sizeof(uint4) + HCJ_MAX_COMP * 128 * sizeof(int32_t);
+  static int grid = 0;
   if (!grid) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(IdctStage)));
     grid = HCJ_IDCT_CTAS_PER_SM * sms;
-    const char *e = getenv("HCJ_IDCT_PERSISTENT");
-    persistent = !(e && e[0] == '0');  // default; HCJ_IDCT_PERSISTENT=0 selects the one-tile-per-CTA kernel
   }
-  if (persistent) {
-    uint64_t total = (uint64_t)(b.img_hi - b.img_lo) * b.max_idct_tiles;
-    k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * sizeof(IdctStage), s>>>(b, mode);
-  } else {
-    k_idct<<<dim3(b.max_idct_tiles, b.img_hi - b.img_lo), IDCT_MAX_THREADS, smem1, s>>>(b, mode);
-  }
+  const uint64_t total = (uint64_t)(b.img_hi - b.img_lo) * b.max_idct_tiles;
+  k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * sizeof(IdctStage), s>>>(b, mode);
 }
 
 // Debug tap: Component.recon of caller-provided blocks (hcj_idct_blocks).
@@ -1573,7 +1485,7 @@ void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt
 // ================================================================================================
 // K9: Planar_444 up-sampling (tools/src/planar_444.ml:25-33,82-103) + YCbCr -> RGB24 (stated formula,
 // JFIF full range, 16-bit fixed point).  One thread per 4 horizontally adjacent pixels.
-// Reads the padded planes written by k_idct (mode 2); the up-sampling clamps at the CROPPED plane
+// Reads the padded planes written by k_idct_persistent (mode 2); the up-sampling clamps at the CROPPED plane
 // edge, as Planar_444 does on the cropped frame.
 // ================================================================================================
 __device__ __forceinline__ int up_sample(const uint8_t *p, int stride, int w, int h, int x, int y, int hs_log, int vs_log) {
