@@ -491,6 +491,14 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     hcj_batch_destroy(c, b);
     return st;
   }
+  dv.total_blocks = total_blocks;
+  {
+    int tm = hcjk::make_coef_tensor_map(&dv);
+    if (tm != 0) {
+      hcj_batch_destroy(c, b);
+      return HCJ_ERR_CUDA - tm;
+    }
+  }
   dv.n = n;
   dv.descs = d_descs;
   dv.files = d_files;

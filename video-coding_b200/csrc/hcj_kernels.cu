@@ -15,6 +15,7 @@
 // None of this is GEMM-shaped: no tensor cores.  The entropy kernels are bound by instruction issue and
 // shared-memory table look-ups, the IDCT kernel by integer issue at 50 % of the HBM roofline (DESIGN.md has
 // the byte counts and the ncu numbers).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -1234,15 +1235,50 @@ __device__ __noinline__ void wide_block_store(const uint32_t *cw, const int32_t 
 // transformed.  The thread -> block mapping depends only on (image geometry, tile width): it is computed
 // when either changes and kept in registers, so the per-tile overhead is a handful of instructions.
 // mode: 0 = HCJ_OUT_YUV (cropped planes, packed), 1 = padded planes into b.out, 2 = padded planes into b.planes
-constexpr int IDCT_TILE_U4 = IDCT_MAX_THREADS * IDCT_ROW_U4;
 constexpr int IDCT_Q_I32 = HCJ_MAX_COMP * 128;
 constexpr int IDCT_FLAG_U4 = 3;  // 256 blocks = 8 flag words, at any alignment inside 3 x 16 bytes
 
-struct IdctStage {  // one pipeline stage in shared memory
-  uint4 tile[IDCT_TILE_U4];
+// One pipeline stage in shared memory.  The tile is dense (128 bytes per block, no padding) and laid out by the
+// TMA unit with its 128-byte swizzle: 16-byte chunk j of block r sits at chunk j ^ (r & 7) of row r, so the eight
+// lanes of a quarter-warp, which read the same chunk of eight consecutive blocks, hit eight different bank groups.
+struct alignas(1024) IdctStage {
+  uint4 tile[IDCT_MAX_THREADS * 8];
   int32_t q[IDCT_Q_I32];
   uint4 flags[IDCT_FLAG_U4 + 1];
+  uint64_t full;  // mbarrier: the TMA copies of the stage complete their bytes on it
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (quant tables, flags)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 2-D tensor tile copy: the box of `map` whose first row is `row`
+__device__ __forceinline__ void tma_tile_g2s(void *dst, const void *map, int32_t row, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(0), "r"(row), "r"(smem_u32(bar))
+      : "memory");
+}
 
 // The CTA's walk over its range of tile ids (id = image * max_idct_tiles + tile within the image).  All the
 // divisions that turn an id into (image, MCU row, first MCU) are done once per image; from one tile to the
@@ -1316,24 +1352,24 @@ struct TileCursor {
   }
 };
 
-// Requests one tile: 16-byte chunk g of the run of blocks goes to row g / 8, column g % 8 of the padded stage;
-// thread tid takes chunks tid, tid + T, ...: eight copies whose addresses differ by constants.
-__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctWork &t, IdctStage &st, int tid) {
+// Requests one tile (thread 0 only): one TMA tensor copy brings the run of blocks that starts at the tile's first
+// block (always a full box of HCJ_IDCT_THREADS blocks: the rows behind the tile's own belong to the next tile or
+// are filled with zeros past the end of the buffer), two small bulk copies the quant tables and the 48 bytes of
+// wide-block flags; all of them complete on the stage's mbarrier.
+__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctWork &t, IdctStage &st) {
   const HcjImageDesc *d = t.d;
-  const int n8 = t.nblk * 8;
-  const uint64_t blk0 = t.blk0;
-  const int16_t *src = b.coefs + blk0 * 64 + tid * 8;
-  uint4 *dst = &st.tile[(tid >> 3) * IDCT_ROW_U4 + (tid & 7)];
-#pragma unroll
-  for (int k = 0; k < 8; k++)
-    if (tid + k * IDCT_MAX_THREADS < n8) cp_async16(dst + k * (IDCT_MAX_THREADS / 8) * IDCT_ROW_U4, src + k * IDCT_MAX_THREADS * 8);
-  if (tid < d->ncomp * 32) cp_async16(st.q + tid * 4, b.qtables + d->qt_off + tid * 4);  // comp k uses table slot k
-  if (tid < IDCT_FLAG_U4) cp_async16(&st.flags[tid], reinterpret_cast<const uint4 *>(b.wide_flags) + (blk0 >> 7) + tid);
+  const uint32_t qbytes = (uint32_t)d->ncomp * 512u;
+  mbar_arrive_expect_tx(&st.full, IDCT_MAX_THREADS * 128u + qbytes + IDCT_FLAG_U4 * 16u);
+  tma_tile_g2s(st.tile, b.coef_map, (int32_t)t.blk0, &st.full);
+  bulk_g2s(st.q, b.qtables + d->qt_off, qbytes, &st.full);  // comp k uses table slot k
+  bulk_g2s(st.flags, reinterpret_cast<const uint4 *>(b.wide_flags) + (t.blk0 >> 7), IDCT_FLAG_U4 * 16u, &st.full);
 }
 
-__global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct_persistent(DecodeBatchDev b, int mode) {
+__global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
+    k_idct_persistent(const __grid_constant__ DecodeBatchDev b, int mode) {
   extern __shared__ uint4 s_dyn[];
-  IdctStage *stages = reinterpret_cast<IdctStage *>(s_dyn);
+  // 1 KiB alignment for the swizzled tiles (the launch asks for 1 KiB more than two stages)
+  IdctStage *stages = reinterpret_cast<IdctStage *>(reinterpret_cast<uint8_t *>(s_dyn) + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u));
   const int tid = threadIdx.x;
   const uint32_t total = (b.img_hi - b.img_lo) * b.max_idct_tiles;
   const uint32_t chunk = (total + gridDim.x - 1) / gridDim.x;
@@ -1360,18 +1396,20 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct
     s_cur.init(b, begin, end);
     s_have[0] = s_cur.next(b, s_work[0]);
     s_have[1] = s_have[0] && s_cur.next(b, s_work[1]);
+    mbar_init(&stages[0].full, 1);
+    mbar_init(&stages[1].full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (s_have[0]) idct_issue(b, s_work[0], stages[0]);
   }
   __syncthreads();
-  if (s_have[0]) idct_issue(b, s_work[0], stages[0], tid);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
   for (int i = 0; s_have[i & 3]; i++) {
     const int buf = i & 1;
     IdctStage &st = stages[buf];
-    if (tid == 0) s_have[(i + 2) & 3] = s_have[(i + 1) & 3] && s_cur.next(b, s_work[(i + 2) & 3]);
-    if (s_have[(i + 1) & 3]) idct_issue(b, s_work[(i + 1) & 3], stages[buf ^ 1], tid);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    __syncthreads();
+    if (tid == 0) {
+      s_have[(i + 2) & 3] = s_have[(i + 1) & 3] && s_cur.next(b, s_work[(i + 2) & 3]);
+      if (s_have[(i + 1) & 3]) idct_issue(b, s_work[(i + 1) & 3], stages[buf ^ 1]);
+    }
+    mbar_wait(&st.full, (uint32_t)(i >> 1) & 1u);  // the stage's (i / 2)-th use
     const IdctWork &t = s_work[i & 3];
     {
       const HcjImageDesc &d = *t.d;
@@ -1412,7 +1450,7 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct
         uint32_t cw[32];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          uint4 u = st.tile[slot * IDCT_ROW_U4 + j];
+          uint4 u = st.tile[slot * 8 + (j ^ (slot & 7))];
           cw[4 * j] = u.x;
           cw[4 * j + 1] = u.y;
           cw[4 * j + 2] = u.z;
@@ -1424,7 +1462,7 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct
         const int32_t *q = st.q + qoff;
         uint32_t pix[16];
         if (wide || !reconstruct_fast<false>(cw, q + 64, pix))
-          wide_block_store(reinterpret_cast<const uint32_t *>(&st.tile[slot * IDCT_ROW_U4]), q, plane, stride, x, y, w_limit, h_limit);
+          wide_block_store(cw, q, plane, stride, x, y, w_limit, h_limit);
         else
           store_block_rows(pix, plane, stride, x, y, w_limit, h_limit);
       }
@@ -1433,6 +1471,8 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM) k_idct
   }
 }
 
+constexpr size_t IDCT_SMEM = 2 * sizeof(IdctStage) + 1024;
+
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_idct_tiles == 0) return;
   static int grid = 0;
@@ -1440,11 +1480,37 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(IdctStage)));
+    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
     grid = HCJ_IDCT_CTAS_PER_SM * sms;
   }
   const uint64_t total = (uint64_t)(b.img_hi - b.img_lo) * b.max_idct_tiles;
-  k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, 2 * sizeof(IdctStage), s>>>(b, mode);
+  k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
+}
+
+// The coefficient buffer as the TMA unit sees it: uint16 [total blocks][64], box = HCJ_IDCT_THREADS blocks x 64,
+// 128-byte swizzle, zeros out of bounds.  cuTensorMapEncodeTiled is looked up through the runtime (no -lcuda).
+int make_coef_tensor_map(DecodeBatchDev *b) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return (int)e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  static_assert(sizeof(CUtensorMap) == sizeof(b->coef_map), "CUtensorMap is 128 bytes");
+  const cuuint64_t dims[2] = {64, b->total_blocks ? b->total_blocks : 1};
+  const cuuint64_t strides[1] = {128};  // bytes from one block to the next
+  const cuuint32_t box[2] = {64, IDCT_MAX_THREADS};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap *>(b->coef_map), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, b->coefs, dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
 // Debug tap: Component.recon of caller-provided blocks (hcj_idct_blocks).

@@ -24,6 +24,9 @@ struct DecodeBatchDev {
   const uint16_t *lut_full;       // full LUT pool
   const int32_t *qtables;         // quant tables pool, zig-zag order, one int32 per entry
   int16_t *coefs;                 // [total blocks][64], zig-zag, DC resolved
+  // TMA tensor map of `coefs` as a 2-D uint16 tensor [total blocks][64], box = one IDCT tile (HCJ_IDCT_THREADS
+  // blocks), 128-byte swizzle (a CUtensorMap: opaque 128 bytes, built by make_coef_tensor_map)
+  alignas(64) unsigned char coef_map[128];
   uint32_t *wide_flags;           // 1 bit per block: take the 64-bit IDCT (zeroed before every decode)
   uint8_t *planes;                // padded planes (scratch for RGB mode, the output for PLANES mode)
   uint8_t *out;                   // outputs
@@ -60,6 +63,8 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
 int huff_spec_kernel_count();
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s);
+// Fills b->coef_map for b->coefs / b->total_blocks.  Returns a cudaError_t-compatible code (0 = ok).
+int make_coef_tensor_map(DecodeBatchDev *b);
 void launch_rgb(const DecodeBatchDev &b, cudaStream_t s);
 void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
                         cudaStream_t s);
