@@ -232,7 +232,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   size_t total_sub = 0, total_ds_tiles = 0;
   uint32_t max_ds_tiles = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
-  if (const char *e = getenv("HCJ_SUB_LOG2")) sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));  // experiments
+  bool sub_log2_env = false;
+  if (const char *e = getenv("HCJ_SUB_LOG2")) {  // experiments
+    sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));
+    sub_log2_env = true;
+  }
   const int tile_mcus = HCJ_IDCT_THREADS;  // upper bound on MCUs per IDCT tile (one thread per block)
   // Decoder.Header.decode + the geometry of Decoder.init for every image: independent per image, so spread over
   // a few host threads (it is the serial prologue of every batch: 6 ms single-threaded for 1024 files)
@@ -431,9 +435,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       list_spec.push_back((uint32_t)i);
       // subsequences of 2^sub_log2 bits: long enough for the decoder to resynchronise inside one almost always
       // (a couple of MCUs), short enough for one thread each to fill the GPU
-      d.sub_log2 = sub_log2;
+      // measured: 4096 bits for 65-bit blocks (1080p q75: 7.8 ms vs 8.0 ms at 8192), 8192 bits for 175-bit blocks
+      // (4k 4:4:4 q95: 11.5 ms vs 12.9 ms at 4096): the per-subsequence work is per block, not per bit
+      d.sub_log2 = sub_log2_env ? sub_log2 : ((uint64_t)(d.file_len - d.scan_start) * 8 > (uint64_t)d.nblocks * 120 ? 13u : 12u);
       d.sub_off = (uint32_t)total_sub;
-      const size_t nsub_max = (((size_t)d.ent_cap * 8) >> sub_log2) + 2;
+      const size_t nsub_max = (((size_t)d.ent_cap * 8) >> d.sub_log2) + 2;
       total_sub += nsub_max + 1;
       max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max + 255) / 256));
     }
