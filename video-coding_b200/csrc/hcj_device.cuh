@@ -943,28 +943,33 @@ namespace hcjdev {
 // dcdiff: quant.(0) - dc_pred.  dc_codes[size], ac_codes[(run << 4) | size] = (code << 8) | length.
 // Returns false if a symbol has no code (the model raises an index-out-of-bounds exception).
 // ------------------------------------------------------------------------------------------------
-template <class Emit>
-HCJ_HD bool encode_block_fields(const int16_t *q, int32_t dcdiff, const uint32_t *dc_codes, const uint32_t *ac_codes,
-                                Emit &emit) {
+// `coef(k)` returns quantised coefficient k (zig-zag order).  The loop over k is written to be fully unrolled, so
+// that a kernel can keep the block in registers (coef(k) with a constant k) instead of a local-memory array.
+// WITH_DC = false emits the AC fields only (the DC differential needs the neighbouring block's DC).
+template <bool WITH_DC = true, class Coef, class Emit>
+HCJ_HD bool encode_block_fields_from(Coef coef, int32_t dcdiff, const uint32_t *dc_codes, const uint32_t *ac_codes, Emit &emit) {
   bool ok = true;
-  uint32_t size = coef_size(dcdiff);
-  uint32_t code = size < 16u ? dc_codes[size] : 0u;
-  ok &= (code & 0xffu) != 0u;
-  emit(code >> 8, code & 0xffu);
-  emit(coef_magnitude(dcdiff, size), size);
+  uint32_t size, code;
+  if (WITH_DC) {
+    size = coef_size(dcdiff);
+    code = size < 16u ? dc_codes[size] : 0u;
+    ok &= (code & 0xffu) != 0u;
+    emit(code >> 8, code & 0xffu);
+    emit(coef_magnitude(dcdiff, size), size);
+  }
   uint32_t run = 0;
+#pragma unroll
   for (int k = 1; k < 64; k++) {
-    int32_t v = q[k];
+    const int32_t v = coef(k);
     if (k == 63 && v == 0) {  // [ { run; value = 0 } ] -> end of block (encoder.ml:172-175)
       code = ac_codes[0x00];
       ok &= (code & 0xffu) != 0u;
       emit(code >> 8, code & 0xffu);
     } else if (v != 0) {
-      while (run >= 16u) {  // runs (encoder.ml:178-185)
+      for (; run >= 16u; run -= 16u) {  // runs (encoder.ml:178-185)
         code = ac_codes[0xf0];
         ok &= (code & 0xffu) != 0u;
         emit(code >> 8, code & 0xffu);
-        run -= 16u;
       }
       size = coef_size(v);
       code = size < 16u ? ac_codes[(run << 4) | size] : 0u;
@@ -977,6 +982,18 @@ HCJ_HD bool encode_block_fields(const int16_t *q, int32_t dcdiff, const uint32_t
     }
   }
   return ok;
+}
+
+template <class Emit>
+HCJ_HD bool encode_block_fields(const int16_t *q, int32_t dcdiff, const uint32_t *dc_codes, const uint32_t *ac_codes,
+                                Emit &emit) {
+  return encode_block_fields_from([q](int k) { return (int32_t)q[k]; }, dcdiff, dc_codes, ac_codes, emit);
+}
+
+// coefficient k of a block held as 32 words of two int16 each (the layout of the coefficient buffer)
+HCJ_HD int32_t packed_coef(const uint32_t *qw, int k) {
+  const uint32_t w = qw[k >> 1];
+  return (k & 1) ? (int32_t)w >> 16 : (int32_t)(int16_t)(w & 0xffffu);
 }
 
 }  // namespace hcjdev

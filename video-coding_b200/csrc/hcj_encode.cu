@@ -6,9 +6,9 @@
 //   k_pack         E8,E9     per block: write code + magnitude fields at their bit offset (big-endian
 //                            32-bit words, atomicOr only on the two boundary words), 1-fill at the end of
 //                            every segment (flush_with_1s, bitstream_writer.ml:45-49)
-//   k_seg_count    E9        per segment: stuffed byte count (bytes + number of FF bytes)
-//   k_seg_scan     per frame: prefix sum of segment sizes -> output offsets; copies the header
-//   k_stuff        E9,E10    per segment: byte copy with FF -> FF 00, RSTn between segments, EOI
+//   k_seg_count    E9        per unit (segment, or 1 KiB of a lone segment): stuffed byte count
+//   k_seg_scan     per frame: prefix sum of unit sizes -> output offsets; copies the header
+//   k_stuff        E9,E10    per unit: byte copy with FF -> FF 00, RSTn between segments, EOI
 //
 // Results are byte-identical to the model's Writer.get_buffer (tests/test_gpu_encode.py).
 #include <cuda_runtime.h>
@@ -110,15 +110,19 @@ __global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *statu
   const uint32_t frame = blockIdx.y;
   if (blk >= e.nblocks) return;
   const int16_t *q = e.quant + ((uint64_t)frame * e.nblocks + blk) * 64;
-  int16_t loc[64];
+  uint32_t qw[32];  // the block in registers: the field loop is fully unrolled
   const uint4 *src = reinterpret_cast<const uint4 *>(q);
 #pragma unroll
-  for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(loc + 8 * j) = __ldg(src + j);
+  for (int j = 0; j < 8; j++) {
+    const uint4 u = __ldg(src + j);
+    qw[4 * j] = u.x, qw[4 * j + 1] = u.y, qw[4 * j + 2] = u.z, qw[4 * j + 3] = u.w;
+  }
   int64_t pb = dc_pred_block(e, blk);
   int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
   const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
   BitCounter cnt;
-  bool ok = encode_block_fields(loc, (int32_t)loc[0] - pred, t.dc[tsel], t.ac[tsel], cnt);
+  bool ok = encode_block_fields_from([&qw](int k) { return packed_coef(qw, k); }, packed_coef(qw, 0) - pred, t.dc[tsel],
+                                     t.ac[tsel], cnt);
   if (!ok) atomicCAS(status + frame, 0, HCJ_ERR_ENCODER_PARAMS);
   e.blk_bits[(uint64_t)frame * (e.nblocks + 1) + blk] = cnt.bits;
 }
@@ -217,16 +221,19 @@ __global__ void __launch_bounds__(128) k_pack(EncodeBatchDev e) {
   const uint32_t seg_byte = (P[first] >> 3) + seg;
   const uint64_t bitpos = (uint64_t)seg_byte * 8 + (P[blk] - P[first]);
 
-  int16_t loc[64];
+  uint32_t qw[32];
   const uint4 *src = reinterpret_cast<const uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk) * 64);
 #pragma unroll
-  for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(loc + 8 * j) = __ldg(src + j);
+  for (int j = 0; j < 8; j++) {
+    const uint4 u = __ldg(src + j);
+    qw[4 * j] = u.x, qw[4 * j + 1] = u.y, qw[4 * j + 2] = u.z, qw[4 * j + 3] = u.w;
+  }
   int64_t pb = dc_pred_block(e, blk);
   int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
   const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
   BitPacker pk;
   pk.init(e.raw + (uint64_t)frame * e.raw_stride, bitpos);
-  encode_block_fields(loc, (int32_t)loc[0] - pred, t.dc[tsel], t.ac[tsel], pk);
+  encode_block_fields_from([&qw](int k) { return packed_coef(qw, k); }, packed_coef(qw, 0) - pred, t.dc[tsel], t.ac[tsel], pk);
   if (blk + 1 == next) {  // last block of the segment: flush_with_1s
     uint32_t segbits = P[next] - P[first];
     uint32_t pad = (8u - (segbits & 7u)) & 7u;
