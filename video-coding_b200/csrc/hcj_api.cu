@@ -34,6 +34,7 @@ struct hcj_batch {
   size_t coef_bytes = 0;
   int kernels = 0;
   std::vector<uint32_t> list_restart, list_spec;  // host copies (sorted by image index) for chunked launches
+  std::vector<uint32_t> tile_base;                // [n + 1] first IDCT tile of every image in the batch tile plan
 };
 
 extern "C" {
@@ -228,6 +229,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   std::vector<uint32_t> list_restart, list_spec;
   size_t file_bytes = 0, ent_bytes = 0, nsegs = 0, out_total = 0, plane_total = 0;
   uint64_t total_blocks = 0;
+  uint32_t total_tiles = 0;
   uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0, max_sub_chunks = 0;
   size_t total_sub = 0, total_ds_tiles = 0;
   uint32_t max_ds_tiles = 0;
@@ -446,6 +448,9 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     int tm_max = std::max(1, std::min(tile_mcus, HCJ_IDCT_THREADS / d.bpm));
     uint32_t tiles = (uint32_t)((d.mcus_wide + tm_max - 1) / tm_max) * (uint32_t)d.mcus_high;
     max_tiles = std::max(max_tiles, tiles);
+    d.idct_tile_off = total_tiles;
+    d.idct_tiles = tiles;
+    total_tiles += tiles;
     max_rows = std::max(max_rows, (uint32_t)f.height);
     max_width = std::max(max_width, (uint32_t)f.width);
   }
@@ -491,6 +496,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   BALLOC(coefs, int16_t *, b->coef_bytes + 16);
   BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4 + 64);  // + slack: k_idct stages 48 bytes per tile
   BALLOC(out, uint8_t *, out_total + 16);
+  BALLOC(idct_plan, hcjk::IdctTile *, hcjk::idct_plan_bytes(total_tiles));
   if (mode == HCJ_OUT_RGB24) BALLOC(planes, uint8_t *, plane_total + 16);
 #undef BALLOC
   if (st != HCJ_OK) {
@@ -522,6 +528,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.max_sub_chunks = max_sub_chunks;
   dv.max_ds_tiles = max_ds_tiles;
   dv.max_idct_tiles = max_tiles;
+  dv.total_idct_tiles = total_tiles;
+  dv.tile_lo = 0;
+  dv.tile_hi = total_tiles;
+  b->tile_base.assign((size_t)n + 1, 0);
+  for (int i = 0; i < n; i++) b->tile_base[i + 1] = b->tile_base[i] + b->descs[i].idct_tiles;
   dv.tile_mcus = tile_mcus;
   dv.max_rgb_rows = max_rows;
   dv.max_width = max_width;
@@ -538,7 +549,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     const char *e = getenv("HCJ_DEBUG");
     dv.debug = e ? atoi(e) : 0;
   }
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + 1 + (mode == HCJ_OUT_RGB24 ? 1 : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (mode == HCJ_OUT_RGB24 ? 1 : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;
@@ -713,6 +724,8 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       hcjk::DecodeBatchDev dv = b->dev;
       dv.img_lo = (uint32_t)(k * chunk);
       dv.img_hi = (uint32_t)std::min(n, (k + 1) * chunk);
+      dv.tile_lo = b->tile_base[dv.img_lo];
+      dv.tile_hi = b->tile_base[dv.img_hi];
       dv.lr_lo = (uint32_t)lr;
       while (lr < b->list_restart.size() && b->list_restart[lr] < dv.img_hi) lr++;
       dv.lr_hi = (uint32_t)lr;

@@ -94,6 +94,8 @@ struct HcjImageDesc {
   uint32_t sub_log2;     // scans without restart markers: log2 of the subsequence length in bits
   uint32_t sub_off;      // index of the image's first subsequence record in the batch arrays
   uint32_t ds_off;       // index of the image's first destuff tile record
+  uint32_t idct_tile_off;// index of the image's first IDCT tile in the batch tile plan
+  uint32_t idct_tiles;   // tiles of this image (tiles per MCU row x MCU rows; 0 for an invalid image)
 };
 
 // Written by the destuff kernel, read by the decode kernels and fetched for debugging.

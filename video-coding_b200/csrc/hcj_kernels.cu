@@ -1293,119 +1293,110 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const void *map, int32_t
       : "memory");
 }
 
-// The CTA's walk over its range of tile ids (id = image * max_idct_tiles + tile within the image).  All the
-// divisions that turn an id into (image, MCU row, first MCU) are done once per image; from one tile to the
-// next the cursor only increments.  (Recomputing them per tile cost every thread some 400 instructions per
-// block, a third of the kernel: profiles/r02_idct_before_cursor.)
-struct IdctWork {  // one tile, everything the load and the transform need
-  const HcjImageDesc *d;
-  int my, m0, tm, nblk;
-  uint64_t blk0;  // first block of the tile in the batch coefficient buffer
-  uint32_t qt_off, qbytes;  // the image's quant tables
-  int remap;      // the thread -> block mapping of the previous tile does not apply (other image or tile width)
+// The batch's tile plan: one 32-byte record per IDCT tile, image after image (HcjImageDesc::idct_tile_off), written
+// by k_idct_plan before the transform.  With the plan in HBM the persistent CTAs do no per-tile geometry at all:
+// thread 0 pulls the records two tiles ahead into shared memory (cp.async) and issues the loads from them.  (Walking
+// the tiles with a cursor in thread 0 cost its warp ~130 instructions per tile on top of the ~1030 of the transform,
+// and the other three warps waited for it at the tile barrier: profiles/r01s3_ncu_full_restart8_b296.csv.)
+struct alignas(16) IdctTile {
+  uint64_t blk0;     // first block of the tile in the batch coefficient buffer
+  uint32_t img;      // image index
+  uint32_t qt_off;   // the image's quant tables in the pool
+  uint16_t my, m0;   // MCU row, first MCU
+  uint16_t tm, nblk; // MCUs and blocks in the tile
+  uint16_t qbytes;   // bytes of quant tables (512 per component)
+  uint16_t remap;    // the thread -> block mapping differs from the previous tile's (first tile of an image, other width)
+  uint32_t pad_;
 };
-struct TileCursor {
-  uint32_t id, end, tile;  // next tile id; end of the range; tile index within the image
-  uint32_t rel;            // image, relative to img_lo
-  const HcjImageDesc *d;
-  int tiles_per_row, tm_bal, ntiles, my, tx;
-  uint64_t blk;            // first block of the next tile
-  // the image's fields the walk needs, read from global memory once per image
-  int mcus_wide, bpm;
-  uint32_t qt_off, qbytes;
-  uint64_t coef_off;
-  const HcjImageDesc *last_d;  // image and width of the tile handed out last
-  int last_tm;
+static_assert(sizeof(IdctTile) == 32, "two 16-byte cp.async per record");
 
-  __device__ __forceinline__ void load_image(const DecodeBatchDev &b) {
-    d = &b.descs[rel + b.img_lo];
-    ntiles = 0;
-    if (d->valid) {
-      mcus_wide = d->mcus_wide;
-      bpm = d->bpm;
-      qt_off = d->qt_off;
-      qbytes = (uint32_t)d->ncomp * 512u;
-      coef_off = d->coef_off;
-      const int tm_max = min(b.tile_mcus, IDCT_MAX_THREADS / bpm);
-      tiles_per_row = (mcus_wide + tm_max - 1) / tm_max;
-      tm_bal = (mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
-      ntiles = tiles_per_row * d->mcus_high;
-    }
-  }
-  __device__ __forceinline__ void init(const DecodeBatchDev &b, uint32_t begin, uint32_t end_) {
-    id = begin;
-    end = end_;
-    rel = begin / b.max_idct_tiles;
-    tile = begin - rel * b.max_idct_tiles;
-    last_d = nullptr;
-    last_tm = -1;
-    load_image(b);
-    my = tx = 0;
-    blk = 0;
-    if ((int)tile < ntiles) {
-      my = (int)tile / tiles_per_row;
-      tx = (int)tile - my * tiles_per_row;
-      blk = coef_off + ((uint64_t)my * mcus_wide + (uint64_t)tx * tm_bal) * bpm;
-    }
-  }
-  // the next tile of the range, or false
-  __device__ __forceinline__ bool next(const DecodeBatchDev &b, IdctWork &w) {
-    while (id < end) {
-      if ((int)tile >= ntiles) {  // past the image's last tile (or an invalid image): on to the next image
-        id += b.max_idct_tiles - tile;
-        rel++;
-        tile = 0;
-        if (id >= end) return false;
-        load_image(b);
-        my = tx = 0;
-        blk = ntiles ? coef_off : 0;
-        continue;
-      }
-      w.d = d;
-      w.my = my;
-      w.m0 = tx * tm_bal;
-      w.tm = min(tm_bal, mcus_wide - w.m0);
-      w.nblk = w.tm * bpm;
-      w.blk0 = blk;
-      w.qt_off = qt_off;
-      w.qbytes = qbytes;
-      w.remap = d != last_d || w.tm != last_tm;
-      last_d = d;
-      last_tm = w.tm;
-      blk += (uint64_t)w.nblk;
-      id++;
-      tile++;
-      if (++tx == tiles_per_row) {
-        tx = 0;
-        my++;
-      }
-      return true;
-    }
-    return false;
-  }
-};
+size_t idct_plan_bytes(uint32_t tiles) { return ((size_t)tiles + 4) * sizeof(IdctTile); }
+int idct_kernel_count() { return 2; }
+
+__device__ __forceinline__ int idct_tile_width(const DecodeBatchDev &b, const HcjImageDesc &d, int &tiles_per_row) {
+  const int tm_max = max(1, min(b.tile_mcus, IDCT_MAX_THREADS / d.bpm));
+  tiles_per_row = (d.mcus_wide + tm_max - 1) / tm_max;
+  return (d.mcus_wide + tiles_per_row - 1) / tiles_per_row;  // balanced tile width
+}
+
+// grid (ceil(max tiles of an image / 128), images of the launch)
+__global__ void __launch_bounds__(128) k_idct_plan(DecodeBatchDev b) {
+  const uint32_t img = b.img_lo + blockIdx.y;
+  const HcjImageDesc &d = b.descs[img];
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!d.valid || tile >= d.idct_tiles) return;
+  int tpr;
+  const int tm_bal = idct_tile_width(b, d, tpr);
+  const int my = (int)tile / tpr, tx = (int)tile - my * tpr;
+  const int m0 = tx * tm_bal;
+  const int tm = min(tm_bal, d.mcus_wide - m0);
+  const int ptx = tx ? tx - 1 : tpr - 1;  // the tile before this one in the image
+  const int ptm = min(tm_bal, d.mcus_wide - ptx * tm_bal);
+  IdctTile t;
+  t.blk0 = d.coef_off + ((uint64_t)my * d.mcus_wide + (uint64_t)m0) * d.bpm;
+  t.img = img;
+  t.qt_off = d.qt_off;
+  t.my = (uint16_t)my;
+  t.m0 = (uint16_t)m0;
+  t.tm = (uint16_t)tm;
+  t.nblk = (uint16_t)(tm * d.bpm);
+  t.qbytes = (uint16_t)(d.ncomp * 512);
+  t.remap = (uint16_t)(tile == 0 || tm != ptm);
+  t.pad_ = 0;
+  b.idct_plan[d.idct_tile_off + tile] = t;
+}
 
 // A thread's block inside the tile, valid for one (image geometry, tile width); kept in shared memory: the 64 values
 // of a block need the registers, and what the compiler spills instead goes to local memory, which at 5 CTAs per SM
 // does not fit the L1 that the tile stages leave (measured: 18 % of the kernel's stall samples were those reloads).
-struct alignas(16) IdctMap {
+struct IdctMap {
   uint8_t *plane;      // the component's plane in the image's output / plane buffer
   int32_t stride;      // = crop width
   int32_t h_limit;
   uint32_t xy;         // sample offset of the block inside the tile's MCU row: x | y << 16
   uint32_t misc;       // staged block index | quant table << 8 | mine << 10 | wide << 11 | hs8 << 12 | vs8 << 18
-  uint32_t pad_[2];
+};
+// stored as two arrays (16 + 8 bytes per thread) so that a warp's reads are conflict free
+struct IdctMapSmem {
+  uint4 a[IDCT_MAX_THREADS];
+  uint2 b[IDCT_MAX_THREADS];
+  __device__ __forceinline__ void put(int t, const IdctMap &m) {
+    const uint64_t p = reinterpret_cast<uint64_t>(m.plane);
+    a[t] = make_uint4((uint32_t)p, (uint32_t)(p >> 32), (uint32_t)m.stride, (uint32_t)m.h_limit);
+    b[t] = make_uint2(m.xy, m.misc);
+  }
+  __device__ __forceinline__ IdctMap get(int t) const {
+    const uint4 u = a[t];
+    const uint2 v = b[t];
+    IdctMap m;
+    m.plane = reinterpret_cast<uint8_t *>((uint64_t)u.x | (uint64_t)u.y << 32);
+    m.stride = (int32_t)u.z;
+    m.h_limit = (int32_t)u.w;
+    m.xy = v.x;
+    m.misc = v.y;
+    return m;
+  }
 };
 
 // Requests one tile (thread 0 only): one TMA tensor copy brings the run of blocks that starts at the tile's first
 // block (always a full box of HCJ_IDCT_THREADS blocks: the rows behind the tile's own belong to the next tile or
 // are filled with zeros past the end of the buffer), two small bulk copies the quant tables and the 48 bytes of
 // wide-block flags; all of them complete on the stage's mbarrier.
-__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctWork &t, IdctStage &st) {
+__device__ __forceinline__ void idct_issue(const DecodeBatchDev &b, const IdctTile &t, IdctStage &st) {
   mbar_arrive_expect_tx(&st.full, IDCT_MAX_THREADS * 128u + t.qbytes + IDCT_FLAG_U4 * 16u);
   tma_tile_g2s(st.tile, b.coef_map, (int32_t)t.blk0, &st.full);
   bulk_g2s(st.q, b.qtables + t.qt_off, t.qbytes, &st.full);  // comp k uses table slot k
   bulk_g2s(st.flags, reinterpret_cast<const uint4 *>(b.wide_flags) + (t.blk0 >> 7), IDCT_FLAG_U4 * 16u, &st.full);
+}
+
+constexpr int IDCT_RING = 4;  // plan records in shared memory: tiles i .. i + 3
+
+__device__ __forceinline__ void idct_fetch_record(const DecodeBatchDev &b, IdctTile *ring, uint32_t id, uint32_t end) {
+  if (id < end) {
+    cp_async16(&ring[id % IDCT_RING], &b.idct_plan[id]);
+    cp_async16(reinterpret_cast<uint4 *>(&ring[id % IDCT_RING]) + 1, reinterpret_cast<const uint4 *>(&b.idct_plan[id]) + 1);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");  // one group per call, empty past the end
 }
 
 __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
@@ -1414,53 +1405,53 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
   // 1 KiB alignment for the swizzled tiles (the launch asks for 1 KiB more than two stages)
   IdctStage *stages = reinterpret_cast<IdctStage *>(reinterpret_cast<uint8_t *>(s_dyn) + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u));
   const int tid = threadIdx.x;
-  const uint32_t total = (b.img_hi - b.img_lo) * b.max_idct_tiles;
+  const uint32_t total = b.tile_hi - b.tile_lo;
   const uint32_t chunk = (total + gridDim.x - 1) / gridDim.x;
-  const uint32_t begin = min(blockIdx.x * chunk, total), end = min(begin + chunk, total);
+  const uint32_t begin = b.tile_lo + min(blockIdx.x * chunk, total), end = b.tile_lo + min((blockIdx.x + 1) * chunk, total);
   if (begin >= end) return;
 
-  // The cursor lives in shared memory and is advanced by thread 0 two tiles ahead of the transform, so that
-  // its state costs no registers in the threads that need them for the 64 values of a block.
-  __shared__ TileCursor s_cur;
-  __shared__ IdctWork s_work[4];
-  __shared__ int s_have[4];
-  __shared__ IdctMap s_map[IDCT_MAX_THREADS];
+  __shared__ IdctTile s_ring[IDCT_RING];  // record of tile id at s_ring[id % IDCT_RING]
+  __shared__ IdctMapSmem s_map;
   if (tid == 0) {
-    s_cur.init(b, begin, end);
-    s_have[0] = s_cur.next(b, s_work[0]);
-    s_have[1] = s_have[0] && s_cur.next(b, s_work[1]);
     mbar_init(&stages[0].full, 1);
     mbar_init(&stages[1].full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (s_have[0]) idct_issue(b, s_work[0], stages[0]);
+    idct_fetch_record(b, s_ring, begin, end);
+    idct_fetch_record(b, s_ring, begin + 1, end);
+    idct_fetch_record(b, s_ring, begin + 2, end);
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // records of begin and begin + 1 are in
+    idct_issue(b, s_ring[begin % IDCT_RING], stages[0]);
   }
   __syncthreads();
-  for (int i = 0; s_have[i & 3]; i++) {
-    const int buf = i & 1;
+  for (uint32_t id = begin; id < end; id++) {
+    const int buf = (int)(id - begin) & 1;
     IdctStage &st = stages[buf];
     if (tid == 0) {
-      s_have[(i + 2) & 3] = s_have[(i + 1) & 3] && s_cur.next(b, s_work[(i + 2) & 3]);
-      if (s_have[(i + 1) & 3]) idct_issue(b, s_work[(i + 1) & 3], stages[buf ^ 1]);
+      // the record of id + 1 arrived before the previous barrier; ask for id + 3, whose slot held id - 1
+      idct_fetch_record(b, s_ring, id + 3, end);
+      if (id + 1 < end) idct_issue(b, s_ring[(id + 1) % IDCT_RING], stages[buf ^ 1]);
     }
-    const IdctWork &t = s_work[i & 3];
-    if (t.remap) {  // CTA-uniform: new image or a narrower last tile in the row; only this thread reads its entry
-      const HcjImageDesc &d = *t.d;
+    const IdctTile &t = s_ring[id % IDCT_RING];
+    if (t.remap || id == begin) {  // CTA-uniform: new image or a narrower last tile in the row; only this thread reads its entry
+      const HcjImageDesc &d = b.descs[t.img];
+      const int tm = t.tm;
       int rem = tid, c = 0;
       for (; c < d.ncomp - 1; c++) {
-        int n = t.tm * d.comp[c].hs * d.comp[c].vs;
+        int n = tm * d.comp[c].hs * d.comp[c].vs;
         if (rem < n) break;
         rem -= n;
       }
       const HcjCompGeom &g = d.comp[c];
-      const int rowlen = t.tm * g.hs;
+      const int rowlen = tm * g.hs;
       const int by = (rem >= rowlen) + (rem >= 2 * rowlen) + (rem >= 3 * rowlen);  // vs <= 4
       const int r2 = rem - by * rowlen;
       const int m = g.hs == 1 ? r2 : g.hs == 2 ? r2 >> 1 : g.hs == 4 ? r2 >> 2 : r2 / 3;
       const int bx = r2 - m * g.hs;
       const uint32_t slot = (uint32_t)(m * d.bpm + g.first_blk + by * g.hs + bx);
+      const bool mine = tid < (int)t.nblk;
       IdctMap mp;
       mp.xy = (uint32_t)(m * g.hs * 8 + bx * 8) | (uint32_t)(by * 8) << 16;
-      mp.misc = (tid < t.nblk ? slot : 0u) | (uint32_t)c << 8 | (tid < t.nblk ? 1u << 10 : 0u) | (d.wide_idct ? 1u << 11 : 0u) |
+      mp.misc = (mine ? slot : 0u) | (uint32_t)c << 8 | (mine ? 1u << 10 : 0u) | (d.wide_idct ? 1u << 11 : 0u) |
                 (uint32_t)(g.hs * 8) << 12 | (uint32_t)(g.vs * 8) << 18;
       if (mode == 0) {
         mp.plane = b.out + d.out_off + g.out_off;
@@ -1471,11 +1462,10 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
         mp.stride = g.decoded_w;
         mp.h_limit = g.decoded_h;
       }
-      mp.pad_[0] = mp.pad_[1] = 0;
-      s_map[tid] = mp;
+      s_map.put(tid, mp);
     }
-    mbar_wait(&st.full, (uint32_t)(i >> 1) & 1u);  // the stage's (i / 2)-th use
-    const IdctMap mp = s_map[tid];
+    mbar_wait(&st.full, (uint32_t)((id - begin) >> 1) & 1u);  // the stage's ((id - begin) / 2)-th use
+    const IdctMap mp = s_map.get(tid);
     if (mp.misc & (1u << 10)) {
       const int slot = (int)(mp.misc & 255u);
       uint32_t cw[32];
@@ -1489,8 +1479,8 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
       }
       const uint32_t fbit = (uint32_t)(t.blk0 & 127u) + slot;  // bit index inside the staged flag chunks
       const bool wide = (mp.misc & (1u << 11)) || ((reinterpret_cast<const uint32_t *>(st.flags)[fbit >> 5] >> (fbit & 31u)) & 1u);
-      const int x = t.m0 * (int)((mp.misc >> 12) & 63u) + (int)(mp.xy & 0xffffu);
-      const int y = t.my * (int)((mp.misc >> 18) & 63u) + (int)(mp.xy >> 16);
+      const int x = (int)t.m0 * (int)((mp.misc >> 12) & 63u) + (int)(mp.xy & 0xffffu);
+      const int y = (int)t.my * (int)((mp.misc >> 18) & 63u) + (int)(mp.xy >> 16);
       const int32_t *q = st.q + ((mp.misc >> 8) & 3u) * 128u;
       if (wide) {
         wide_block_store_staged(st.tile, slot, q, mp.plane, mp.stride, x, y, mp.stride, mp.h_limit);
@@ -1500,14 +1490,15 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
         store_block_rows(pix, mp.plane, mp.stride, x, y, mp.stride, mp.h_limit);
       }
     }
-    __syncthreads();  // this stage is refilled by the next iteration's prefetch
+    if (tid == 0) asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // the record of id + 2 is in (id + 3 may be in flight)
+    __syncthreads();  // this stage is refilled by the next iteration's prefetch; the ring slot of id by the next fetch
   }
 }
 
 constexpr size_t IDCT_SMEM = 2 * sizeof(IdctStage) + 1024;
 
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
-  if (b.img_hi <= b.img_lo || b.max_idct_tiles == 0) return;
+  if (b.img_hi <= b.img_lo || b.tile_hi <= b.tile_lo) return;
   static int grid = 0;
   if (!grid) {
     int dev = 0, sms = 148;
@@ -1516,8 +1507,9 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
     cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
     grid = HCJ_IDCT_CTAS_PER_SM * sms;
   }
-  const uint64_t total = (uint64_t)(b.img_hi - b.img_lo) * b.max_idct_tiles;
-  k_idct_persistent<<<(unsigned)(total < (uint64_t)grid ? total : grid), IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
+  k_idct_plan<<<dim3((b.max_idct_tiles + 127) / 128, b.img_hi - b.img_lo), 128, 0, s>>>(b);
+  const uint32_t total = b.tile_hi - b.tile_lo;
+  k_idct_persistent<<<(unsigned)(total < (uint32_t)grid ? total : grid), IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
 }
 
 // The coefficient buffer as the TMA unit sees it: uint16 [total blocks][64], box = HCJ_IDCT_THREADS blocks x 64,

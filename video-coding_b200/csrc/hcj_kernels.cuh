@@ -8,6 +8,7 @@
 namespace hcjk {
 
 struct DsTile;
+struct IdctTile;
 
 // Everything the decode kernels need about one batch resident in HBM.
 struct DecodeBatchDev {
@@ -46,6 +47,9 @@ struct DecodeBatchDev {
   uint32_t *sub_list;             // scratch: subsequences to decode again in the current fix-point round
   uint32_t max_sub_chunks;        // max over list_spec of ceil(subsequences / 256)
   uint32_t max_idct_tiles;        // max over images of tiles_per_row * mcus_high
+  struct IdctTile *idct_plan;     // one record per IDCT tile of the batch (k_idct_plan), image after image
+  uint32_t total_idct_tiles;
+  uint32_t tile_lo, tile_hi;      // tiles of the images [img_lo, img_hi)
   int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
   uint32_t max_rgb_rows;          // max image height (RGB mode)
   uint32_t max_width;
@@ -63,6 +67,8 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
 int huff_spec_kernel_count();
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s);
+int idct_kernel_count();
+size_t idct_plan_bytes(uint32_t tiles);
 // Fills b->coef_map for b->coefs / b->total_blocks.  Returns a cudaError_t-compatible code (0 = ok).
 int make_coef_tensor_map(DecodeBatchDev *b);
 void launch_rgb(const DecodeBatchDev &b, cudaStream_t s);
