@@ -100,6 +100,8 @@ typedef struct hcj_header { /* Decoder.Header.t, decoder.ml:6-13 */
 
 /* Decoder.Header.decode : Bits.t -> Header.t (decoder.ml:37-70).  Host only. */
 int hcj_header_decode(const uint8_t *jpeg, size_t len, hcj_header *out);
+/* The same with HCJ_FLAG_* (below): HCJ_FLAG_T81_TABLES reads every table of a DQT / DHT segment. */
+int hcj_header_decode_ex(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *out);
 
 /* Geometry fixed by Decoder.init (decoder.ml:304-345) and decode_seq (:374-383).  Host only. */
 typedef struct hcj_frame_info {
@@ -116,7 +118,8 @@ typedef struct hcj_frame_info {
   size_t rgb_bytes;     /* width*height*3 (0 if chroma == 0) */
 } hcj_frame_info;
 
-int hcj_frame_info_get(const uint8_t *jpeg, size_t len, hcj_frame_info *out);
+int hcj_frame_info_get(const uint8_t *jpeg, size_t len, hcj_frame_info *out); /* flags = HCJ_FLAG_DEFAULT */
+int hcj_frame_info_get_ex(const uint8_t *jpeg, size_t len, unsigned flags, hcj_frame_info *out);
 
 /* ---- context: one per GPU (the model's `Decoder.t` / `Encoder.t` values own no device state) -- */
 typedef struct hcj_ctx hcj_ctx;
@@ -133,10 +136,18 @@ void hcj_host_free(void *p);
 typedef enum hcj_out_mode {
   HCJ_OUT_YUV = 0,    /* Decoder.get_yuv_frame -> Frame.output: cropped planar Y,U,V (decoder.ml:403-420, frame.ml:66-70) */
   HCJ_OUT_PLANES = 1, /* Decoder.get_decoded_planes: padded planes in scan order (decoder.ml:399-401) */
-  HCJ_OUT_RGB24 = 2   /* extension: Planar_444 up-sampling (tools/src/planar_444.ml:25-33,82-103) + stated YCbCr->RGB */
+  HCJ_OUT_RGB24 = 2,  /* extension: Planar_444 up-sampling (tools/src/planar_444.ml:25-33,82-103) + stated YCbCr->RGB */
+  HCJ_OUT_YUV444 = 3  /* `oyuv convert` to 4:4:4 on the device: Planar_444.convert_from_420 / convert_from_422
+                         (tools/src/planar_444.ml:52-61,122-131) of the cropped frame, planar Y,U,V of width*height
+                         bytes each (hcj_frame_info.rgb_bytes in total) */
 } hcj_out_mode;
 
 #define HCJ_FLAG_RESTART_EXT 1u /* honour DRI / RSTn (T.81 semantics).  Without it: pure model semantics (decoder.ml:261-281) */
+/* Stated extension for files the model's parser cannot read (markers.ml:162-168,210-220 take ONE table per DQT / DHT
+ * segment and then hunt for the next FF): every table of a segment is read, parsing continues at the end of the
+ * segment, and 0xFF fill bytes in front of a marker code are skipped (T.81 B.1.1.2, B.2.4.1, B.2.4.2).  Files the
+ * model reads correctly decode identically with and without it. */
+#define HCJ_FLAG_T81_TABLES 2u
 #define HCJ_FLAG_DEFAULT HCJ_FLAG_RESTART_EXT
 
 /* Decoder.decode_a_frame (decoder.ml:422-427) for n independent images; host buffers in and out.
@@ -189,6 +200,20 @@ int hcj_encode_quantized(hcj_ctx *ctx, const uint8_t *yuv, int width, int height
 /* Ocompare.square_error / max_difference per plane (tools/src/ocompare.ml:8-52) of two host frames. */
 int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,
                        int *max_difference);
+
+/* `oyuv compare` for a whole decoded batch, on the device: Ocompare.square_error / total_difference / max_difference
+ * (tools/src/ocompare.ml:8-46) per plane between image i's output resident in HBM (after hcj_batch_decode) and the
+ * reference frame ref[i] in host memory, which has the layout and size of the batch's output mode.  Planes: Y,U,V
+ * for HCJ_OUT_YUV / HCJ_OUT_YUV444, one per scan component for HCJ_OUT_PLANES, one (all bytes) for HCJ_OUT_RGB24.
+ * mean_square_error = square_error / samples; psnr = 10 log10(255^2 / mean_square_error) (ocompare.ml:48-56). */
+typedef struct hcj_plane_metrics {
+  int status;                  /* the image's status; metrics are zero unless it is HCJ_OK */
+  int max_difference[4];
+  int64_t square_error[4];
+  int64_t total_difference[4];
+  int64_t samples[4];          /* width * height of the plane; 0 = no such plane */
+} hcj_plane_metrics;
+int hcj_batch_compare(hcj_ctx *ctx, hcj_batch *b, const uint8_t *const *ref, const size_t *ref_len, hcj_plane_metrics *out);
 
 /* ---- timing helpers for benchmarks --------------------------------------------------------------- */
 /* One decode pass with a CUDA event between consecutive stages (on the context's stream); fills

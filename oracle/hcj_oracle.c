@@ -159,16 +159,24 @@ static void sos_decode(orc_bits *b, orc_sos *s) { /* markers.ml:84-89,111-129 */
   s->successive_approximation_bit_high = (int)get(b, 4);
   s->successive_approximation_bit_low = (int)get(b, 4);
 }
+static void dqt_table_decode(orc_bits *b, orc_dqt *q);
 static void dqt_decode(orc_bits *b, orc_dqt *q) { /* markers.ml:162-168: ONE table per segment */
   q->length = (int)get(b, 16);
+  dqt_table_decode(b, q);
+}
+static void dqt_table_decode(orc_bits *b, orc_dqt *q) {
   int pq = (int)get(b, 4);
   if (pq > 1) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY); /* stated domain limit: 8- or 16-bit elements only */
   q->element_precision = 8 << pq;
   q->table_identifier = (int)get(b, 4);
   for (int i = 0; i < 64; i++) q->elements[i] = get(b, q->element_precision);
 }
+static void dht_table_decode(orc_bits *b, orc_dht *h);
 static void dht_decode(orc_bits *b, orc_dht *h) { /* markers.ml:210-220: ONE table per segment */
   h->length = (int)get(b, 16);
+  dht_table_decode(b, h);
+}
+static void dht_table_decode(orc_bits *b, orc_dht *h) {
   h->table_class = (int)get(b, 4);
   h->destination_identifier = (int)get(b, 4);
   int total = 0;
@@ -190,11 +198,17 @@ static void find_marker(orc_bits *b) { /* decoder.ml:24-29 */
   }
 }
 
-static void header_decode(orc_bits *b, orc_header *h) { /* decoder.ml:37-70 */
+/* flags & ORC_FLAG_T81_TABLES (stated extension): a DQT / DHT segment holds as many tables as
+ * its length field covers (T.81 B.2.4.1, B.2.4.2) and the cursor continues at the end of the segment; 0xFF fill
+ * bytes in front of a marker code are skipped (T.81 B.1.1.2).  Without it: the model verbatim. */
+static void header_decode(orc_bits *b, orc_header *h, int flags) { /* decoder.ml:37-70 */
+  const int t81 = (flags & ORC_FLAG_T81_TABLES) != 0;
   memset(h, 0, sizeof(*h));
   for (;;) {
     find_marker(b);
     int code = (int)get(b, 8);
+    while (t81 && code == 0xff && b->bit_pos < b->length_in_bits) code = (int)get(b, 8);
+
     if (code == M_SOF0) {
       sof_decode(b, &h->frame);
     } else if (code == M_SOS) {
@@ -204,13 +218,29 @@ static void header_decode(orc_bits *b, orc_header *h) { /* decoder.ml:37-70 */
     } else if (code == M_DQT) { /* list cons: newest first (:51) */
       if (h->n_quant_tables == ORC_MAX_TABLES) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY);
       memmove(&h->quant_tables[1], &h->quant_tables[0], sizeof(orc_dqt) * (size_t)h->n_quant_tables);
+      const i64 seg_end = b->bit_pos + 8 * show(b, 16);
       dqt_decode(b, &h->quant_tables[0]);
       h->n_quant_tables++;
+      while (t81 && b->bit_pos < seg_end) { /* further tables: Pq/Tq + 64 elements each, no length field */
+        if (h->n_quant_tables == ORC_MAX_TABLES) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY);
+        memmove(&h->quant_tables[1], &h->quant_tables[0], sizeof(orc_dqt) * (size_t)h->n_quant_tables);
+        h->n_quant_tables++;
+        dqt_table_decode(b, &h->quant_tables[0]);
+      }
+      if (t81 && b->bit_pos < seg_end) b->bit_pos = seg_end;
     } else if (code == M_DHT) { /* :55 */
       if (h->n_huffman_tables == ORC_MAX_TABLES) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY);
       memmove(&h->huffman_tables[1], &h->huffman_tables[0], sizeof(orc_dht) * (size_t)h->n_huffman_tables);
+      const i64 seg_end = b->bit_pos + 8 * show(b, 16);
       dht_decode(b, &h->huffman_tables[0]);
       h->n_huffman_tables++;
+      while (t81 && b->bit_pos < seg_end) {
+        if (h->n_huffman_tables == ORC_MAX_TABLES) orc_raise(ORC_ERR_UNSUPPORTED_GEOMETRY);
+        memmove(&h->huffman_tables[1], &h->huffman_tables[0], sizeof(orc_dht) * (size_t)h->n_huffman_tables);
+        h->n_huffman_tables++;
+        dht_table_decode(b, &h->huffman_tables[0]);
+      }
+      if (t81 && b->bit_pos < seg_end) b->bit_pos = seg_end;
     } else if (code == M_DRI) { /* markers.ml:193-197 */
       h->restart_interval_present = 1;
       h->restart_interval_length = (int)get(b, 16);
@@ -226,13 +256,14 @@ static void header_decode(orc_bits *b, orc_header *h) { /* decoder.ml:37-70 */
   }
 }
 
-int orc_header_decode(const uint8_t *jpeg, i64 len, orc_header *h) {
+int orc_header_decode_ex(const uint8_t *jpeg, i64 len, int flags, orc_header *h) {
   orc_bits b;
   orc_bits_create(&b, jpeg, len);
-  ORC_TRY(st) { header_decode(&b, h); }
+  ORC_TRY(st) { header_decode(&b, h, flags); }
   ORC_END_TRY;
   return st;
 }
+int orc_header_decode(const uint8_t *jpeg, i64 len, orc_header *h) { return orc_header_decode_ex(jpeg, len, 0, h); }
 
 /* decoder.ml:261-281.  Stops at the first FF xx with xx != 00.  With restart_ext, FF D0..D7 ends
  * an interval instead (stated extension); seg_off (if non-NULL) receives the destuffed offset at
@@ -693,7 +724,7 @@ static int decode_impl(const uint8_t *jpeg, i64 len, int flags, int want_blocks,
   orc_bits bits;
   orc_bits_create(&bits, jpeg, len);
   ORC_TRY(st) {
-    header_decode(&bits, h);
+    header_decode(&bits, h, flags);
     /* init (:304-345) */
     if (!h->frame.present || !h->scan.present) orc_raise(ORC_ERR_NO_FRAME_OR_SCAN);
     const orc_sof *frame = &h->frame;

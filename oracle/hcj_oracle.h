@@ -136,6 +136,7 @@ typedef struct {
 } orc_header;
 
 int orc_header_decode(const uint8_t *jpeg, int64_t len, orc_header *h);
+int orc_header_decode_ex(const uint8_t *jpeg, int64_t len, int flags, orc_header *h);
 
 /* For_testing.extract_entropy_coded_bits (decoder.ml:261-281).  out must hold len bytes. */
 int orc_extract_entropy_coded_bits(const uint8_t *jpeg, int64_t len, int64_t start_byte,
@@ -172,6 +173,7 @@ int orc_rle(const int64_t quant[64], int64_t *dc_pred, int64_t runs[65], int64_t
 
 /* ---- Decoder (jpeg/model/src/decoder.ml) ---- */
 #define ORC_FLAG_RESTART_EXT 1 /* stated extension: honour DRI/RSTn (T.81 semantics) */
+#define ORC_FLAG_T81_TABLES 2  /* stated extension: several tables per DQT/DHT segment, FF fill bytes before markers */
 
 typedef struct {
   int status;

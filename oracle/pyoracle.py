@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 
 FLAG_RESTART_EXT = 1
+FLAG_T81_TABLES = 2
 
 
 def build(force=False):
@@ -169,6 +170,7 @@ def lib():
         L.orc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Encoded)]
         L.orc_encoded_free.argtypes = [C.POINTER(Encoded)]
         L.orc_header_decode.argtypes = [C.c_char_p, C.c_int64, C.POINTER(Header)]
+        L.orc_header_decode_ex.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.POINTER(Header)]
         L.orc_extract_entropy_coded_bits.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
         L.orc_write_headers.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.orc_chen_inverse_8x8.argtypes = [C.c_void_p]
@@ -258,9 +260,10 @@ class DecodeResult:
         return c
 
 
-def decode(jpeg, restart_ext=True, want_blocks=False):
+def decode(jpeg, restart_ext=True, want_blocks=False, t81_tables=False):
     d = Decoded()
-    st = lib().orc_decode(jpeg, len(jpeg), FLAG_RESTART_EXT if restart_ext else 0, int(want_blocks), C.byref(d))
+    flags = (FLAG_RESTART_EXT if restart_ext else 0) | (FLAG_T81_TABLES if t81_tables else 0)
+    st = lib().orc_decode(jpeg, len(jpeg), flags, int(want_blocks), C.byref(d))
     if st != 0:
         raise OracleError(st)
     try:
@@ -269,9 +272,10 @@ def decode(jpeg, restart_ext=True, want_blocks=False):
         lib().orc_decoded_free(C.byref(d))
 
 
-def decode_status(jpeg, restart_ext=True):
+def decode_status(jpeg, restart_ext=True, t81_tables=False):
     d = Decoded()
-    st = lib().orc_decode(jpeg, len(jpeg), FLAG_RESTART_EXT if restart_ext else 0, 0, C.byref(d))
+    flags = (FLAG_RESTART_EXT if restart_ext else 0) | (FLAG_T81_TABLES if t81_tables else 0)
+    st = lib().orc_decode(jpeg, len(jpeg), flags, 0, C.byref(d))
     if st == 0:
         lib().orc_decoded_free(C.byref(d))
     return st
@@ -319,9 +323,9 @@ def encode(yuv, width, height, chroma=420, quality=75, restart_interval=0, want_
         lib().orc_encoded_free(C.byref(e))
 
 
-def header_decode(jpeg):
+def header_decode(jpeg, flags=0):
     h = Header()
-    st = lib().orc_header_decode(jpeg, len(jpeg), C.byref(h))
+    st = lib().orc_header_decode_ex(jpeg, len(jpeg), flags, C.byref(h))
     if st != 0:
         raise OracleError(st)
     return h

@@ -27,3 +27,34 @@ def frame(seed, w, h, chroma=420):
     cw = w if chroma == 444 else w // 2
     ch = h // 2 if chroma == 420 else h
     return plane(rng, w, h).tobytes() + plane(rng, cw, ch).tobytes() + plane(rng, cw, ch).tobytes()
+
+
+def jpeg_segments(jpg):
+    """[(marker code, payload without the length field)] of the header up to and including SOS, then the rest."""
+    segs, p = [], 2
+    assert jpg[:2] == b"\xff\xd8"
+    while True:
+        assert jpg[p] == 0xFF, p
+        code = jpg[p + 1]
+        n = int.from_bytes(jpg[p + 2:p + 4], "big")
+        segs.append((code, jpg[p + 4:p + 2 + n]))
+        p += 2 + n
+        if code == 0xDA:
+            return segs, jpg[p:]
+
+
+def merge_table_segments(jpg, fill=2):
+    """The same image with all DQT tables in one segment, all DHT tables in one segment (what ffmpeg and many
+    cameras write) and `fill` 0xFF fill bytes in front of every marker: T.81-legal, unreadable by the model's parser."""
+    segs, rest = jpeg_segments(jpg)
+    dqt = b"".join(p for c, p in segs if c == 0xDB)
+    dht = b"".join(p for c, p in segs if c == 0xC4)
+    out, done = [b"\xff\xd8"], set()
+    for c, p in segs:
+        if c in (0xDB, 0xC4):
+            if c in done:
+                continue
+            done.add(c)
+            p = dqt if c == 0xDB else dht
+        out.append(b"\xff" * fill + bytes([0xFF, c]) + (len(p) + 2).to_bytes(2, "big") + p)
+    return b"".join(out) + rest

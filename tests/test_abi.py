@@ -116,6 +116,37 @@ def test_header_decode_pillow_streams(hcj, orc):
         assert [(f.actual_width[i], f.actual_height[i]) for i in range(3)] == dec.actual_size
 
 
+def test_t81_table_segments_extension(hcj, orc):
+    """HCJ_FLAG_T81_TABLES (stated extension): merged DQT / DHT segments and FF fill bytes parse to the same tables
+    as the one-table-per-segment file; without the flag the library fails exactly like the model's parser."""
+    for chroma, ri in ((420, 0), (444, 4), (422, 0)):
+        jpg = orc.encode(synth.frame(7, 72, 40, chroma), 72, 40, chroma, 60, restart_interval=ri)
+        for fill in (0, 1, 3):
+            merged = synth.merge_table_segments(jpg, fill)
+            a, b = hcj.header_decode(merged, hcj.FLAG_T81_TABLES), orc.header_decode(merged, orc.FLAG_T81_TABLES)
+            _same_header(a, b)
+            ref = hcj.header_decode(jpg)
+            assert a.n_quant_tables == ref.n_quant_tables == 2 and a.n_huffman_tables == ref.n_huffman_tables == 4
+            for i in range(2):
+                assert list(a.quant_tables[i].elements) == list(ref.quant_tables[i].elements)
+            for i in range(4):
+                assert list(a.huffman_tables[i].lengths) == list(ref.huffman_tables[i].lengths)
+            assert orc.decode(merged, t81_tables=True).yuv() == orc.decode(jpg).yuv()
+            f1, f2 = hcj.frame_info(merged, hcj.FLAG_DEFAULT | hcj.FLAG_T81_TABLES), hcj.frame_info(jpg)
+            assert (f1.nblocks, f1.restart_interval, f1.yuv_bytes) == (f2.nblocks, f2.restart_interval, f2.yuv_bytes)
+            # model semantics on the same bytes: whatever the oracle does, the library does
+            try:
+                o = orc.header_decode(merged)
+            except orc.OracleError as e:
+                with pytest.raises(hcj.HcjError) as ei:
+                    hcj.header_decode(merged)
+                assert ei.value.status == e.status
+            else:
+                _same_header(hcj.header_decode(merged), o)
+        # the flag changes nothing for a file the model reads
+        _same_header(hcj.header_decode(jpg, hcj.FLAG_T81_TABLES), orc.header_decode(jpg))
+
+
 def test_header_errors_match_oracle(hcj, orc, data):
     jpg = data("mini.jpg")
     cases = [

@@ -98,9 +98,19 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode_name", ["yuv", "planes", "rgb"])
+def oracle_yuv444(orc, dec):
+    """Planar_444.convert_from_420 / _422 of the cropped frame into a fresh (zero) 4:4:4 frame."""
+    y, u, v = orc.upsample_to_444(dec.cropped[:3], dec.chroma)
+    h, w = y.shape
+    out = np.zeros((3, h, w), np.uint8)
+    for k, p in enumerate((y, u, v)):
+        out[k, : min(h, p.shape[0]), : min(w, p.shape[1])] = p[:h, :w]
+    return out
+
+
+@pytest.mark.parametrize("mode_name", ["yuv", "planes", "rgb", "yuv444"])
 def test_batch_matches_oracle(hcj, ctx, orc, mode_name):
-    mode = {"yuv": hcj.OUT_YUV, "planes": hcj.OUT_PLANES, "rgb": hcj.OUT_RGB24}[mode_name]
+    mode = {"yuv": hcj.OUT_YUV, "planes": hcj.OUT_PLANES, "rgb": hcj.OUT_RGB24, "yuv444": hcj.OUT_YUV444}[mode_name]
     jpgs = [orc.encode(synth.frame(100 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(CASES)]
     outs, st = ctx.decode_batch(jpgs, mode)
     assert st == [0] * len(jpgs)
@@ -110,9 +120,47 @@ def test_batch_matches_oracle(hcj, ctx, orc, mode_name):
             want = dec.yuv()
         elif mode == hcj.OUT_PLANES:
             want = b"".join(p.tobytes() for p in dec.planes)
+        elif mode == hcj.OUT_YUV444:
+            want = oracle_yuv444(orc, dec).tobytes()
         else:
             want = oracle_rgb(orc, dec).tobytes()
         assert bytes(out) == want, case
+
+
+def test_batch_compare_on_device(hcj, ctx, orc, goldens, data):
+    """`oyuv compare` for a whole batch on the device (hcj_batch_compare): the reference's cram PSNR strings
+    (jpeg/test/model-encode-and-decode.t) and exact integer metrics against numpy on seeded frames."""
+    runs = goldens["cram_encode_decode"]["runs"]
+    srcs = [data(r["input"]) for r in runs]
+    jpgs = [orc.encode(s, 64, 64, int(r["chroma"]), r["quality"]) for s, r in zip(srcs, runs)]
+    with ctx.batch(jpgs, hcj.OUT_YUV) as b:
+        b.decode()
+        for m, r in zip(b.compare(srcs), runs):
+            assert m.status == 0
+            for k in range(3):
+                assert abs(m.psnr(k) - float(r["psnr"][k])) < 1e-9, (r, k, m.psnr(k))
+    frames = [synth.frame(100 + i, w, h, c) for i, (c, q, w, h, ri) in enumerate(CASES)]
+    jpgs = [orc.encode(f, w, h, c, q, restart_interval=ri) for f, (c, q, w, h, ri) in zip(frames, CASES)]
+    with ctx.batch(jpgs + [b"junk"], hcj.OUT_YUV) as b:
+        b.decode()
+        outs, st = b.fetch()
+        ms = b.compare(frames + [None])
+        assert ms[-1].status != 0 and st[-1] != 0
+        for f, o, m, (c, q, w, h, ri) in zip(frames, outs, ms, CASES):
+            a, d = np.frombuffer(f, np.uint8).astype(np.int64), o.astype(np.int64)
+            cw, ch = (w if c == 444 else w // 2), (h // 2 if c == 420 else h)
+            cuts = [0, w * h, w * h + cw * ch, w * h + 2 * cw * ch]
+            for k in range(3):
+                dlt = np.abs(a[cuts[k]:cuts[k + 1]] - d[cuts[k]:cuts[k + 1]])
+                assert m.samples[k] == cuts[k + 1] - cuts[k]
+                assert (m.square_error[k], m.total_difference[k], m.max_difference[k]) == (int((dlt * dlt).sum()), int(dlt.sum()), int(dlt.max()))
+    # a reference of the wrong size is reported per image
+    with ctx.batch(jpgs[:2], hcj.OUT_YUV444) as b:
+        b.decode()
+        ms = b.compare([oracle_yuv444(orc, orc.decode(jpgs[0])).tobytes(), frames[1] + b"x"])
+        assert ms[0].status == 0 and list(ms[0].square_error)[:3] == [0, 0, 0] and list(ms[0].samples)[:3] == [256 * 192] * 3
+        assert ms[0].psnr(0) == float("inf")
+        assert ms[1].status == -31  # HCJ_ERR_INVALID_ARG: reference of the wrong size
 
 
 def test_coefficients_and_entropy_taps(hcj, ctx, orc):
@@ -142,6 +190,28 @@ def test_restart_extension_equivalence(hcj, ctx, orc):
         assert st == [0] and bytes(outs[0]) == want
     except orc.OracleError as e:
         assert st == [e.status]
+
+
+def test_t81_table_segments_decode(hcj, ctx, orc):
+    """Merged DQT / DHT segments + fill bytes (HCJ_FLAG_T81_TABLES) decode to the pixels of the plain file; the same
+    bytes without the flag fail like the model."""
+    plain, merged = [], []
+    for i, (chroma, ri) in enumerate(((420, 0), (420, 8), (444, 0), (422, 3))):
+        j = orc.encode(synth.frame(40 + i, 200, 120, chroma), 200, 120, chroma, 70, restart_interval=ri)
+        plain.append(j)
+        merged.append(synth.merge_table_segments(j, fill=i))
+    want = [orc.decode(j).yuv() for j in plain]
+    outs, st = ctx.decode_batch(merged + plain, hcj.OUT_YUV, hcj.FLAG_DEFAULT | hcj.FLAG_T81_TABLES)
+    assert st == [0] * 8
+    for o, w in zip(outs, want + want):
+        assert bytes(o) == w
+    for m in merged:
+        assert bytes(orc.decode(m, t81_tables=True).yuv()) == bytes(outs[merged.index(m)])
+    outs, st = ctx.decode_batch(merged + plain)
+    assert st[:4] == [orc.decode_status(m) for m in merged] and st[4:] == [0] * 4
+    assert all(s != 0 for s in st[:4])
+    for o, w in zip(outs[4:], want):
+        assert bytes(o) == w
 
 
 def test_pillow_streams(hcj, ctx, orc):

@@ -37,6 +37,9 @@ struct hcj_batch {
   std::vector<uint32_t> tile_base;                // [n + 1] first IDCT tile of every image in the batch tile plan
 };
 
+// output modes produced by the Planar_444 kernel from the padded planes
+static inline bool post_444(int mode) { return mode == HCJ_OUT_RGB24 || mode == HCJ_OUT_YUV444; }
+
 extern "C" {
 
 int hcj_version(void) { return HCJ_VERSION; }
@@ -72,18 +75,24 @@ const char *hcj_strerror(int status) {
   return "unknown status";
 }
 
-int hcj_header_decode(const uint8_t *jpeg, size_t len, hcj_header *out) {
+int hcj_header_decode(const uint8_t *jpeg, size_t len, hcj_header *out) { return hcj_header_decode_ex(jpeg, len, 0u, out); }
+
+int hcj_header_decode_ex(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *out) {
   if (!jpeg || !out) return HCJ_ERR_INVALID_ARG;
-  return hcj::header_decode(jpeg, len, out);
+  return hcj::header_decode(jpeg, len, out, flags);
 }
 
 int hcj_frame_info_get(const uint8_t *jpeg, size_t len, hcj_frame_info *out) {
+  return hcj_frame_info_get_ex(jpeg, len, HCJ_FLAG_DEFAULT, out);
+}
+
+int hcj_frame_info_get_ex(const uint8_t *jpeg, size_t len, unsigned flags, hcj_frame_info *out) {
   if (!jpeg || !out) return HCJ_ERR_INVALID_ARG;
   hcj_header *h = new (std::nothrow) hcj_header;
   if (!h) return HCJ_ERR_OUT_OF_MEMORY;
-  int st = hcj::header_decode(jpeg, len, h);
+  int st = hcj::header_decode(jpeg, len, h, flags);
   hcj::ImagePlan plan;
-  if (st == HCJ_OK) st = hcj::plan_image(*h, HCJ_FLAG_DEFAULT, &plan);
+  if (st == HCJ_OK) st = hcj::plan_image(*h, flags, &plan);
   if (st == HCJ_OK) *out = plan.info;
   delete h;
   return st;
@@ -209,7 +218,7 @@ static cudaError_t upload_files(const hcj_batch *b, const uint8_t *const *jpeg, 
 
 static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                         int *status, hcj_batch **out, bool with_files) {
-  if (!c || !out || n < 0 || n > HCJ_MAX_BATCH || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > 2) return HCJ_ERR_INVALID_ARG;
+  if (!c || !out || n < 0 || n > HCJ_MAX_BATCH || (n > 0 && (!jpeg || !len)) || mode < 0 || mode > HCJ_OUT_YUV444) return HCJ_ERR_INVALID_ARG;
   *out = nullptr;
   CU_TRY(cudaSetDevice(c->device));
   hcj_batch *b = new (std::nothrow) hcj_batch;
@@ -265,7 +274,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   {
     auto work = [&](int lo, int hi) {
       for (int i = lo; i < hi; i++) {
-        int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i]) : HCJ_ERR_INVALID_ARG;
+        int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i], flags) : HCJ_ERR_INVALID_ARG;
         if (st == HCJ_OK) st = hcj::plan_image(hdrs[i], flags, &plans[i]);
         parse_st[i] = st;
       }
@@ -354,7 +363,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
         for (int p = 0; p < npairs; p++) prev_pair_dc[p] = pair_dc[p], prev_pair_ac[p] = pair_ac[p];
       }
     }
-    if (st == HCJ_OK && (mode == HCJ_OUT_YUV || mode == HCJ_OUT_RGB24)) {
+    if (st == HCJ_OK && (mode == HCJ_OUT_YUV || post_444(mode))) {
       if (f.ncomp < 3) st = HCJ_ERR_NEED_3_COMPONENTS;  // decoder.ml:415-420
       else if (f.chroma == 0) st = HCJ_ERR_FRAME_INFER;  // frame.ml:44,55
     }
@@ -412,7 +421,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       g.qt = k;
       g.first_blk = first_blk;
       first_blk += g.hs * g.vs;
-      g.plane_off = (mode == HCJ_OUT_RGB24 ? plane_total : 0) + plane_acc;
+      g.plane_off = (post_444(mode) ? plane_total : 0) + plane_acc;
       plane_acc += (size_t)g.decoded_w * g.decoded_h;
       g.out_off = yuv_acc;
       yuv_acc += (size_t)g.actual_w * g.actual_h;
@@ -424,7 +433,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       for (int e = 0; e < 64; e++)  // "dp2a form" used by the 32-bit path (see HCJ_QD in hcj_device.cuh)
         qt_pool.push_back((e & 1) ? (int32_t)(q.elements[e] & 0xff) << 8 : (int32_t)(q.elements[e] & 0xff));
     }
-    if (mode == HCJ_OUT_RGB24) plane_total += align_up(plane_acc, 256);
+    if (post_444(mode)) plane_total += align_up(plane_acc, 256);
     for (int k = 0; k < f.blocks_per_mcu && k < HCJ_MAX_BPM; k++) {
       d.blk_comp[k] = (uint8_t)plan.blk_comp[k];
       d.blk_bx[k] = (uint8_t)plan.blk_bx[k];
@@ -497,7 +506,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   BALLOC(wide_flags, uint32_t *, (size_t)(total_blocks / 32 + 2) * 4 + 64);  // + slack: k_idct stages 48 bytes per tile
   BALLOC(out, uint8_t *, out_total + 16);
   BALLOC(idct_plan, hcjk::IdctTile *, hcjk::idct_plan_bytes(total_tiles));
-  if (mode == HCJ_OUT_RGB24) BALLOC(planes, uint8_t *, plane_total + 16);
+  if (post_444(mode)) BALLOC(planes, uint8_t *, plane_total + 16);
 #undef BALLOC
   if (st != HCJ_OK) {
     hcj_batch_destroy(c, b);
@@ -549,7 +558,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     const char *e = getenv("HCJ_DEBUG");
     dv.debug = e ? atoi(e) : 0;
   }
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (mode == HCJ_OUT_RGB24 ? 1 : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? 1 : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;
@@ -594,7 +603,7 @@ int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
   hcjk::launch_huff_restart(b->dev, s);
   hcjk::launch_huff_spec(b->dev, s);
   hcjk::launch_idct(b->dev, b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2, s);
-  if (b->mode == HCJ_OUT_RGB24) hcjk::launch_rgb(b->dev, s);
+  if (post_444(b->mode)) hcjk::launch_rgb(b->dev, b->mode == HCJ_OUT_YUV444, s);
   CU_TRY(cudaGetLastError());
   return HCJ_OK;
 }
@@ -621,7 +630,7 @@ int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, i
   cudaEventRecord(ev[4], s);
   hcjk::launch_idct(b->dev, mode, s);
   cudaEventRecord(ev[5], s);
-  if (b->mode == HCJ_OUT_RGB24) hcjk::launch_rgb(b->dev, s);
+  if (post_444(b->mode)) hcjk::launch_rgb(b->dev, b->mode == HCJ_OUT_YUV444, s);
   cudaEventRecord(ev[6], s);
   cudaError_t e = cudaEventSynchronize(ev[6]);
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -738,7 +747,7 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       hcjk::launch_huff_restart(dv, s);
       hcjk::launch_huff_spec(dv, s);
       hcjk::launch_idct(dv, kmode, s);
-      if (mode == HCJ_OUT_RGB24) hcjk::launch_rgb(dv, s);
+      if (post_444(mode)) hcjk::launch_rgb(dv, mode == HCJ_OUT_YUV444, s);
       e = cudaGetLastError();
       if (e == cudaSuccess) e = cudaEventRecord(c->chunk_events[k], s);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, c->chunk_events[k], 0);
@@ -842,6 +851,72 @@ int hcj_idct_blocks(hcj_ctx *c, const int16_t *coefs, size_t nblocks, const uint
   c->release(d_o);
   if (st != HCJ_OK) return st;
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
+int hcj_batch_compare(hcj_ctx *c, hcj_batch *b, const uint8_t *const *ref, const size_t *ref_len, hcj_plane_metrics *out) {
+  if (!c || !b || !ref || !ref_len || !out) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  const int n = b->n;
+  if (n == 0) return HCJ_OK;
+  // planes of every image in its output and in the reference buffer
+  std::vector<hcjk::ComparePlane> planes((size_t)n * 4);
+  std::vector<uint64_t> ref_off((size_t)n, 0);
+  uint64_t ref_total = 0;
+  for (int i = 0; i < n; i++) {
+    memset(&out[i], 0, sizeof(out[i]));
+    const HcjImageDesc &d = b->descs[i];
+    out[i].status = b->host_status[i];
+    if (out[i].status == HCJ_OK && (!ref[i] || ref_len[i] != b->out_bytes[i])) out[i].status = HCJ_ERR_INVALID_ARG;
+    if (out[i].status != HCJ_OK) continue;
+    ref_off[i] = ref_total;
+    ref_total += (b->out_bytes[i] + 15) & ~(uint64_t)15;
+    uint64_t acc = 0;
+    const int np = b->mode == HCJ_OUT_RGB24 ? 1 : b->mode == HCJ_OUT_PLANES ? d.ncomp : 3;
+    for (int k = 0; k < np; k++) {
+      uint64_t bytes;
+      if (b->mode == HCJ_OUT_RGB24) bytes = (uint64_t)d.width * d.height * 3;
+      else if (b->mode == HCJ_OUT_YUV444) bytes = (uint64_t)d.width * d.height;
+      else if (b->mode == HCJ_OUT_PLANES) bytes = (uint64_t)d.comp[k].decoded_w * d.comp[k].decoded_h;
+      else bytes = (uint64_t)d.comp[k].actual_w * d.comp[k].actual_h;
+      planes[(size_t)i * 4 + k] = hcjk::ComparePlane{d.out_off + acc, ref_off[i] + acc, bytes};
+      out[i].samples[k] = (int64_t)bytes;
+      acc += bytes;
+    }
+  }
+  void *d_ref = nullptr, *d_pl = nullptr, *d_acc = nullptr;
+  const size_t acc_bytes = (size_t)n * 16 * sizeof(unsigned long long);
+  std::vector<unsigned long long> res((size_t)n * 16, 0);
+  int st = c->alloc(&d_ref, ref_total + 16);
+  if (st == HCJ_OK) st = c->alloc(&d_pl, planes.size() * sizeof(hcjk::ComparePlane));
+  if (st == HCJ_OK) st = c->alloc(&d_acc, acc_bytes);
+  cudaError_t e = cudaSuccess;
+  if (st == HCJ_OK) {
+    for (int i = 0; i < n && e == cudaSuccess; i++)
+      if (out[i].status == HCJ_OK)
+        e = cudaMemcpyAsync((uint8_t *)d_ref + ref_off[i], ref[i], b->out_bytes[i], cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_pl, planes.data(), planes.size() * sizeof(hcjk::ComparePlane), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, acc_bytes, c->stream);
+    if (e == cudaSuccess) {
+      hcjk::launch_compare_planes(b->dev.out, (const uint8_t *)d_ref, (const hcjk::ComparePlane *)d_pl, (unsigned long long *)d_acc, n,
+                                  c->stream);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res.data(), d_acc, acc_bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  c->release(d_ref);
+  c->release(d_pl);
+  c->release(d_acc);
+  if (st != HCJ_OK) return st;
+  if (e != cudaSuccess) return HCJ_ERR_CUDA - (int)e;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < 4; k++) {
+      out[i].square_error[k] = (int64_t)res[((size_t)i * 4 + k) * 4 + 0];
+      out[i].total_difference[k] = (int64_t)res[((size_t)i * 4 + k) * 4 + 1];
+      out[i].max_difference[k] = (int)res[((size_t)i * 4 + k) * 4 + 2];
+    }
+  return HCJ_OK;
 }
 
 int hcj_compare_planes(hcj_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error, int *max_difference) {

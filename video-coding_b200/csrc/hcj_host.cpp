@@ -76,11 +76,15 @@ void push_front(T *arr, int *n, const T &v) {  // OCaml list cons: newest first
   (*n)++;
 }
 
-void decode_impl(Bits &b, hcj_header *h) {  // decoder.ml:37-70
+// flags & HCJ_FLAG_T81_TABLES (stated extension): DQT / DHT segments hold as many tables as their length covers and
+// parsing continues at the end of the segment; 0xFF fill bytes in front of a marker code are skipped.
+void decode_impl(Bits &b, hcj_header *h, unsigned flags) {  // decoder.ml:37-70
+  const bool t81 = (flags & HCJ_FLAG_T81_TABLES) != 0;
   memset(h, 0, sizeof(*h));
   for (;;) {
     find_marker(b);
     int code = (int)b.get(8);
+    while (t81 && code == 0xff && b.bit_pos() < b.length_in_bits()) code = (int)b.get(8);
     if (code == SOF0) {  // markers.ml:49-59
       h->has_frame = 1;
       h->sof_length = b.get(16);
@@ -113,31 +117,41 @@ void decode_impl(Bits &b, hcj_header *h) {  // decoder.ml:37-70
       h->successive_approximation_bit_low = b.get(4);
       h->scan_byte_pos = (int64_t)(b.bit_pos() >> 3);
       return;
-    } else if (code == DQT) {  // markers.ml:162-168 — one table per segment
-      hcj_dqt q;
-      memset(&q, 0, sizeof(q));
-      q.length = b.get(16);
-      int pq = b.get(4);
-      if (pq > 1) throw Raise{HCJ_ERR_UNSUPPORTED_GEOMETRY};
-      q.element_precision = 8 << pq;
-      q.table_identifier = b.get(4);
-      for (int i = 0; i < 64; i++) q.elements[i] = (int)b.get(q.element_precision);
-      push_front(h->quant_tables, &h->n_quant_tables, q);
-    } else if (code == DHT) {  // markers.ml:210-220 — one table per segment
-      hcj_dht t;
-      memset(&t, 0, sizeof(t));
-      t.length = b.get(16);
-      t.table_class = b.get(4);
-      t.destination_identifier = b.get(4);
-      int total = 0;
-      for (int i = 0; i < 16; i++) {
-        t.lengths[i] = b.get(8);
-        total += t.lengths[i];
-      }
-      if (total > 256) throw Raise{HCJ_ERR_BAD_HUFFMAN_TABLE};
-      t.nvalues = total;
-      for (int i = 0; i < total; i++) t.values[i] = (uint8_t)b.get(8);
-      push_front(h->huffman_tables, &h->n_huffman_tables, t);
+    } else if (code == DQT) {  // markers.ml:162-168 — one table per segment (more with HCJ_FLAG_T81_TABLES)
+      const uint64_t seg_end = b.bit_pos() + 8ull * b.show(16);
+      const int seg_len = (int)b.get(16);
+      do {
+        hcj_dqt q;
+        memset(&q, 0, sizeof(q));
+        q.length = seg_len;
+        int pq = b.get(4);
+        if (pq > 1) throw Raise{HCJ_ERR_UNSUPPORTED_GEOMETRY};
+        q.element_precision = 8 << pq;
+        q.table_identifier = b.get(4);
+        for (int i = 0; i < 64; i++) q.elements[i] = (int)b.get(q.element_precision);
+        push_front(h->quant_tables, &h->n_quant_tables, q);
+      } while (t81 && b.bit_pos() < seg_end);
+      if (t81 && b.bit_pos() < seg_end) b.advance(seg_end - b.bit_pos());
+    } else if (code == DHT) {  // markers.ml:210-220 — one table per segment (more with HCJ_FLAG_T81_TABLES)
+      const uint64_t seg_end = b.bit_pos() + 8ull * b.show(16);
+      const int seg_len = (int)b.get(16);
+      do {
+        hcj_dht t;
+        memset(&t, 0, sizeof(t));
+        t.length = seg_len;
+        t.table_class = b.get(4);
+        t.destination_identifier = b.get(4);
+        int total = 0;
+        for (int i = 0; i < 16; i++) {
+          t.lengths[i] = b.get(8);
+          total += t.lengths[i];
+        }
+        if (total > 256) throw Raise{HCJ_ERR_BAD_HUFFMAN_TABLE};
+        t.nvalues = total;
+        for (int i = 0; i < total; i++) t.values[i] = (uint8_t)b.get(8);
+        push_front(h->huffman_tables, &h->n_huffman_tables, t);
+      } while (t81 && b.bit_pos() < seg_end);
+      if (t81 && b.bit_pos() < seg_end) b.advance(seg_end - b.bit_pos());
     } else if (code == DRI) {  // markers.ml:193-197
       h->has_restart_interval = 1;
       h->dri_length = b.get(16);
@@ -157,10 +171,10 @@ int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out) {
+int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags) {
   Bits b(jpeg, len);
   try {
-    decode_impl(b, out);
+    decode_impl(b, out, flags);
   } catch (const Raise &r) {
     return r.code;
   }

@@ -15,7 +15,7 @@
 namespace hcj {
 
 // Decoder.Header.decode (decoder.ml:37-70) over a From_string bit reader.
-int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out);
+int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags = 0);
 
 // Decoder.init geometry (decoder.ml:304-345) + which tables each scan component binds to.
 struct ImagePlan {

@@ -1609,6 +1609,7 @@ __device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
 // Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16).  4:4:4 images whose rows keep
 // 16-byte alignment (width and padded width multiples of 16) take the vector path: one 16-byte load per
 // plane, three 16-byte stores; everything else goes pixel by pixel through up_sample.
+template <bool PLANAR>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
 __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
   if (!d.valid || d.chroma == 0) return;
@@ -1618,6 +1619,19 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
                 *pv = b.planes + d.comp[2].plane_off;
   uint8_t *dst = b.out + d.out_off + ((size_t)y * d.width + x0) * 3;
   const int sy = d.comp[0].decoded_w;
+  if (PLANAR) {
+    const size_t plane = (size_t)d.width * d.height;
+    uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0, *ou = oy + plane, *ov = ou + plane;
+    const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
+    const int n = min(16, d.width - x0);
+    for (int i = 0; i < n; i++) {
+      const int x = x0 + i;
+      oy[i] = py[(size_t)y * sy + x];
+      ou[i] = (uint8_t)up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log);
+      ov[i] = (uint8_t)up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
+    }
+    return;
+  }
   const bool vec = d.chroma == 444 && ((d.width | sy | d.comp[1].decoded_w | d.comp[2].decoded_w) & 15) == 0 &&
                    (((uintptr_t)py | (uintptr_t)pu | (uintptr_t)pv | (uintptr_t)(b.out + d.out_off)) & 15u) == 0;
   if (vec) {
@@ -1656,11 +1670,12 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
   }
 }
 
-void launch_rgb(const DecodeBatchDev &b, cudaStream_t s) {
+void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
   dim3 block(128);
   dim3 grid((b.max_width / 16 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
-  k_rgb<<<grid, block, 0, s>>>(b);
+  if (planar444) k_rgb<true><<<grid, block, 0, s>>>(b);
+  else k_rgb<false><<<grid, block, 0, s>>>(b);
 }
 
 // Ocompare.square_error / max_difference (tools/src/ocompare.ml:8-52).
@@ -1681,6 +1696,39 @@ __global__ void k_compare(const uint8_t *a, const uint8_t *bb, size_t n, unsigne
     atomicAdd(sse, acc);
     atomicMax(maxdiff, mx);
   }
+}
+
+// The same per (image, plane) of a decoded batch against reference frames (hcj_batch_compare): grid (chunks, 4, images).
+__global__ void __launch_bounds__(256) k_compare_planes(const uint8_t *out, const uint8_t *ref, const ComparePlane *planes,
+                                                         unsigned long long *acc /* [images][4][4] */) {
+  const ComparePlane pl = planes[blockIdx.z * 4 + blockIdx.y];
+  if (pl.bytes == 0) return;
+  const uint8_t *a = out + pl.out_off, *r = ref + pl.ref_off;
+  unsigned long long se = 0, td = 0;
+  unsigned mx = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pl.bytes; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned dlt = (unsigned)abs((int)a[i] - (int)r[i]);
+    se += dlt * dlt;
+    td += dlt;
+    mx = max(mx, dlt);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, s);
+    td += __shfl_xor_sync(0xffffffffu, td, s);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *o = acc + ((size_t)blockIdx.z * 4 + blockIdx.y) * 4;
+    atomicAdd(o + 0, se);
+    atomicAdd(o + 1, td);
+    atomicMax(o + 2, (unsigned long long)mx);
+  }
+}
+void launch_compare_planes(const uint8_t *out, const uint8_t *ref, const ComparePlane *planes, unsigned long long *acc, int images,
+                           cudaStream_t s) {
+  if (images <= 0) return;
+  k_compare_planes<<<dim3(32, 4, images), 256, 0, s>>>(out, ref, planes, acc);
 }
 
 void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff, cudaStream_t s) {

@@ -71,11 +71,19 @@ int idct_kernel_count();
 size_t idct_plan_bytes(uint32_t tiles);
 // Fills b->coef_map for b->coefs / b->total_blocks.  Returns a cudaError_t-compatible code (0 = ok).
 int make_coef_tensor_map(DecodeBatchDev *b);
-void launch_rgb(const DecodeBatchDev &b, cudaStream_t s);
+void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s);
 void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
                         cudaStream_t s);
 void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff,
                     cudaStream_t s);
+
+struct ComparePlane {
+  uint64_t out_off;  // plane in the batch output buffer
+  uint64_t ref_off;  // the same plane in the uploaded reference frames
+  uint64_t bytes;    // 0: no such plane
+};
+void launch_compare_planes(const uint8_t *out, const uint8_t *ref, const ComparePlane *planes, unsigned long long *acc, int images,
+                           cudaStream_t s);
 
 // ---- encoder ----
 struct EncodeBatchDev {

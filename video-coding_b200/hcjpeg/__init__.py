@@ -16,8 +16,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_ROOT, "lib", "libhcjpeg.so")
 
-OUT_YUV, OUT_PLANES, OUT_RGB24 = 0, 1, 2
+OUT_YUV, OUT_PLANES, OUT_RGB24, OUT_YUV444 = 0, 1, 2, 3
 FLAG_RESTART_EXT = 1
+FLAG_T81_TABLES = 2
 FLAG_DEFAULT = FLAG_RESTART_EXT
 
 MAX_COMPONENTS = 4
@@ -147,6 +148,8 @@ _SIGS = {
     "hcj_version": (C.c_int, []),
     "hcj_header_decode": (C.c_int, [C.c_char_p, C.c_size_t, _P(Header)]),
     "hcj_frame_info_get": (C.c_int, [C.c_char_p, C.c_size_t, _P(FrameInfo)]),
+    "hcj_header_decode_ex": (C.c_int, [C.c_char_p, C.c_size_t, C.c_uint, _P(Header)]),
+    "hcj_frame_info_get_ex": (C.c_int, [C.c_char_p, C.c_size_t, C.c_uint, _P(FrameInfo)]),
     "hcj_ctx_create": (C.c_int, [C.c_int, C.c_void_p, _P(C.c_void_p)]),
     "hcj_ctx_destroy": (None, [C.c_void_p]),
     "hcj_ctx_synchronize": (C.c_int, [C.c_void_p]),
@@ -167,12 +170,32 @@ _SIGS = {
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "hcj_batch_compare": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
     "hcj_batch_decode_stages": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
     "hcj_decode_stage_name": (C.c_char_p, [C.c_int]),
     "hcj_encode_last_device_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "hcj_timer_start": (C.c_int, [C.c_void_p]),
     "hcj_timer_stop": (C.c_int, [C.c_void_p, _P(C.c_float)]),
 }
+
+class PlaneMetrics(C.Structure):
+    """hcj_plane_metrics: Ocompare results per plane of one image (tools/src/ocompare.ml:8-56)."""
+    _fields_ = [("status", C.c_int), ("max_difference", C.c_int * 4), ("square_error", C.c_int64 * 4),
+                ("total_difference", C.c_int64 * 4), ("samples", C.c_int64 * 4)]
+
+    def mean_square_error(self, k):
+        return self.square_error[k] / self.samples[k]
+
+    def mean_difference(self, k):
+        return self.total_difference[k] / self.samples[k]
+
+    def psnr(self, k, r=255.0):
+        """Ocompare.psnr (ocompare.ml:54-56): 10 log10(r^2 / mse); inf for identical planes, like the model's float division."""
+        import math
+
+        mse = self.mean_square_error(k)
+        return math.inf if mse == 0 else 10.0 * math.log10(r * r / mse)
+
 
 _lib = None
 
@@ -241,22 +264,22 @@ def _ptr_array(bufs):
     return arr, keep
 
 
-def header_decode(jpeg):
-    """Decoder.Header.decode (decoder.ml:37-70)."""
+def header_decode(jpeg, flags=0):
+    """Decoder.Header.decode (decoder.ml:37-70); flags=FLAG_T81_TABLES reads every table of a DQT / DHT segment."""
     h = Header()
-    _check(lib().hcj_header_decode(jpeg, len(jpeg), C.byref(h)), "Header.decode")
+    _check(lib().hcj_header_decode_ex(jpeg, len(jpeg), flags, C.byref(h)), "Header.decode")
     return h
 
 
-def frame_info(jpeg):
+def frame_info(jpeg, flags=FLAG_DEFAULT):
     """Geometry fixed by Decoder.init (decoder.ml:304-345)."""
     f = FrameInfo()
-    _check(lib().hcj_frame_info_get(jpeg, len(jpeg), C.byref(f)), "Decoder.init")
+    _check(lib().hcj_frame_info_get_ex(jpeg, len(jpeg), flags, C.byref(f)), "Decoder.init")
     return f
 
 
 def out_size(info, mode):
-    return {OUT_YUV: info.yuv_bytes, OUT_PLANES: info.planes_bytes, OUT_RGB24: info.rgb_bytes}[mode]
+    return {OUT_YUV: info.yuv_bytes, OUT_PLANES: info.planes_bytes, OUT_RGB24: info.rgb_bytes, OUT_YUV444: info.rgb_bytes}[mode]
 
 
 class Context:
@@ -303,7 +326,7 @@ class Context:
         infos, caps, outs = [], [], []
         for j in jpegs:
             f = FrameInfo()
-            st = lib().hcj_frame_info_get(j, len(j), C.byref(f))
+            st = lib().hcj_frame_info_get_ex(j, len(j), flags, C.byref(f))
             size = out_size(f, mode) if st == 0 else 0
             infos.append(f if st == 0 else None)
             caps.append(size)
@@ -384,7 +407,7 @@ class Batch:
         self.infos = []
         for j in jpegs:
             f = FrameInfo()
-            self.infos.append(f if lib().hcj_frame_info_get(j, len(j), C.byref(f)) == 0 else None)
+            self.infos.append(f if lib().hcj_frame_info_get_ex(j, len(j), flags, C.byref(f)) == 0 else None)
 
     def decode(self):
         _check(lib().hcj_batch_decode(self.ctx._h, self._h), "hcj_batch_decode")
@@ -409,6 +432,17 @@ class Batch:
         _check(lib().hcj_batch_fetch(self.ctx._h, self._h, op, capa, status), "hcj_batch_fetch")
         st = [status[i] for i in range(self.n)]
         return [outs[i][: caps[i]] if st[i] == 0 else None for i in range(self.n)], st
+
+    def compare(self, refs):
+        """`oyuv compare` of every decoded image (resident in HBM) with refs[i] (bytes in the batch's output layout):
+        a PlaneMetrics per image."""
+        assert len(refs) == self.n
+        bufs = [np.frombuffer(r, np.uint8) if r is not None else np.zeros(1, np.uint8) for r in refs]
+        rp, keep = _ptr_array(bufs)
+        lens = (C.c_size_t * max(self.n, 1))(*[len(r) if r is not None else 0 for r in refs])
+        out = (PlaneMetrics * max(self.n, 1))()
+        _check(lib().hcj_batch_compare(self.ctx._h, self._h, rp, lens, out), "hcj_batch_compare")
+        return [out[i] for i in range(self.n)]
 
     def coefficients(self, i):
         """Component.coefs of image i (int16 zig-zag, DC resolved), decode_seq order."""
