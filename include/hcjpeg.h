@@ -156,6 +156,15 @@ typedef enum hcj_out_mode {
 int hcj_decode_batch(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      uint8_t *const *out, const size_t *out_capacity, int *status);
 
+/* Motion JPEG (jpeg/README.md:33 lists it as the model's next step: "just testing processing of multiple frames"):
+ * a stream of whole JPEG files back to back.  hcj_mjpeg_split finds the frames (host only; pass offsets = NULL to
+ * count them); hcj_decode_stream decodes all of them like hcj_decode_batch (files up, kernels and frames down
+ * overlapped chunk by chunk) into one buffer: frame i at out + out_offsets[i], out_offsets[nframes] = bytes used
+ * (each frame starts at a 256-byte boundary; out_offsets needs capacity + 1 entries). */
+int hcj_mjpeg_split(const uint8_t *stream, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes);
+int hcj_decode_stream(hcj_ctx *ctx, const uint8_t *stream, size_t len, int mode, unsigned flags, uint8_t *out,
+                      size_t out_capacity, size_t *out_offsets, int *status, int capacity, int *nframes);
+
 /* The same in three steps, for pipelines that keep data resident in HBM. */
 typedef struct hcj_batch hcj_batch;
 /* Header.decode + init for every image, then upload (H2D) of the compressed bytes and tables.
@@ -177,6 +186,19 @@ void hcj_batch_destroy(hcj_ctx *ctx, hcj_batch *b);
 int hcj_batch_fetch_coefficients(hcj_ctx *ctx, hcj_batch *b, int i, int16_t *coefs, size_t capacity_blocks);
 /* For_testing.extract_entropy_coded_bits (decoder.ml:261-281): destuffed entropy-coded segment of image i. */
 int hcj_batch_fetch_entropy(hcj_ctx *ctx, hcj_batch *b, int i, uint8_t *out, size_t capacity, size_t *len);
+/* `model decode log` (jpeg/bin/model.ml:46-68): Decoder.Component.Summary (decoder.ml:189-203) of blocks
+ * [first_block, first_block + count) of image i in decode_seq order, computed on the device from the decoded
+ * coefficient blocks with the model's 64-bit arithmetic. */
+typedef struct hcj_block_log {
+  int32_t x, y;        /* origin of the block in its component's padded plane (decoder.ml:353-360) */
+  int32_t dc_pred;     /* the component's predictor after the block */
+  int32_t component;   /* scan component index; its identifier is hcj_header.scan_components[component].selector */
+  int16_t coefs[64];   /* zig-zag order, coefs[0] = the DC differential as decoded (Component.coefs) */
+  int32_t dequant[64]; /* natural order (Component.dequant) */
+  int32_t idct[64];    /* Dct.Chen.inverse_8x8 of dequant, before clipping (Component.idct) */
+  uint8_t recon[64];   /* clip + level shift (Component.recon) */
+} hcj_block_log;
+int hcj_batch_fetch_block_log(hcj_ctx *ctx, hcj_batch *b, int i, size_t first_block, size_t count, hcj_block_log *out);
 /* dequantize + Dct.Chen.inverse_8x8 + recon (decoder.ml:142-149,213-224; dct.ml:100-107) on caller-provided
  * zig-zag blocks (DC absolute): out = nblocks*64 reconstructed samples, block-major (Component.recon). */
 int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const uint16_t quant_table[64], uint8_t *out);

@@ -147,6 +147,30 @@ def test_t81_table_segments_extension(hcj, orc):
         _same_header(hcj.header_decode(jpg, hcj.FLAG_T81_TABLES), orc.header_decode(jpg))
 
 
+def mjpeg_stream(orc, data):
+    js = [orc.encode(synth.frame(i, 64, 48, c), 64, 48, c, 75, restart_interval=ri) for i, (c, ri) in enumerate([(420, 0), (444, 2), (422, 0), (420, 1)])]
+    js.append(data("Mouse480.jpg"))
+    js.append(synth.merge_table_segments(js[0], fill=2))
+    stream, want = b"", []
+    for i, j in enumerate(js):
+        stream += b"\x00\xff\x12garbage" * (i % 2)
+        want.append((len(stream), len(j)))
+        stream += j
+    return js, stream, want
+
+
+def test_mjpeg_split(hcj, orc, data):
+    js, stream, want = mjpeg_stream(orc, data)
+    assert hcj.mjpeg_split(stream) == want
+    assert hcj.mjpeg_split(stream + b"\xff\xd8\xff\xe0\x00\x04ab") == want  # a frame cut short at the end is dropped
+    assert hcj.mjpeg_split(stream[: want[-1][0] + 100]) == want[:-1]
+    assert hcj.mjpeg_split(b"") == [] and hcj.mjpeg_split(b"\xff\xd8\xff\xd9") == [(0, 4)]
+    n = C.c_int()
+    off, ln = (C.c_size_t * 2)(), (C.c_size_t * 2)()
+    assert hcj.lib().hcj_mjpeg_split(stream, len(stream), off, ln, 2, C.byref(n)) == -30 and n.value == len(want)  # BUFFER_TOO_SMALL
+    assert [(off[i], ln[i]) for i in range(2)] == want[:2]
+
+
 def test_header_errors_match_oracle(hcj, orc, data):
     jpg = data("mini.jpg")
     cases = [

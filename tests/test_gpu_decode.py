@@ -174,6 +174,28 @@ def test_coefficients_and_entropy_taps(hcj, ctx, orc):
         assert b.kernels() >= 3
 
 
+def test_block_log_tap(hcj, ctx, orc, data):
+    """`model decode log` on the device: Component.Summary of every block against the oracle's per-block taps."""
+    jpgs = [orc.encode(synth.frame(300 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(CASES[:5])]
+    jpgs.append(data("Mouse480.jpg"))
+    with ctx.batch(jpgs, hcj.OUT_PLANES) as b:
+        b.decode()
+        for i, j in enumerate(jpgs):
+            dec = orc.decode(j, want_blocks=True)
+            log = b.block_log(i)
+            assert len(log) == dec.nblocks
+            assert np.array_equal(log["coefs"], dec.coefs) and np.array_equal(log["dc_pred"], dec.dc_abs)
+            assert np.array_equal(log["dequant"], dec.dequant) and np.array_equal(log["recon"], dec.recon)
+            assert np.array_equal(log["component"], dec.block_comp)
+            for k in (0, 1, dec.nblocks // 2, dec.nblocks - 1):
+                assert np.array_equal(log["idct"][k], orc.chen_inverse(dec.dequant[k]))
+                c = int(dec.block_comp[k])  # the block sits where recon says in the component's padded plane
+                x, y = int(log["x"][k]), int(log["y"][k])
+                assert np.array_equal(dec.planes[c][y:y + 8, x:x + 8].ravel(), dec.recon[k])
+            part = b.block_log(i, 3, 5)
+            assert part.tobytes() == log[3:8].tobytes()
+
+
 def test_restart_extension_equivalence(hcj, ctx, orc):
     """Stated extension pin: decode(DRI stream) == pure-model decode of the same blocks coded without DRI."""
     w, h = 208, 112
@@ -212,6 +234,30 @@ def test_t81_table_segments_decode(hcj, ctx, orc):
     assert all(s != 0 for s in st[:4])
     for o, w in zip(outs[4:], want):
         assert bytes(o) == w
+
+
+def test_mjpeg_stream_decode(hcj, ctx, orc, data):
+    """hcj_decode_stream: every frame of a Motion-JPEG stream equals the oracle's decode of that frame."""
+    from test_abi import mjpeg_stream
+
+    js, stream, want = mjpeg_stream(orc, data)
+    flags = hcj.FLAG_DEFAULT | hcj.FLAG_T81_TABLES
+    for mode in (hcj.OUT_YUV, hcj.OUT_RGB24):
+        frames, st = ctx.decode_stream(stream, mode, flags)
+        assert st == [0] * len(js)
+        for j, f in zip(js, frames):
+            dec = orc.decode(j, t81_tables=True)
+            assert bytes(f) == (dec.yuv() if mode == hcj.OUT_YUV else oracle_rgb(orc, dec).tobytes())
+    # a longer stream: 70 frames of mixed geometry, one of them corrupt
+    many = [js[i % 4] for i in range(70)]
+    many[33] = many[33][:-300] + b"\xff\xd9"  # scan cut short: decodes (zero-extended reader) or fails exactly like the oracle
+    many[50] = many[50][:200]  # header cut short: not a frame, the splitter moves on to the next SOI
+    frames, st = ctx.decode_stream(b"".join(many))
+    good = [m for i, m in enumerate(many) if i != 50]
+    assert len(st) == 69 and st == [orc.decode_status(m) for m in good]
+    for i in (0, 1, 2, 3, 33, 34, 49, 50, 68):
+        if st[i] == 0:
+            assert bytes(frames[i]) == orc.decode(good[i]).yuv()
 
 
 def test_pillow_streams(hcj, ctx, orc):

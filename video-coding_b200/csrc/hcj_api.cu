@@ -853,6 +853,66 @@ int hcj_idct_blocks(hcj_ctx *c, const int16_t *coefs, size_t nblocks, const uint
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
 }
 
+int hcj_batch_fetch_block_log(hcj_ctx *c, hcj_batch *b, int i, size_t first_block, size_t count, hcj_block_log *out) {
+  static_assert(sizeof(hcj_block_log) == sizeof(hcjk::BlockLog), "hcj_block_log layout");
+  if (!c || !b || i < 0 || i >= b->n || !out) return HCJ_ERR_INVALID_ARG;
+  if (b->host_status[i] != HCJ_OK) return b->host_status[i];
+  const HcjImageDesc &d = b->descs[i];
+  if (first_block > d.nblocks || count > d.nblocks - first_block) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  std::vector<HcjImageState> states;
+  int r = fetch_states(c, b, &states);
+  if (r != HCJ_OK) return r;
+  if (states[i].status != 0) return states[i].status;
+  if (count == 0) return HCJ_OK;
+  void *d_out = nullptr;
+  int st = c->alloc(&d_out, count * sizeof(hcj_block_log));
+  if (st != HCJ_OK) return st;
+  hcjk::launch_block_log(b->dev, (uint32_t)i, (uint32_t)first_block, (uint32_t)count, (hcjk::BlockLog *)d_out, c->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, count * sizeof(hcj_block_log), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  c->release(d_out);
+  return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
+int hcj_mjpeg_split(const uint8_t *stream, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes) {
+  if (!stream || !nframes || capacity < 0) return HCJ_ERR_INVALID_ARG;
+  return hcj::mjpeg_split(stream, len, offsets, lengths, capacity, nframes);
+}
+
+int hcj_decode_stream(hcj_ctx *c, const uint8_t *stream, size_t len, int mode, unsigned flags, uint8_t *out, size_t out_capacity,
+                      size_t *out_offsets, int *status, int capacity, int *nframes) {
+  if (!c || !stream || !nframes || capacity < 0) return HCJ_ERR_INVALID_ARG;
+  int n = 0;
+  std::vector<size_t> off((size_t)capacity + 1), ln((size_t)capacity + 1);
+  int st = hcj::mjpeg_split(stream, len, off.data(), ln.data(), capacity, &n);
+  *nframes = n;
+  if (st != HCJ_OK) return st;
+  if (n == 0) return HCJ_OK;
+  if (!out || !out_offsets || !status) return HCJ_ERR_INVALID_ARG;
+  // frames are laid out back to back, each at a 256-byte boundary like in the device buffer: consecutive good
+  // frames then leave in one device-to-host copy
+  std::vector<const uint8_t *> jp((size_t)n);
+  std::vector<uint8_t *> op((size_t)n);
+  std::vector<size_t> cap((size_t)n);
+  size_t acc = 0;
+  for (int i = 0; i < n; i++) {
+    jp[i] = stream + off[i];
+    hcj_frame_info f;
+    size_t bytes = 0;
+    if (hcj_frame_info_get_ex(jp[i], ln[i], flags, &f) == HCJ_OK)
+      bytes = mode == HCJ_OUT_YUV ? f.yuv_bytes : mode == HCJ_OUT_PLANES ? f.planes_bytes : f.rgb_bytes;
+    out_offsets[i] = acc;
+    cap[i] = bytes;
+    acc += (bytes + 255) & ~(size_t)255;
+  }
+  out_offsets[n] = acc;
+  if (acc > out_capacity) return HCJ_ERR_BUFFER_TOO_SMALL;
+  for (int i = 0; i < n; i++) op[i] = out + out_offsets[i];
+  return hcj_decode_batch(c, jp.data(), ln.data(), n, mode, flags, op.data(), cap.data(), status);
+}
+
 int hcj_batch_compare(hcj_ctx *c, hcj_batch *b, const uint8_t *const *ref, const size_t *ref_len, hcj_plane_metrics *out) {
   if (!c || !b || !ref || !ref_len || !out) return HCJ_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(c->device));

@@ -181,6 +181,75 @@ int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned fla
   return HCJ_OK;
 }
 
+// Motion JPEG: frames are whole JPEG files back to back.  A frame starts at FF D8; its header segments are stepped
+// over by their length fields up to SOS; the entropy-coded bytes run to the first marker that is neither a stuffed
+// FF 00, a fill FF, nor RSTn; the frame ends behind the EOI that follows (further segments, e.g. more scans of a
+// file the decoder would reject anyway, are stepped over the same way).  Bytes between frames are skipped, and so
+// is a would-be frame whose length fields do not lead from marker to marker.
+int mjpeg_split(const uint8_t *s, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes) {
+  int n = 0;
+  size_t p = 0;
+  while (p + 1 < len) {
+    const uint8_t *q = (const uint8_t *)memchr(s + p, 0xff, len - 1 - p);
+    if (!q) break;
+    p = (size_t)(q - s);
+    if (s[p + 1] != 0xd8) {
+      p++;
+      continue;
+    }
+    const size_t start = p;
+    p += 2;
+    bool done = false, ok = false;
+    while (!done && p + 1 < len) {
+      if (s[p] != 0xff) {  // a length field led somewhere else than to a marker: not a frame, look for the next SOI
+        done = true;
+        p = start + 2;
+        break;
+      }
+      const int code = s[p + 1];
+      if (code == 0xff) {  // fill byte
+        p++;
+      } else if (code == 0xd9) {  // EOI
+        p += 2;
+        done = ok = true;
+      } else if (code == 0xd8) {  // a new SOI before EOI: the frame was cut short
+        done = true;
+      } else if (code == 0x00 || (code >= 0xd0 && code <= 0xd7) || code == 0x01) {  // stuffed byte / RSTn / TEM: no length
+        p += 2;
+      } else {
+        if (p + 3 >= len) break;
+        const size_t seg = ((size_t)s[p + 2] << 8) | s[p + 3];
+        p += 2 + seg;
+        if (code == 0xda) {  // SOS: entropy-coded data follows, up to the next real marker
+          while (p + 1 < len) {
+            const uint8_t *r = (const uint8_t *)memchr(s + p, 0xff, len - 1 - p);
+            if (!r) {
+              p = len;
+              break;
+            }
+            p = (size_t)(r - s);
+            const int c2 = s[p + 1];
+            if (c2 == 0x00 || (c2 >= 0xd0 && c2 <= 0xd7)) p += 2;
+            else if (c2 == 0xff) p++;
+            else break;
+          }
+        }
+      }
+    }
+    if (ok) {
+      if (n < capacity && offsets && lengths) {
+        offsets[n] = start;
+        lengths[n] = p - start;
+      }
+      n++;
+    } else if (!done) {
+      break;  // ran off the end inside a frame
+    }
+  }
+  *nframes = n;
+  return n > capacity && offsets ? HCJ_ERR_BUFFER_TOO_SMALL : HCJ_OK;
+}
+
 int plan_image(const hcj_header &h, unsigned flags, ImagePlan *plan) {
   memset(plan, 0, sizeof(*plan));
   hcj_frame_info &f = plan->info;

@@ -17,6 +17,9 @@ namespace hcj {
 // Decoder.Header.decode (decoder.ml:37-70) over a From_string bit reader.
 int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags = 0);
 
+// Frame boundaries of a Motion-JPEG stream (whole files back to back).
+int mjpeg_split(const uint8_t *stream, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes);
+
 // Decoder.init geometry (decoder.ml:304-345) + which tables each scan component binds to.
 struct ImagePlan {
   hcj_frame_info info;

@@ -1678,6 +1678,44 @@ void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   else k_rgb<false><<<grid, block, 0, s>>>(b);
 }
 
+// Debug tap: Decoder.Component.Summary (decoder.ml:189-203) of `count` blocks of one image, from its coefficient
+// blocks: position, predictor, coefs with the DC differential restored, dequant, idct (before clipping), recon.
+// One thread per block, the model's 64-bit arithmetic verbatim.
+__global__ void k_block_log(DecodeBatchDev b, uint32_t img, uint32_t first, uint32_t count, BlockLog *out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const HcjImageDesc &d = b.descs[img];
+  const uint32_t blk = first + t, mcu = blk / d.bpm, j = blk - mcu * d.bpm;
+  const int c = d.blk_comp[j];
+  const HcjCompGeom &g = d.comp[c];
+  const int16_t *cf = b.coefs + (d.coef_off + blk) * 64;
+  int32_t pred = 0;  // the component's dc_pred before this block (decoder.ml:151-165; reset per restart interval)
+  if (d.blk_bx[j] != 0 || d.blk_by[j] != 0) pred = cf[-64];
+  else if (mcu != 0 && !(d.ri && mcu % d.ri == 0)) pred = b.coefs[(d.coef_off + (uint64_t)(mcu - 1) * d.bpm + g.first_blk + g.hs * g.vs - 1) * 64];
+  BlockLog &o = out[t];
+  o.x = (int32_t)((mcu % d.mcus_wide) * g.hs + d.blk_bx[j]) * 8;  // decoder.ml:353-360
+  o.y = (int32_t)((mcu / d.mcus_wide) * g.vs + d.blk_by[j]) * 8;
+  o.dc_pred = cf[0];
+  o.component = c;
+  const int32_t *q = b.qtables + d.qt_off + c * 128;
+  int64_t w[64];
+  for (int i = 0; i < 64; i++) {
+    o.coefs[i] = i ? cf[i] : (int16_t)(cf[0] - pred);
+    const int64_t v = (int64_t)cf[i] * q[i];  // decoder.ml:142-149 (the DC is dc_pred + coefs.(0) = the resolved value)
+    w[zigzag_inverse(i)] = v;
+  }
+  for (int i = 0; i < 64; i++) o.dequant[i] = (int32_t)w[i];
+  idct_8x8<int64_t>(w);
+  for (int i = 0; i < 64; i++) {
+    o.idct[i] = (int32_t)w[i];
+    const int64_t sv = w[i] < -128 ? -128 : w[i] > 127 ? 127 : w[i];  // decoder.ml:213-224
+    o.recon[i] = (uint8_t)(sv + 128);
+  }
+}
+void launch_block_log(const DecodeBatchDev &b, uint32_t img, uint32_t first, uint32_t count, BlockLog *out, cudaStream_t s) {
+  if (count) k_block_log<<<(count + 63) / 64, 64, 0, s>>>(b, img, first, count, out);
+}
+
 // Ocompare.square_error / max_difference (tools/src/ocompare.ml:8-52).
 __global__ void k_compare(const uint8_t *a, const uint8_t *bb, size_t n, unsigned long long *sse, int *maxdiff) {
   unsigned long long acc = 0;

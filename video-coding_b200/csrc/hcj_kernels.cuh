@@ -77,6 +77,15 @@ void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt
 void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff,
                     cudaStream_t s);
 
+struct BlockLog {  // = hcj_block_log (include/hcjpeg.h)
+  int32_t x, y, dc_pred, component;
+  int16_t coefs[64];
+  int32_t dequant[64];
+  int32_t idct[64];
+  uint8_t recon[64];
+};
+void launch_block_log(const DecodeBatchDev &b, uint32_t img, uint32_t first, uint32_t count, BlockLog *out, cudaStream_t s);
+
 struct ComparePlane {
   uint64_t out_off;  // plane in the batch output buffer
   uint64_t ref_off;  // the same plane in the uploaded reference frames

@@ -170,6 +170,9 @@ _SIGS = {
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "hcj_batch_fetch_block_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "hcj_mjpeg_split": (C.c_int, [C.c_char_p, C.c_size_t, _P(C.c_size_t), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
+    "hcj_decode_stream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_int), C.c_int, _P(C.c_int)]),
     "hcj_batch_compare": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
     "hcj_batch_decode_stages": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
     "hcj_decode_stage_name": (C.c_char_p, [C.c_int]),
@@ -177,6 +180,10 @@ _SIGS = {
     "hcj_timer_start": (C.c_int, [C.c_void_p]),
     "hcj_timer_stop": (C.c_int, [C.c_void_p, _P(C.c_float)]),
 }
+
+BLOCK_LOG_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("dc_pred", np.int32), ("component", np.int32),
+                            ("coefs", np.int16, 64), ("dequant", np.int32, 64), ("idct", np.int32, 64), ("recon", np.uint8, 64)])
+
 
 class PlaneMetrics(C.Structure):
     """hcj_plane_metrics: Ocompare results per plane of one image (tools/src/ocompare.ml:8-56)."""
@@ -278,6 +285,15 @@ def frame_info(jpeg, flags=FLAG_DEFAULT):
     return f
 
 
+def mjpeg_split(stream):
+    """Frame boundaries [(offset, length)] of a Motion-JPEG stream (whole JPEG files back to back)."""
+    n = C.c_int()
+    _check(lib().hcj_mjpeg_split(stream, len(stream), None, None, 0, C.byref(n)), "hcj_mjpeg_split")
+    off, ln = (C.c_size_t * max(n.value, 1))(), (C.c_size_t * max(n.value, 1))()
+    _check(lib().hcj_mjpeg_split(stream, len(stream), off, ln, n.value, C.byref(n)), "hcj_mjpeg_split")
+    return [(off[i], ln[i]) for i in range(n.value)]
+
+
 def out_size(info, mode):
     return {OUT_YUV: info.yuv_bytes, OUT_PLANES: info.planes_bytes, OUT_RGB24: info.rgb_bytes, OUT_YUV444: info.rgb_bytes}[mode]
 
@@ -342,6 +358,26 @@ class Context:
             for s in st:
                 _check(s, "Decoder.decode_a_frame")
         return [outs[i][: caps[i]] if st[i] == 0 else None for i in range(n)], st
+
+    def decode_stream(self, stream, mode=OUT_YUV, flags=FLAG_DEFAULT):
+        """Every frame of a Motion-JPEG stream: (frames, status), frames[i] a uint8 array (None where status[i] != 0)."""
+        frames = mjpeg_split(stream)
+        n = len(frames)
+        total = 0
+        for o, l in frames:
+            f = FrameInfo()
+            if lib().hcj_frame_info_get_ex(stream[o:o + l], l, flags, C.byref(f)) == 0:
+                total += (out_size(f, mode) + 255) & ~255
+        out = np.zeros(max(total, 1), np.uint8)
+        offs, status, nf = (C.c_size_t * (n + 1))(), (C.c_int * max(n, 1))(), C.c_int()
+        _check(lib().hcj_decode_stream(self._h, stream, len(stream), mode, flags, out.ctypes.data, out.size, offs, status, n, C.byref(nf)), "hcj_decode_stream")
+        assert nf.value == n
+        res = []
+        for i, (o, l) in enumerate(frames):
+            f = FrameInfo()
+            ok = status[i] == 0 and lib().hcj_frame_info_get_ex(stream[o:o + l], l, flags, C.byref(f)) == 0
+            res.append(out[offs[i]: offs[i] + out_size(f, mode)] if ok else None)
+        return res, [status[i] for i in range(n)]
 
     def batch(self, jpegs, mode=OUT_YUV, flags=FLAG_DEFAULT):
         return Batch(self, jpegs, mode, flags)
@@ -450,6 +486,14 @@ class Batch:
         out = np.zeros((nb, 64), np.int16)
         _check(lib().hcj_batch_fetch_coefficients(self.ctx._h, self._h, i, out.ctypes.data, nb), "coefficients")
         return out
+
+    def block_log(self, i, first=0, count=None):
+        """`model decode log`: Decoder.Component.Summary of blocks [first, first + count) of image i as a structured array
+        (fields x, y, dc_pred, component, coefs, dequant, idct, recon)."""
+        count = self.infos[i].nblocks - first if count is None else count
+        out = np.zeros(max(count, 1), BLOCK_LOG_DTYPE)
+        _check(lib().hcj_batch_fetch_block_log(self.ctx._h, self._h, i, first, count, out.ctypes.data), "block_log")
+        return out[:count]
 
     def entropy(self, i):
         """For_testing.extract_entropy_coded_bits of image i."""
