@@ -244,6 +244,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t max_ds_tiles = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
   bool sub_log2_env = false;
+  const bool sub_bits_fixed = getenv("HCJ_SUB_FIXED") != nullptr;  // experiments: exactly 2^HCJ_SUB_LOG2 bits
   if (const char *e = getenv("HCJ_SUB_LOG2")) {  // experiments
     sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));
     sub_log2_env = true;
@@ -448,9 +449,16 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       // (a couple of MCUs), short enough for one thread each to fill the GPU
       // measured: 4096 bits for 65-bit blocks (1080p q75: 7.8 ms vs 8.0 ms at 8192), 8192 bits for 175-bit blocks
       // (4k 4:4:4 q95: 11.5 ms vs 12.9 ms at 4096): the per-subsequence work is per block, not per bit
-      d.sub_log2 = sub_log2_env ? sub_log2 : ((uint64_t)(d.file_len - d.scan_start) * 8 > (uint64_t)d.nblocks * 120 ? 13u : 12u);
+      const uint64_t est_bits = (uint64_t)(d.file_len - d.scan_start) * 8;
+      const uint32_t s0 = sub_log2_env ? 1u << sub_log2 : (est_bits > (uint64_t)d.nblocks * 120 ? 8192u : 4096u);
+      // ... and cut so that the subsequences fill whole CTAs of the exact pass (512 threads): 1080p q75 has ~800
+      // subsequences of 4096 bits, i.e. a second CTA with 44 % of its lanes idle; 1024 of ~3150 bits keep all busy
+      const uint64_t ctas = std::max<uint64_t>(1, (est_bits + 256ull * s0) / (512ull * s0));
+      uint64_t sb = (est_bits + 512 * ctas - 1) / (512 * ctas);
+      sb = (sb + 31) & ~31ull;
+      d.sub_bits = sub_bits_fixed ? s0 : (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(sb, s0 / 2));
       d.sub_off = (uint32_t)total_sub;
-      const size_t nsub_max = (((size_t)d.ent_cap * 8) >> d.sub_log2) + 2;
+      const size_t nsub_max = ((size_t)d.ent_cap * 8) / d.sub_bits + 2;
       total_sub += nsub_max + 1;
       max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max + 255) / 256));
     }

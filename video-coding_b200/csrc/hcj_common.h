@@ -91,7 +91,7 @@ struct HcjImageDesc {
   uint64_t out_bytes;
   int32_t chroma;        // 420 / 422 / 444 / 0
   int32_t width, height;
-  uint32_t sub_log2;     // scans without restart markers: log2 of the subsequence length in bits
+  uint32_t sub_bits;     // scans without restart markers: subsequence length in bits (a multiple of 32)
   uint32_t sub_off;      // index of the image's first subsequence record in the batch arrays
   uint32_t ds_off;       // index of the image's first destuff tile record
   uint32_t idct_tile_off;// index of the image's first IDCT tile in the batch tile plan

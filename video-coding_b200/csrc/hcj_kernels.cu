@@ -828,7 +828,8 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
 
 // ================================================================================================
 // K3: scans without restart markers (the reference encoder's own format): self-synchronising speculative
-// decode.  The scan of every image is cut into subsequences of 2^sub_log2 bits; a decoder state between
+// decode.  The scan of every image is cut into subsequences of sub_bits bits (chosen per image on the host so
+// that the subsequences fill whole CTAs of the exact pass); a decoder state between
 // symbols is (bit position, block-in-MCU, zig-zag index), 16 bits packed relative to the subsequence
 // boundary.  Four kernels, the first, second and last of them over ALL subsequences of the batch at once
 // (one thread each, so the grid is full whatever the number of images):
@@ -960,8 +961,8 @@ __device__ __forceinline__ bool spec_image(const DecodeBatchDev &b, uint32_t lis
   si.state = b.states + img;
   if (si.state->status != 0) return false;
   si.L = si.state->ent_len * 8u;
-  si.S = 1u << si.d->sub_log2;
-  si.nsub = (si.L + si.S - 1u) >> si.d->sub_log2;
+  si.S = si.d->sub_bits;
+  si.nsub = (si.L + si.S - 1u) / si.S;
   si.start = b.sub_start + si.d->sub_off;
   si.end = b.sub_end + si.d->sub_off;
   si.end2 = b.sub_end2 + si.d->sub_off;
@@ -987,7 +988,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_sync(DecodeBatchDev b,
 
   const uint32_t j = blockIdx.x * SPEC_THREADS + threadIdx.x;
   bool valid = j < si.nsub;
-  const uint32_t lo = (valid ? j : 0u) << si.d->sub_log2, hi = min(lo + si.S, si.L);
+  const uint32_t lo = (valid ? j : 0u) * si.S, hi = min(lo + si.S, si.L);
   // Pass 0 only has to find the state at the END of the subsequence, and a decoder started from a guess is
   // in step with the real one after a couple of MCUs: it decodes the last SPEC_GUESS_BITS bits only (the
   // first subsequence, whose start is exact, in full).  Where that was not enough, pass 1 starts from a wrong
@@ -1072,7 +1073,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_fix(DecodeBatchDev b) 
       const bool valid = k < nredo;
       const uint32_t j = valid ? list[k] : 1u;
       const uint32_t ns = si.end2[j - 1];  // reads within a round are unsynchronised (chaotic relaxation): the fix-point is unique
-      const uint32_t lo = j << d.sub_log2, hi = min(lo + si.S, si.L);
+      const uint32_t lo = j * si.S, hi = min(lo + si.S, si.L);
       uint32_t p, cz;
       spec_unpack(ns, lo, p, cz);
       SubResult r;
@@ -1146,7 +1147,7 @@ __global__ void __launch_bounds__(SPEC_WRITE_THREADS, 2) k_spec_write(DecodeBatc
   PassIn in;
   in.valid = j < si.nsub;
   const uint32_t jj = in.valid ? j : 0u;
-  const uint32_t lo = jj << d.sub_log2, hi = min(lo + si.S, si.L);
+  const uint32_t lo = jj * si.S, hi = min(lo + si.S, si.L);
   spec_unpack(si.start[jj], lo, in.p, in.cz);
   const int4 dc = si.dc[jj];
   in.pred[0] = dc.x, in.pred[1] = dc.y, in.pred[2] = dc.z, in.pred[3] = dc.w;
