@@ -149,10 +149,10 @@ class ClockSampler:
 
 def measured_traffic(kernel, n_images):
     """dram__bytes_read + dram__bytes_write of `kernel` for one launch over n_images images, from the committed
-    ncu --set full capture (profiles/r01s2_traffic.json: per-image bytes on the same synthetic 1080p images; the
+    ncu --set full capture (profiles/r01s3_traffic.json: per-image bytes on the same synthetic 1080p images; the
     capture ran 296 images per launch).  None for kernels / workloads that were not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01s2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01s3_traffic.json")) as f:
             per_image = json.load(f)["dram_bytes_per_image"].get(kernel)
         return None if per_image is None else per_image * n_images
     except Exception:
@@ -334,7 +334,7 @@ def main():
         traffic = measured_traffic(dom, batch_n) if (w, h, chroma, quality) == (1920, 1080, 420, 75) else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg[dom],
-                    "traffic_source": "profiles/r01s2_traffic.json (ncu --set full, dram read + write per image x batch)" if traffic else None,
+                    "traffic_source": "profiles/r01s3_traffic.json (ncu --set full, dram read + write per image x batch)" if traffic else None,
                     "peak_source": peak_src,
                     "stages": {k: {"ms": v, "algorithmic_GBps": alg[k] / (v * 1e-3) / 1e9 if v > 0 else None,
                                    "frac": alg[k] / (v * 1e-3) / 1e9 / peak if v > 0 else None} for k, v in stages.items()}}

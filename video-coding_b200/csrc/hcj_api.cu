@@ -275,7 +275,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   {
     auto work = [&](int lo, int hi) {
       for (int i = lo; i < hi; i++) {
-        int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i], flags) : HCJ_ERR_INVALID_ARG;
+        int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i], flags, false) : HCJ_ERR_INVALID_ARG;
         if (st == HCJ_OK) st = hcj::plan_image(hdrs[i], flags, &plans[i]);
         parse_st[i] = st;
       }

@@ -9,6 +9,7 @@
 //   Encoder.Parameters / headers   jpeg/model/src/encoder.ml:207-264,287-418
 #include "hcj_host.h"
 
+#include <stddef.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,9 +29,12 @@ class Bits {
   Bits(const uint8_t *buf, size_t len) : buf_(buf), len_(len) {}
   uint32_t show(int n) const {
     if ((uint64_t)n >= (uint64_t)len_ * 8) throw Raise{HCJ_ERR_BITS_OUT_OF_BOUNDS};
-    uint32_t v = 0;
-    for (int i = 0; i < n; i++) v = (v << 1) | bit(pos_ + i);
-    return v;
+    // the n <= 16 bits at pos_ lie inside the three bytes from pos_ / 8 on (bytes past the end read as zero):
+    // the same value as the model's bit-by-bit loop
+    const uint64_t byte_no = pos_ >> 3;
+    uint32_t w = 0;
+    for (int k = 0; k < 3; k++) w = (w << 8) | (byte_no + k < len_ ? buf_[byte_no + k] : 0u);
+    return n ? (w >> (24 - (pos_ & 7) - n)) & ((1u << n) - 1u) : 0u;
   }
   uint32_t get(int n) {
     uint32_t v = show(n);
@@ -78,9 +82,15 @@ void push_front(T *arr, int *n, const T &v) {  // OCaml list cons: newest first
 
 // flags & HCJ_FLAG_T81_TABLES (stated extension): DQT / DHT segments hold as many tables as their length covers and
 // parsing continues at the end of the segment; 0xFF fill bytes in front of a marker code are skipped.
-void decode_impl(Bits &b, hcj_header *h, unsigned flags) {  // decoder.ml:37-70
+void decode_impl(Bits &b, hcj_header *h, unsigned flags, bool clear_tables) {  // decoder.ml:37-70
   const bool t81 = (flags & HCJ_FLAG_T81_TABLES) != 0;
-  memset(h, 0, sizeof(*h));
+  if (clear_tables) {
+    memset(h, 0, sizeof(*h));
+  } else {  // batch path: the 64 + 64 table slots (38 KB) are written when a table is pushed; only the rest is cleared
+    memset(h, 0, offsetof(hcj_header, quant_tables));
+    h->n_huffman_tables = 0;
+    h->scan_byte_pos = 0;
+  }
   for (;;) {
     find_marker(b);
     int code = (int)b.get(8);
@@ -171,10 +181,10 @@ int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags) {
+int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags, bool clear_tables) {
   Bits b(jpeg, len);
   try {
-    decode_impl(b, out, flags);
+    decode_impl(b, out, flags, clear_tables);
   } catch (const Raise &r) {
     return r.code;
   }

@@ -15,7 +15,8 @@
 namespace hcj {
 
 // Decoder.Header.decode (decoder.ml:37-70) over a From_string bit reader.
-int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags = 0);
+// clear_tables = false leaves the unused quant / Huffman table slots of `out` as they were (batch path).
+int header_decode(const uint8_t *jpeg, size_t len, hcj_header *out, unsigned flags = 0, bool clear_tables = true);
 
 // Frame boundaries of a Motion-JPEG stream (whole files back to back).
 int mjpeg_split(const uint8_t *stream, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes);
