@@ -223,6 +223,13 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   CU_TRY(cudaSetDevice(c->device));
   hcj_batch *b = new (std::nothrow) hcj_batch;
   if (!b) return HCJ_ERR_OUT_OF_MEMORY;
+  const bool trace = getenv("HCJ_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what) {
+    if (trace)
+      fprintf(stderr, "[batch_create]     %-28s %8.3f ms\n", what,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   b->n = n;
   b->mode = mode;
   b->flags = flags;
@@ -290,6 +297,13 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       work(0, std::min(n, per));
       for (auto &th : pool) th.join();
     }
+  }
+  mark("headers parsed");
+  try {
+    qt_pool.reserve((size_t)n * 3 * 128);
+  } catch (const std::bad_alloc &) {
+    delete b;
+    return HCJ_ERR_OUT_OF_MEMORY;
   }
   int prev_pairs = -1, prev_pair_dc[HCJ_MAX_COMPONENTS], prev_pair_ac[HCJ_MAX_COMPONENTS], prev_img = -1;
 
@@ -427,12 +441,15 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       g.out_off = yuv_acc;
       yuv_acc += (size_t)g.actual_w * g.actual_h;
       const hcj_dqt &q = h->quant_tables[plan.qt_index[k]];
-      for (int e = 0; e < 64; e++) {  // plain values, used by the 64-bit path
-        qt_pool.push_back((int32_t)q.elements[e]);
+      const size_t q0 = qt_pool.size();
+      qt_pool.resize(q0 + 128);
+      int32_t *qp = qt_pool.data() + q0;
+      for (int e = 0; e < 64; e++) {
+        qp[e] = (int32_t)q.elements[e];  // plain values, used by the 64-bit path
         if (q.elements[e] > 255) d.wide_idct = 1;
+        // "dp2a form" used by the 32-bit path (see HCJ_QD in hcj_device.cuh)
+        qp[64 + e] = (e & 1) ? (int32_t)(q.elements[e] & 0xff) << 8 : (int32_t)(q.elements[e] & 0xff);
       }
-      for (int e = 0; e < 64; e++)  // "dp2a form" used by the 32-bit path (see HCJ_QD in hcj_device.cuh)
-        qt_pool.push_back((e & 1) ? (int32_t)(q.elements[e] & 0xff) << 8 : (int32_t)(q.elements[e] & 0xff));
     }
     if (post_444(mode)) plane_total += align_up(plane_acc, 256);
     for (int k = 0; k < f.blocks_per_mcu && k < HCJ_MAX_BPM; k++) {
@@ -474,6 +491,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   if (status)
     for (int i = 0; i < n; i++) status[i] = b->host_status[i];
 
+  mark("descriptors and tables built");
   // ---- device buffers
   hcjk::DecodeBatchDev &dv = b->dev;
   int st = HCJ_OK;
@@ -516,6 +534,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   BALLOC(idct_plan, hcjk::IdctTile *, hcjk::idct_plan_bytes(total_tiles));
   if (post_444(mode)) BALLOC(planes, uint8_t *, plane_total + 16);
 #undef BALLOC
+  mark("device buffers");
   if (st != HCJ_OK) {
     hcj_batch_destroy(c, b);
     return st;
@@ -583,6 +602,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   up(d_ls, list_spec.data(), 4 * list_spec.size());
   if (e == cudaSuccess && with_files) e = upload_files(b, jpeg, len, 0, n, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // host staging vectors go out of scope
+  mark("tables on the device");
   if (e != cudaSuccess) {
     hcj_batch_destroy(c, b);
     return HCJ_ERR_CUDA - (int)e;
@@ -715,8 +735,12 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   }
   cudaStream_t s = c->stream, cs = c->copy_stream, us = c->up_stream;
   cudaError_t e = cudaSuccess;
+  // Chunk boundaries: the first chunks are small (a quarter, then half of the regular size) so that the first frames
+  // start down the link as early as possible; the regular chunk keeps the per-launch overhead small.
   const int chunk = std::max(16, std::min(128, (n + 7) / 8));
-  const int nchunks = n ? (n + chunk - 1) / chunk : 0;
+  std::vector<int> bound(1, 0);
+  for (int sz = std::max(8, chunk / 4); bound.back() < n; sz = std::min(chunk, sz * 2)) bound.push_back(std::min(n, bound.back() + sz));
+  const int nchunks = (int)bound.size() - 1;
   while ((int)c->chunk_events.size() < nchunks + 1) {
     cudaEvent_t ev;
     if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
@@ -730,7 +754,7 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   std::vector<int> host_st(b->host_status);
   if (n > 0 && (int)c->chunk_events.size() >= nchunks + 1 && (int)c->up_events.size() >= nchunks + 1) {
     for (int k = 0; k < nchunks && e == cudaSuccess; k++) {
-      e = upload_files(b, jpeg, len, k * chunk, std::min(n, (k + 1) * chunk), us);
+      e = upload_files(b, jpeg, len, bound[k], bound[k + 1], us);
       if (e == cudaSuccess) e = cudaEventRecord(c->up_events[k], us);
     }
     e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
@@ -739,8 +763,8 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     size_t lr = 0, ls = 0;
     for (int k = 0; k < nchunks && e == cudaSuccess; k++) {
       hcjk::DecodeBatchDev dv = b->dev;
-      dv.img_lo = (uint32_t)(k * chunk);
-      dv.img_hi = (uint32_t)std::min(n, (k + 1) * chunk);
+      dv.img_lo = (uint32_t)bound[k];
+      dv.img_hi = (uint32_t)bound[k + 1];
       dv.tile_lo = b->tile_base[dv.img_lo];
       dv.tile_hi = b->tile_base[dv.img_hi];
       dv.lr_lo = (uint32_t)lr;
