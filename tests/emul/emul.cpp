@@ -430,6 +430,10 @@ int64_t emu_quantize_check(int fmax) {
 
 // k_block_bits / k_pack symbol stream for a whole frame of quantised blocks -> entropy-coded bytes with
 // stuffing, 1-fill and (optionally) RSTn, i.e. everything between the SOS header and EOI.
+struct FieldLog {  // records the (bits, length) fields a block emits
+  std::vector<std::pair<uint32_t, uint32_t>> f;
+  void operator()(uint32_t bits, uint32_t n) { f.emplace_back(bits, n); }
+};
 struct ByteWriter {
   std::vector<uint8_t> *out;
   uint64_t acc = 0;
@@ -473,7 +477,17 @@ int64_t emu_entropy_encode(const int16_t *quant, int width, int height, int chro
     for (int k = 0; k < p.bpm; k++) {
       const int16_t *q = quant + (mcu * p.bpm + k) * 64;
       int c = p.blk_comp[k];
-      if (!encode_block_fields(q, (int32_t)q[0] - pred[c], dc[c ? 1 : 0], ac[c ? 1 : 0], w)) return -2;
+      // the literal 63-step loop and the non-zero-map loop the kernels run must write the same fields
+      uint32_t qw[32];
+      for (int j = 0; j < 32; j++) qw[j] = (uint32_t)(uint16_t)q[2 * j] | ((uint32_t)(uint16_t)q[2 * j + 1] << 16);
+      FieldLog a, b2;
+      bool ok1 = encode_block_fields(q, (int32_t)q[0] - pred[c], dc[c ? 1 : 0], ac[c ? 1 : 0], a);
+      bool ok2 = encode_block_fields_sparse(nonzero_map(qw), [q](int k) { return (int32_t)q[k]; }, (int32_t)q[0] - pred[c],
+                                            dc[c ? 1 : 0], ac[c ? 1 : 0], b2);
+      if (ok1 != ok2 || a.f != b2.f) return -4;
+      if (!encode_block_fields_sparse(nonzero_map(qw), [q](int k) { return (int32_t)q[k]; }, (int32_t)q[0] - pred[c],
+                                      dc[c ? 1 : 0], ac[c ? 1 : 0], w))
+        return -2;
       pred[c] = q[0];
     }
   }

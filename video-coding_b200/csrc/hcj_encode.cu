@@ -3,6 +3,8 @@
 //   k_fdct_quant   E2,E4-E6  zero-padded block fetch, level shift, Chen FDCT, quantise, zig-zag
 //   k_block_bits   E7,E8     per block: DC differential + (run, size) symbols -> code length in bits
 //   k_scan_bits    per frame: exclusive prefix sum of block bit lengths (one CTA walks the frame)
+//   (k_block_bits and k_pack stage the block in shared memory and walk its non-zero map: one loop iteration per
+//    non-zero coefficient, encode_block_fields_sparse)
 //   k_pack         E8,E9     per block: write code + magnitude fields at their bit offset (big-endian
 //                            32-bit words, atomicOr only on the two boundary words), 1-fill at the end of
 //                            every segment (flush_with_1s, bitstream_writer.ml:45-49)
@@ -25,53 +27,81 @@
 namespace hcjk {
 using namespace hcjdev;
 
+// Rows of 144 bytes per thread / block in shared memory: 16-byte aligned, and conflict free for per-thread 16-byte accesses.
+constexpr int ENC_ROW_WORDS = 36;
+
 // ---- K6 ------------------------------------------------------------------------------------------
+// One thread per block.  The quant table and its reciprocals come from shared memory (16-byte reads: they were 128
+// scalar loads per block through L1), and the finished blocks leave through shared memory as one contiguous 16 KiB
+// run per CTA (a thread storing its own 128-byte block costs eight L1 wavefronts per store instruction; the LSU data
+// pipe was 82 % busy).
 __global__ void __launch_bounds__(128) k_fdct_quant(EncodeBatchDev e) {
-  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ __align__(16) uint32_t s_rows[128 * ENC_ROW_WORDS];
+  __shared__ __align__(16) uint16_t s_qt[2][64];
+  __shared__ __align__(16) uint32_t s_qr[2][64];
+  s_qt[threadIdx.x >> 6][threadIdx.x & 63] = e.qt[threadIdx.x];
+  s_qr[threadIdx.x >> 6][threadIdx.x & 63] = e.qrecip[threadIdx.x];
+  __syncthreads();
+  const uint32_t blk0 = blockIdx.x * blockDim.x, blk = blk0 + threadIdx.x;
   const uint32_t frame = blockIdx.y;
-  if (blk >= e.nblocks) return;
-  const uint32_t mcu = blk / e.bpm, k = blk - mcu * e.bpm;
-  const int c = e.blk_comp[k];
-  const int my = mcu / e.mcus_wide, mx = mcu - my * e.mcus_wide;
-  const int x0 = (mx * e.hs[c] + e.blk_bx[k]) * 8, y0 = (my * e.vs[c] + e.blk_by[k]) * 8;
-  const uint8_t *src = e.src + (uint64_t)frame * e.frame_bytes + e.src_off[c];
-  const int sw = e.src_w[c], sh = e.src_h[c];
-  int32_t v[64];
-  // level_shifted_input_block over the zero-initialised padded plane (encoder.ml:81-90, plane.ml:11-17)
-  const bool inside = x0 + 8 <= sw && y0 + 8 <= sh;
-  if (inside && ((((uintptr_t)src + (size_t)y0 * sw + x0) & 7u) == 0) && (sw & 7) == 0) {
+  if (blk < e.nblocks) {
+    const uint32_t mcu = blk / e.bpm, k = blk - mcu * e.bpm;
+    const int c = e.blk_comp[k];
+    const int my = mcu / e.mcus_wide, mx = mcu - my * e.mcus_wide;
+    const int x0 = (mx * e.hs[c] + e.blk_bx[k]) * 8, y0 = (my * e.vs[c] + e.blk_by[k]) * 8;
+    const uint8_t *src = e.src + (uint64_t)frame * e.frame_bytes + e.src_off[c];
+    const int sw = e.src_w[c], sh = e.src_h[c];
+    int32_t v[64];
+    // level_shifted_input_block over the zero-initialised padded plane (encoder.ml:81-90, plane.ml:11-17)
+    const bool inside = x0 + 8 <= sw && y0 + 8 <= sh;
+    if (inside && ((((uintptr_t)src + (size_t)y0 * sw + x0) & 7u) == 0) && (sw & 7) == 0) {
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      uint2 u = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(y0 + y) * sw + x0));
+      for (int y = 0; y < 8; y++) {
+        uint2 u = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(y0 + y) * sw + x0));
 #pragma unroll
-      for (int x = 0; x < 4; x++) {
-        v[y * 8 + x] = (int32_t)((u.x >> (8 * x)) & 0xffu) - 128;
-        v[y * 8 + 4 + x] = (int32_t)((u.y >> (8 * x)) & 0xffu) - 128;
+        for (int x = 0; x < 4; x++) {
+          v[y * 8 + x] = (int32_t)((u.x >> (8 * x)) & 0xffu) - 128;
+          v[y * 8 + 4 + x] = (int32_t)((u.y >> (8 * x)) & 0xffu) - 128;
+        }
       }
+    } else {
+#pragma unroll
+      for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+          int px = x0 + x, py = y0 + y;
+          int p = (px < sw && py < sh) ? (int)__ldg(src + (size_t)py * sw + px) : 0;
+          v[y * 8 + x] = p - 128;
+        }
     }
-  } else {
+    fdct_8x8(v);
+    const uint4 *qt4 = reinterpret_cast<const uint4 *>(s_qt[c ? 1 : 0]);
+    const uint4 *qr4 = reinterpret_cast<const uint4 *>(s_qr[c ? 1 : 0]);
+    uint4 *row = reinterpret_cast<uint4 *>(s_rows + threadIdx.x * ENC_ROW_WORDS);
 #pragma unroll
-    for (int y = 0; y < 8; y++)
+    for (int g = 0; g < 8; g++) {  // quant (encoder.ml:103-108): zig-zag position z <- natural inverse(z), eight at a time
+      const uint4 q = qt4[g], ra = qr4[2 * g], rb = qr4[2 * g + 1];
+      const uint32_t qq[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
+      const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+      uint32_t o[4];
 #pragma unroll
-      for (int x = 0; x < 8; x++) {
-        int px = x0 + x, py = y0 + y;
-        int p = (px < sw && py < sh) ? (int)__ldg(src + (size_t)py * sw + px) : 0;
-        v[y * 8 + x] = p - 128;
+      for (int i = 0; i < 4; i++) {
+        const int z = 8 * g + 2 * i;
+        const int32_t a = quantize(v[zigzag_inverse(z)], qq[2 * i], rr[2 * i]);
+        const int32_t b = quantize(v[zigzag_inverse(z + 1)], qq[2 * i + 1], rr[2 * i + 1]);
+        o[i] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
       }
+      row[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
-  fdct_8x8(v);
-  const uint16_t *qt = e.qt + (c ? 64 : 0);
-  const uint32_t *qr = e.qrecip + (c ? 64 : 0);
-  uint32_t packed[32];
+  __syncthreads();
+  uint4 *dst = reinterpret_cast<uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk0) * 64);
+  const uint32_t nchunks = min(128u, e.nblocks - blk0) * 8u;
 #pragma unroll
-  for (int z = 0; z < 64; z += 2) {  // quant (encoder.ml:103-108): zig-zag position z <- natural inverse(z)
-    int32_t a = quantize(v[zigzag_inverse(z)], __ldg(qt + z), __ldg(qr + z));
-    int32_t b = quantize(v[zigzag_inverse(z + 1)], __ldg(qt + z + 1), __ldg(qr + z + 1));
-    packed[z >> 1] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+  for (int i = 0; i < 8; i++) {
+    const uint32_t c = threadIdx.x + 128u * i;
+    if (c < nchunks) dst[c] = *reinterpret_cast<const uint4 *>(s_rows + (c >> 3) * ENC_ROW_WORDS + (c & 7u) * 4u);
   }
-  uint4 *dst = reinterpret_cast<uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk) * 64);
-#pragma unroll
-  for (int j = 0; j < 8; j++) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
 }
 
 // Index (within the frame) of the block whose DC is this block's predictor, or -1 (start of a segment).
@@ -101,6 +131,31 @@ __device__ __forceinline__ void load_enc_tables(EncTablesSmem &t, const EncodeBa
   for (int i = threadIdx.x; i < 512; i += blockDim.x) t.ac[i >> 8][i & 255] = e.ac_codes[i];
 }
 
+// The 128 blocks of a CTA are one contiguous 16 KiB run of the coefficient buffer: the CTA copies it into shared memory
+// with fully coalesced 16-byte loads (a thread reading its own 128-byte block costs eight L1 wavefronts per load
+// instruction, and the LSU data pipe was what bound these kernels: 80 % busy), into rows of 144 bytes (16-byte
+// aligned, conflict free for the per-thread 16-byte reads).  Each thread then takes its row: the non-zero map from
+// eight 16-byte reads, single coefficients by a run-time index in the field loop.  Ends with a CTA barrier.
+__device__ __forceinline__ void stage_cta_blocks(const int16_t *frame_quant, uint32_t blk0, uint32_t nblocks, uint32_t *s_rows) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(frame_quant + (uint64_t)blk0 * 64);
+  const uint32_t nchunks = min(128u, nblocks - blk0) * 8u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t c = threadIdx.x + 128u * i;
+    if (c < nchunks) *reinterpret_cast<uint4 *>(s_rows + (c >> 3) * ENC_ROW_WORDS + (c & 7u) * 4u) = __ldg(src + c);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ uint64_t row_nonzero_map(const uint32_t *row) {
+  uint32_t qw[32];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint4 u = reinterpret_cast<const uint4 *>(row)[j];
+    qw[4 * j] = u.x, qw[4 * j + 1] = u.y, qw[4 * j + 2] = u.z, qw[4 * j + 3] = u.w;
+  }
+  return nonzero_map(qw);
+}
+
 // ---- K7a -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *status) {
   __shared__ EncTablesSmem t;
@@ -108,21 +163,18 @@ __global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *statu
   __syncthreads();
   const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t frame = blockIdx.y;
+  __shared__ __align__(16) uint32_t s_rows[128 * ENC_ROW_WORDS];
+  stage_cta_blocks(e.quant + (uint64_t)frame * e.nblocks * 64, blockIdx.x * blockDim.x, e.nblocks, s_rows);
   if (blk >= e.nblocks) return;
-  const int16_t *q = e.quant + ((uint64_t)frame * e.nblocks + blk) * 64;
-  uint32_t qw[32];  // the block in registers: the field loop is fully unrolled
-  const uint4 *src = reinterpret_cast<const uint4 *>(q);
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const uint4 u = __ldg(src + j);
-    qw[4 * j] = u.x, qw[4 * j + 1] = u.y, qw[4 * j + 2] = u.z, qw[4 * j + 3] = u.w;
-  }
+  const uint32_t *row = s_rows + threadIdx.x * ENC_ROW_WORDS;
+  const uint64_t nz = row_nonzero_map(row);
+  const int16_t *row16 = reinterpret_cast<const int16_t *>(row);
   int64_t pb = dc_pred_block(e, blk);
   int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
   const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
   BitCounter cnt;
-  bool ok = encode_block_fields_from([&qw](int k) { return packed_coef(qw, k); }, packed_coef(qw, 0) - pred, t.dc[tsel],
-                                     t.ac[tsel], cnt);
+  bool ok = encode_block_fields_sparse(nz, [row16](int k) { return (int32_t)row16[k]; }, (int32_t)row16[0] - pred, t.dc[tsel],
+                                       t.ac[tsel], cnt);
   if (!ok) atomicCAS(status + frame, 0, HCJ_ERR_ENCODER_PARAMS);
   e.blk_bits[(uint64_t)frame * (e.nblocks + 1) + blk] = cnt.bits;
 }
@@ -214,6 +266,8 @@ __global__ void __launch_bounds__(128) k_pack(EncodeBatchDev e) {
   __syncthreads();
   const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t frame = blockIdx.y;
+  __shared__ __align__(16) uint32_t s_rows[128 * ENC_ROW_WORDS];
+  stage_cta_blocks(e.quant + (uint64_t)frame * e.nblocks * 64, blockIdx.x * blockDim.x, e.nblocks, s_rows);
   if (blk >= e.nblocks) return;
   const uint32_t *P = e.blk_bits + (uint64_t)frame * (e.nblocks + 1);
   const uint32_t seg = e.restart_interval ? (blk / e.bpm) / e.restart_interval : 0;
@@ -221,19 +275,15 @@ __global__ void __launch_bounds__(128) k_pack(EncodeBatchDev e) {
   const uint32_t seg_byte = (P[first] >> 3) + seg;
   const uint64_t bitpos = (uint64_t)seg_byte * 8 + (P[blk] - P[first]);
 
-  uint32_t qw[32];
-  const uint4 *src = reinterpret_cast<const uint4 *>(e.quant + ((uint64_t)frame * e.nblocks + blk) * 64);
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const uint4 u = __ldg(src + j);
-    qw[4 * j] = u.x, qw[4 * j + 1] = u.y, qw[4 * j + 2] = u.z, qw[4 * j + 3] = u.w;
-  }
+  const uint32_t *row = s_rows + threadIdx.x * ENC_ROW_WORDS;
+  const uint64_t nz = row_nonzero_map(row);
+  const int16_t *row16 = reinterpret_cast<const int16_t *>(row);
   int64_t pb = dc_pred_block(e, blk);
   int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[((uint64_t)frame * e.nblocks + pb) * 64];
   const int tsel = e.blk_comp[blk % e.bpm] ? 1 : 0;
   BitPacker pk;
   pk.init(e.raw + (uint64_t)frame * e.raw_stride, bitpos);
-  encode_block_fields_from([&qw](int k) { return packed_coef(qw, k); }, packed_coef(qw, 0) - pred, t.dc[tsel], t.ac[tsel], pk);
+  encode_block_fields_sparse(nz, [row16](int k) { return (int32_t)row16[k]; }, (int32_t)row16[0] - pred, t.dc[tsel], t.ac[tsel], pk);
   if (blk + 1 == next) {  // last block of the segment: flush_with_1s
     uint32_t segbits = P[next] - P[first];
     uint32_t pad = (8u - (segbits & 7u)) & 7u;
