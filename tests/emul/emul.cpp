@@ -236,7 +236,6 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
   sc.bpm = bpm;
   for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
   sc.wide_flags = wide_flags;
-  sc.debug = 0;
   sc.blk_base = 0;
   unsigned long long err_key = ~0ull;
   for (uint32_t seg = 0; seg < nseg; seg++) {  // <- thread index
@@ -288,7 +287,6 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
   sc.bpm = (uint32_t)f.blocks_per_mcu;
   for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
   sc.wide_flags = wide_flags;
-  sc.debug = 0;
   sc.blk_base = 0;
   const uint32_t L = sc.total_bits;
   const int64_t nblocks = f.nblocks;

@@ -251,8 +251,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t max_ds_tiles = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
   bool sub_log2_env = false;
-  const bool sub_bits_fixed = getenv("HCJ_SUB_FIXED") != nullptr;  // experiments: exactly 2^HCJ_SUB_LOG2 bits
-  if (const char *e = getenv("HCJ_SUB_LOG2")) {  // experiments
+  if (const char *e = getenv("HCJ_SUB_LOG2")) {  // tuning knob: preferred subsequence length, log2 of bits
     sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));
     sub_log2_env = true;
   }
@@ -473,7 +472,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       const uint64_t ctas = std::max<uint64_t>(1, (est_bits + 256ull * s0) / (512ull * s0));
       uint64_t sb = (est_bits + 512 * ctas - 1) / (512 * ctas);
       sb = (sb + 31) & ~31ull;
-      d.sub_bits = sub_bits_fixed ? s0 : (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(sb, s0 / 2));
+      d.sub_bits = (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(sb, s0 / 2));
       d.sub_off = (uint32_t)total_sub;
       const size_t nsub_max = ((size_t)d.ent_cap * 8) / d.sub_bits + 2;
       total_sub += nsub_max + 1;
@@ -581,10 +580,6 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.ls_hi = (uint32_t)list_spec.size();
   b->list_restart = list_restart;
   b->list_spec = list_spec;
-  {
-    const char *e = getenv("HCJ_DEBUG");
-    dv.debug = e ? atoi(e) : 0;
-  }
   b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? 1 : 0);
 
   // ---- upload

@@ -280,7 +280,6 @@ struct ScanCtx {
   uint32_t total_bits;         // 8 * destuffed length
   uint32_t bpm;                // blocks per MCU
   Tables tab[HCJ_MAX_COMP];    // per scan component
-  int debug;                   // experiment switches
   uint32_t *wide_flags;        // bit (blk_base + blk): the block needs the 64-bit IDCT (see HCJ_IDCT_L1_LIMIT)
   uint64_t blk_base;           // index of the image's first block in the batch
 };
@@ -425,7 +424,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
       if (blk != prezeroed_blk) zero_block(out);
     }
     if (isdc || (s.size != 0u && !eob)) {
-      if (!(sc.debug & 1)) out[zi] = (int16_t)v;
+      out[zi] = (int16_t)v;
       share += (uint32_t)(v < 0 ? -v : v) * (uint32_t)q[zi];
     }
     z = eob ? 64u : zi + 1u;

@@ -454,7 +454,6 @@ __device__ __forceinline__ void fill_scan_ctx(ScanCtx &sc, const SmemTables &st,
     sc.total_bits = total_bits;
     sc.bpm = d.bpm;
     sc.wide_flags = b.wide_flags;
-    sc.debug = b.debug;
     sc.blk_base = d.coef_off;
   }
   if (threadIdx.x < (uint32_t)d.ncomp) sc.tab[threadIdx.x] = tables_of(st, threadIdx.x);
@@ -901,8 +900,8 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   int st = !entered ? 2 : s.z != 0u ? 0 : 1;  // 0 = mid-block, 1 = at a block boundary, 2 = left
   // Unlike the exact pass, the per-block code is light here (no write-out), and when decoding from a
   // guessed state the "blocks" of the lanes are of wildly different lengths: lanes at a block boundary are
-  // served as soon as a quarter of the running lanes are waiting (HCJ_DEBUG bits 4..6 change the fraction).
-  const int thr = (sc.debug & 0x70) ? ((sc.debug >> 4) & 7) - 1 : 2;
+  // served as soon as a quarter of the running lanes are waiting (measured against a half and an eighth).
+  const int thr = 2;
   for (;;) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {

@@ -54,7 +54,6 @@ struct DecodeBatchDev {
   uint32_t max_rgb_rows;          // max image height (RGB mode)
   uint32_t max_width;
   uint64_t total_blocks;
-  int debug;                      // experiment switches (HCJ_DEBUG env var); 0 in production
   // sub-range of the batch handled by one launch (the pipelined host path decodes chunk by chunk)
   uint32_t img_lo, img_hi;        // images [img_lo, img_hi)
   uint32_t lr_lo, lr_hi;          // entries of list_restart
