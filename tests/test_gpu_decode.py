@@ -282,6 +282,30 @@ def test_pillow_streams(hcj, ctx, orc):
         assert s == 0 and bytes(out) == want
 
 
+def test_independent_decoder_cross_check(hcj, ctx, orc, data):
+    """The reference's own external check (jpeg/test/mouse-decode.t:10-13: max abs difference <= 1 against ffmpeg), with
+    libjpeg-turbo (Pillow) as the independent decoder: a different IDCT (jidctint), so luma may differ by one LSB, never
+    more; 4:4:4 chroma likewise (subsampled chroma goes through libjpeg's own up-sampling and is not comparable)."""
+    Image = pytest.importorskip("PIL.Image")
+    cases = [(data("Mouse480.jpg"), 420)]
+    for i, (c, q) in enumerate(((420, 75), (444, 95), (422, 30), (444, 50))):
+        cases.append((orc.encode(synth.frame(900 + i, 320, 200, c), 320, 200, c, q), c))
+    outs, st = ctx.decode_batch([j for j, _ in cases])
+    assert st == [0] * len(cases)
+    for (j, chroma), o in zip(cases, outs):
+        im = Image.open(io.BytesIO(j))
+        im.draft("YCbCr", im.size)
+        assert im.mode == "YCbCr"
+        ref = np.asarray(im).astype(np.int32)
+        h, w = ref.shape[:2]
+        y = o[: w * h].reshape(h, w).astype(np.int32)
+        assert np.abs(y - ref[:, :, 0]).max() <= 1
+        if chroma == 444:
+            for k in (1, 2):
+                p = o[k * w * h: (k + 1) * w * h].reshape(h, w).astype(np.int32)
+                assert np.abs(p - ref[:, :, k]).max() <= 1
+
+
 def test_corrupt_streams_do_not_poison_batch(hcj, ctx, orc, data):
     good = data("Mouse480.jpg")
     start = orc.header_decode(good).scan_bit_pos // 8

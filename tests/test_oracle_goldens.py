@@ -302,3 +302,20 @@ def test_planar_444_vectors(orc, goldens):
     assert np.concatenate([p.ravel() for p in sub]).tolist() == f420
     up = [sub[0]] + [orc.supersample_hv2(p) for p in sub[1:]]
     assert np.concatenate([p.ravel() for p in up]).tolist() == back
+
+
+def test_oracle_against_independent_decoder(orc, data):
+    """External anchor for the oracle itself: libjpeg-turbo's luma is within one LSB of the oracle's on the
+    reference's own test image and on oracle-encoded frames, as the reference's mouse-decode.t reports against ffmpeg."""
+    Image = pytest.importorskip("PIL.Image")
+    import io
+
+    import synth
+
+    files = [data("Mouse480.jpg")] + [orc.encode(synth.frame(900 + i, 160, 96, c), 160, 96, c, q) for i, (c, q) in enumerate(((420, 75), (444, 95), (422, 30)))]
+    for j in files:
+        im = Image.open(io.BytesIO(j))
+        im.draft("YCbCr", im.size)
+        ref = np.asarray(im).astype(np.int32)
+        y = orc.decode(j).cropped[0].astype(np.int32)
+        assert np.abs(y - ref[:, :, 0]).max() <= 1
