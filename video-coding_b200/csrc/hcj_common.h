@@ -17,7 +17,9 @@
 #ifndef HCJ_IDCT_THREADS
 #define HCJ_IDCT_THREADS 128              // threads (= blocks) per IDCT tile
 #endif
+#ifndef HCJ_IDCT_CTAS_PER_SM
 #define HCJ_IDCT_CTAS_PER_SM 5                 // 96 registers: measured best (4 -> 3.09 ms, 5 -> 2.92 ms, 6 -> 3.99 ms with blocks in local memory)
+#endif
 
 // Internal status values produced on the device (same numbering as include/hcjpeg.h).
 #define HCJ_DEV_OK 0
