@@ -204,8 +204,10 @@ int hcj_batch_fetch_block_log(hcj_ctx *ctx, hcj_batch *b, int i, size_t first_bl
 int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const uint16_t quant_table[64], uint8_t *out);
 
 /* ---- encode --------------------------------------------------------------------------------- */
-/* Encoder.encode_420 / encode_422 / encode_444 (encoder.ml:522-541) for n frames of identical
- * geometry.  yuv[i]: planar Y,U,V as Frame.input reads it (frame.ml:72-76).  chroma: 420/422/444.
+/* Encoder.encode_420 / encode_422 / encode_444 / encode_monochrome (encoder.ml:522-552) for n frames of identical
+ * geometry.  yuv[i]: planar Y,U,V as Frame.input reads it (frame.ml:72-76).  chroma: 420/422/444, or 400 for
+ * encode_monochrome (one plane of width * height bytes; like the model, the plane is copied into its padded
+ * plane linearly, so a width that is not a multiple of 8 shears the image: Plane.blit, plane.ml:20).
  * restart_interval 0 reproduces the model byte-for-byte; >0 is the stated DRI/RSTn extension. */
 int hcj_encode_batch(hcj_ctx *ctx, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
                      int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,

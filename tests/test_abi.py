@@ -201,7 +201,7 @@ def test_mirror_interface_shapes(hcj):
 
     for name in ("decode_a_frame", "init", "decode", "get_decoded_planes", "get_yuv_frame", "Header", "For_testing"):
         assert hasattr(model.Decoder, name)
-    for name in ("encode_420", "encode_422", "encode_444", "write_headers", "Parameters"):
+    for name in ("encode_420", "encode_422", "encode_444", "encode_monochrome", "write_headers", "Parameters"):
         assert hasattr(model.Encoder, name)
     f = model.Frame.create(420, 64, 48)
     assert (f.u.width, f.u.height) == (32, 24) and f.width == 64 and f.height == 48

@@ -127,3 +127,22 @@ def test_encode_device_time_and_long_single_segment(hcj, ctx, orc):
     ms = C.c_float()
     hcj._check(hcj.lib().hcj_encode_last_device_ms(ctx._h, C.byref(ms)))
     assert 0.0 < ms.value < 1000.0
+
+
+def test_encode_monochrome(hcj, ctx, orc):
+    """Encoder.encode_monochrome (encoder.ml:543-552): one component, luma tables only, and the model's linear
+    Plane.blit into the padded plane (widths that are not a multiple of 8 shear the image) - byte-identical files;
+    the one-component file decodes through get_decoded_planes like the oracle's."""
+    rng = np.random.default_rng(11)
+    for w, h, q, ri in ((64, 48, 75, 0), (61, 35, 50, 0), (8, 8, 90, 2), (200, 120, 95, 0), (131, 77, 20, 5), (1, 1, 75, 0)):
+        frames = [synth.plane(rng, w, h).tobytes() for _ in range(3)]
+        outs, st = ctx.encode_batch(frames, w, h, 400, q, ri)
+        assert st == [0, 0, 0], (w, h, q, ri)
+        for f, o in zip(frames, outs):
+            assert o == orc.encode(f, w, h, 400, q, restart_interval=ri), (w, h, q, ri)
+        planes, st = ctx.decode_batch(outs, hcj.OUT_PLANES)
+        assert st == [0, 0, 0]
+        for o, pl in zip(outs, planes):
+            assert bytes(pl) == b"".join(p.tobytes() for p in orc.decode(o).planes)
+        _, st = ctx.decode_batch(outs[:1], hcj.OUT_YUV)  # Decoder.get_yuv_frame needs three components (decoder.ml:415-420)
+        assert st == [-12]

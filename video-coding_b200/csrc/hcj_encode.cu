@@ -54,7 +54,19 @@ __global__ void __launch_bounds__(128) k_fdct_quant(EncodeBatchDev e) {
     int32_t v[64];
     // level_shifted_input_block over the zero-initialised padded plane (encoder.ml:81-90, plane.ml:11-17)
     const bool inside = x0 + 8 <= sw && y0 + 8 <= sh;
-    if (inside && ((((uintptr_t)src + (size_t)y0 * sw + x0) & 7u) == 0) && (sw & 7) == 0) {
+    if (e.linear_blit && sw != e.plane_w[c]) {
+      // encode_monochrome fills its padded plane with Plane.blit: ONE linear copy of the source bytes (encoder.ml:548,
+      // plane.ml:20), so with a width that is not a multiple of 8 the rows of the plane are not the rows of the frame
+      const int pw = e.plane_w[c];
+      const int64_t nsrc = (int64_t)sw * sh;
+#pragma unroll
+      for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+          const int64_t at = (int64_t)(y0 + y) * pw + (x0 + x);
+          v[y * 8 + x] = (at < nsrc ? (int)__ldg(src + at) : 0) - 128;
+        }
+    } else if (inside && ((((uintptr_t)src + (size_t)y0 * sw + x0) & 7u) == 0) && (sw & 7) == 0) {
 #pragma unroll
       for (int y = 0; y < 8; y++) {
         uint2 u = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(y0 + y) * sw + x0));
@@ -481,7 +493,8 @@ int setup_encode(hcj_ctx *c, int n, int width, int height, int chroma, int quali
   e.ncomp = p.ncomp;
   e.bpm = p.bpm;
   uint64_t off = 0;
-  for (int i = 0; i < 3; i++) {
+  e.linear_blit = chroma == 400 ? 1 : 0;
+  for (int i = 0; i < p.ncomp; i++) {
     e.hs[i] = p.hs[i];
     e.vs[i] = p.vs[i];
     e.plane_w[i] = p.plane_w[i];

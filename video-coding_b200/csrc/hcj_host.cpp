@@ -501,7 +501,8 @@ void encoder_tables(int which_dc, int which_ac, uint32_t dc[16], uint32_t ac[256
 int plan_encode(int width, int height, int chroma, int quality, int restart_interval, EncodePlan *p) {
   memset(p, 0, sizeof(*p));
   static const int s420[6] = {2, 2, 1, 1, 1, 1}, s422[6] = {2, 2, 1, 2, 1, 2}, s444[6] = {1, 1, 1, 1, 1, 1};
-  const int *s = chroma == 420 ? s420 : chroma == 422 ? s422 : chroma == 444 ? s444 : nullptr;  // encoder.ml:347-349
+  // encoder.ml:347-349; 400 = Parameters.monochrome (:351-368): one component, luma tables only
+  const int *s = chroma == 420 ? s420 : chroma == 422 ? s422 : (chroma == 444 || chroma == 400) ? s444 : nullptr;
   if (!s || width < 1 || height < 1 || width > 65535 || height > 65535 || restart_interval < 0 || restart_interval > 65535)
     return HCJ_ERR_ENCODER_PARAMS;
   p->width = width;
@@ -509,18 +510,18 @@ int plan_encode(int width, int height, int chroma, int quality, int restart_inte
   p->chroma = chroma;
   p->quality = quality;
   p->restart_interval = restart_interval;
-  p->ncomp = 3;
+  p->ncomp = chroma == 400 ? 1 : 3;
   quant_scale(false, quality, p->qt[0]);
   quant_scale(true, quality, p->qt[1]);
   int max_h = 0, max_v = 0;
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < p->ncomp; i++) {
     p->hs[i] = s[2 * i];
     p->vs[i] = s[2 * i + 1];
     max_h = std::max(max_h, p->hs[i]);
     max_v = std::max(max_v, p->vs[i]);
   }
   int bpm = 0;
-  for (int i = 0; i < 3; i++) {  // Encoder.create, encoder.ml:450-463
+  for (int i = 0; i < p->ncomp; i++) {  // Encoder.create, encoder.ml:450-463
     int64_t w = (int64_t)width * p->hs[i] / max_h, h = (int64_t)height * p->vs[i] / max_v;
     p->plane_w[i] = (int)round_up(w, 8 * p->hs[i]);
     p->plane_h[i] = (int)round_up(h, 8 * p->vs[i]);
@@ -540,7 +541,7 @@ int plan_encode(int width, int height, int chroma, int quality, int restart_inte
   p->nblocks = (int64_t)p->mcus_wide * p->mcus_high * bpm;
   // encode_block reads through a bounds-checked Plane (encoder.ml:85): per-component rounding can
   // disagree for odd sizes and the model raises.
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < p->ncomp; i++)
     if (p->mcus_wide * p->hs[i] * 8 > p->plane_w[i] || p->mcus_high * p->vs[i] * 8 > p->plane_h[i])
       return HCJ_ERR_PLANE_BOUNDS;
   return HCJ_OK;
@@ -563,7 +564,8 @@ void write_headers(const EncodePlan &p, std::vector<uint8_t> *o) {  // encoder.m
   marker(o, APP0);
   put16(o, 2 + (int)strlen(tag));
   o->insert(o->end(), tag, tag + strlen(tag));
-  for (int t = 0; t < 2; t++) {  // write_dqt + Dqt.encode, markers.ml:170-183
+  const int ntab = p.ncomp == 1 ? 1 : 2;  // Parameters.monochrome carries one table of each kind (encoder.ml:351-368)
+  for (int t = 0; t < ntab; t++) {  // write_dqt + Dqt.encode, markers.ml:170-183
     marker(o, DQT);
     put16(o, 3 + 64);
     o->push_back((uint8_t)t);  // Pq = 0, Tq = t
@@ -581,7 +583,7 @@ void write_headers(const EncodePlan &p, std::vector<uint8_t> *o) {  // encoder.m
     o->push_back((uint8_t)(i ? 1 : 0));
   }
   for (int cls = 0; cls < 2; cls++)  // dc 0, dc 1, ac 0, ac 1 (encoder.ml:405-408)
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < ntab; t++) {
       const uint8_t *lengths, *values;
       int nv;
       default_spec(cls * 2 + t, &lengths, &values, &nv);

@@ -103,6 +103,7 @@ struct EncodeBatchDev {
   uint64_t src_off[3];        // offset of each source plane inside one frame
   uint64_t frame_bytes;       // bytes of one source frame
   int mcus_wide, mcus_high;
+  int linear_blit;            // monochrome: the source plane is copied linearly into the padded plane (encode_monochrome)
   uint32_t nblocks;           // per frame
   uint32_t restart_interval;  // 0 = none
   uint32_t nseg;              // segments per frame (1 if no restart)

@@ -225,3 +225,11 @@ class Encoder:
     @staticmethod
     def encode_444(frame, quality, writer, ctx=None):  # encoder.ml:536-541
         Encoder._encode(frame, quality, writer, 444, ctx)
+
+    @staticmethod
+    def encode_monochrome(frame, quality, writer, ctx=None):  # encoder.ml:543-552; ``frame`` is a Plane
+        ctx = ctx or default_context()
+        outs, st = ctx.encode_batch([np.ascontiguousarray(frame.plane, np.uint8).ravel()], frame.width, frame.height, 400, quality, 0)
+        if st[0] != 0:
+            raise HcjError(st[0], "Encoder.encode_monochrome")
+        writer._buf += outs[0]
