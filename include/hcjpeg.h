@@ -220,6 +220,13 @@ int hcj_write_headers(int width, int height, int chroma, int quality, int restar
 int hcj_encode_quantized(hcj_ctx *ctx, const uint8_t *yuv, int width, int height, int chroma, int quality,
                          int16_t *quant, size_t capacity_blocks);
 
+/* Scalar helpers the reference exposes for its tests, evaluated on the host by the same functions the kernels call:
+ * Decoder.For_testing.mag (decoder.mli:64-65, decoder.ml:73-79: signed value of `cat` magnitude bits `code`),
+ * Encoder.size and Encoder.magnitude (encoder.ml:143-147; pinned by test_encode_codewords.ml). */
+int hcj_mag(int cat, int code);
+int hcj_size(int value);
+int hcj_magnitude(int size, int value);
+
 /* ---- on-device frame tools (tools/src) ------------------------------------------------------- */
 /* Ocompare.square_error / max_difference per plane (tools/src/ocompare.ml:8-52) of two host frames. */
 int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,

@@ -171,6 +171,19 @@ def test_mjpeg_split(hcj, orc, data):
     assert [(off[i], ln[i]) for i in range(2)] == want[:2]
 
 
+def test_size_and_magnitude_goldens(hcj, goldens):
+    """jpeg/model/test/test_encode_codewords.ml through the library's own scalar functions (the ones the kernels call)."""
+    L = hcj.lib()
+    for r in goldens["size_ranges"]["rows"]:
+        assert L.hcj_size(r["lo"]) == r["size_lo"] and L.hcj_size(r["hi"]) == r["size_hi"] and L.hcj_size(-r["hi"]) == r["size_hi"]
+    for r in goldens["magnitude"]["rows"]:
+        size = L.hcj_size(r["value"])
+        assert size == r["size"] and L.hcj_magnitude(size, r["value"]) == r["emag"] and L.hcj_mag(size, r["emag"]) == r["dmag"]
+    from hcjpeg import model
+
+    assert model.Decoder.For_testing.mag(4, 0) == -15 and model.Decoder.For_testing.mag(4, 15) == 15
+
+
 def test_header_errors_match_oracle(hcj, orc, data):
     jpg = data("mini.jpg")
     cases = [

@@ -146,3 +146,21 @@ def test_encode_monochrome(hcj, ctx, orc):
             assert bytes(pl) == b"".join(p.tobytes() for p in orc.decode(o).planes)
         _, st = ctx.decode_batch(outs[:1], hcj.OUT_YUV)  # Decoder.get_yuv_frame needs three components (decoder.ml:415-420)
         assert st == [-12]
+
+
+def test_chen_example_on_device(hcj, ctx, goldens):
+    """jpeg/model/test/test_chen_dct.ml:47-94 through the kernels: the example block as the luma block of an 8 x 8 4:4:4
+    frame at quality 100 (every quant entry 1, so Block.quant is the test's (f +/- 2) / 4) gives the pinned FDCT values,
+    and hcj_idct_blocks of those the pinned IDCT values (after the decoder's clip and level shift)."""
+    g = goldens["chen_example"]
+    x = np.array(g["input"], np.int64)
+    assert x.min() >= -128 and x.max() <= 127
+    y = (x + 128).astype(np.uint8).tobytes()
+    quant = ctx.encode_quantized(y + bytes(128), 8, 8, 444, 100)
+    zz = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+    nat = np.zeros(64, np.int64)
+    nat[zz] = quant[0]
+    assert nat.tolist() == g["fdct"]
+    recon = ctx.idct_blocks(quant[:1], np.ones(64, np.uint16))
+    assert recon[0].tolist() == (np.clip(np.array(g["idct"]), -128, 127) + 128).tolist()

@@ -569,6 +569,16 @@ void teardown_encode(hcj_ctx *c, EncodeSetup *S) {
 
 extern "C" {
 
+/* The scalar helpers of the model, evaluated on the host by the very functions the kernels call (hcj_device.cuh). */
+int hcj_mag(int cat, int code) {  // Decoder.For_testing.mag' (decoder.ml:73-79)
+  if (cat <= 0 || cat > 16) return 0;
+  return (int)hcjdev::extend((uint32_t)code & ((1u << cat) - 1u), (uint32_t)cat);
+}
+int hcj_size(int value) { return (int)hcjdev::coef_size((int32_t)value); }  // Encoder.size (encoder.ml:143)
+int hcj_magnitude(int size, int value) {  // Encoder.magnitude (encoder.ml:145-147)
+  return (int)hcjdev::coef_magnitude((int32_t)value, (uint32_t)size);
+}
+
 size_t hcj_encode_bound(int width, int height, int chroma) {
   hcj::EncodePlan p;
   if (hcj::plan_encode(width, height, chroma, 75, 0, &p) != HCJ_OK) return 0;

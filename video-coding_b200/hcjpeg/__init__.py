@@ -170,6 +170,9 @@ _SIGS = {
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "hcj_mag": (C.c_int, [C.c_int, C.c_int]),
+    "hcj_size": (C.c_int, [C.c_int]),
+    "hcj_magnitude": (C.c_int, [C.c_int, C.c_int]),
     "hcj_batch_fetch_block_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
     "hcj_mjpeg_split": (C.c_int, [C.c_char_p, C.c_size_t, _P(C.c_size_t), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
     "hcj_decode_stream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_int), C.c_int, _P(C.c_int)]),

@@ -171,6 +171,12 @@ class Decoder:
 
     class For_testing:
         @staticmethod
+        def mag(cat, code):  # decoder.mli:64-65 (mag' of decoder.ml:73-79)
+            from . import lib
+
+            return lib().hcj_mag(cat, code)
+
+        @staticmethod
         def extract_entropy_coded_bits(bits, ctx=None):  # decoder.ml:261-281
             ctx = ctx or default_context()
             with ctx.batch([bits], OUT_PLANES, 0) as b:
