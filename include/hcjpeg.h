@@ -156,6 +156,9 @@ typedef enum hcj_out_mode {
 int hcj_decode_batch(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      uint8_t *const *out, const size_t *out_capacity, int *status);
 
+/* Decoder.decode_a_frame (decoder.ml:422-427) for one image: a batch of one; returns the image's status. */
+int hcj_decode_a_frame(hcj_ctx *ctx, const uint8_t *jpeg, size_t len, int mode, unsigned flags, uint8_t *out, size_t out_capacity);
+
 /* Motion JPEG (jpeg/README.md:33 lists it as the model's next step: "just testing processing of multiple frames"):
  * a stream of whole JPEG files back to back.  hcj_mjpeg_split finds the frames (host only; pass offsets = NULL to
  * count them); hcj_decode_stream decodes all of them like hcj_decode_batch (files up, kernels and frames down
@@ -223,6 +226,11 @@ int hcj_encode_quantized(hcj_ctx *ctx, const uint8_t *yuv, int width, int height
 /* Scalar helpers the reference exposes for its tests, evaluated on the host by the same functions the kernels call:
  * Decoder.For_testing.mag (decoder.mli:64-65, decoder.ml:73-79: signed value of `cat` magnitude bits `code`),
  * Encoder.size and Encoder.magnitude (encoder.ml:143-147; pinned by test_encode_codewords.ml). */
+/* Quant_tables.scale luma / chroma (quant_tables.ml:139-147; test_quant_tables.ml) and one entry of
+ * Tables.Encoder.dc_table / ac_table for the default specifications (tables.ml:504-545; test_tables.ml):
+ * table 0 dc_luma, 1 dc_chroma, 2 ac_luma, 3 ac_chroma; *length = 0 when the table has no such code. */
+int hcj_quant_scale(int chroma_table, int quality, uint16_t out[64]);
+int hcj_encoder_code(int table, int run, int size, int *bits, int *length);
 int hcj_mag(int cat, int code);
 int hcj_size(int value);
 int hcj_magnitude(int size, int value);

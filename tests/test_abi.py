@@ -184,6 +184,34 @@ def test_size_and_magnitude_goldens(hcj, goldens):
     assert model.Decoder.For_testing.mag(4, 0) == -15 and model.Decoder.For_testing.mag(4, 15) == 15
 
 
+def test_quant_scale_and_code_table_goldens(hcj, goldens):
+    """test_quant_tables.ml and test_tables.ml through the library's host functions (what the kernels are given)."""
+    L = hcj.lib()
+    for q, want in goldens["quant_scale_luma"]["by_quality"].items():
+        out = np.zeros(64, np.uint16)
+        assert L.hcj_quant_scale(0, int(q), out.ctypes.data) == 0 and out.tolist() == want
+    t = goldens["encoder_tables"]["tables"]
+    bits, length = C.c_int(), C.c_int()
+    for table, name in enumerate(["dc_luma", "dc_chroma"]):
+        for e in t[name]:
+            assert L.hcj_encoder_code(table, 0, e["data"], C.byref(bits), C.byref(length)) == 0
+            assert (length.value, bits.value) == (e["length"], e["bits"]), (name, e)
+    for table, name in enumerate(["ac_luma", "ac_chroma"]):
+        seen = set()
+        for row in t[name]:
+            for e in row:
+                if e["length"] == 0:  # filler of the model's [run][size] arrays, not a code
+                    continue
+                assert L.hcj_encoder_code(2 + table, e["run"], e["size"], C.byref(bits), C.byref(length)) == 0
+                assert (length.value, bits.value) == (e["length"], e["bits"]), (name, e)
+                seen.add((e["run"], e["size"]))
+        assert len(seen) == 162
+        for run in range(16):  # and nothing else has a code
+            for size in range(16):
+                L.hcj_encoder_code(2 + table, run, size, C.byref(bits), C.byref(length))
+                assert (length.value != 0) == ((run, size) in seen)
+
+
 def test_header_errors_match_oracle(hcj, orc, data):
     jpg = data("mini.jpg")
     cases = [

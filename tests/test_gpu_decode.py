@@ -65,6 +65,14 @@ def test_mouse480_golden(hcj, ctx, orc, data):
     assert all(np.array_equal(p.plane, w) for p, w in zip(planes, want))
 
 
+def test_decode_a_frame_entry(hcj, ctx, orc, data):
+    jpg = data("Mouse480.jpg")
+    assert bytes(ctx.decode_a_frame(jpg)) == orc.decode(jpg).yuv()
+    with pytest.raises(hcj.HcjError) as e:
+        ctx.decode_a_frame(jpg[:2] + b"\xff\xc2" + jpg[4:])  # progressive SOF: "unsupported marker code"
+    assert e.value.status == -1
+
+
 def test_mini_jpg_golden(hcj, ctx, orc, data):
     outs, st = ctx.decode_batch([data("mini.jpg")])
     assert st == [0]

@@ -903,6 +903,14 @@ int hcj_batch_fetch_block_log(hcj_ctx *c, hcj_batch *b, int i, size_t first_bloc
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
 }
 
+int hcj_decode_a_frame(hcj_ctx *c, const uint8_t *jpeg, size_t len, int mode, unsigned flags, uint8_t *out, size_t out_capacity) {
+  int status = HCJ_OK;
+  const uint8_t *in[1] = {jpeg};
+  uint8_t *o[1] = {out};
+  int st = hcj_decode_batch(c, in, &len, 1, mode, flags, o, &out_capacity, &status);
+  return st != HCJ_OK ? st : status;
+}
+
 int hcj_mjpeg_split(const uint8_t *stream, size_t len, size_t *offsets, size_t *lengths, int capacity, int *nframes) {
   if (!stream || !nframes || capacity < 0) return HCJ_ERR_INVALID_ARG;
   return hcj::mjpeg_split(stream, len, offsets, lengths, capacity, nframes);

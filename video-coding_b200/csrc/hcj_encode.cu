@@ -579,6 +579,21 @@ int hcj_magnitude(int size, int value) {  // Encoder.magnitude (encoder.ml:145-1
   return (int)hcjdev::coef_magnitude((int32_t)value, (uint32_t)size);
 }
 
+int hcj_quant_scale(int chroma_table, int quality, uint16_t out[64]) {  // Quant_tables.scale (quant_tables.ml:139-147)
+  if (!out) return HCJ_ERR_INVALID_ARG;
+  hcj::quant_scale(chroma_table != 0, quality, out);
+  return HCJ_OK;
+}
+int hcj_encoder_code(int table, int run, int size, int *bits, int *length) {  // Tables.Encoder.dc_table / ac_table (tables.ml:504-545)
+  if (table < 0 || table > 3 || run < 0 || run > 15 || size < 0 || size > 15 || !bits || !length) return HCJ_ERR_INVALID_ARG;
+  uint32_t dc[16], ac[256];
+  hcj::encoder_tables(table & 1, 2 + (table & 1), dc, ac);  // exactly what setup_encode uploads for the kernels
+  const uint32_t e = table < 2 ? (run == 0 ? dc[size] : 0u) : ac[(run << 4) | size];
+  *bits = (int)(e >> 8);
+  *length = (int)(e & 0xffu);  // 0: no such code
+  return HCJ_OK;
+}
+
 size_t hcj_encode_bound(int width, int height, int chroma) {
   hcj::EncodePlan p;
   if (hcj::plan_encode(width, height, chroma, 75, 0, &p) != HCJ_OK) return 0;

@@ -170,10 +170,13 @@ _SIGS = {
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "hcj_quant_scale": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "hcj_encoder_code": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "hcj_mag": (C.c_int, [C.c_int, C.c_int]),
     "hcj_size": (C.c_int, [C.c_int]),
     "hcj_magnitude": (C.c_int, [C.c_int, C.c_int]),
     "hcj_batch_fetch_block_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "hcj_decode_a_frame": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t]),
     "hcj_mjpeg_split": (C.c_int, [C.c_char_p, C.c_size_t, _P(C.c_size_t), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
     "hcj_decode_stream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_int), C.c_int, _P(C.c_int)]),
     "hcj_batch_compare": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
@@ -361,6 +364,13 @@ class Context:
             for s in st:
                 _check(s, "Decoder.decode_a_frame")
         return [outs[i][: caps[i]] if st[i] == 0 else None for i in range(n)], st
+
+    def decode_a_frame(self, jpeg, mode=OUT_YUV, flags=FLAG_DEFAULT):
+        """Decoder.decode_a_frame (decoder.ml:422-427): the frame as a uint8 array; raises HcjError like the model raises."""
+        f = frame_info(jpeg, flags)
+        out = np.zeros(max(out_size(f, mode), 1), np.uint8)
+        _check(lib().hcj_decode_a_frame(self._h, jpeg, len(jpeg), mode, flags, out.ctypes.data, out.size), "Decoder.decode_a_frame")
+        return out[: out_size(f, mode)]
 
     def decode_stream(self, stream, mode=OUT_YUV, flags=FLAG_DEFAULT):
         """Every frame of a Motion-JPEG stream: (frames, status), frames[i] a uint8 array (None where status[i] != 0)."""
