@@ -240,6 +240,13 @@ int hcj_magnitude(int size, int value);
 int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,
                        int *max_difference);
 
+/* `oyuv convert` on the device (tools/src/oconv.ml:111-133): a planar frame of `chroma` (420 / 422 / 444, planes as
+ * Frame.create lays them out) is taken to 4:4:4 (Planar_444.convert_from_420 / _422), cropped to dst_width x dst_height
+ * at (x_off, y_off) with the edge clamp of Yuv.crop (yuv.ml:43-62), and sub-sampled to `dst_chroma`
+ * (Planar_444.convert_to_420 / _422).  Host buffers in and out. */
+int hcj_yuv_convert(hcj_ctx *ctx, const uint8_t *src, int width, int height, int chroma, int x_off, int y_off, uint8_t *dst,
+                    int dst_width, int dst_height, int dst_chroma, size_t dst_capacity);
+
 /* `oyuv compare` for a whole decoded batch, on the device: Ocompare.square_error / total_difference / max_difference
  * (tools/src/ocompare.ml:8-46) per plane between image i's output resident in HBM (after hcj_batch_decode) and the
  * reference frame ref[i] in host memory, which has the layout and size of the batch's output mode.  Planes: Y,U,V

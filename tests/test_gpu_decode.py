@@ -97,6 +97,53 @@ def test_cram_psnr_flow(hcj, ctx, orc, goldens, data):
         assert dev_sse == got[0] and dev_max == int(np.abs(a[:y].astype(int) - b[:y].astype(int)).max())
 
 
+def test_yuv_convert_on_device(hcj, ctx, orc, data):
+    """`oyuv convert` (oconv.ml:111-133) on the device against the oracle's Planar_444 / Yuv.crop chain, including the
+    conversion the reference's odd-size cram test does (64 x 64 4:2:0 -> 52 x 44 4:2:0 through 4:4:4)."""
+    def chain(frame, w, h, chroma, dw, dh, dchroma, x, y):
+        planes = orc.split_yuv(frame, w, h, chroma)
+        up = orc.upsample_to_444(planes, chroma)
+        full = []
+        for p in up:  # a fresh (zero) 4:4:4 frame: an odd last column / row is never written
+            f = np.zeros((h, w), np.uint8)
+            f[: min(h, p.shape[0]), : min(w, p.shape[1])] = p[:h, :w]
+            full.append(orc.crop_clamp(f, dw, dh, x, y))
+        if dchroma == 420:
+            full[1:] = [orc.subsample_hv2(p) for p in full[1:]]
+        elif dchroma == 422:
+            full[1:] = [orc.subsample_h2(p) for p in full[1:]]
+        return b"".join(p.tobytes() for p in full)
+
+    src = data("mini64x64.420")
+    assert bytes(ctx.yuv_convert(src, 64, 64, 420, 52, 44, 420)) == chain(src, 64, 64, 420, 52, 44, 420, 0, 0)
+    rng = np.random.default_rng(3)
+    for chroma, w, h in ((420, 64, 48), (422, 61, 35), (444, 33, 20), (420, 51, 37), (422, 8, 8)):
+        f = synth.frame(int(rng.integers(1000)), w, h, chroma)
+        for dchroma in (420, 422, 444):
+            for dw, dh, x, y in ((w, h, 0, 0), (w + 9, h + 5, -3, -2), (max(2, w - 10), max(2, h - 7), 4, 3), (17, 11, w - 5, h - 4)):
+                got = ctx.yuv_convert(f, w, h, chroma, dw, dh, dchroma, x, y)
+                assert bytes(got) == chain(f, w, h, chroma, dw, dh, dchroma, x, y), (chroma, w, h, dchroma, dw, dh, x, y)
+
+
+def test_cram_52x44_flow(hcj, ctx, orc, goldens, data):
+    """jpeg/test/test-nonstandard-sizes.t:3-15 with the encoder, the decoder and the comparison on the device: a 52 x 44
+    frame (partial MCUs: zero padding on encode, crop on decode) at q95 gives the reference's 1923 bytes and PSNR strings."""
+    g = goldens["cram_52x44"]
+    y, u, v = orc.split_yuv(data("mini64x64.420"), 64, 64, 420)
+    y4, u4, v4 = orc.upsample_to_444((y, u, v), 420)
+    w, h = g["size"]
+    yc, uc, vc = (orc.crop_clamp(p, w, h) for p in (y4, u4, v4))
+    src = yc.tobytes() + orc.subsample_hv2(uc).tobytes() + orc.subsample_hv2(vc).tobytes()
+    enc, st = ctx.encode_batch([src], w, h, 420, g["quality"])
+    assert st == [0] and len(enc[0]) == 1923 and enc[0] == orc.encode(src, w, h, 420, g["quality"])
+    with ctx.batch(enc, hcj.OUT_YUV) as b:
+        b.decode()
+        m = b.compare([src])[0]
+        assert [m.samples[k] for k in range(3)] == [52 * 44, 26 * 22, 26 * 22]
+        for k in range(3):
+            assert abs(m.psnr(k) - float(g["psnr"][k])) < 1e-9
+
+
 # ---- oracle parity on seeded synthetic images -----------------------------------------------------------
 CASES = [
     # (chroma, quality, w, h, restart_interval)

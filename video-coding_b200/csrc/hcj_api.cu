@@ -948,6 +948,34 @@ int hcj_decode_stream(hcj_ctx *c, const uint8_t *stream, size_t len, int mode, u
   return hcj_decode_batch(c, jp.data(), ln.data(), n, mode, flags, op.data(), cap.data(), status);
 }
 
+int hcj_yuv_convert(hcj_ctx *c, const uint8_t *src, int width, int height, int chroma, int x_off, int y_off, uint8_t *dst, int dst_width,
+                    int dst_height, int dst_chroma, size_t dst_capacity) {
+  auto ok = [](int ch) { return ch == 420 || ch == 422 || ch == 444; };
+  if (!c || !src || !dst || width < 1 || height < 1 || dst_width < 1 || dst_height < 1 || !ok(chroma) || !ok(dst_chroma))
+    return HCJ_ERR_INVALID_ARG;
+  const size_t nin = hcjk::yuv_frame_bytes(width, height, chroma), nout = hcjk::yuv_frame_bytes(dst_width, dst_height, dst_chroma);
+  if (dst_capacity < nout) return HCJ_ERR_BUFFER_TOO_SMALL;
+  CU_TRY(cudaSetDevice(c->device));
+  void *d_in = nullptr, *d_out = nullptr;
+  int st = c->alloc(&d_in, nin + 16);
+  if (st == HCJ_OK) st = c->alloc(&d_out, nout + 16);
+  cudaError_t e = cudaSuccess;
+  if (st == HCJ_OK) {
+    e = cudaMemcpyAsync(d_in, src, nin, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+      hcjk::launch_yuv_convert((const uint8_t *)d_in, width, height, chroma, x_off, y_off, (uint8_t *)d_out, dst_width, dst_height, dst_chroma,
+                               c->stream);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_out, nout, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  c->release(d_in);
+  c->release(d_out);
+  if (st != HCJ_OK) return st;
+  return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
 int hcj_batch_compare(hcj_ctx *c, hcj_batch *b, const uint8_t *const *ref, const size_t *ref_len, hcj_plane_metrics *out) {
   if (!c || !b || !ref || !ref_len || !out) return HCJ_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(c->device));

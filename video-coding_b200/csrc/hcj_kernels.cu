@@ -1678,6 +1678,60 @@ void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   else k_rgb<false><<<grid, block, 0, s>>>(b);
 }
 
+// `oyuv convert` (tools/src/oconv.ml:111-133): planar frame -> 4:4:4 (Planar_444.convert_from_420 / _422) -> Yuv.crop with
+// edge clamp (yuv.ml:43-62) -> Planar_444.convert_to_420 / _422 (planar_444.ml:18-23,36-50,68-80,105-120), one
+// output sample per thread, nothing materialised in between.
+struct ConvertArgs {
+  const uint8_t *src;
+  uint8_t *dst;
+  int sw, sh, schroma;  // source frame
+  int dw, dh, dchroma;  // destination frame
+  int x_off, y_off;     // position of the destination's origin in the source (crop)
+};
+__device__ __forceinline__ int conv_sample_444(const ConvertArgs &a, int c, int x, int y) {
+  // sample (x, y) of plane c of the destination-sized 4:4:4 frame = the source's 4:4:4 frame at the clamped position
+  x = min(max(x + a.x_off, 0), a.sw - 1);
+  y = min(max(y + a.y_off, 0), a.sh - 1);
+  if (c == 0) return a.src[(size_t)y * a.sw + x];
+  const int hs_log = a.schroma == 444 ? 0 : 1, vs_log = a.schroma == 420 ? 1 : 0;
+  const int cw = a.sw >> hs_log, ch = a.sh >> vs_log;
+  const uint8_t *p = a.src + (size_t)a.sw * a.sh + (size_t)(c - 1) * cw * ch;
+  return up_sample(p, cw, cw, ch, x, y, hs_log, vs_log);
+}
+__global__ void __launch_bounds__(256) k_yuv_convert(ConvertArgs a) {
+  const int hs_log = a.dchroma == 444 ? 0 : 1, vs_log = a.dchroma == 420 ? 1 : 0;
+  const int cw = a.dw >> hs_log, ch = a.dh >> vs_log;
+  const size_t ny = (size_t)a.dw * a.dh, nc = (size_t)cw * ch;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ny + 2 * nc) return;
+  int v;
+  if (i < ny) {
+    v = conv_sample_444(a, 0, (int)(i % a.dw), (int)(i / a.dw));
+  } else {
+    const int c = i < ny + nc ? 1 : 2;
+    const size_t k = i - ny - (c - 1) * nc;
+    const int x = (int)(k % cw), y = (int)(k / cw);
+    if (hs_log && vs_log)
+      v = (conv_sample_444(a, c, 2 * x, 2 * y) + conv_sample_444(a, c, 2 * x + 1, 2 * y) + conv_sample_444(a, c, 2 * x, 2 * y + 1) +
+           conv_sample_444(a, c, 2 * x + 1, 2 * y + 1) + 2) >> 2;
+    else if (hs_log)
+      v = (conv_sample_444(a, c, 2 * x, y) + conv_sample_444(a, c, 2 * x + 1, y) + 1) >> 1;
+    else
+      v = conv_sample_444(a, c, x, y);
+  }
+  a.dst[i] = (uint8_t)v;
+}
+void launch_yuv_convert(const uint8_t *src, int sw, int sh, int schroma, int x_off, int y_off, uint8_t *dst, int dw, int dh, int dchroma,
+                        cudaStream_t s) {
+  ConvertArgs a{src, dst, sw, sh, schroma, dw, dh, dchroma, x_off, y_off};
+  const size_t n = yuv_frame_bytes(dw, dh, dchroma);
+  if (n) k_yuv_convert<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+}
+size_t yuv_frame_bytes(int w, int h, int chroma) {  // Frame.create (frame.ml:32-40)
+  const size_t cw = chroma == 444 ? w : w / 2, ch = chroma == 420 ? h / 2 : h;
+  return (size_t)w * h + 2 * cw * ch;
+}
+
 // Debug tap: Decoder.Component.Summary (decoder.ml:189-203) of `count` blocks of one image, from its coefficient
 // blocks: position, predictor, coefs with the DC differential restored, dequant, idct (before clipping), recon.
 // One thread per block, the model's 64-bit arithmetic verbatim.

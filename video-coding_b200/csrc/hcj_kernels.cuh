@@ -76,6 +76,10 @@ void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt
 void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff,
                     cudaStream_t s);
 
+size_t yuv_frame_bytes(int w, int h, int chroma);
+void launch_yuv_convert(const uint8_t *src, int sw, int sh, int schroma, int x_off, int y_off, uint8_t *dst, int dw, int dh, int dchroma,
+                        cudaStream_t s);
+
 struct BlockLog {  // = hcj_block_log (include/hcjpeg.h)
   int32_t x, y, dc_pred, component;
   int16_t coefs[64];

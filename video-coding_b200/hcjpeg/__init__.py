@@ -179,6 +179,7 @@ _SIGS = {
     "hcj_decode_a_frame": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t]),
     "hcj_mjpeg_split": (C.c_int, [C.c_char_p, C.c_size_t, _P(C.c_size_t), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
     "hcj_decode_stream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_int), C.c_int, _P(C.c_int)]),
+    "hcj_yuv_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t]),
     "hcj_batch_compare": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
     "hcj_batch_decode_stages": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
     "hcj_decode_stage_name": (C.c_char_p, [C.c_int]),
@@ -430,6 +431,15 @@ class Context:
         out = np.zeros((f.nblocks, 64), np.int16)
         buf = np.frombuffer(frame, np.uint8)
         _check(lib().hcj_encode_quantized(self._h, buf.ctypes.data, width, height, chroma, quality, out.ctypes.data, f.nblocks), "hcj_encode_quantized")
+        return out
+
+    def yuv_convert(self, frame, width, height, chroma, dst_width=None, dst_height=None, dst_chroma=444, x_off=0, y_off=0):
+        """`oyuv convert`: planar frame -> 4:4:4 -> crop with edge clamp -> dst_chroma, on the device."""
+        dw, dh = dst_width or width, dst_height or height
+        cw, ch = (dw if dst_chroma == 444 else dw // 2), (dh // 2 if dst_chroma == 420 else dh)
+        out = np.zeros(dw * dh + 2 * cw * ch, np.uint8)
+        src = np.frombuffer(frame, np.uint8)
+        _check(lib().hcj_yuv_convert(self._h, src.ctypes.data, width, height, chroma, x_off, y_off, out.ctypes.data, dw, dh, dst_chroma, out.size), "hcj_yuv_convert")
         return out
 
     def compare_planes(self, a, b):
