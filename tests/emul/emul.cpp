@@ -428,9 +428,11 @@ int64_t emu_quantize_check(int fmax) {
 
 // k_block_bits / k_pack symbol stream for a whole frame of quantised blocks -> entropy-coded bytes with
 // stuffing, 1-fill and (optionally) RSTn, i.e. everything between the SOS header and EOI.
-struct FieldLog {  // records the (bits, length) fields a block emits
-  std::vector<std::pair<uint32_t, uint32_t>> f;
-  void operator()(uint32_t bits, uint32_t n) { f.emplace_back(bits, n); }
+struct FieldLog {  // the bits a block emits, one per element (fields may be merged or split differently)
+  std::vector<uint8_t> f;
+  void operator()(uint32_t bits, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) f.push_back((uint8_t)((bits >> (n - 1 - i)) & 1u));
+  }
 };
 struct ByteWriter {
   std::vector<uint8_t> *out;
