@@ -37,6 +37,7 @@ WORKLOADS = {
     "restart8": (1920, 1080, 420, 75, 8, "yuv", 1024),   # BASELINE configs[1]
     "norestart": (1920, 1080, 420, 75, 0, "yuv", 1024),  # BASELINE configs[2] (8192 / 8 GPUs)
     "4k444rgb": (3840, 2160, 444, 95, 0, "rgb", 128),    # BASELINE configs[3]
+    "restart8rgb": (1920, 1080, 420, 75, 8, "rgb", 1024),  # configs[1] with RGB24 output (Planar_444 up-sampling + colour)
     "encode": (1920, 1080, 420, 75, 0, "jpeg", 512),     # BASELINE configs[4]
 }
 

@@ -218,6 +218,18 @@ def test_batch_compare_on_device(hcj, ctx, orc, goldens, data):
         assert ms[1].status == -31  # HCJ_ERR_INVALID_ARG: reference of the wrong size
 
 
+def test_rgb_vector_paths(hcj, ctx, orc):
+    """RGB24 from sub-sampled chroma with 16-pixel-aligned rows (the register path of k_rgb): 4:2:0 and 4:2:2, even and
+    odd heights (the last luma row of an odd-height 4:2:0 image has no chroma row), single and many 16-pixel groups."""
+    cases = [(420, 64, 48), (420, 48, 35), (420, 16, 2), (420, 16, 3), (420, 32, 5), (422, 64, 48), (422, 32, 19), (422, 16, 3),
+             (420, 320, 200), (422, 320, 203), (420, 1920, 1080)]  # (heights of 1 mod 16 are sizes the model's encoder rejects)
+    jpgs = [orc.encode(synth.frame(700 + i, w, h, c), w, h, c, 75, restart_interval=(8 if w > 1000 else 0)) for i, (c, w, h) in enumerate(cases)]
+    outs, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
+    assert st == [0] * len(jpgs)
+    for j, o, case in zip(jpgs, outs, cases):
+        assert bytes(o) == oracle_rgb(orc, orc.decode(j)).tobytes(), case
+
+
 def test_coefficients_and_entropy_taps(hcj, ctx, orc):
     jpgs = [orc.encode(synth.frame(200 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(CASES[:6])]
     with ctx.batch(jpgs, hcj.OUT_PLANES) as b:

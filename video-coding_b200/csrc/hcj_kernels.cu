@@ -1662,6 +1662,67 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
     return;
   }
   const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
+  // 4:2:0 / 4:2:2 with rows that keep 16-byte alignment: 16 luma samples and the 9 chroma samples (of one or two
+  // rows) they need in registers, Planar_444's interpolation on those, three 16-byte stores.  The neighbours are
+  // clamped at the cropped plane's edge, where avg2 (a, a) = a and avg4 (a, a, c, c) = avg2 (a, c) are the model's
+  // edge cases; past the last chroma row of an odd-height image the 4:4:4 plane is still zero.
+  const int cw = d.comp[1].actual_w, chh = d.comp[1].actual_h, cs = d.comp[1].decoded_w;
+  if (hs_log && ((d.width | sy) & 15) == 0 && ((cs | d.comp[2].decoded_w) & 7) == 0 && d.comp[2].actual_w == cw &&
+      d.comp[2].actual_h == chh && cw * 2 >= d.width &&
+      (((uintptr_t)py | (uintptr_t)(b.out + d.out_off)) & 15u) == 0 && (((uintptr_t)pu | (uintptr_t)pv) & 7u) == 0) {
+    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
+    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w};
+    const int cy = y >> vs_log, cx0 = x0 >> 1;
+    const bool below = cy >= chh;               // odd height: no chroma row for the last luma row
+    const bool oy = vs_log && (y & 1);
+    const int cy1 = min(cy + 1, chh - 1), cx8 = min(cx0 + 8, cw - 1);
+    int cu[2][9], cv[2][9];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int row = r ? cy1 : cy;
+      uint2 a = make_uint2(0u, 0u), c = make_uint2(0u, 0u);
+      int a8 = 0, c8 = 0;
+      if (!below && (r == 0 || oy)) {
+        a = __ldg(reinterpret_cast<const uint2 *>(pu + (size_t)row * cs + cx0));
+        c = __ldg(reinterpret_cast<const uint2 *>(pv + (size_t)row * d.comp[2].decoded_w + cx0));
+        a8 = __ldg(pu + (size_t)row * cs + cx8);
+        c8 = __ldg(pv + (size_t)row * d.comp[2].decoded_w + cx8);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        cu[r][k] = (int)(((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xffu);
+        cv[r][k] = (int)(((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0xffu);
+      }
+      cu[r][8] = a8;
+      cv[r][8] = c8;
+    }
+    uint32_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
+      uint32_t px[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int n = 4 * k + i, cpos = n >> 1;
+        int Cb, Cr;
+        if (!oy) {
+          Cb = (n & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + 1) >> 1 : cu[0][cpos];
+          Cr = (n & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + 1) >> 1 : cv[0][cpos];
+        } else {
+          Cb = (n & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + cu[1][cpos] + cu[1][cpos + 1] + 2) >> 2 : (cu[0][cpos] + cu[1][cpos] + 1) >> 1;
+          Cr = (n & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + cv[1][cpos] + cv[1][cpos + 1] + 2) >> 2 : (cv[0][cpos] + cv[1][cpos] + 1) >> 1;
+        }
+        px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, Cb, Cr);
+      }
+      o[3 * k + 0] = px[0] | (px[1] << 24);
+      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    return;
+  }
   const int n = min(16, d.width - x0);
   for (int i = 0; i < n; i++) {
     const int x = x0 + i;
