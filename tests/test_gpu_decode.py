@@ -228,6 +228,10 @@ def test_rgb_vector_paths(hcj, ctx, orc):
     assert st == [0] * len(jpgs)
     for j, o, case in zip(jpgs, outs, cases):
         assert bytes(o) == oracle_rgb(orc, orc.decode(j)).tobytes(), case
+    outs, st = ctx.decode_batch(jpgs, hcj.OUT_YUV444)  # the same paths, planar 4:4:4 out
+    assert st == [0] * len(jpgs)
+    for j, o, case in zip(jpgs, outs, cases):
+        assert bytes(o) == oracle_yuv444(orc, orc.decode(j)).tobytes(), case
 
 
 def test_coefficients_and_entropy_taps(hcj, ctx, orc):

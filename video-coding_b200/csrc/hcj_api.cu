@@ -485,6 +485,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     d.idct_tiles = tiles;
     total_tiles += tiles;
     max_rows = std::max(max_rows, (uint32_t)f.height);
+    (f.chroma == 444 ? b->dev.has_444 : b->dev.has_subsampled) = 1;
     max_width = std::max(max_width, (uint32_t)f.width);
   }
   if (status)
@@ -580,7 +581,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.ls_hi = (uint32_t)list_spec.size();
   b->list_restart = list_restart;
   b->list_spec = list_spec;
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? 1 : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;

@@ -1611,69 +1611,72 @@ __device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
   return (uint32_t)min(255, max(0, r)) | ((uint32_t)min(255, max(0, g)) << 8) | ((uint32_t)min(255, max(0, bl)) << 16);
 }
 
-// Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16).  4:4:4 images whose rows keep
-// 16-byte alignment (width and padded width multiples of 16) take the vector path: one 16-byte load per
-// plane, three 16-byte stores; everything else goes pixel by pixel through up_sample.
-template <bool PLANAR>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
+// The 16 pixels of a thread from their luma word and the 16 up-sampled chroma samples (packed, four per word):
+// RGB24 as three 16-byte stores, or planar 4:4:4 as one 16-byte store per plane.
+template <bool PLANAR>
+__device__ __forceinline__ void rgb_store16(const DecodeBatchDev &b, const HcjImageDesc &d, int x0, int y, const uint32_t wy[4],
+                                            const uint32_t wu[4], const uint32_t wv[4]) {
+  if (PLANAR) {
+    const size_t plane = (size_t)d.width * d.height;
+    uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0;
+    *reinterpret_cast<uint4 *>(oy) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
+    *reinterpret_cast<uint4 *>(oy + plane) = make_uint4(wu[0], wu[1], wu[2], wu[3]);
+    *reinterpret_cast<uint4 *>(oy + 2 * plane) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    return;
+  }
+  uint32_t o[12];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
+    uint32_t px[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, (wu[k] >> (8 * i)) & 0xff, (wv[k] >> (8 * i)) & 0xff);
+    o[3 * k + 0] = px[0] | (px[1] << 24);
+    o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+    o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+  }
+  uint4 *d4 = reinterpret_cast<uint4 *>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3);
+  d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+}
+
+// Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16).  Images whose rows keep 16-byte alignment
+// (width a multiple of 16; for PLANAR also width * height) work in registers: one 16-byte load per plane for 4:4:4,
+// and for 4:2:0 / 4:2:2 the 16 luma samples plus the 9 chroma samples (of one or two rows) they need, with
+// Planar_444's interpolation on those - the neighbours clamped at the cropped plane's edge, where avg2 (a, a) = a and
+// avg4 (a, a, c, c) = avg2 (a, c) are the model's edge cases; past the last chroma row of an odd-height image the
+// 4:4:4 plane is still zero.  Everything else goes pixel by pixel through up_sample.
+// Two instances per output format, one for 4:4:4 images and one for sub-sampled ones (SUB), each skipping the other's
+// images: the 4:4:4 path needs far fewer registers, and a batch is normally of one kind (launch_rgb starts only
+// the instances the batch needs).
+template <bool PLANAR, bool SUB>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
 __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
-  if (!d.valid || d.chroma == 0) return;
+  if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB) return;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
   if (y >= d.height || x0 >= d.width) return;
   const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off,
                 *pv = b.planes + d.comp[2].plane_off;
-  uint8_t *dst = b.out + d.out_off + ((size_t)y * d.width + x0) * 3;
-  const int sy = d.comp[0].decoded_w;
-  if (PLANAR) {
-    const size_t plane = (size_t)d.width * d.height;
-    uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0, *ou = oy + plane, *ov = ou + plane;
-    const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
-    const int n = min(16, d.width - x0);
-    for (int i = 0; i < n; i++) {
-      const int x = x0 + i;
-      oy[i] = py[(size_t)y * sy + x];
-      ou[i] = (uint8_t)up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log);
-      ov[i] = (uint8_t)up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
-    }
-    return;
-  }
-  const bool vec = d.chroma == 444 && ((d.width | sy | d.comp[1].decoded_w | d.comp[2].decoded_w) & 15) == 0 &&
-                   (((uintptr_t)py | (uintptr_t)pu | (uintptr_t)pv | (uintptr_t)(b.out + d.out_off)) & 15u) == 0;
-  if (vec) {
-    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
-    const uint4 vu = __ldg(reinterpret_cast<const uint4 *>(pu + (size_t)y * d.comp[1].decoded_w + x0));
-    const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pv + (size_t)y * d.comp[2].decoded_w + x0));
-    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w}, wv[4] = {vv.x, vv.y, vv.z, vv.w};
-    uint32_t o[12];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
-      uint32_t px[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, (wu[k] >> (8 * i)) & 0xff, (wv[k] >> (8 * i)) & 0xff);
-      o[3 * k + 0] = px[0] | (px[1] << 24);
-      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
-      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
-    }
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-    return;
-  }
+  const int sy = d.comp[0].decoded_w, su = d.comp[1].decoded_w, sv = d.comp[2].decoded_w;
   const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
-  // 4:2:0 / 4:2:2 with rows that keep 16-byte alignment: 16 luma samples and the 9 chroma samples (of one or two
-  // rows) they need in registers, Planar_444's interpolation on those, three 16-byte stores.  The neighbours are
-  // clamped at the cropped plane's edge, where avg2 (a, a) = a and avg4 (a, a, c, c) = avg2 (a, c) are the model's
-  // edge cases; past the last chroma row of an odd-height image the 4:4:4 plane is still zero.
-  const int cw = d.comp[1].actual_w, chh = d.comp[1].actual_h, cs = d.comp[1].decoded_w;
-  if (hs_log && ((d.width | sy) & 15) == 0 && ((cs | d.comp[2].decoded_w) & 7) == 0 && d.comp[2].actual_w == cw &&
-      d.comp[2].actual_h == chh && cw * 2 >= d.width &&
-      (((uintptr_t)py | (uintptr_t)(b.out + d.out_off)) & 15u) == 0 && (((uintptr_t)pu | (uintptr_t)pv) & 7u) == 0) {
+  const bool rows16 = ((d.width | sy) & 15) == 0 && (((uintptr_t)py | (uintptr_t)(b.out + d.out_off)) & 15u) == 0 &&
+                      (!PLANAR || (((size_t)d.width * d.height) & 15u) == 0);
+  if (!SUB && rows16 && !hs_log && ((su | sv) & 15) == 0 && (((uintptr_t)pu | (uintptr_t)pv) & 15u) == 0) {
+    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
+    const uint4 vu = __ldg(reinterpret_cast<const uint4 *>(pu + (size_t)y * su + x0));
+    const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pv + (size_t)y * sv + x0));
+    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w}, wv[4] = {vv.x, vv.y, vv.z, vv.w};
+    rgb_store16<PLANAR>(b, d, x0, y, wy, wu, wv);
+    return;
+  }
+  const int cw = d.comp[1].actual_w, chh = d.comp[1].actual_h;
+  if (SUB && rows16 && hs_log && ((su | sv) & 7) == 0 && d.comp[2].actual_w == cw && d.comp[2].actual_h == chh && cw * 2 >= d.width &&
+      (((uintptr_t)pu | (uintptr_t)pv) & 7u) == 0) {
     const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
     const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w};
     const int cy = y >> vs_log, cx0 = x0 >> 1;
-    const bool below = cy >= chh;               // odd height: no chroma row for the last luma row
+    const bool below = cy >= chh;  // odd height: no chroma row for the last luma row
     const bool oy = vs_log && (y & 1);
     const int cy1 = min(cy + 1, chh - 1), cx8 = min(cx0 + 8, cw - 1);
     int cu[2][9], cv[2][9];
@@ -1683,10 +1686,10 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
       uint2 a = make_uint2(0u, 0u), c = make_uint2(0u, 0u);
       int a8 = 0, c8 = 0;
       if (!below && (r == 0 || oy)) {
-        a = __ldg(reinterpret_cast<const uint2 *>(pu + (size_t)row * cs + cx0));
-        c = __ldg(reinterpret_cast<const uint2 *>(pv + (size_t)row * d.comp[2].decoded_w + cx0));
-        a8 = __ldg(pu + (size_t)row * cs + cx8);
-        c8 = __ldg(pv + (size_t)row * d.comp[2].decoded_w + cx8);
+        a = __ldg(reinterpret_cast<const uint2 *>(pu + (size_t)row * su + cx0));
+        c = __ldg(reinterpret_cast<const uint2 *>(pv + (size_t)row * sv + cx0));
+        a8 = __ldg(pu + (size_t)row * su + cx8);
+        c8 = __ldg(pv + (size_t)row * sv + cx8);
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
@@ -1696,7 +1699,7 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
       cu[r][8] = a8;
       cv[r][8] = c8;
     }
-    uint32_t o[12];
+    uint32_t wu[4] = {0u, 0u, 0u, 0u}, wv[4] = {0u, 0u, 0u, 0u}, o[12];
 #pragma unroll
     for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
       uint32_t px[4];
@@ -1711,24 +1714,47 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
           Cb = (n & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + cu[1][cpos] + cu[1][cpos + 1] + 2) >> 2 : (cu[0][cpos] + cu[1][cpos] + 1) >> 1;
           Cr = (n & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + cv[1][cpos] + cv[1][cpos + 1] + 2) >> 2 : (cv[0][cpos] + cv[1][cpos] + 1) >> 1;
         }
-        px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, Cb, Cr);
+        if (PLANAR) {
+          wu[k] |= (uint32_t)Cb << (8 * i);
+          wv[k] |= (uint32_t)Cr << (8 * i);
+        } else {
+          px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, Cb, Cr);
+        }
       }
-      o[3 * k + 0] = px[0] | (px[1] << 24);
-      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
-      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+      if (!PLANAR) {
+        o[3 * k + 0] = px[0] | (px[1] << 24);
+        o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+        o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+      }
     }
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    if (PLANAR) {
+      rgb_store16<true>(b, d, x0, y, wy, wu, wv);
+    } else {
+      uint4 *d4 = reinterpret_cast<uint4 *>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3);
+      d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
     return;
   }
   const int n = min(16, d.width - x0);
+  if (PLANAR) {
+    const size_t plane = (size_t)d.width * d.height;
+    uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0, *ou = oy + plane, *ov = ou + plane;
+    for (int i = 0; i < n; i++) {
+      const int x = x0 + i;
+      oy[i] = py[(size_t)y * sy + x];
+      ou[i] = (uint8_t)up_sample(pu, su, cw, chh, x, y, hs_log, vs_log);
+      ov[i] = (uint8_t)up_sample(pv, sv, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
+    }
+    return;
+  }
+  uint8_t *dst = b.out + d.out_off + ((size_t)y * d.width + x0) * 3;
   for (int i = 0; i < n; i++) {
     const int x = x0 + i;
     const int Y = py[(size_t)y * sy + x];
-    const int Cb = up_sample(pu, d.comp[1].decoded_w, d.comp[1].actual_w, d.comp[1].actual_h, x, y, hs_log, vs_log);
-    const int Cr = up_sample(pv, d.comp[2].decoded_w, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
+    const int Cb = up_sample(pu, su, cw, chh, x, y, hs_log, vs_log);
+    const int Cr = up_sample(pv, sv, d.comp[2].actual_w, d.comp[2].actual_h, x, y, hs_log, vs_log);
     const uint32_t px = ycc_to_rgb(Y, Cb, Cr);
     dst[3 * i + 0] = (uint8_t)px;
     dst[3 * i + 1] = (uint8_t)(px >> 8);
@@ -1740,8 +1766,14 @@ void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
   dim3 block(128);
   dim3 grid((b.max_width / 16 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
-  if (planar444) k_rgb<true><<<grid, block, 0, s>>>(b);
-  else k_rgb<false><<<grid, block, 0, s>>>(b);
+  if (b.has_444) {
+    if (planar444) k_rgb<true, false><<<grid, block, 0, s>>>(b);
+    else k_rgb<false, false><<<grid, block, 0, s>>>(b);
+  }
+  if (b.has_subsampled) {
+    if (planar444) k_rgb<true, true><<<grid, block, 0, s>>>(b);
+    else k_rgb<false, true><<<grid, block, 0, s>>>(b);
+  }
 }
 
 // `oyuv convert` (tools/src/oconv.ml:111-133): planar frame -> 4:4:4 (Planar_444.convert_from_420 / _422) -> Yuv.crop with

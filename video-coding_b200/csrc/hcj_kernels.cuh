@@ -52,6 +52,7 @@ struct DecodeBatchDev {
   uint32_t tile_lo, tile_hi;      // tiles of the images [img_lo, img_hi)
   int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
   uint32_t max_rgb_rows;          // max image height (RGB mode)
+  int has_444, has_subsampled;    // the batch holds 4:4:4 / sub-sampled images: which instances of k_rgb to launch
   uint32_t max_width;
   uint64_t total_blocks;
   // sub-range of the batch handled by one launch (the pipelined host path decodes chunk by chunk)
