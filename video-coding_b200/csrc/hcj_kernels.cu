@@ -1608,7 +1608,11 @@ __device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
   const int r = Y + ((91881 * Cr + 32768) >> 16);
   const int g = Y + ((-22554 * Cb - 46802 * Cr + 32768) >> 16);
   const int bl = Y + ((116130 * Cb + 32768) >> 16);
-  return (uint32_t)min(255, max(0, r)) | ((uint32_t)min(255, max(0, g)) << 8) | ((uint32_t)min(255, max(0, bl)) << 16);
+  // clamp to [0, 255] and pack: two saturating packs instead of six min / max and the shifts
+  uint32_t t, px;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(0), "r"(bl), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(t));
+  return px;
 }
 
 // The 16 pixels of a thread from their luma word and the 16 up-sampled chroma samples (packed, four per word):
