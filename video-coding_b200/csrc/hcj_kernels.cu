@@ -1615,47 +1615,127 @@ __device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
   return px;
 }
 
-// The 16 pixels of a thread from their luma word and the 16 up-sampled chroma samples (packed, four per word):
-// RGB24 as three 16-byte stores, or planar 4:4:4 as one 16-byte store per plane.
-template <bool PLANAR>
-__device__ __forceinline__ void rgb_store16(const DecodeBatchDev &b, const HcjImageDesc &d, int x0, int y, const uint32_t wy[4],
-                                            const uint32_t wu[4], const uint32_t wv[4]) {
-  if (PLANAR) {
-    const size_t plane = (size_t)d.width * d.height;
-    uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0;
-    *reinterpret_cast<uint4 *>(oy) = make_uint4(wy[0], wy[1], wy[2], wy[3]);
-    *reinterpret_cast<uint4 *>(oy + plane) = make_uint4(wu[0], wu[1], wu[2], wu[3]);
-    *reinterpret_cast<uint4 *>(oy + 2 * plane) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-    return;
+// NW words to `nbytes` bytes at any address: 16-byte stores when the address allows and all bytes are wanted,
+// 4-byte stores when it is word aligned, bytes otherwise (and for the tail).
+template <int NW>
+__device__ __forceinline__ void store_any(uint8_t *dst, const uint32_t (&w)[NW], int nbytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+  if ((a & 15u) == 0 && nbytes == NW * 4) {
+#pragma unroll
+    for (int k = 0; k < NW / 4; k++) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  } else if ((a & 3u) == 0) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+      if (4 * k + 4 <= nbytes) {
+        reinterpret_cast<uint32_t *>(dst)[k] = w[k];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (4 * k + i < nbytes) dst[4 * k + i] = (uint8_t)(w[k] >> (8 * i));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (4 * k + i < nbytes) dst[4 * k + i] = (uint8_t)(w[k] >> (8 * i));
+  }
+}
+// 16 bytes from an 8-byte aligned address
+__device__ __forceinline__ void load16(const uint8_t *p, uint32_t (&w)[4]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+  } else {
+    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(p)), c = __ldg(reinterpret_cast<const uint2 *>(p) + 1);
+    w[0] = a.x, w[1] = a.y, w[2] = c.x, w[3] = c.y;
+  }
+}
+
+// The sub-sampled group of k_rgb.  EDGE: the group is the short last one of its row (or touches the odd last column):
+// only then are neighbours replicated inside the group and samples past the chroma plane zeroed.  Returns true if
+// it has stored the pixels (RGB24), false if the caller stores the planar words.
+template <bool PLANAR, bool EDGE>
+__device__ __forceinline__ bool rgb_sub_group(const DecodeBatchDev &b, const HcjImageDesc &d, const uint8_t *pu, const uint8_t *pv, int su,
+                                              int sv, int cw, int chh, int vs_log, int x0, int y, int n, const uint32_t (&wy)[4],
+                                              uint32_t (&wu)[4], uint32_t (&wv)[4]) {
+  const int cy = y >> vs_log, cx0 = x0 >> 1;
+  const bool below = cy >= chh;  // odd height: no chroma row for the last luma row
+  const bool oy = vs_log && (y & 1);
+  const int cy1 = min(cy + 1, chh - 1), cx8 = max(min(cx0 + 8, cw - 1), 0);
+  int cu[2][9], cv[2][9];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int row = r ? cy1 : cy;
+    uint2 a = make_uint2(0u, 0u), c = make_uint2(0u, 0u);
+    int a8 = 0, c8 = 0;
+    if (!below && (r == 0 || oy)) {
+      a = __ldg(reinterpret_cast<const uint2 *>(pu + (size_t)row * su + cx0));
+      c = __ldg(reinterpret_cast<const uint2 *>(pv + (size_t)row * sv + cx0));
+      a8 = __ldg(pu + (size_t)row * su + cx8);
+      c8 = __ldg(pv + (size_t)row * sv + cx8);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      cu[r][k] = (int)(((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xffu);
+      cv[r][k] = (int)(((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0xffu);
+    }
+    cu[r][8] = a8;
+    cv[r][8] = c8;
+    if (EDGE)
+#pragma unroll
+      for (int k = 1; k < 8; k++)  // a short last group: the neighbour to the right of the last sample is that sample
+        if (cx0 + k > cw - 1) cu[r][k] = cu[r][k - 1], cv[r][k] = cv[r][k - 1];
   }
   uint32_t o[12];
 #pragma unroll
   for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
     uint32_t px[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, (wu[k] >> (8 * i)) & 0xff, (wv[k] >> (8 * i)) & 0xff);
-    o[3 * k + 0] = px[0] | (px[1] << 24);
-    o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
-    o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    for (int j = 0; j < 4; j++) {
+      const int i = 4 * k + j, cpos = i >> 1;
+      int Cb, Cr;
+      if (!oy) {
+        Cb = (i & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + 1) >> 1 : cu[0][cpos];
+        Cr = (i & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + 1) >> 1 : cv[0][cpos];
+      } else {
+        Cb = (i & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + cu[1][cpos] + cu[1][cpos + 1] + 2) >> 2 : (cu[0][cpos] + cu[1][cpos] + 1) >> 1;
+        Cr = (i & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + cv[1][cpos] + cv[1][cpos + 1] + 2) >> 2 : (cv[0][cpos] + cv[1][cpos] + 1) >> 1;
+      }
+      if (EDGE && cx0 + cpos >= cw) Cb = Cr = 0;  // odd width: the last luma column has no chroma sample
+      if (PLANAR) {
+        wu[k] |= (uint32_t)Cb << (8 * j);
+        wv[k] |= (uint32_t)Cr << (8 * j);
+      } else {
+        px[j] = ycc_to_rgb((wy[k] >> (8 * j)) & 0xff, Cb, Cr);  // straight from the interpolated values
+      }
+    }
+    if (!PLANAR) {
+      o[3 * k + 0] = px[0] | (px[1] << 24);
+      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
   }
-  uint4 *d4 = reinterpret_cast<uint4 *>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3);
-  d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-  d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+  if (!PLANAR) {
+    store_any<12>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3, o, 3 * n);
+    return true;
+  }
+  return false;
 }
 
-// Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16).  Images whose rows keep 16-byte alignment
-// (width a multiple of 16; for PLANAR also width * height) work in registers: one 16-byte load per plane for 4:4:4,
-// and for 4:2:0 / 4:2:2 the 16 luma samples plus the 9 chroma samples (of one or two rows) they need, with
-// Planar_444's interpolation on those - the neighbours clamped at the cropped plane's edge, where avg2 (a, a) = a and
-// avg4 (a, a, c, c) = avg2 (a, c) are the model's edge cases; past the last chroma row of an odd-height image the
-// 4:4:4 plane is still zero.  Everything else goes pixel by pixel through up_sample.
+// Each thread converts 16 horizontally adjacent pixels (x0 a multiple of 16; the last group of a row may be short) in
+// registers: 16 bytes per plane for 4:4:4; for 4:2:0 / 4:2:2 the 16 luma samples plus the 9 chroma samples (of one or
+// two rows) they need, with Planar_444's interpolation on those - the neighbours clamped at the cropped plane's
+// edge, where avg2 (a, a) = a and avg4 (a, a, c, c) = avg2 (a, c) are the model's edge cases; past the last chroma
+// row / column of an odd-sized image the 4:4:4 plane is still zero.  The padded planes keep every row 8-byte
+// aligned, so the loads are always vector loads; the stores adapt to the alignment of the output row (store_any).
 // Two instances per output format, one for 4:4:4 images and one for sub-sampled ones (SUB), each skipping the other's
 // images: the 4:4:4 path needs far fewer registers, and a batch is normally of one kind (launch_rgb starts only
-// the instances the batch needs).
+// the instances the batch needs).  (Planes that are not 8-byte aligned - never produced by the library - go pixel by
+// pixel through up_sample.)
 template <bool PLANAR, bool SUB>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
-__global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
+__global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
   if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB) return;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
@@ -1664,84 +1744,44 @@ __global__ void __launch_bounds__(128) k_rgb(DecodeBatchDev b) {
                 *pv = b.planes + d.comp[2].plane_off;
   const int sy = d.comp[0].decoded_w, su = d.comp[1].decoded_w, sv = d.comp[2].decoded_w;
   const int hs_log = d.chroma == 444 ? 0 : 1, vs_log = d.chroma == 420 ? 1 : 0;
-  const bool rows16 = ((d.width | sy) & 15) == 0 && (((uintptr_t)py | (uintptr_t)(b.out + d.out_off)) & 15u) == 0 &&
-                      (!PLANAR || (((size_t)d.width * d.height) & 15u) == 0);
-  if (!SUB && rows16 && !hs_log && ((su | sv) & 15) == 0 && (((uintptr_t)pu | (uintptr_t)pv) & 15u) == 0) {
-    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
-    const uint4 vu = __ldg(reinterpret_cast<const uint4 *>(pu + (size_t)y * su + x0));
-    const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pv + (size_t)y * sv + x0));
-    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w}, wv[4] = {vv.x, vv.y, vv.z, vv.w};
-    rgb_store16<PLANAR>(b, d, x0, y, wy, wu, wv);
-    return;
-  }
   const int cw = d.comp[1].actual_w, chh = d.comp[1].actual_h;
-  if (SUB && rows16 && hs_log && ((su | sv) & 7) == 0 && d.comp[2].actual_w == cw && d.comp[2].actual_h == chh && cw * 2 >= d.width &&
-      (((uintptr_t)pu | (uintptr_t)pv) & 7u) == 0) {
-    const uint4 vy = __ldg(reinterpret_cast<const uint4 *>(py + (size_t)y * sy + x0));
-    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w};
-    const int cy = y >> vs_log, cx0 = x0 >> 1;
-    const bool below = cy >= chh;  // odd height: no chroma row for the last luma row
-    const bool oy = vs_log && (y & 1);
-    const int cy1 = min(cy + 1, chh - 1), cx8 = min(cx0 + 8, cw - 1);
-    int cu[2][9], cv[2][9];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int row = r ? cy1 : cy;
-      uint2 a = make_uint2(0u, 0u), c = make_uint2(0u, 0u);
-      int a8 = 0, c8 = 0;
-      if (!below && (r == 0 || oy)) {
-        a = __ldg(reinterpret_cast<const uint2 *>(pu + (size_t)row * su + cx0));
-        c = __ldg(reinterpret_cast<const uint2 *>(pv + (size_t)row * sv + cx0));
-        a8 = __ldg(pu + (size_t)row * su + cx8);
-        c8 = __ldg(pv + (size_t)row * sv + cx8);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        cu[r][k] = (int)(((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xffu);
-        cv[r][k] = (int)(((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0xffu);
-      }
-      cu[r][8] = a8;
-      cv[r][8] = c8;
+  const int n = min(16, d.width - x0);  // pixels of this group
+  const bool aligned8 = ((sy | su | sv) & 7) == 0 && (((uintptr_t)py | (uintptr_t)pu | (uintptr_t)pv) & 7u) == 0 &&
+                        d.comp[2].actual_w == cw && d.comp[2].actual_h == chh;
+  uint32_t wy[4], wu[4] = {0u, 0u, 0u, 0u}, wv[4] = {0u, 0u, 0u, 0u};
+  if (aligned8 && (!SUB ? !hs_log : (hs_log && su * 2 >= sy && sv * 2 >= sy))) {
+    load16(py + (size_t)y * sy + x0, wy);
+    if (!SUB) {
+      load16(pu + (size_t)y * su + x0, wu);
+      load16(pv + (size_t)y * sv + x0, wv);
+    } else {
+      const bool edge = n < 16 || ((x0 + 15) >> 1) > cw - 1;
+      if (edge ? rgb_sub_group<PLANAR, true>(b, d, pu, pv, su, sv, cw, chh, vs_log, x0, y, n, wy, wu, wv)
+               : rgb_sub_group<PLANAR, false>(b, d, pu, pv, su, sv, cw, chh, vs_log, x0, y, n, wy, wu, wv))
+        return;
     }
-    uint32_t wu[4] = {0u, 0u, 0u, 0u}, wv[4] = {0u, 0u, 0u, 0u}, o[12];
+    if (PLANAR) {
+      const size_t plane = (size_t)d.width * d.height;
+      uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0;
+      store_any<4>(oy, wy, n);
+      store_any<4>(oy + plane, wu, n);
+      store_any<4>(oy + 2 * plane, wv, n);
+      return;
+    }
+    uint32_t o[12];
 #pragma unroll
     for (int k = 0; k < 4; k++) {  // 4 pixels -> 12 bytes = 3 words
       uint32_t px[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int n = 4 * k + i, cpos = n >> 1;
-        int Cb, Cr;
-        if (!oy) {
-          Cb = (n & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + 1) >> 1 : cu[0][cpos];
-          Cr = (n & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + 1) >> 1 : cv[0][cpos];
-        } else {
-          Cb = (n & 1) ? (cu[0][cpos] + cu[0][cpos + 1] + cu[1][cpos] + cu[1][cpos + 1] + 2) >> 2 : (cu[0][cpos] + cu[1][cpos] + 1) >> 1;
-          Cr = (n & 1) ? (cv[0][cpos] + cv[0][cpos + 1] + cv[1][cpos] + cv[1][cpos + 1] + 2) >> 2 : (cv[0][cpos] + cv[1][cpos] + 1) >> 1;
-        }
-        if (PLANAR) {
-          wu[k] |= (uint32_t)Cb << (8 * i);
-          wv[k] |= (uint32_t)Cr << (8 * i);
-        } else {
-          px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, Cb, Cr);
-        }
-      }
-      if (!PLANAR) {
-        o[3 * k + 0] = px[0] | (px[1] << 24);
-        o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
-        o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
-      }
+      for (int i = 0; i < 4; i++)
+        px[i] = ycc_to_rgb((wy[k] >> (8 * i)) & 0xff, (wu[k] >> (8 * i)) & 0xff, (wv[k] >> (8 * i)) & 0xff);
+      o[3 * k + 0] = px[0] | (px[1] << 24);
+      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
     }
-    if (PLANAR) {
-      rgb_store16<true>(b, d, x0, y, wy, wu, wv);
-    } else {
-      uint4 *d4 = reinterpret_cast<uint4 *>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3);
-      d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-      d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-    }
+    store_any<12>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3, o, 3 * n);
     return;
   }
-  const int n = min(16, d.width - x0);
   if (PLANAR) {
     const size_t plane = (size_t)d.width * d.height;
     uint8_t *oy = b.out + d.out_off + (size_t)y * d.width + x0, *ou = oy + plane, *ov = ou + plane;
