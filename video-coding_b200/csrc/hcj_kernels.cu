@@ -1635,11 +1635,25 @@ __device__ __forceinline__ void store_any(uint8_t *dst, const uint32_t (&w)[NW],
       }
     }
   } else {
+    // not word aligned: up to three head bytes, then the words of the byte sequence shifted by the head (funnel
+    // shifts over neighbouring words), then up to three tail bytes - instead of a byte store per byte
+    const int head = (4 - (int)(a & 3u)) & 3, sh = 8 * head;
 #pragma unroll
-    for (int k = 0; k < NW; k++)
+    for (int i = 0; i < 3; i++)
+      if (i < head && i < nbytes) dst[i] = (uint8_t)(w[0] >> (8 * i));
+    const int nw = nbytes > head ? (nbytes - head) >> 2 : 0;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+    uint32_t tail = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (4 * k + i < nbytes) dst[4 * k + i] = (uint8_t)(w[k] >> (8 * i));
+    for (int k = 0; k < NW; k++) {
+      const uint32_t v = __funnelshift_r(w[k], k + 1 < NW ? w[k + 1] : 0u, sh);  // bytes head + 4k .. head + 4k + 3
+      if (k < nw) d32[k] = v;
+      if (k == nw) tail = v;
+    }
+    const int done = head + 4 * nw;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      if (done + i < nbytes) dst[done + i] = (uint8_t)(tail >> (8 * i));
   }
 }
 // 16 bytes from an 8-byte aligned address
