@@ -1,12 +1,17 @@
 """Randomised GPU parity sweeps: seeded geometry / content / corruption, every result bit-exact against the oracle
 (decoded frames, statuses, coefficient taps, encoded files).  The cases are drawn from one PCG64 stream per test, so a
-failure reproduces from the printed case."""
+failure reproduces from the printed case.  HCJ_FUZZ_SEED (default 0) shifts every stream: `tools/fuzz_soak.sh` walks
+it for a soak run on a GPU box."""
+import os
+
 import numpy as np
 import pytest
 
 import synth
 
 pytestmark = pytest.mark.gpu
+
+SEED = int(os.environ.get("HCJ_FUZZ_SEED", "0"))
 
 
 @pytest.fixture(scope="module")
@@ -70,7 +75,7 @@ def encode_cases(orc, rng, cases):
 
 
 def test_fuzz_decode_all_modes(hcj, ctx, orc):
-    rng = np.random.default_rng(20261018)
+    rng = np.random.default_rng(20261018 + SEED)
     cases, jpgs = encode_cases(orc, rng, random_cases(rng, 120))
     # (a restart interval of <= 16 bits makes the model's `show` bound observable: status -9, also a defined result)
     want_st = [orc.decode_status(j) for j in jpgs]
@@ -93,7 +98,7 @@ def test_fuzz_decode_all_modes(hcj, ctx, orc):
 
 
 def test_fuzz_coefficients(hcj, ctx, orc):
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(7 + SEED)
     cases, jpgs = encode_cases(orc, rng, random_cases(rng, 40, 200, 120))
     with ctx.batch(jpgs, hcj.OUT_PLANES) as b:
         b.decode()
@@ -107,7 +112,7 @@ def test_fuzz_coefficients(hcj, ctx, orc):
 def test_fuzz_corrupt_streams(hcj, ctx, orc):
     """Byte flips, insertions and cuts in the entropy-coded segment: the model mostly decodes garbage without raising;
     whatever the oracle does (frame or status), the library does, image by image."""
-    rng = np.random.default_rng(99)
+    rng = np.random.default_rng(99 + SEED)
     cases, good = encode_cases(orc, rng, random_cases(rng, 60, 160, 120))
     bad = []
     for j in good:
@@ -135,7 +140,7 @@ def test_fuzz_corrupt_streams(hcj, ctx, orc):
 
 
 def test_fuzz_encode(hcj, ctx, orc):
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + SEED)
     for _ in range(40):
         chroma = int(rng.choice([420, 422, 444]))
         w, h = int(rng.integers(2, 260)), int(rng.integers(2, 180))
