@@ -211,7 +211,9 @@ int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const ui
  * geometry.  yuv[i]: planar Y,U,V as Frame.input reads it (frame.ml:72-76).  chroma: 420/422/444, or 400 for
  * encode_monochrome (one plane of width * height bytes; like the model, the plane is copied into its padded
  * plane linearly, so a width that is not a multiple of 8 shears the image: Plane.blit, plane.ml:20).
- * restart_interval 0 reproduces the model byte-for-byte; >0 is the stated DRI/RSTn extension. */
+ * restart_interval 0 reproduces the model byte-for-byte; >0 is the stated DRI/RSTn extension.
+ * out_len[i] is the length of frame i's file whether or not it fitted: with HCJ_ERR_BUFFER_TOO_SMALL in status[i] it is
+ * the capacity a second call needs (hcj_encode_bound is the bound that never fails). */
 int hcj_encode_batch(hcj_ctx *ctx, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
                      int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
                      int *status);

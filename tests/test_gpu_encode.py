@@ -90,6 +90,25 @@ def test_extreme_content(hcj, ctx, orc):
             assert o == orc.encode(f, w, h, 444, q), q
 
 
+def test_dense_frame_exceeds_default_capacity(hcj, ctx, orc):
+    """Saturated noise, 4:4:4, quality 100 is more than 3 bytes per pixel (found by tools/fuzz_soak.sh, seed 30): the C ABI
+    answers HCJ_ERR_BUFFER_TOO_SMALL with the length the frame needs, the front-end's default capacity retries at that size."""
+    w, h = 245, 137
+    rng = np.random.default_rng(30)
+    noise = bytes(rng.choice([0, 255], w * h * 3).astype(np.uint8))
+    flat = bytes(w * h * 3)
+    want = [orc.encode(f, w, h, 444, 100) for f in (noise, flat)]
+    assert len(want[0]) > w * h * 3 + (1 << 16)
+    assert len(want[0]) <= hcj.lib().hcj_encode_bound(w, h, 444)
+    outs, st = ctx.encode_batch([noise, flat], w, h, 444, 100)
+    assert st == [0, 0] and outs == want
+    outs, st = ctx.encode_batch([noise, flat], w, h, 444, 100, capacity=len(want[0]) - 1)
+    assert st == [-30, 0]  # HCJ_ERR_BUFFER_TOO_SMALL
+    assert outs[0] is None and outs[1] == want[1]
+    outs, st = ctx.encode_batch([noise], w, h, 444, 100, capacity=len(want[0]))
+    assert st == [0] and outs == want[:1]
+
+
 def test_plane_bounds_status(hcj, ctx, orc):
     """W = 17 at 4:2:0: per-component rounding disagrees and the model raises."""
     f = synth.frame(1, 17, 16, 420)

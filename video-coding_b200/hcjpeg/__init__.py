@@ -408,8 +408,9 @@ class Context:
     def encode_batch(self, frames, width, height, chroma=420, quality=75, restart_interval=0, capacity=None):
         """Encoder.encode_420/422/444 for every raw planar frame (bytes / uint8 arrays) in ``frames``."""
         n = len(frames)
-        if capacity is None:
-            capacity = width * height * 3 + (1 << 16)  # far above any real frame; hcj_encode_bound is the hard bound
+        auto = capacity is None
+        if auto:
+            capacity = width * height * 3 + (1 << 16)  # above any natural frame; hcj_encode_bound is the hard bound
         outs = [np.zeros(capacity, np.uint8) for _ in range(n)]
         fp, keep = _ptr_array(frames)
         op, keep2 = _ptr_array(outs)
@@ -421,7 +422,17 @@ class Context:
             "hcj_encode_batch",
         )
         st = [status[i] for i in range(n)]
-        return [outs[i][: lens[i]].tobytes() if st[i] == 0 else None for i in range(n)], st
+        res = [outs[i][: lens[i]].tobytes() if st[i] == 0 else None for i in range(n)]
+        # The default capacity is a guess (dense 4:4:4 content at quality 100 exceeds 3 bytes per pixel); the library
+        # reports the length a frame needs with HCJ_ERR_BUFFER_TOO_SMALL, so those frames go through once more at that size.
+        redo = [i for i in range(n) if st[i] == -30] if auto else []
+        if redo:
+            again, st2 = self.encode_batch(
+                [frames[i] for i in redo], width, height, chroma, quality, restart_interval, capacity=max(lens[i] for i in redo)
+            )
+            for i, o, s2 in zip(redo, again, st2):
+                res[i], st[i] = o, s2
+        return res, st
 
     def encode_quantized(self, frame, width, height, chroma=420, quality=75):
         """Block.quant of every block in encode_seq order (encoder.ml:56-66)."""
