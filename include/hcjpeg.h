@@ -156,6 +156,16 @@ typedef enum hcj_out_mode {
 int hcj_decode_batch(hcj_ctx *ctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode, unsigned flags,
                      uint8_t *const *out, const size_t *out_capacity, int *status);
 
+/* One process, several GPUs (the model's callers are single processes: jpeg/bin/model.ml:29-44).  Images are
+ * independent (decoder.ml:422-427), so context k - one per device, all distinct - decodes the contiguous index range
+ * hcj_shard_range(n, k, nctx) on its own host thread with its own streams; no data moves between devices.  Arguments
+ * and results as hcj_decode_batch; returns the first failing context's code. */
+int hcj_decode_batch_multi(hcj_ctx *const *ctx, int nctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode,
+                           unsigned flags, uint8_t *const *out, const size_t *out_capacity, int *status);
+/* [*lo, *hi) = the batch indices part `part` of `nparts` handles: floor(n part / nparts) .. floor(n (part + 1) / nparts). */
+void hcj_shard_range(int n, int part, int nparts, int *lo, int *hi);
+int hcj_device_count(void); /* CUDA devices visible to the process (0 without a driver) */
+
 /* Decoder.decode_a_frame (decoder.ml:422-427) for one image: a batch of one; returns the image's status. */
 int hcj_decode_a_frame(hcj_ctx *ctx, const uint8_t *jpeg, size_t len, int mode, unsigned flags, uint8_t *out, size_t out_capacity);
 
@@ -217,6 +227,10 @@ int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const ui
 int hcj_encode_batch(hcj_ctx *ctx, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
                      int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
                      int *status);
+/* The same over several GPUs from one process: context k encodes frames hcj_shard_range(n, k, nctx) (see hcj_decode_batch_multi). */
+int hcj_encode_batch_multi(hcj_ctx *const *ctx, int nctx, const uint8_t *const *yuv, int n, int width, int height, int chroma,
+                           int quality, int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
+                           int *status);
 size_t hcj_encode_bound(int width, int height, int chroma); /* worst-case bytes of one encoded frame */
 /* Encoder.write_headers (encoder.ml:371-418).  Host only. */
 int hcj_write_headers(int width, int height, int chroma, int quality, int restart_interval, uint8_t *out,
@@ -224,6 +238,27 @@ int hcj_write_headers(int width, int height, int chroma, int quality, int restar
 /* Block.quant (encoder.ml:56-66): quantised zig-zag blocks of one frame in encode_seq order. */
 int hcj_encode_quantized(hcj_ctx *ctx, const uint8_t *yuv, int width, int height, int chroma, int quality,
                          int16_t *quant, size_t capacity_blocks);
+
+/* `model encode log [-verbose]` (jpeg/bin/model.ml:108-142): Encoder.Block.t (encoder.ml:56-66) of blocks
+ * [first_block, first_block + count) of one frame in encode_seq order (encoder.ml:476-505), computed on the device
+ * with the model's arithmetic; the reconstruction (Block.decoded, encoder.ml:37-55,110-125) is always filled. */
+typedef struct hcj_encoder_block {
+  int32_t x_pos, y_pos;      /* origin of the block in its component's padded plane (encoder.ml:486-489) */
+  int32_t dc_pred;           /* the component's predictor after the block (= quant[0]) */
+  int32_t component;         /* scan component index */
+  int32_t nrle;              /* entries of rle_run / rle_value in use */
+  uint8_t input_pixels[64];  /* Block.input_pixels (before the level shift) */
+  int32_t fdct[64];          /* Dct.Chen.forward_8x8 of the level-shifted block, natural order (4 x the orthonormal DCT) */
+  int16_t quant[64];         /* zig-zag order, quant[0] absolute */
+  int16_t rle_run[64];       /* Block.rle (encoder.ml:127-141): entry 0 = { run = 0; value = DC differential }, */
+  int16_t rle_value[64];     /*   then the AC pairs; position 63 is always emitted (value 0 = end of block) */
+  int32_t dequant[64];       /* Decoded.dequant, natural order */
+  int32_t idct[64];          /* Decoded.idct */
+  uint8_t recon[64];         /* Decoded.recon = clamp (idct + 128) */
+  uint8_t error[64];         /* Decoded.error = |recon - input_pixels| */
+} hcj_encoder_block;
+int hcj_encode_block_log(hcj_ctx *ctx, const uint8_t *yuv, int width, int height, int chroma, int quality, int restart_interval,
+                         size_t first_block, size_t count, hcj_encoder_block *out);
 
 /* Scalar helpers the reference exposes for its tests, evaluated on the host by the same functions the kernels call:
  * Decoder.For_testing.mag (decoder.mli:64-65, decoder.ml:73-79: signed value of `cat` magnitude bits `code`),

@@ -552,3 +552,79 @@ def test_speculative_many_subsequences_and_rounds(hcj, ctx, orc):
     assert st == [0] * len(jpgs)
     for j, o in zip(jpgs, outs):
         assert bytes(o) == orc.decode(j).yuv()
+
+
+def test_rgb_colour_vs_pillow(hcj, ctx, orc):
+    """D13 on the device: the RGB24 output of 4:4:4 images against Pillow's YCbCr -> RGB applied to the device's own
+    planar 4:4:4 output of the same images: +-1 (an independent colour conversion; the oracle's formula is pinned the
+    same way over the whole cube in test_oracle_goldens.py), and exact against the oracle's stated formula."""
+    Image = pytest.importorskip("PIL.Image")
+    w, h = 200, 120
+    jpgs = [orc.encode(synth.frame(700 + i, w, h, c), w, h, c, q) for i, (c, q) in enumerate(((444, 95), (444, 40), (420, 75), (422, 75)))]
+    rgb, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
+    yuv, st2 = ctx.decode_batch(jpgs, hcj.OUT_YUV444)
+    assert st == [0] * 4 and st2 == [0] * 4
+    for r, p in zip(rgb, yuv):
+        planes = [Image.fromarray(p[k * w * h:(k + 1) * w * h].reshape(h, w)) for k in range(3)]
+        pil = np.asarray(Image.merge("YCbCr", planes).convert("RGB")).astype(np.int32)
+        assert np.abs(r.reshape(h, w, 3).astype(np.int32) - pil).max() <= 1
+        y, u, v = (p[k * w * h:(k + 1) * w * h].reshape(h, w) for k in range(3))
+        assert np.array_equal(r.reshape(h, w, 3), orc.ycbcr_to_rgb24(y, u, v))
+
+
+def test_single_image_truncated_at_sos(hcj, ctx, orc, data):
+    """A file that ends right after its SOS header has a scan of zero bytes: no terminator, alone in a batch or not."""
+    jpg = data("mini.jpg")
+    cut = hcj.header_decode(jpg).scan_byte_pos
+    short = jpg[:cut]
+    _, st1 = ctx.decode_batch([short])
+    _, st2 = ctx.decode_batch([jpg, short, jpg])
+    assert st1 == [-20] and st2 == [0, -20, 0]
+    assert orc.decode_status(short) == -20
+
+
+def test_two_contexts_in_one_process(hcj, ctx, orc):
+    """hcj_decode_batch_multi / hcj_encode_batch_multi: images sharded by index over several contexts of one process, a
+    host thread per context (here on one device when only one is present: the contexts are still independent)."""
+    ndev = max(1, hcj.device_count())
+    ctxs = [hcj.Context(k % ndev) for k in range(max(2, ndev))]
+    try:
+        w, h = 160, 96
+        frames = [synth.frame(800 + i, w, h, 420) for i in range(11)]
+        jpgs, st = hcj.encode_batch_multi(ctxs, frames, w, h, 420, 75, 0)
+        assert st == [0] * 11
+        for f, j in zip(frames, jpgs):
+            assert j == orc.encode(f, w, h, 420, 75)
+        jr, _ = ctx.encode_batch(frames[:5], w, h, 420, 75, 4)
+        batch = jpgs + jr + [b"\xff\xd8garbage"]
+        outs, st = hcj.decode_batch_multi(ctxs, batch)
+        assert st[:-1] == [0] * 16 and st[-1] != 0
+        for j, o in zip(batch[:-1], outs):
+            assert bytes(o) == orc.decode(j).yuv()
+        lo_hi = [hcj.shard_range(len(batch), k, len(ctxs)) for k in range(len(ctxs))]
+        assert lo_hi[0][0] == 0 and lo_hi[-1][1] == len(batch) and all(a[1] == b[0] for a, b in zip(lo_hi, lo_hi[1:]))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_multi_gpu_contexts(hcj, orc):
+    """The same across real devices (skipped below 2 GPUs): per-device kernel attributes and SM counts."""
+    if hcj.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctxs = [hcj.Context(k) for k in range(hcj.device_count())]
+    try:
+        w, h = 256, 160
+        frames = [synth.frame(820 + i, w, h, 420) for i in range(4 * len(ctxs))]
+        for ri in (0, 8):
+            jpgs, st = hcj.encode_batch_multi(ctxs, frames, w, h, 420, 75, ri)
+            assert not any(st)
+            outs, st = hcj.decode_batch_multi(ctxs, jpgs, hcj.OUT_RGB24)
+            assert not any(st)
+            for j, o in zip(jpgs, outs):
+                d = orc.decode(j)
+                y, u, v = orc.upsample_to_444(d.cropped, 420)
+                assert np.array_equal(o.reshape(h, w, 3), orc.ycbcr_to_rgb24(y, u, v))
+    finally:
+        for c in ctxs:
+            c.close()

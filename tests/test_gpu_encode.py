@@ -183,3 +183,58 @@ def test_chen_example_on_device(hcj, ctx, goldens):
     assert nat.tolist() == g["fdct"]
     recon = ctx.idct_blocks(quant[:1], np.ones(64, np.uint16))
     assert recon[0].tolist() == (np.clip(np.array(g["idct"]), -128, 127) + 128).tolist()
+
+
+@pytest.mark.parametrize("case", [(420, 75, 80, 48, 0), (422, 40, 72, 40, 0), (444, 95, 33, 17, 0), (420, 75, 64, 64, 3), (400, 60, 43, 29, 0)])
+def test_encode_block_log(hcj, ctx, orc, case):
+    """`model encode log -verbose`: Encoder.Block.t of every block (x_pos, y_pos, input_pixels, fdct, quant, dc_pred, rle,
+    decoded) against the oracle's per-block taps and the oracle's rle / inverse transform."""
+    chroma, q, w, h, ri = case
+    f = synth.frame(40, w, h, 444)[: w * h] if chroma == 400 else synth.frame(40, w, h, chroma)
+    _, quant, fdct = orc.encode(f, w, h, chroma, q, restart_interval=ri, want_blocks=True)
+    log = ctx.encode_block_log(f, w, h, chroma, q, ri)
+    assert len(log) == len(quant)
+    assert np.array_equal(log["quant"], quant.astype(np.int16))
+    assert np.array_equal(log["fdct"], fdct)
+    info = hcj.frame_info(orc.encode(f, w, h, chroma, q, restart_interval=ri))
+    bpm, ncomp = info.blocks_per_mcu, info.ncomp
+    order = [(c, bx, by) for c in range(ncomp) for by in range(info.vs[c]) for bx in range(info.hs[c])]
+    qts = [orc.quant_scale(False, q)] + [orc.quant_scale(True, q)] * 2
+    preds = [0] * ncomp
+    planes = orc.split_yuv(f, w, h, chroma)
+    for i, b in enumerate(log):
+        mcu, k = divmod(i, bpm)
+        c, bx, by = order[k]
+        my, mx = divmod(mcu, info.mcus_wide)
+        assert (b["component"], b["x_pos"], b["y_pos"]) == (c, (mx * info.hs[c] + bx) * 8, (my * info.vs[c] + by) * 8)
+        if ri and k == 0 and mcu % ri == 0:
+            preds = [0] * ncomp
+        pairs, preds[c] = orc.rle(quant[i], preds[c])
+        n = len(pairs)
+        assert b["nrle"] == n and list(zip(b["rle_run"][:n].tolist(), b["rle_value"][:n].tolist())) == pairs, i
+        assert b["dc_pred"] == preds[c] == int(quant[i][0])
+        # input pixels: the zero-padded plane (linear blit for monochrome)
+        src = np.asarray(planes[c])
+        ph, pw = info.decoded_height[c], info.decoded_width[c]
+        padded = np.zeros((ph, pw), np.uint8)
+        if chroma == 400:
+            padded.reshape(-1)[: src.size] = src.reshape(-1)
+        else:
+            padded[: src.shape[0], : src.shape[1]] = src
+        blk = padded[b["y_pos"]: b["y_pos"] + 8, b["x_pos"]: b["x_pos"] + 8].reshape(64)
+        assert np.array_equal(b["input_pixels"], blk)
+        # Block.decoded
+        zz = np.array(ZIGZAG_INVERSE)
+        deq = np.zeros(64, np.int64)
+        deq[zz] = quant[i].astype(np.int64) * np.asarray(qts[c], np.int64)
+        assert np.array_equal(b["dequant"], deq)
+        idct = orc.chen_inverse(deq)
+        assert np.array_equal(b["idct"], idct)
+        rec = np.clip(np.asarray(idct) + 128, 0, 255)
+        assert np.array_equal(b["recon"], rec)
+        assert np.array_equal(b["error"], np.abs(rec - blk.astype(np.int64)))
+
+
+ZIGZAG_INVERSE = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47,
+                  55, 62, 63]

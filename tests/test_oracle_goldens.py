@@ -319,3 +319,21 @@ def test_oracle_against_independent_decoder(orc, data):
         ref = np.asarray(im).astype(np.int32)
         y = orc.decode(j).cropped[0].astype(np.int32)
         assert np.abs(y - ref[:, :, 0]).max() <= 1
+
+
+def test_rgb_formula_pinned_by_pillow_and_opencv(orc):
+    """D13: YCbCr -> RGB is absent from the reference, so the stated formula (JFIF full range, libjpeg's
+    16-bit constants) is pinned against two independent implementations over the WHOLE (Y, Cb, Cr) cube: Pillow's
+    YCbCr -> RGB conversion and OpenCV's COLOR_YCrCb2RGB agree with it to +-1 everywhere (SURVEY 8c ii)."""
+    Image = pytest.importorskip("PIL.Image")
+    cv2 = pytest.importorskip("cv2")
+    cb, cr = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    worst_pil = worst_cv = 0
+    for y in range(256):
+        Y = np.full_like(cb, y)
+        got = orc.ycbcr_to_rgb24(Y, cb, cr).astype(np.int32)
+        pil = np.asarray(Image.merge("YCbCr", [Image.fromarray(Y), Image.fromarray(cb), Image.fromarray(cr)]).convert("RGB"))
+        ocv = cv2.cvtColor(np.dstack([Y, cr, cb]), cv2.COLOR_YCrCb2RGB)
+        worst_pil = max(worst_pil, int(np.abs(got - pil.astype(np.int32)).max()))
+        worst_cv = max(worst_cv, int(np.abs(got - ocv.astype(np.int32)).max()))
+    assert worst_pil <= 1 and worst_cv <= 1, (worst_pil, worst_cv)

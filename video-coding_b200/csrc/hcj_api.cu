@@ -105,6 +105,13 @@ int hcj_ctx_create(int device, void *cuda_stream, hcj_ctx **out) {
   hcj_ctx *c = new (std::nothrow) hcj_ctx;
   if (!c) return HCJ_ERR_OUT_OF_MEMORY;
   c->device = device;
+  {
+    const int ce = hcjk::configure_device(&c->sm_count);
+    if (ce != 0) {
+      delete c;
+      return HCJ_ERR_CUDA - ce;
+    }
+  }
   if (cuda_stream) {
     c->stream = (cudaStream_t)cuda_stream;
   } else {
@@ -283,6 +290,8 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       for (int i = lo; i < hi; i++) {
         int st = (jpeg[i] && len[i] < 0xfffffff0u) ? hcj::header_decode(jpeg[i], len[i], &hdrs[i], flags, false) : HCJ_ERR_INVALID_ARG;
         if (st == HCJ_OK) st = hcj::plan_image(hdrs[i], flags, &plans[i]);
+        // bit positions inside a scan are 32-bit on the device: scans of 512 MiB and more are outside the domain
+        if (st == HCJ_OK && len[i] - std::min<size_t>(len[i], (size_t)hdrs[i].scan_byte_pos) >= ((size_t)1 << 29)) st = HCJ_ERR_UNSUPPORTED_GEOMETRY;
         parse_st[i] = st;
       }
     };
@@ -548,6 +557,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     }
   }
   dv.n = n;
+  dv.sm_count = c->sm_count;
   dv.descs = d_descs;
   dv.files = d_files;
   dv.table_sets = d_sets;
@@ -753,7 +763,7 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       e = upload_files(b, jpeg, len, bound[k], bound[k + 1], us);
       if (e == cudaSuccess) e = cudaEventRecord(c->up_events[k], us);
     }
-    e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * n, s);
     const int kmode = mode == HCJ_OUT_YUV ? 0 : mode == HCJ_OUT_PLANES ? 1 : 2;
     size_t lr = 0, ls = 0;
@@ -812,6 +822,8 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
     if (e == cudaSuccess) {
       int r = fetch_states(c, b, &states);
       if (r != HCJ_OK) {
+        cudaStreamSynchronize(us);
+        cudaStreamSynchronize(cs);
         hcj_batch_destroy(c, b);
         return r;
       }
@@ -823,9 +835,60 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
   }
   if (status)
     for (int i = 0; i < n; i++) status[i] = host_st[i];
+  if (e != cudaSuccess) {  // copies may still be reading the caller's files / writing the caller's frames
+    cudaStreamSynchronize(us);
+    cudaStreamSynchronize(cs);
+  }
   hcj_batch_destroy(c, b);
   mark("batch released");
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
+}
+
+int hcj_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void hcj_shard_range(int n, int part, int nparts, int *lo, int *hi) {
+  if (nparts < 1) nparts = 1;
+  part = std::min(std::max(part, 0), nparts - 1);
+  if (lo) *lo = (int)((int64_t)n * part / nparts);
+  if (hi) *hi = (int)((int64_t)n * (part + 1) / nparts);
+}
+
+// One process, several GPUs (one hcj_ctx + host thread + CUDA stream set per device): images are
+// independent, so context k decodes the contiguous index range hcj_shard_range(n, k, nctx) with its own pipelined
+// hcj_decode_batch on its own host thread; nothing is exchanged between devices.
+int hcj_decode_batch_multi(hcj_ctx *const *ctx, int nctx, const uint8_t *const *jpeg, const size_t *len, int n, int mode,
+                           unsigned flags, uint8_t *const *out, const size_t *out_capacity, int *status) {
+  if (!ctx || nctx < 1 || n < 0 || (n > 0 && (!jpeg || !len || !out || !out_capacity))) return HCJ_ERR_INVALID_ARG;
+  for (int k = 0; k < nctx; k++)
+    if (!ctx[k]) return HCJ_ERR_INVALID_ARG;
+  for (int k = 0; k < nctx; k++)
+    for (int j = 0; j < k; j++)
+      if (ctx[k] == ctx[j]) return HCJ_ERR_INVALID_ARG;  // a context is not thread-safe
+  std::vector<int> rc((size_t)nctx, HCJ_OK);
+  auto work = [&](int k) {
+    int lo, hi;
+    hcj_shard_range(n, k, nctx, &lo, &hi);
+    rc[k] = hcj_decode_batch(ctx[k], jpeg + lo, len + lo, hi - lo, mode, flags, out + lo, out_capacity + lo, status ? status + lo : nullptr);
+  };
+  std::vector<std::thread> pool;
+  try {
+    for (int k = 1; k < nctx; k++) pool.emplace_back(work, k);
+  } catch (...) {
+    for (auto &t : pool) t.join();
+    return HCJ_ERR_OUT_OF_MEMORY;
+  }
+  work(0);
+  for (auto &t : pool) t.join();
+  for (int k = 0; k < nctx; k++)
+    if (rc[k] != HCJ_OK) return rc[k];
+  return HCJ_OK;
 }
 
 int hcj_batch_fetch_coefficients(hcj_ctx *c, hcj_batch *b, int i, int16_t *coefs, size_t capacity_blocks) {
@@ -945,6 +1008,10 @@ int hcj_decode_stream(hcj_ctx *c, const uint8_t *stream, size_t len, int mode, u
   }
   out_offsets[n] = acc;
   if (acc > out_capacity) return HCJ_ERR_BUFFER_TOO_SMALL;
+  // the slot of every frame but the last reaches to the next frame: hcj_decode_batch then merges consecutive frames
+  // into one device-to-host copy (it needs capacity >= the distance to the next frame in the device buffer)
+  for (int i = 0; i + 1 < n; i++)
+    if (cap[i]) cap[i] = out_offsets[i + 1] - out_offsets[i];
   for (int i = 0; i < n; i++) op[i] = out + out_offsets[i];
   return hcj_decode_batch(c, jp.data(), ln.data(), n, mode, flags, op.data(), cap.data(), status);
 }

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "hcj_device.cuh"
@@ -467,6 +468,91 @@ static void launch_entropy(const EncodeBatchDev &e, cudaStream_t s) {
   k_stuff<<<gs, 128, 0, s>>>(e);
 }
 
+// ---- debug tap: Encoder.Block.t of encode_seq (encoder.ml:56-66,195-205,476-505) -------------------
+// One thread per block; reads the quantised blocks k_fdct_quant has written (for the DC predictor) and recomputes
+// everything else of the block with the model's arithmetic, reconstruction included (Block.decoded, `-verbose`).
+struct EncodeBlockLog {  // = hcj_encoder_block (include/hcjpeg.h)
+  int32_t x_pos, y_pos, dc_pred, component, nrle;
+  uint8_t input_pixels[64];
+  int32_t fdct[64];
+  int16_t quant[64];
+  int16_t rle_run[64], rle_value[64];
+  int32_t dequant[64], idct[64];
+  uint8_t recon[64], error[64];
+};
+__global__ void k_encode_block_log(EncodeBatchDev e, uint32_t first, uint32_t count, EncodeBlockLog *out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint32_t blk = first + t;
+  const uint32_t mcu = blk / e.bpm, k = blk - mcu * e.bpm;
+  const int c = e.blk_comp[k];
+  const int my = mcu / e.mcus_wide, mx = mcu - my * e.mcus_wide;
+  const int x0 = (mx * e.hs[c] + e.blk_bx[k]) * 8, y0 = (my * e.vs[c] + e.blk_by[k]) * 8;  // encoder.ml:486-489
+  const uint8_t *src = e.src + e.src_off[c];
+  const int sw = e.src_w[c], sh = e.src_h[c], pw = e.plane_w[c];
+  const int64_t nsrc = (int64_t)sw * sh;
+  EncodeBlockLog &o = out[t];
+  o.x_pos = x0;
+  o.y_pos = y0;
+  o.component = c;
+  int32_t v[64];
+  for (int y = 0; y < 8; y++)
+    for (int x = 0; x < 8; x++) {  // level_shifted_input_block over the zero-initialised padded plane (encoder.ml:81-90)
+      int p;
+      if (e.linear_blit) {  // encode_monochrome: Plane.blit is one linear copy (encoder.ml:548, plane.ml:20)
+        const int64_t at = (int64_t)(y0 + y) * pw + (x0 + x);
+        p = at < nsrc ? (int)src[at] : 0;
+      } else {
+        p = (x0 + x < sw && y0 + y < sh) ? (int)src[(size_t)(y0 + y) * sw + x0 + x] : 0;
+      }
+      o.input_pixels[y * 8 + x] = (uint8_t)p;
+      v[y * 8 + x] = p - 128;
+    }
+  fdct_8x8(v);
+  const uint16_t *qt = e.qt + (c ? 64 : 0);
+  const uint32_t *qr = e.qrecip + (c ? 64 : 0);
+  int32_t q[64];
+  for (int i = 0; i < 64; i++) {
+    o.fdct[i] = v[i];
+    const int z = zigzag_forward(i);  // encoder.ml:103-108
+    q[z] = quantize(v[i], qt[z], qr[z]);
+  }
+  for (int z = 0; z < 64; z++) o.quant[z] = (int16_t)q[z];
+  // rle (encoder.ml:127-141): the DC differential first, position 63 always emitted
+  const int64_t pb = dc_pred_block(e, blk);
+  const int32_t pred = pb < 0 ? 0 : (int32_t)e.quant[(uint64_t)pb * 64];
+  int n = 0, run = 0;
+  o.rle_run[n] = 0;
+  o.rle_value[n++] = (int16_t)(q[0] - pred);
+  for (int pos = 1; pos < 64; pos++) {
+    if (pos == 63 || q[pos] != 0) {
+      o.rle_run[n] = (int16_t)run;
+      o.rle_value[n++] = (int16_t)q[pos];
+      run = 0;
+    } else {
+      run++;
+    }
+  }
+  o.nrle = n;
+  for (int i = n; i < 64; i++) o.rle_run[i] = o.rle_value[i] = 0;
+  o.dc_pred = q[0];
+  // Block.decoded (encoder.ml:110-125): dequant, idct, recon, error
+  int64_t w[64];
+  for (int z = 0; z < 64; z++) w[zigzag_inverse(z)] = (int64_t)q[z] * qt[z];
+  for (int i = 0; i < 64; i++) o.dequant[i] = (int32_t)w[i];
+  idct_8x8<int64_t>(w);
+  for (int i = 0; i < 64; i++) {
+    o.idct[i] = (int32_t)w[i];
+    const int64_t r = w[i] + 128 < 0 ? 0 : w[i] + 128 > 255 ? 255 : w[i] + 128;
+    o.recon[i] = (uint8_t)r;
+    const int d = (int)r - (int)o.input_pixels[i];
+    o.error[i] = (uint8_t)(d < 0 ? -d : d);
+  }
+}
+void launch_encode_block_log(const EncodeBatchDev &e, uint32_t first, uint32_t count, void *out, cudaStream_t s) {
+  if (count) k_encode_block_log<<<(count + 63) / 64, 64, 0, s>>>(e, first, count, reinterpret_cast<EncodeBlockLog *>(out));
+}
+
 }  // namespace hcjk
 
 // ================================================================================================
@@ -683,12 +769,71 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
   return err == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)err;
 }
 
+// The encoder mirror of hcj_decode_batch_multi: context k encodes frames hcj_shard_range(n, k, nctx) on its own host thread.
+int hcj_encode_batch_multi(hcj_ctx *const *ctx, int nctx, const uint8_t *const *yuv, int n, int width, int height, int chroma,
+                           int quality, int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
+                           int *status) {
+  if (!ctx || nctx < 1 || n < 0 || (n > 0 && (!yuv || !out || !out_capacity || !out_len))) return HCJ_ERR_INVALID_ARG;
+  for (int k = 0; k < nctx; k++) {
+    if (!ctx[k]) return HCJ_ERR_INVALID_ARG;
+    for (int j = 0; j < k; j++)
+      if (ctx[k] == ctx[j]) return HCJ_ERR_INVALID_ARG;
+  }
+  std::vector<int> rc((size_t)nctx, HCJ_OK);
+  auto work = [&](int k) {
+    int lo, hi;
+    hcj_shard_range(n, k, nctx, &lo, &hi);
+    rc[k] = hcj_encode_batch(ctx[k], yuv + lo, hi - lo, width, height, chroma, quality, restart_interval, out + lo, out_capacity + lo,
+                             out_len + lo, status ? status + lo : nullptr);
+  };
+  std::vector<std::thread> pool;
+  try {
+    for (int k = 1; k < nctx; k++) pool.emplace_back(work, k);
+  } catch (...) {
+    for (auto &t : pool) t.join();
+    return HCJ_ERR_OUT_OF_MEMORY;
+  }
+  work(0);
+  for (auto &t : pool) t.join();
+  for (int k = 0; k < nctx; k++)
+    if (rc[k] != HCJ_OK) return rc[k];
+  return HCJ_OK;
+}
+
 int hcj_encode_last_device_ms(hcj_ctx *c, float *ms) {
   if (!c || !ms) return HCJ_ERR_INVALID_ARG;
   if (!c->enc_timed) return HCJ_ERR_INVALID_ARG;
   CU_TRY(cudaEventSynchronize(c->enc1));
   CU_TRY(cudaEventElapsedTime(ms, c->enc0, c->enc1));
   return HCJ_OK;
+}
+
+int hcj_encode_block_log(hcj_ctx *c, const uint8_t *yuv, int width, int height, int chroma, int quality, int restart_interval,
+                         size_t first_block, size_t count, hcj_encoder_block *out) {
+  static_assert(sizeof(hcj_encoder_block) == sizeof(hcjk::EncodeBlockLog), "hcj_encode_block_log layout");
+  if (!c || !yuv || !out) return HCJ_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(c->device));
+  EncodeSetup S;
+  int st = setup_encode(c, 1, width, height, chroma, quality, restart_interval, false, &S);
+  if (st == HCJ_OK && (first_block > S.dev.nblocks || count > S.dev.nblocks - first_block)) st = HCJ_ERR_INVALID_ARG;
+  cudaError_t err = cudaSuccess;
+  void *d_out = nullptr;
+  if (st == HCJ_OK && count) st = c->alloc(&d_out, count * sizeof(hcj_encoder_block));
+  if (st == HCJ_OK && count) {
+    S.owned.push_back(d_out);
+    hcjk::EncodeBatchDev &e = S.dev;
+    err = cudaMemcpyAsync(const_cast<uint8_t *>(e.src), yuv, e.frame_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (err == cudaSuccess) {
+      hcjk::launch_encode(e, c->stream);  // Block.quant of every block: the DC predictors
+      hcjk::launch_encode_block_log(e, (uint32_t)first_block, (uint32_t)count, d_out, c->stream);
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out, d_out, count * sizeof(hcj_encoder_block), cudaMemcpyDeviceToHost, c->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  }
+  teardown_encode(c, &S);
+  if (st != HCJ_OK) return st;
+  return err == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)err;
 }
 
 int hcj_encode_quantized(hcj_ctx *c, const uint8_t *yuv, int width, int height, int chroma, int quality, int16_t *quant,

@@ -539,6 +539,8 @@ int plan_encode(int width, int height, int chroma, int quality, int restart_inte
   p->mcus_wide = p->plane_w[0] / (8 * p->hs[0]);  // encoder.ml:477-480
   p->mcus_high = p->plane_h[0] / (8 * p->vs[0]);
   p->nblocks = (int64_t)p->mcus_wide * p->mcus_high * bpm;
+  // bit offsets within a frame are 32-bit on the device: a block is at most 3456 bits (hcj_encode_bound)
+  if (p->nblocks * 3456 >= ((int64_t)1 << 32)) return HCJ_ERR_UNSUPPORTED_GEOMETRY;
   // encode_block reads through a bounds-checked Plane (encoder.ml:85): per-component rounding can
   // disagree for odd sizes and the model raises.
   for (int i = 0; i < p->ncomp; i++)

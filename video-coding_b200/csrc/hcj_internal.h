@@ -24,6 +24,7 @@ struct FreeBlock {
 
 struct hcj_ctx {
   int device = 0;
+  int sm_count = 148;  // of `device` (hcjk::configure_device)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -366,11 +366,12 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
 }
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
-  if (b.img_hi <= b.img_lo || b.max_ds_tiles == 0) return;
+  if (b.img_hi <= b.img_lo) return;
+  // the per-image scan always runs: it writes the image state (a scan of zero bytes has no terminator)
   const dim3 grid(b.max_ds_tiles, b.img_hi - b.img_lo);
-  k_destuff_count<<<grid, DS_THREADS, 0, s>>>(b);
+  if (b.max_ds_tiles) k_destuff_count<<<grid, DS_THREADS, 0, s>>>(b);
   k_destuff_scan<<<b.img_hi - b.img_lo, DS_THREADS, 0, s>>>(b);
-  k_destuff_write<<<grid, DS_THREADS, 0, s>>>(b);
+  if (b.max_ds_tiles) k_destuff_write<<<grid, DS_THREADS, 0, s>>>(b);
 }
 int destuff_kernel_count() { return 3; }
 
@@ -816,11 +817,6 @@ void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.lr_hi <= b.lr_lo) return;
   const size_t smem = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) +
                       (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t) + lut_smem_bytes(b);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   dim3 grid((b.max_segments + HR_THREADS - 1) / HR_THREADS, b.lr_hi - b.lr_lo);
   k_huff_restart<<<grid, HR_THREADS, smem, s>>>(b);
 }
@@ -1167,13 +1163,6 @@ void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   if (b.ls_hi <= b.ls_lo || b.max_sub_chunks == 0) return;
   const size_t base = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + lut_smem_bytes(b);
   const size_t smem_write = base + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
-  static size_t configured = 0;
-  if (smem_write > configured) {
-    cudaFuncSetAttribute(k_spec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-    cudaFuncSetAttribute(k_spec_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-    cudaFuncSetAttribute(k_spec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write);
-    configured = smem_write;
-  }
   const dim3 grid(b.max_sub_chunks, b.ls_hi - b.ls_lo);
   k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 0);
   k_spec_sync<<<grid, SPEC_THREADS, base, s>>>(b, 1);
@@ -1504,14 +1493,7 @@ constexpr size_t IDCT_SMEM = 2 * sizeof(IdctStage) + 1024;
 
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.tile_hi <= b.tile_lo) return;
-  static int grid = 0;
-  if (!grid) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
-    grid = HCJ_IDCT_CTAS_PER_SM * sms;
-  }
+  const int grid = HCJ_IDCT_CTAS_PER_SM * (b.sm_count > 0 ? b.sm_count : 148);
   k_idct_plan<<<dim3((b.max_idct_tiles + 127) / 128, b.img_hi - b.img_lo), 128, 0, s>>>(b);
   const uint32_t total = b.tile_hi - b.tile_lo;
   k_idct_persistent<<<(unsigned)(total < (uint32_t)grid ? total : grid), IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
@@ -1984,6 +1966,28 @@ void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long 
   size_t want = (n + 255) / 256;
   unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   k_compare<<<blocks, 256, 0, s>>>(a, b, n, sse, maxdiff);
+}
+
+// Per-device launch configuration, done once per context right after cudaSetDevice (hcj_ctx_create): the opt-in to
+// more than 48 KiB of dynamic shared memory is a per-device attribute of each kernel, so a process that drives
+// several GPUs has to set it on every one of them (worst case over table sets: HCJ_MAX_COMP table pairs).
+int configure_device(int *sm_count) {
+  int dev = 0, sms = 148;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  DecodeBatchDev worst;
+  worst.max_pairs = HCJ_MAX_COMP;
+  const size_t base = ((sizeof(SmemTables) + 15) & ~size_t(15)) + ((sizeof(ScanCtx) + 15) & ~size_t(15)) + lut_smem_bytes(worst);
+  const size_t stage = (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + stage));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_spec_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(base + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
+  if (sm_count) *sm_count = sms;
+  return (int)e;
 }
 
 }  // namespace hcjk

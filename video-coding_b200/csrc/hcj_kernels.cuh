@@ -13,6 +13,7 @@ struct IdctTile;
 // Everything the decode kernels need about one batch resident in HBM.
 struct DecodeBatchDev {
   int n;                          // images
+  int sm_count;                   // SMs of the context's device (persistent grids)
   const HcjImageDesc *descs;      // [n]
   HcjImageState *states;          // [n]
   const uint8_t *files;           // compressed files, each starting at a 16-byte boundary
@@ -61,6 +62,9 @@ struct DecodeBatchDev {
   uint32_t ls_lo, ls_hi;          // entries of list_spec
 };
 
+// Once per context, with its device current: shared-memory opt-ins of the kernels (a per-device attribute) and the
+// SM count.  Returns a cudaError_t-compatible code.
+int configure_device(int *sm_count);
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
 int destuff_kernel_count();
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
@@ -131,6 +135,7 @@ struct EncodeBatchDev {
   uint32_t header_len;
 };
 void launch_encode(const EncodeBatchDev &e, cudaStream_t s);
+void launch_encode_block_log(const EncodeBatchDev &e, uint32_t first, uint32_t count, void *out /* hcj_encoder_block[count] */, cudaStream_t s);
 int encode_kernel_count();
 
 }  // namespace hcjk

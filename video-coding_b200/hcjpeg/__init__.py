@@ -156,6 +156,11 @@ _SIGS = {
     "hcj_host_alloc": (C.c_void_p, [C.c_size_t]),
     "hcj_host_free": (None, [C.c_void_p]),
     "hcj_decode_batch": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_int, C.c_int, C.c_uint, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_int)]),
+    "hcj_decode_batch_multi": (C.c_int, [_P(C.c_void_p), C.c_int, _P(C.c_void_p), _P(C.c_size_t), C.c_int, C.c_int, C.c_uint, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_int)]),
+    "hcj_encode_batch_multi": (C.c_int, [_P(C.c_void_p), C.c_int, _P(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_int)]),
+    "hcj_shard_range": (None, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
+    "hcj_device_count": (C.c_int, []),
+    "hcj_encode_block_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
     "hcj_batch_create": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), C.c_int, C.c_int, C.c_uint, _P(C.c_int), _P(C.c_void_p)]),
     "hcj_batch_decode": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcj_batch_fetch": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_int)]),
@@ -190,6 +195,12 @@ _SIGS = {
 
 BLOCK_LOG_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("dc_pred", np.int32), ("component", np.int32),
                             ("coefs", np.int16, 64), ("dequant", np.int32, 64), ("idct", np.int32, 64), ("recon", np.uint8, 64)])
+
+
+ENCODER_BLOCK_DTYPE = np.dtype([("x_pos", np.int32), ("y_pos", np.int32), ("dc_pred", np.int32), ("component", np.int32),
+                                ("nrle", np.int32), ("input_pixels", np.uint8, 64), ("fdct", np.int32, 64), ("quant", np.int16, 64),
+                                ("rle_run", np.int16, 64), ("rle_value", np.int16, 64), ("dequant", np.int32, 64),
+                                ("idct", np.int32, 64), ("recon", np.uint8, 64), ("error", np.uint8, 64)])
 
 
 class PlaneMetrics(C.Structure):
@@ -444,6 +455,20 @@ class Context:
         _check(lib().hcj_encode_quantized(self._h, buf.ctypes.data, width, height, chroma, quality, out.ctypes.data, f.nblocks), "hcj_encode_quantized")
         return out
 
+    def encode_block_log(self, frame, width, height, chroma=420, quality=75, restart_interval=0, first=0, count=None):
+        """`model encode log -verbose`: Encoder.Block.t of blocks [first, first + count) in encode_seq order as a structured
+        array (x_pos, y_pos, dc_pred, component, nrle, input_pixels, fdct, quant, rle_run, rle_value, dequant, idct, recon, error)."""
+        if count is None:
+            f = FrameInfo()
+            hdr = write_headers(width, height, chroma, quality) + b"\xff\xd9"
+            _check(lib().hcj_frame_info_get(hdr, len(hdr), C.byref(f)))
+            count = f.nblocks - first
+        out = np.zeros(max(count, 1), ENCODER_BLOCK_DTYPE)
+        buf = np.frombuffer(frame, np.uint8)
+        _check(lib().hcj_encode_block_log(self._h, buf.ctypes.data, width, height, chroma, quality, restart_interval, first, count,
+                                          out.ctypes.data), "hcj_encode_block_log")
+        return out[:count]
+
     def yuv_convert(self, frame, width, height, chroma, dst_width=None, dst_height=None, dst_chroma=444, x_off=0, y_off=0):
         """`oyuv convert`: planar frame -> 4:4:4 -> crop with edge clamp -> dst_chroma, on the device."""
         dw, dh = dst_width or width, dst_height or height
@@ -461,6 +486,56 @@ class Context:
         sse, mx = C.c_int64(), C.c_int()
         _check(lib().hcj_compare_planes(self._h, a.ctypes.data, b.ctypes.data, a.size, C.byref(sse), C.byref(mx)))
         return sse.value, mx.value
+
+
+def device_count():
+    """CUDA devices visible to the process."""
+    return lib().hcj_device_count()
+
+
+def shard_range(n, part, nparts):
+    """Batch indices [lo, hi) that part `part` of `nparts` handles (hcj_shard_range)."""
+    lo, hi = C.c_int(), C.c_int()
+    lib().hcj_shard_range(n, part, nparts, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def decode_batch_multi(ctxs, jpegs, mode=OUT_YUV, flags=FLAG_DEFAULT):
+    """hcj_decode_batch_multi: one process, one Context per GPU, images sharded by batch index over them (a host thread
+    per context inside the library).  Returns (outputs, status) like Context.decode_batch."""
+    n = len(jpegs)
+    caps, outs = [], []
+    for j in jpegs:
+        f = FrameInfo()
+        st = lib().hcj_frame_info_get_ex(j, len(j), flags, C.byref(f))
+        caps.append(out_size(f, mode) if st == 0 else 0)
+        outs.append(np.zeros(max(caps[-1], 1), np.uint8))
+    jp, keep = _ptr_array(jpegs)
+    lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+    op, keep2 = _ptr_array(outs)
+    capa = (C.c_size_t * max(n, 1))(*caps)
+    status = (C.c_int * max(n, 1))()
+    hs = (C.c_void_p * len(ctxs))(*[c._h.value for c in ctxs])
+    _check(lib().hcj_decode_batch_multi(hs, len(ctxs), jp, lens, n, mode, flags, op, capa, status), "hcj_decode_batch_multi")
+    st = [status[i] for i in range(n)]
+    return [outs[i][: caps[i]] if st[i] == 0 else None for i in range(n)], st
+
+
+def encode_batch_multi(ctxs, frames, width, height, chroma=420, quality=75, restart_interval=0):
+    """hcj_encode_batch_multi: frames sharded by index over one Context per GPU."""
+    n = len(frames)
+    capacity = lib().hcj_encode_bound(width, height, chroma) if n <= 64 else width * height * 3 + (1 << 16)
+    outs = [np.zeros(capacity, np.uint8) for _ in range(n)]
+    fp, keep = _ptr_array(frames)
+    op, keep2 = _ptr_array(outs)
+    caps = (C.c_size_t * max(n, 1))(*([capacity] * n))
+    lens = (C.c_size_t * max(n, 1))()
+    status = (C.c_int * max(n, 1))()
+    hs = (C.c_void_p * len(ctxs))(*[c._h.value for c in ctxs])
+    _check(lib().hcj_encode_batch_multi(hs, len(ctxs), fp, n, width, height, chroma, quality, restart_interval, op, caps, lens, status),
+           "hcj_encode_batch_multi")
+    st = [status[i] for i in range(n)]
+    return [outs[i][: lens[i]].tobytes() if st[i] == 0 else None for i in range(n)], st
 
 
 class Batch:
