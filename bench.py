@@ -1,23 +1,30 @@
 #!/usr/bin/env python3
 """bench.py — decoded megapixels/sec of the B200 JPEG path (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload restart8|norestart|4k444rgb|encode]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--only]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference          # the reference's CPU algorithm (oracle port) on the host cores
 
-A step = one pass of the hot path over one batch of synthetic images:
-  value   whole-job MP/s with the compressed batch already resident in HBM (kernels + the
-          coefficient-buffer clear only), CUDA events on the library's stream, max over ranks;
-  e2e     the same metric through hcj_decode_batch with pinned HOST buffers: header parse, H2D of the
-          files, kernels, D2H of the frames, all inside the timed region (wall clock around the call);
+A step = one pass of the hot path over one batch of synthetic images.  The headline workload (`--workload`,
+default restart8 = BASELINE configs[1]) fills the top-level keys of the JSON line:
+  value   whole-job MP/s with the compressed batch already resident in HBM (kernels only), CUDA events on the
+          library's stream, max over ranks;
+  e2e     the same metric through hcj_decode_batch with pinned HOST buffers: header parse, H2D of the files,
+          kernels, D2H of the frames, all inside the timed region (wall clock around the call);
   roofline  algorithmic bytes of the dominant kernel / its CUDA-event duration vs MEASURED_PEAKS.json;
-  cpu_baseline  the CPU oracle (a port of the OCaml model) on the host cores, one process per core,
-          on a bounded sample of the same images.
-Images are sharded by batch index (weak scaling: `--batch` images per GPU), no collective on the data path.
+  cpu_baseline  the CPU oracle (a port of the OCaml model) on the host cores, one process per core, on a bounded
+          sample of the same images.
+Unless --only is given the other BASELINE configs are timed in the same run (3 warm-ups, <= 10 steps each) and
+reported under "workloads": norestart (configs[2]: 8192 images over the ranks when N > 1), 4k444rgb (configs[3]),
+encode (configs[4]), plus restart8rgb and restart120 (one MCU row per restart interval: the no-cliff check).
+Every workload is checked against the oracle outside its timed region ("parity_checked": images compared bit for bit).
+Images are sharded by batch index (weak scaling: a fixed batch per GPU), no collective on the data path.
 The synthetic JPEGs are produced by the product's own GPU encoder (byte-identical to the model's encoder,
-tests/test_gpu_encode.py); oracle/ is executed only for cpu_baseline / --impl reference.
+tests/test_gpu_encode.py); oracle/ is executed only as the checker and for cpu_baseline / --impl reference.
 """
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -34,12 +41,15 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (width, height, chroma, quality, restart_interval, out mode name, default batch per GPU)
-    "restart8": (1920, 1080, 420, 75, 8, "yuv", 1024),   # BASELINE configs[1]
-    "norestart": (1920, 1080, 420, 75, 0, "yuv", 1024),  # BASELINE configs[2] (8192 / 8 GPUs)
-    "4k444rgb": (3840, 2160, 444, 95, 0, "rgb", 128),    # BASELINE configs[3]
+    "restart8": (1920, 1080, 420, 75, 8, "yuv", 1024),     # BASELINE configs[1]
+    "norestart": (1920, 1080, 420, 75, 0, "yuv", 1024),    # BASELINE configs[2] (8192 / N per GPU for N >= 2)
+    "4k444rgb": (3840, 2160, 444, 95, 0, "rgb", 128),      # BASELINE configs[3]
     "restart8rgb": (1920, 1080, 420, 75, 8, "rgb", 1024),  # configs[1] with RGB24 output (Planar_444 up-sampling + colour)
-    "encode": (1920, 1080, 420, 75, 0, "jpeg", 512),     # BASELINE configs[4]
+    "restart120": (1920, 1080, 420, 75, 120, "yuv", 1024), # one MCU row per restart interval (camera style)
+    "encode": (1920, 1080, 420, 75, 0, "jpeg", 512),       # BASELINE configs[4]
 }
+EXTRAS = ["norestart", "4k444rgb", "encode", "restart8rgb", "restart120"]
+PARITY_IMAGES = 4
 
 
 def _synth_one(args):
@@ -64,8 +74,7 @@ def _cpu_decode_worker(args):
 
     jpgs, reps = args
     orc.lib()
-    t = orc.time_decode(jpgs, True, reps)
-    return t
+    return orc.time_decode(jpgs, True, reps)
 
 
 def _cpu_encode_worker(args):
@@ -75,6 +84,30 @@ def _cpu_encode_worker(args):
     frames, w, h, chroma, q, ri = args
     orc.lib()
     return sum(orc.time_encode(f, w, h, chroma, q, ri, 1) for f in frames)
+
+
+def _oracle_encode_worker(args):
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as orc
+
+    f, w, h, chroma, q, ri = args
+    return orc.encode(f, w, h, chroma, q, restart_interval=ri)
+
+
+def _oracle_decode_sha(args):
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as orc
+
+    jpg, rgb, chroma = args
+    d = orc.decode(jpg)
+    if not rgb:
+        return hashlib.sha256(d.yuv()).hexdigest()
+    y, u, v = orc.upsample_to_444(d.cropped, chroma)
+    return hashlib.sha256(orc.ycbcr_to_rgb24(y, u, v).tobytes()).hexdigest()
+
+
+def _noop(_):
+    return 0
 
 
 def cpu_arm(kind, items, w, h, chroma, q, ri, target_s=12.0):
@@ -104,10 +137,6 @@ def cpu_arm(kind, items, w, h, chroma, q, ri, target_s=12.0):
     }
 
 
-def _noop(_):
-    return 0
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -133,31 +162,36 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        self.rows = self.rows[self.first:]
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+    def snapshot(self):
+        rows = self.rows[self.first:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v == "Active":
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
 
 def measured_traffic(kernel, n_images):
     """dram__bytes_read + dram__bytes_write of `kernel` for one launch over n_images images, from the committed
-    ncu --set full capture (profiles/r01s3_traffic.json: per-image bytes on the same synthetic 1080p images; the
-    capture ran 296 images per launch).  None for kernels / workloads that were not captured."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01s3_traffic.json")) as f:
-            per_image = json.load(f)["dram_bytes_per_image"].get(kernel)
-        return None if per_image is None else per_image * n_images
-    except Exception:
-        return None
+    ncu --set full capture (profiles/*_traffic.json, the newest round first: per-image bytes on the same synthetic
+    1080p images).  None for kernels / workloads that were not captured."""
+    for name in ("r02_traffic.json", "r01s3_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                per_image = json.load(f)["dram_bytes_per_image"].get(kernel)
+            if per_image is not None:
+                return per_image * n_images, "profiles/%s (ncu --set full, dram read + write per image x batch)" % name
+        except Exception:
+            pass
+    return None, None
 
 
 def bind_to_gpu_numa_node(index):
@@ -206,6 +240,234 @@ def emit(obj):
         os.write(_REAL_STDOUT, data)
 
 
+def workload_config(name, batch_n, unique):
+    w, h, chroma, quality, ri, out_name, _ = WORKLOADS[name]
+    return {"workload": "%s: %d x %dx%d %d q%d %s per GPU -> %s" % (
+        name, batch_n, w, h, chroma, quality, "DRI=%d MCUs" % ri if ri else "no restart markers", out_name),
+        "batch_per_gpu": batch_n, "unique_images": unique, "sharding": "batch index, no collective",
+        "l2": "per-step working set (compressed batch + coefficient buffer) exceeds the 126 MB L2"}
+
+
+def batch_for(name, world, override=0):
+    if override:
+        return override
+    if name == "norestart" and world >= 2:
+        return 8192 // world  # BASELINE configs[2]: 8192 images sharded over 2 / 4 / 8 GPUs
+    return WORKLOADS[name][6]
+
+
+class Env:
+    """What every workload needs: the context, the barrier / reduction helpers, the per-stage byte counts."""
+
+    def __init__(self, ctx, world, barrier, max_over_ranks, sampler):
+        self.ctx, self.world, self.barrier, self.max_over_ranks, self.sampler = ctx, world, barrier, max_over_ranks, sampler
+
+
+def run_decode(env, name, frames, batch_n, steps, warmup, e2e_steps, parity=PARITY_IMAGES):
+    """One decode workload: resident (`value`), per-stage roofline, end to end, oracle check of `parity` images."""
+    import hcjpeg
+
+    ctx = env.ctx
+    w, h, chroma, quality, ri, out_name, _ = WORKLOADS[name]
+    mode = {"yuv": hcjpeg.OUT_YUV, "rgb": hcjpeg.OUT_RGB24}[out_name]
+    unique = len(frames)
+    mp_per_step = batch_n * w * h / 1e6
+    # compressed inputs from the GPU encoder (byte-identical to the model's encoder)
+    jpgs, st = [], []
+    for i in range(0, unique, 16):
+        o, s = ctx.encode_batch(frames[i:i + 16], w, h, chroma, quality, ri)
+        jpgs += o
+        st += s
+    assert all(s == 0 for s in st), st
+    batch_jpgs = [jpgs[i % unique] for i in range(batch_n)]
+    comp_bytes = sum(len(j) for j in batch_jpgs)
+
+    # ---- value: resident inputs, kernels only
+    b = ctx.batch(batch_jpgs, mode)
+    assert all(s == 0 for s in b.host_status)
+    env.sampler.mark()
+    for _ in range(max(warmup, 3)):
+        b.decode()
+    ctx.synchronize()
+    env.barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        b.decode()
+    ms = ctx.timer_stop()
+    env.barrier()
+    ms_per_step = env.max_over_ranks(ms) / steps
+    # per-stage timing for the roofline of the dominant kernel (separate passes, same stream, CUDA events)
+    stages = {}
+    for _ in range(steps):
+        for k, v in b.decode_stages().items():
+            stages[k] = stages.get(k, 0.0) + v / steps
+    clocks = env.sampler.snapshot()
+    outs, st = b.fetch()
+    assert all(s == 0 for s in st), [s for s in st if s][:4]
+    nblocks = sum(f.nblocks for f in b.infos)
+    out_bytes = sum(hcjpeg.out_size(f, mode) for f in b.infos)
+    launches = b.kernels() * steps
+    fused_rgb = "rgb" not in {k for k, v in stages.items() if v > 0.02}
+    b.close()
+    # ---- parity: a few of the benched images against the oracle, outside the timed region
+    import multiprocessing as mp
+
+    npar = min(parity, unique)
+    with mp.get_context("spawn").Pool(min(npar, os.cpu_count() or 1)) as pool:
+        want = pool.map(_oracle_decode_sha, [(jpgs[i], mode == hcjpeg.OUT_RGB24, chroma) for i in range(npar)])
+    for i in range(npar):
+        assert hashlib.sha256(outs[i].tobytes()).hexdigest() == want[i], "%s: image %d differs from the oracle" % (name, i)
+    alg = {  # algorithmic bytes per launch (SURVEY 8d / DESIGN.md)
+        "destuff": 2 * comp_bytes,
+        "huffman_restart": comp_bytes + 128 * nblocks,
+        "huffman_speculative": comp_bytes + 128 * nblocks,
+        # planar output: coefficient blocks in, frames out; RGB: fused = coefficient blocks in, RGB out; two kernels = planes in between
+        "idct": 128 * nblocks + (out_bytes if (mode != hcjpeg.OUT_RGB24 or fused_rgb) else nblocks * 64),
+        "rgb": nblocks * 64 + out_bytes,
+        "clear_flags": nblocks // 8,
+    }
+    stages = {k: v for k, v in stages.items() if v > 0.02}  # stages that did not launch read as ~0.003 ms
+    kernels_only = {k: v for k, v in stages.items() if k != "clear_flags"}
+    dom = max(kernels_only, key=kernels_only.get)
+    peak, peak_src = peaks()
+    achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(dom, batch_n) if (w, h, chroma, quality, ri) == (1920, 1080, 420, 75, 8) else (None, None)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg[dom],
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "stages": {k: {"ms": v, "algorithmic_GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak}
+                           for k, v in stages.items()}}
+    if mode == hcjpeg.OUT_RGB24:  # the pixel stage as a whole (north_star: dequant + IDCT + up-sampling + colour), one kernel or two
+        pix_ms = stages.get("idct", 0.0) + stages.get("rgb", 0.0)
+        pix_bytes = 128 * nblocks + out_bytes
+        roofline["pixel_stage"] = {"ms": pix_ms, "kernels": 1 if fused_rgb else 2, "algorithmic_bytes": pix_bytes,
+                                   "frac": pix_bytes / (pix_ms * 1e-3) / 1e9 / peak}
+    res = {"metric": "decoded megapixels/sec (%dx%d %d baseline)" % (w, h, chroma), "ms_per_step": ms_per_step,
+           "value": env.world * mp_per_step / (ms_per_step * 1e-3), "unit": "MP/s", "steps": steps, "roofline": roofline,
+           "gpu_launches": launches, "clocks": clocks, "parity_checked": npar, "config": workload_config(name, batch_n, unique)}
+
+    # ---- e2e: host buffers in and out through hcj_decode_batch (calls of at most 1024 images reuse the pinned buffers)
+    if e2e_steps > 0:
+        L = hcjpeg.lib()
+        call_n = min(batch_n, 1024)
+        in_bytes = sum((len(j) + 31) // 16 * 16 for j in batch_jpgs[:call_n])
+        sizes = [hcjpeg.out_size(hcjpeg.frame_info(j), mode) for j in jpgs]
+        out_cap = sum((sizes[i % unique] + 255) // 256 * 256 for i in range(call_n))
+        pin_in = L.hcj_host_alloc(in_bytes + 64)
+        pin_out = L.hcj_host_alloc(out_cap + 256)
+        assert pin_in and pin_out
+        jp = (C.c_void_p * call_n)()
+        lens = (C.c_size_t * call_n)()
+        op = (C.c_void_p * call_n)()
+        caps = (C.c_size_t * call_n)()
+        status = (C.c_int * call_n)()
+        off_i = off_o = 0
+        for i in range(call_n):
+            j = batch_jpgs[i]
+            C.memmove(pin_in + off_i, j, len(j))
+            jp[i], lens[i] = pin_in + off_i, len(j)
+            off_i += (len(j) + 31) // 16 * 16
+            op[i], caps[i] = pin_out + off_o, sizes[i % unique]
+            off_o += (sizes[i % unique] + 255) // 256 * 256
+        ncalls = (batch_n + call_n - 1) // call_n
+
+        def one_step():
+            for _ in range(ncalls):
+                hcjpeg._check(L.hcj_decode_batch(ctx._h, jp, lens, call_n, mode, hcjpeg.FLAG_DEFAULT, op, caps, status))
+
+        one_step()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one_step()
+        ctx.synchronize()
+        env.barrier()
+        dt = env.max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        assert all(status[i] == 0 for i in range(call_n))
+        for i in range(npar):  # the e2e leg's own outputs against the oracle too
+            got = np.ctypeslib.as_array(C.cast(op[i], C.POINTER(C.c_uint8)), shape=(caps[i],))
+            assert hashlib.sha256(got.tobytes()).hexdigest() == want[i], "%s: e2e image %d differs from the oracle" % (name, i)
+        res["e2e"] = {"value": env.world * (ncalls * call_n * w * h / 1e6) / dt, "unit": "MP/s",
+                      "h2d_bytes_per_step": comp_bytes * ncalls * call_n // batch_n,
+                      "d2h_bytes_per_step": (out_bytes + 4 * batch_n) * ncalls * call_n // batch_n, "ms_per_step": dt * 1e3,
+                      "steps": e2e_steps, "images_per_call": call_n}
+        L.hcj_host_free(pin_in)
+        L.hcj_host_free(pin_out)
+    return res, jpgs
+
+
+def run_encode(env, name, frames, batch_n, steps, warmup, parity=PARITY_IMAGES):
+    """Encode workload: frames in pinned host memory -> files in pinned host memory through hcj_encode_batch."""
+    import hcjpeg
+
+    ctx = env.ctx
+    w, h, chroma, quality, ri, _, _ = WORKLOADS[name]
+    L = hcjpeg.lib()
+    unique = len(frames)
+    mp_per_step = batch_n * w * h / 1e6
+    frame_bytes = len(frames[0])
+    cap = 1 << 20
+    pin_in = L.hcj_host_alloc(frame_bytes * batch_n)
+    pin_out = L.hcj_host_alloc(cap * batch_n)
+    assert pin_in and pin_out
+    fp = (C.c_void_p * batch_n)()
+    op = (C.c_void_p * batch_n)()
+    caps = (C.c_size_t * batch_n)(*([cap] * batch_n))
+    lens = (C.c_size_t * batch_n)()
+    status = (C.c_int * batch_n)()
+    for i in range(batch_n):
+        C.memmove(pin_in + i * frame_bytes, frames[i % unique], frame_bytes)
+        fp[i], op[i] = pin_in + i * frame_bytes, pin_out + i * cap
+
+    def run():
+        hcjpeg._check(L.hcj_encode_batch(ctx._h, fp, batch_n, w, h, chroma, quality, ri, op, caps, lens, status))
+        ms = C.c_float()
+        hcjpeg._check(L.hcj_encode_last_device_ms(ctx._h, C.byref(ms)))
+        return ms.value
+
+    for _ in range(max(warmup, 3)):
+        run()
+    env.barrier()
+    env.sampler.mark()
+    dev_ms = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dev_ms.append(run())
+    ctx.synchronize()
+    env.barrier()
+    dt = env.max_over_ranks(time.perf_counter() - t0) / steps
+    clocks = env.sampler.snapshot()
+    assert all(status[i] == 0 for i in range(batch_n))
+    # ---- parity: byte-identical files versus the oracle encoder
+    import multiprocessing as mp
+
+    npar = min(parity, unique)
+    with mp.get_context("spawn").Pool(min(npar, os.cpu_count() or 1)) as pool:
+        want = pool.map(_oracle_encode_worker, [(frames[i], w, h, chroma, quality, ri) for i in range(npar)])
+    for i in range(npar):
+        got = bytes(np.ctypeslib.as_array(C.cast(op[i], C.POINTER(C.c_uint8)), shape=(lens[i],)))
+        assert got == want[i], "encode: frame %d differs from the oracle encoder" % i
+    kms = env.max_over_ranks(float(np.mean(dev_ms)))
+    out_total = sum(lens[i] for i in range(batch_n))
+    nblocks = hcjpeg.frame_info(want[0]).nblocks * batch_n
+    # SURVEY 8d: K6 = frames in + 128 Nb out; K7/K8 = 128 Nb in + C out  ->  in + 256 Nb + C for the pipeline
+    alg = frame_bytes * batch_n + 2 * 128 * nblocks + out_total
+    peak, peak_src = peaks()
+    res = {"metric": "encoded megapixels/sec (%dx%d %d baseline)" % (w, h, chroma), "ms_per_step": kms,
+           "value": env.world * mp_per_step / (kms * 1e-3), "unit": "MP/s", "steps": steps,
+           "gpu_launches": L.hcj_encode_count_kernels() * steps, "clocks": clocks, "parity_checked": npar,
+           "config": workload_config(name, batch_n, unique),
+           "roofline": {"kernel": "encode pipeline (fdct_quant + bit lengths + pack + stuff)", "bound": "hbm",
+                        "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (kms * 1e-3) / 1e9 / peak,
+                        "traffic": None, "algorithmic_bytes": alg, "peak_source": peak_src,
+                        "note": "algorithmic bytes (SURVEY 8d): frames in + coefficient blocks written and read once + files out"},
+           "e2e": {"value": env.world * mp_per_step / dt, "unit": "MP/s", "h2d_bytes_per_step": frame_bytes * batch_n,
+                   "d2h_bytes_per_step": out_total, "ms_per_step": dt * 1e3, "steps": steps}}
+    L.hcj_host_free(pin_in)
+    L.hcj_host_free(pin_out)
+    return res
+
+
 def main():
     # Libraries print to stdout on their own (NCCL announces its version there at communicator creation): everything
     # but the JSON line goes to stderr.
@@ -219,7 +481,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="restart8", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: per workload)")
+    ap.add_argument("--only", action="store_true", help="time the headline workload only (no `workloads` section)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU of the headline workload (default: per workload)")
     ap.add_argument("--unique", type=int, default=64, help="distinct images cycled to fill the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -228,32 +491,29 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    w, h, chroma, quality, ri, out_name, default_batch = WORKLOADS[args.workload]
-    batch_n = args.batch or default_batch
+    w, h, chroma, quality, ri, out_name, _ = WORKLOADS[args.workload]
+    batch_n = batch_for(args.workload, world, args.batch)
     unique = max(1, min(args.unique, batch_n))
-    config = {"workload": "%s: %d x %dx%d %d q%d %s per GPU -> %s" % (
-        args.workload, batch_n, w, h, chroma, quality, "DRI=%d MCUs" % ri if ri else "no restart markers", out_name),
-        "batch_per_gpu": batch_n, "unique_images": unique, "sharding": "batch index, no collective",
-        "l2": "per-step working set (compressed batch + coefficient buffer) exceeds the 126 MB L2"}
+    config = workload_config(args.workload, batch_n, unique)
 
     if args.impl == "reference" and rank != 0:
         return 0
 
-    # ---- synthetic inputs (host cores, before CUDA is touched)
-    frames = make_frames(unique if args.impl == "ours" else min(unique, 16), w, h, chroma, 1000 * (1 + rank))
+    # ---- synthetic inputs (host cores, before CUDA is touched); both arms use the same `unique` images
+    frames = make_frames(unique, w, h, chroma, 1000 * (1 + rank))
 
     import hcjpeg
 
     hcjpeg.build()
     if args.impl == "reference":
         # The reference's own CPU implementation cannot run here (OCaml, no toolchain): the oracle port of its
-        # algorithm is timed on all host cores.  Inputs are produced by the GPU encoder when a GPU is present
-        # (byte-identical), else by the oracle encoder.
-        from oracle import pyoracle as orc
+        # algorithm is timed on all host cores, on inputs from the oracle encoder.
+        import multiprocessing as mp
 
         kind = "encode" if args.workload == "encode" else "decode"
         if kind == "decode":
-            items = [orc.encode(f, w, h, chroma, quality, restart_interval=ri) for f in frames]
+            with mp.get_context("spawn").Pool(os.cpu_count() or 1) as pool:
+                items = pool.map(_oracle_encode_worker, [(f, w, h, chroma, quality, ri) for f in frames])
         else:
             items = frames
         vals = []
@@ -272,8 +532,18 @@ def main():
             "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
+    # extra workloads: their frames are generated before CUDA starts as well
+    extras = [] if args.only else [x for x in EXTRAS if x != args.workload]
+    extra_frames = {}
+    for name in extras:
+        ew, eh, ec = WORKLOADS[name][:3]
+        key = (ew, eh, ec)
+        if key == (w, h, chroma):
+            extra_frames[key] = frames
+        elif key not in extra_frames:
+            extra_frames[key] = make_frames(min(unique, 16), ew, eh, ec, 7000 * (1 + rank))
+
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    config["numa_node"] = numa
     import torch
 
     torch.cuda.set_device(local)
@@ -286,180 +556,33 @@ def main():
     from hcjpeg import shard
 
     dist_mod = dist if world > 1 else None
-
-    def barrier():
-        shard.barrier(dist_mod, torch.cuda.synchronize)
-
-    def max_over_ranks(x):
-        return shard.max_over_ranks(x, dist_mod, "cuda")
-
     ctx = hcjpeg.Context(local)
-    mode = {"yuv": hcjpeg.OUT_YUV, "rgb": hcjpeg.OUT_RGB24, "jpeg": None}[out_name]
-    mp_per_step = batch_n * w * h / 1e6
     sampler = ClockSampler(local)
     sampler.start()
-    result = {}
+    env = Env(ctx, world, lambda: shard.barrier(dist_mod, torch.cuda.synchronize),
+              lambda x: shard.max_over_ranks(x, dist_mod, "cuda"), sampler)
 
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
     if args.workload != "encode":
-        # compressed inputs from the GPU encoder (byte-identical to the model's encoder)
-        jpgs, st = [], []
-        for i in range(0, unique, 16):
-            o, s = ctx.encode_batch(frames[i:i + 16], w, h, chroma, quality, ri)
-            jpgs += o
-            st += s
-        assert all(s == 0 for s in st), st
-        batch_jpgs = [jpgs[i % unique] for i in range(batch_n)]
-        comp_bytes = sum(len(j) for j in batch_jpgs)
-
-        # ---- value: resident inputs, kernels only
-        b = ctx.batch(batch_jpgs, mode)
-        assert all(s == 0 for s in b.host_status)
-        sampler.mark()
-        for _ in range(max(args.warmup, 3)):
-            b.decode()
-        ctx.synchronize()
-        barrier()
-        ctx.timer_start()
-        for _ in range(args.steps):
-            b.decode()
-        ms = ctx.timer_stop()
-        barrier()
-        ms = max_over_ranks(ms)
-        ms_per_step = ms / args.steps
-        # per-stage timing for the roofline of the dominant kernel (separate passes, same stream, CUDA events)
-        stages = {}
-        for _ in range(args.steps):
-            for k, v in b.decode_stages().items():
-                stages[k] = stages.get(k, 0.0) + v / args.steps
-        clocks = sampler.stop()
-        outs, st = b.fetch()
-        assert all(s == 0 for s in st), [s for s in st if s][:4]
-        nblocks = sum(f.nblocks for f in b.infos)
-        out_bytes = sum(hcjpeg.out_size(f, mode) for f in b.infos)
-        launches = b.kernels() * args.steps
-        b.close()
-        alg = {  # algorithmic bytes per launch (SURVEY 8d / DESIGN.md)
-            "destuff": 2 * comp_bytes,
-            "huffman_restart": comp_bytes + 128 * nblocks,
-            "huffman_speculative": comp_bytes + 128 * nblocks,
-            "idct": 128 * nblocks + (out_bytes if mode != hcjpeg.OUT_RGB24 else nblocks * 64),
-            "rgb": nblocks * 64 + out_bytes,
-            "clear_flags": nblocks // 8,
-        }
-        stages = {k: v for k, v in stages.items() if v > 0.02}  # stages that did not launch read as ~0.003 ms
-        kernels_only = {k: v for k, v in stages.items() if k != "clear_flags"}
-        dom = max(kernels_only, key=kernels_only.get)
-        peak, peak_src = peaks()
-        achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
-        traffic = measured_traffic(dom, batch_n) if (w, h, chroma, quality) == (1920, 1080, 420, 75) else None
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg[dom],
-                    "traffic_source": "profiles/r01s3_traffic.json (ncu --set full, dram read + write per image x batch)" if traffic else None,
-                    "peak_source": peak_src,
-                    "stages": {k: {"ms": v, "algorithmic_GBps": alg[k] / (v * 1e-3) / 1e9 if v > 0 else None,
-                                   "frac": alg[k] / (v * 1e-3) / 1e9 / peak if v > 0 else None} for k, v in stages.items()}}
-        result.update(ms_per_step=ms_per_step, value=world * mp_per_step / (ms_per_step * 1e-3), roofline=roofline,
-                      gpu_launches=launches, clocks=clocks)
-
-        # ---- e2e: host buffers in and out through hcj_decode_batch
-        if not args.no_e2e:
-            import ctypes as C
-
-            L = hcjpeg.lib()
-            pin_in = L.hcj_host_alloc(comp_bytes + 64 * batch_n)
-            pin_out = L.hcj_host_alloc(out_bytes + 256 * batch_n)
-            assert pin_in and pin_out
-            jp = (C.c_void_p * batch_n)()
-            lens = (C.c_size_t * batch_n)()
-            op = (C.c_void_p * batch_n)()
-            caps = (C.c_size_t * batch_n)()
-            status = (C.c_int * batch_n)()
-            off_i = off_o = 0
-            for i, j in enumerate(batch_jpgs):
-                C.memmove(pin_in + off_i, j, len(j))
-                jp[i], lens[i] = pin_in + off_i, len(j)
-                off_i += (len(j) + 16 + 15) // 16 * 16
-                size = hcjpeg.out_size(hcjpeg.frame_info(j), mode) if i < unique else caps[i % unique]
-                op[i], caps[i] = pin_out + off_o, size
-                off_o += (size + 255) // 256 * 256
-            e2e_steps = max(1, min(args.steps, 3))
-            for _ in range(1):
-                hcjpeg._check(L.hcj_decode_batch(ctx._h, jp, lens, batch_n, mode, hcjpeg.FLAG_DEFAULT, op, caps, status))
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                hcjpeg._check(L.hcj_decode_batch(ctx._h, jp, lens, batch_n, mode, hcjpeg.FLAG_DEFAULT, op, caps, status))
-            ctx.synchronize()
-            barrier()
-            dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-            assert all(status[i] == 0 for i in range(batch_n))
-            got = np.ctypeslib.as_array(C.cast(op[0], C.POINTER(C.c_uint8)), shape=(caps[0],))
-            assert np.array_equal(got, outs[0]), "e2e output differs from the resident-path output"
-            result["e2e"] = {"value": world * mp_per_step / dt, "unit": "MP/s", "h2d_bytes_per_step": comp_bytes,
-                             "d2h_bytes_per_step": out_bytes + 4 * batch_n, "ms_per_step": dt * 1e3, "steps": e2e_steps}
-            L.hcj_host_free(pin_in)
-            L.hcj_host_free(pin_out)
+        result, jpgs = run_decode(env, args.workload, frames, batch_n, args.steps, args.warmup, e2e_steps)
         cpu_items, cpu_kind = jpgs, "decode"
-        metric = "decoded megapixels/sec (%dx%d %d baseline)" % (w, h, chroma)
     else:
-        # ---- encode: frames in pinned host memory -> files in pinned host memory through hcj_encode_batch
-        import ctypes as C
-
-        L = hcjpeg.lib()
-        frame_bytes = len(frames[0])
-        cap = 1 << 20
-        pin_in = L.hcj_host_alloc(frame_bytes * batch_n)
-        pin_out = L.hcj_host_alloc(cap * batch_n)
-        assert pin_in and pin_out
-        fp = (C.c_void_p * batch_n)()
-        op = (C.c_void_p * batch_n)()
-        caps = (C.c_size_t * batch_n)(*([cap] * batch_n))
-        lens = (C.c_size_t * batch_n)()
-        status = (C.c_int * batch_n)()
-        for i in range(batch_n):
-            C.memmove(pin_in + i * frame_bytes, frames[i % unique], frame_bytes)
-            fp[i], op[i] = pin_in + i * frame_bytes, pin_out + i * cap
-
-        def run():
-            hcjpeg._check(L.hcj_encode_batch(ctx._h, fp, batch_n, w, h, chroma, quality, ri, op, caps, lens, status))
-            ms = C.c_float()
-            hcjpeg._check(L.hcj_encode_last_device_ms(ctx._h, C.byref(ms)))
-            return ms.value
-
-        for _ in range(max(args.warmup, 3)):
-            run()
-        barrier()
-        sampler.mark()
-        dev_ms = []
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            dev_ms.append(run())
-        ctx.synchronize()
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
-        clocks = sampler.stop()
-        assert all(status[i] == 0 for i in range(batch_n))
-        ref, st1 = ctx.encode_batch(frames[:1], w, h, chroma, quality, ri)
-        got = bytes(np.ctypeslib.as_array(C.cast(op[0], C.POINTER(C.c_uint8)), shape=(lens[0],)))
-        assert got == ref[0], "pinned-buffer output differs from the Python front-end's"
-        kms = max_over_ranks(float(np.mean(dev_ms)))
-        out_total = sum(lens[i] for i in range(batch_n))
-        nblocks = hcjpeg.frame_info(ref[0]).nblocks * batch_n
-        # FDCT+quantise stage: reads the frames, writes int16 coefficient blocks (in + 128 Nb)
-        result.update(ms_per_step=kms, value=world * mp_per_step / (kms * 1e-3), gpu_launches=8 * args.steps, clocks=clocks,
-                      roofline={"kernel": "encode pipeline (fdct_quant + bit lengths + pack + stuff)", "bound": "hbm",
-                                "achieved": (frame_bytes * batch_n + 3 * 128 * nblocks + 3 * out_total) / (kms * 1e-3) / 1e9,
-                                "peak": peaks()[0], "unit": "GB/s",
-                                "frac": (frame_bytes * batch_n + 3 * 128 * nblocks + 3 * out_total) / (kms * 1e-3) / 1e9 / peaks()[0],
-                                "traffic": None, "peak_source": peaks()[1],
-                                "note": "algorithmic bytes: frames in + coefficient blocks written once and read twice + packed bits written, read, stuffed bytes written"},
-                      e2e={"value": world * mp_per_step / dt, "unit": "MP/s", "h2d_bytes_per_step": frame_bytes * batch_n,
-                           "d2h_bytes_per_step": out_total, "ms_per_step": dt * 1e3, "steps": args.steps})
-        L.hcj_host_free(pin_in)
-        L.hcj_host_free(pin_out)
+        result = run_encode(env, args.workload, frames, batch_n, args.steps, args.warmup)
         cpu_items, cpu_kind = frames, "encode"
-        metric = "encoded megapixels/sec (%dx%d %d baseline)" % (w, h, chroma)
 
+    workloads = {}
+    for name in extras:
+        ew, eh, ec = WORKLOADS[name][:3]
+        bn = batch_for(name, world)
+        fr = extra_frames[(ew, eh, ec)]
+        steps = max(1, min(args.steps, 10))
+        if name == "encode":
+            r = run_encode(env, name, fr, bn, steps, 3)
+        else:
+            r, _ = run_decode(env, name, fr, bn, steps, 3, 0 if args.no_e2e else min(2, steps))
+        workloads[name] = r
+
+    sampler.stop()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -470,12 +593,14 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_arm(cpu_kind, cpu_items, w, h, chroma, quality, ri)
     line = {
-        "metric": metric, "value": result["value"], "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "metric": result["metric"], "value": result["value"], "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": result["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int16/int32 (integer, bit-exact)", "data": "synthetic", "config": config,
         "clocks": result["clocks"], "e2e": result.get("e2e"), "gpu_launches": result["gpu_launches"],
-        "roofline": result["roofline"], "cpu_baseline": cpu,
+        "roofline": result["roofline"], "cpu_baseline": cpu, "parity_checked": result["parity_checked"], "numa_node": numa,
     }
+    if workloads:
+        line["workloads"] = workloads
     emit(line)
     return 0
 

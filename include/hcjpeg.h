@@ -232,6 +232,7 @@ int hcj_encode_batch_multi(hcj_ctx *const *ctx, int nctx, const uint8_t *const *
                            int quality, int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
                            int *status);
 size_t hcj_encode_bound(int width, int height, int chroma); /* worst-case bytes of one encoded frame */
+int hcj_encode_count_kernels(void); /* kernels one hcj_encode_batch launches */
 /* Encoder.write_headers (encoder.ml:371-418).  Host only. */
 int hcj_write_headers(int width, int height, int chroma, int quality, int restart_interval, uint8_t *out,
                       size_t capacity, size_t *len);

@@ -686,6 +686,8 @@ size_t hcj_encode_bound(int width, int height, int chroma) {
   return 1024 + (size_t)p.nblocks * 432 + 16;  // header + 2 x 216 bytes per block (all bytes stuffed) + EOI
 }
 
+int hcj_encode_count_kernels(void) { return hcjk::encode_kernel_count(); }
+
 int hcj_write_headers(int width, int height, int chroma, int quality, int restart_interval, uint8_t *out, size_t capacity,
                       size_t *len) {
   if (!out || !len) return HCJ_ERR_INVALID_ARG;

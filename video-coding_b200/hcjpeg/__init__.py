@@ -172,6 +172,7 @@ _SIGS = {
     "hcj_idct_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "hcj_encode_batch": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_int)]),
     "hcj_encode_bound": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hcj_encode_count_kernels": (C.c_int, []),
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
