@@ -628,3 +628,36 @@ def test_multi_gpu_contexts(hcj, orc):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_fused_rgb444(hcj, ctx, orc, data):
+    """J4: RGB24 of 4:4:4 images is produced inside the IDCT kernel (no plane round trip through HBM).  Odd sizes (crop in
+    x and y, rows that are not 8-byte aligned), several tiles per MCU row (> 42 MCUs wide), blocks flagged for the 64-bit
+    IDCT (k_rgb444_fix), 16-bit quant tables (not fused), and a mixed batch with sub-sampled images (k_rgb)."""
+    from test_emul_device_logic import _patch_dqt
+
+    cases = [(444, 8, 8, 75), (444, 17, 9, 90), (444, 333, 77, 60), (444, 344, 24, 95), (444, 1000, 40, 100), (420, 64, 48, 75),
+             (444, 3840, 16, 95), (422, 80, 40, 75), (444, 61, 61, 30)]
+    jpgs = [orc.encode(synth.frame(1300 + i, w, h, c), w, h, c, q) for i, (c, w, h, q) in enumerate(cases)]
+    base = orc.encode(data("mini64x64.444"), 64, 64, 444, 100)
+    jpgs += [_patch_dqt(base, 255), _patch_dqt(orc.encode(synth.frame(5, 96, 40, 444), 96, 40, 444, 100, restart_interval=3), 200)]
+    b16 = bytearray()
+    i, src = 0, bytearray(base)
+    while i < len(src):
+        if src[i] == 0xFF and src[i + 1] == 0xDB:
+            b16 += bytes([0xFF, 0xDB, 0x00, 0x83, 0x10 | (src[i + 4] & 15)]) + b"".join(bytes([1 + (k % 3), 0x2C]) for k in range(64))
+            i += 69
+        else:
+            b16.append(src[i])
+            i += 1
+    jpgs.append(bytes(b16))
+    want = [oracle_rgb(orc, orc.decode(j)).tobytes() for j in jpgs]
+    outs, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
+    assert st == [0] * len(jpgs)
+    for k, (o, w_) in enumerate(zip(outs, want)):
+        assert bytes(o) == w_, k
+    # the resident three-step form takes the same kernels
+    with ctx.batch(jpgs, hcj.OUT_RGB24) as b:
+        b.decode()
+        outs, st = b.fetch()
+        assert st == [0] * len(jpgs) and [bytes(o) for o in outs] == want

@@ -255,7 +255,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t total_tiles = 0;
   uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0, max_sub_chunks = 0;
   size_t total_sub = 0, total_ds_tiles = 0;
-  uint32_t max_ds_tiles = 0;
+  uint32_t max_ds_tiles = 0, max_blocks = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
   bool sub_log2_env = false;
   if (const char *e = getenv("HCJ_SUB_LOG2")) {  // tuning knob: preferred subsequence length, log2 of bits
@@ -494,7 +494,14 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     d.idct_tiles = tiles;
     total_tiles += tiles;
     max_rows = std::max(max_rows, (uint32_t)f.height);
-    (f.chroma == 444 ? b->dev.has_444 : b->dev.has_subsampled) = 1;
+    {
+      bool unit_sampling = f.ncomp == 3;
+      for (int k = 0; k < f.ncomp; k++) unit_sampling = unit_sampling && f.hs[k] == 1 && f.vs[k] == 1;
+      d.fused_rgb = mode == HCJ_OUT_RGB24 && f.chroma == 444 && unit_sampling && !d.wide_idct && !getenv("HCJ_NO_FUSED_RGB");
+    }
+    if (d.fused_rgb) b->dev.has_fused = 1;
+    else (f.chroma == 444 ? b->dev.has_444 : b->dev.has_subsampled) = 1;
+    max_blocks = std::max(max_blocks, d.nblocks);
     max_width = std::max(max_width, (uint32_t)f.width);
   }
   if (status)
@@ -573,6 +580,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.n_spec = (int)list_spec.size();
   dv.max_sub_chunks = max_sub_chunks;
   dv.max_ds_tiles = max_ds_tiles;
+  dv.total_ds_tiles = (uint32_t)total_ds_tiles;
   dv.max_idct_tiles = max_tiles;
   dv.total_idct_tiles = total_tiles;
   dv.tile_lo = 0;
@@ -581,6 +589,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   for (int i = 0; i < n; i++) b->tile_base[i + 1] = b->tile_base[i] + b->descs[i].idct_tiles;
   dv.tile_mcus = tile_mcus;
   dv.max_rgb_rows = max_rows;
+  dv.max_blocks = max_blocks;
   dv.max_width = max_width;
   dv.total_blocks = total_blocks;
   dv.img_lo = 0;
@@ -591,7 +600,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.ls_hi = (uint32_t)list_spec.size();
   b->list_restart = list_restart;
   b->list_spec = list_spec;
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled + (mode == HCJ_OUT_RGB24 ? dv.has_fused : 0) : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;
@@ -629,10 +638,7 @@ int hcj_batch_decode(hcj_ctx *c, hcj_batch *b) {
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   if (b->n == 0) return HCJ_OK;
-  // Coefficient blocks are cleared (clear_block, decoder.ml:112-116,160) by the entropy kernels themselves,
-  // block by block, right before they store into them (see zero_block in hcj_device.cuh).
-  CU_TRY(cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s));
-  CU_TRY(cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s));  // overwritten by k_destuff for valid images
+  CU_TRY((cudaError_t)hcjk::decode_prologue(b->dev, s));
   hcjk::launch_destuff(b->dev, s);
   hcjk::launch_huff_restart(b->dev, s);
   hcjk::launch_huff_spec(b->dev, s);
@@ -653,8 +659,7 @@ int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, i
   for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
   const int mode = b->mode == HCJ_OUT_YUV ? 0 : b->mode == HCJ_OUT_PLANES ? 1 : 2;
   cudaEventRecord(ev[0], s);
-  cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
-  cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * b->n, s);
+  hcjk::decode_prologue(b->dev, s);
   cudaEventRecord(ev[1], s);
   hcjk::launch_destuff(b->dev, s);
   cudaEventRecord(ev[2], s);
@@ -763,8 +768,7 @@ int hcj_decode_batch(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *len, 
       e = upload_files(b, jpeg, len, bound[k], bound[k + 1], us);
       if (e == cudaSuccess) e = cudaEventRecord(c->up_events[k], us);
     }
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.wide_flags, 0, (size_t)(b->dev.total_blocks / 32 + 2) * 4, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->dev.states, 0xff, sizeof(HcjImageState) * n, s);
+    if (e == cudaSuccess) e = (cudaError_t)hcjk::decode_prologue(b->dev, s);
     const int kmode = mode == HCJ_OUT_YUV ? 0 : mode == HCJ_OUT_PLANES ? 1 : 2;
     size_t lr = 0, ls = 0;
     for (int k = 0; k < nchunks && e == cudaSuccess; k++) {

@@ -365,7 +365,193 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
   if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_bytes[tail0 + tid];
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same in ONE pass (the input is read once): every tile classifies its bytes, scans them, and learns what
+// lies before it from the records of its predecessors - a chained scan with decoupled look-back (Merrill & Garland)
+// over the tiles of an image.  A tile's record is one 64-bit word, so status and value are published by a
+// single store:
+//   bits 0-31 kept bytes | bits 32-59 restart markers | bit 60 a terminating marker was seen | bits 62-63 status
+//   status 0 = not yet written (the records are zeroed before every decode), 1 = this tile alone, 2 = this tile
+//   and everything before it.
+// Tiles are looked at by warp 0, 32 predecessors per step.  A tile only ever waits for tiles with a smaller block
+// index of the same image row of the grid, which the hardware has dispatched before it.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long DSR_VALUE = (1ull << 60) - 1ull, DSR_TERM = 1ull << 60;
+__device__ __forceinline__ unsigned long long dsr_load(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsr_store(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void ds_write_state(const DecodeBatchDev &b, const HcjImageDesc *d, uint32_t img, uint32_t ent_len,
+                                               uint32_t markers, bool found) {
+  uint32_t *segs = b.seg_offs + d->seg_off;
+  HcjImageState st;
+  st.ent_len = ent_len;
+  st.nseg_found = markers + 1;
+  st.status = HCJ_DEV_OK;
+  st.pad_ = 0;
+  st.err_key = HCJ_NO_ERR_KEY;
+  if (!found) st.status = HCJ_DEV_NO_TERMINATOR;
+  else if (d->ri > 0 && st.nseg_found != d->nseg_expected) st.status = HCJ_DEV_RESTART_COUNT;
+  segs[0] = 0;
+  segs[d->nseg_expected] = ent_len;
+  b.states[img] = st;
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
+  __shared__ uint8_t s_last[DS_THREADS];
+  __shared__ uint32_t s_warp[DS_THREADS / 32];
+  __shared__ uint32_t s_min[DS_THREADS / 32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ __align__(16) uint32_t s_out[(DS_TILE + 32) / 4];
+  const uint32_t img = blockIdx.y + b.img_lo;
+  const HcjImageDesc *d = &b.descs[img];
+  if (!d->valid) return;
+  const uint32_t base0 = d->scan_start & ~15u;
+  const uint32_t ntiles = d->file_len > base0 ? (d->file_len - base0 + DS_TILE - 1) / DS_TILE : 0;
+  const uint32_t t = blockIdx.x;
+  if (t >= ntiles) {
+    if (t == 0 && threadIdx.x == 0) ds_write_state(b, d, img, 0, 0, false);  // a scan of zero bytes has no terminator
+    return;
+  }
+  const uint32_t off = base0 + t * DS_TILE + threadIdx.x * 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4 *>(s_out)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 2) reinterpret_cast<uint4 *>(s_out)[DS_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  const uint32_t tmin = ds_cut_at_terminator(c, off, s_min, lane, warp);
+  // block exclusive scan of (markers << 16 | kept bytes): at most 4096 bytes and 2048 markers per tile
+  const uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
+  const uint32_t incl = warp_incl_scan(cnt, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();  // also orders the zeroing of s_out before the ORs below
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < DS_THREADS / 32; k++) {
+    const uint32_t x = s_warp[k];
+    if (k < warp) wbase += x;
+    total += x;
+  }
+  const uint32_t excl = wbase + incl - cnt;
+  // ---- what lies before this tile
+  unsigned long long *recs = reinterpret_cast<unsigned long long *>(b.ds_tiles + d->ds_off);
+  if (warp == 0) {
+    const unsigned long long mine = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32) |
+                                    (tmin != 0xffffffffu ? DSR_TERM : 0ull);
+    unsigned long long before = 0;  // value and terminator bit of everything before this tile
+    if (t == 0) {
+      if (lane == 0) dsr_store(recs, mine | (2ull << 62));
+    } else {
+      if (lane == 0) dsr_store(recs + t, mine | (1ull << 62));
+      int base = (int)t - 1;
+      for (;;) {
+        const int idx = base - lane;
+        unsigned long long v = 2ull << 62;  // before tile 0: nothing, and final
+        if (idx >= 0) {
+          v = dsr_load(recs + idx);
+          while ((v >> 62) == 0ull) v = dsr_load(recs + idx);
+        }
+        const uint32_t final_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+        const int first = final_mask ? __ffs((int)final_mask) - 1 : 31;  // lanes up to the nearest final record count
+        unsigned long long part = lane <= first ? (v & DSR_VALUE) : 0ull;
+        const uint32_t term_mask = __ballot_sync(0xffffffffu, lane <= first && (v & DSR_TERM) != 0ull);
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sft);
+        before += part;
+        if (term_mask) before |= DSR_TERM;
+        if (final_mask) break;
+        base -= 32;
+      }
+      if (lane == 0) dsr_store(recs + t, ((before & DSR_VALUE) + (mine & DSR_VALUE)) | ((before | mine) & DSR_TERM) | (2ull << 62));
+    }
+    if (lane == 0) s_prefix = before;
+  }
+  __syncthreads();
+  const unsigned long long before = s_prefix;
+  if (before & DSR_TERM) return;  // behind the terminator: the model never looks at these bytes
+  const uint32_t out0 = (uint32_t)before, mk0 = (uint32_t)((before & DSR_VALUE) >> 32);
+  if (tid == 0 && (tmin != 0xffffffffu || t + 1 == ntiles))
+    ds_write_state(b, d, img, out0 + (total & 0xffffu), mk0 + (total >> 16), tmin != 0xffffffffu);
+  // ---- compact the tile (as k_destuff_write)
+  uint8_t *ent = b.entropy + d->ent_off;
+  uint32_t *segs = b.seg_offs + d->seg_off;
+  const uint32_t nseg_expected = d->nseg_expected;
+  const uint32_t phase = out0 & 15u;
+  const uint32_t so = phase + (excl & 0xffffu);
+  if (c.anyff == 0u) {
+    const uint32_t q = so >> 2, sh = (so & 3u) * 8u;
+    if (sh == 0u) {
+      s_out[q] = c.w[0], s_out[q + 1] = c.w[1], s_out[q + 2] = c.w[2], s_out[q + 3] = c.w[3];
+    } else {
+      atomicOr(&s_out[q], c.w[0] << sh);
+      s_out[q + 1] = __funnelshift_l(c.w[0], c.w[1], sh);
+      s_out[q + 2] = __funnelshift_l(c.w[1], c.w[2], sh);
+      s_out[q + 3] = __funnelshift_l(c.w[2], c.w[3], sh);
+      atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
+    }
+  } else {
+    uint32_t o = so, opos = out0 + (excl & 0xffffu), mk = mk0 + (excl >> 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (c.emit[k] == 0x80808080u && c.ffz[k] == 0u) {
+        const uint32_t sh = (o & 3u) * 8u;
+        if (sh == 0u) {
+          s_out[o >> 2] = c.w[k];
+        } else {
+          atomicOr(&s_out[o >> 2], c.w[k] << sh);
+          atomicOr(&s_out[(o >> 2) + 1], c.w[k] >> (32u - sh));
+        }
+        o += 4;
+        opos += 4;
+      } else if ((c.emit[k] | c.mark[k]) != 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t bit = 0x80u << (8 * i);
+          if (c.emit[k] & bit) {
+            const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
+            atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
+            o++;
+            opos++;
+          } else if (c.mark[k] & bit) {
+            mk++;
+            if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint8_t *s_bytes = reinterpret_cast<const uint8_t *>(s_out);
+  const uint32_t nbytes = total & 0xffffu, avail = phase + nbytes;
+  uint8_t *dst0 = ent + (out0 - phase);  // 16-byte aligned
+  const uint32_t w_lo = phase ? 1u : 0u, w_hi = avail >> 4;  // words [w_lo, w_hi) are wholly this tile's
+  for (uint32_t k = w_lo + tid; k < w_hi; k += DS_THREADS)
+    reinterpret_cast<uint4 *>(dst0)[k] = reinterpret_cast<const uint4 *>(s_out)[k];
+  // partial words at both ends (shared with the neighbouring tiles): byte by byte
+  if (phase && (uint32_t)tid < 16u - phase && phase + tid < avail) dst0[phase + tid] = s_bytes[phase + tid];
+  const uint32_t tail0 = max(w_hi << 4, w_lo << 4);
+  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_bytes[tail0 + tid];
+}
+
+static bool destuff_three_pass() {
+  // Measured on a B200 (gpurun_out/r02c_*): the one-pass kernel reads the input once but pays for the look-back with
+  // the whole CTA waiting at the barrier behind it: 1.07 ms against 0.885 ms for the three kernels on 1024 x 1080p
+  // (2.89 against 1.94 ms on 128 x 4k 4:4:4 q95).  The three-pass form stays the default; HCJ_DESTUFF_1PASS=1 selects
+  // the chained scan for A/B measurements.
+  static const bool v = getenv("HCJ_DESTUFF_1PASS") == nullptr;
+  return v;
+}
+
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
+  if (!destuff_three_pass()) {
+    if (b.img_hi <= b.img_lo) return;
+    k_destuff<<<dim3(b.max_ds_tiles ? b.max_ds_tiles : 1u, b.img_hi - b.img_lo), DS_THREADS, 0, s>>>(b);
+    return;
+  }
   if (b.img_hi <= b.img_lo) return;
   // the per-image scan always runs: it writes the image state (a scan of zero bytes has no terminator)
   const dim3 grid(b.max_ds_tiles, b.img_hi - b.img_lo);
@@ -373,7 +559,15 @@ void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
   k_destuff_scan<<<b.img_hi - b.img_lo, DS_THREADS, 0, s>>>(b);
   if (b.max_ds_tiles) k_destuff_write<<<grid, DS_THREADS, 0, s>>>(b);
 }
-int destuff_kernel_count() { return 3; }
+int decode_prologue(const DecodeBatchDev &b, cudaStream_t s) {
+  // Coefficient blocks are cleared (clear_block, decoder.ml:112-116,160) by the entropy kernels themselves, block by
+  // block, right before they store into them (see zero_block in hcj_device.cuh).
+  cudaError_t e = cudaMemsetAsync(b.wide_flags, 0, (size_t)(b.total_blocks / 32 + 2) * 4, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(b.states, 0xff, sizeof(HcjImageState) * (size_t)b.n, s);  // overwritten by k_destuff for valid images
+  if (e == cudaSuccess) e = cudaMemsetAsync(b.ds_tiles, 0, sizeof(DsTile) * ((size_t)b.total_ds_tiles + 1), s);
+  return (int)e;
+}
+int destuff_kernel_count() { return destuff_three_pass() ? 3 : 1; }
 
 // ================================================================================================
 // Huffman tables in shared memory, shared by K2 and K3: per table HCJ_LUT_SIZE fast entries (32 bit,
@@ -1295,7 +1489,7 @@ struct alignas(16) IdctTile {
   uint16_t tm, nblk; // MCUs and blocks in the tile
   uint16_t qbytes;   // bytes of quant tables (512 per component)
   uint16_t remap;    // the thread -> block mapping differs from the previous tile's (first tile of an image, other width)
-  uint32_t pad_;
+  uint32_t fused;    // RGB24 output of a 4:4:4 image: colour conversion inside the tile (HcjImageDesc::fused_rgb)
 };
 static_assert(sizeof(IdctTile) == 32, "two 16-byte cp.async per record");
 
@@ -1331,7 +1525,7 @@ __global__ void __launch_bounds__(128) k_idct_plan(DecodeBatchDev b) {
   t.nblk = (uint16_t)(tm * d.bpm);
   t.qbytes = (uint16_t)(d.ncomp * 512);
   t.remap = (uint16_t)(tile == 0 || tm != ptm);
-  t.pad_ = 0;
+  t.fused = d.fused_rgb;
   b.idct_plan[d.idct_tile_off + tile] = t;
 }
 
@@ -1388,6 +1582,134 @@ __device__ __forceinline__ void idct_fetch_record(const DecodeBatchDev &b, IdctT
   asm volatile("cp.async.commit_group;\n" ::: "memory");  // one group per call, empty past the end
 }
 
+// NW words to `nbytes` bytes at any address: 16-byte stores when the address allows and all bytes are wanted,
+// 4-byte stores when it is word aligned, bytes otherwise (and for the tail).
+template <int NW>
+__device__ __forceinline__ void store_any(uint8_t *dst, const uint32_t (&w)[NW], int nbytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+  if (NW % 4 == 0 && (a & 15u) == 0 && nbytes == NW * 4) {
+#pragma unroll
+    for (int k = 0; k < NW / 4; k++) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  } else if ((a & 3u) == 0) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+      if (4 * k + 4 <= nbytes) {
+        reinterpret_cast<uint32_t *>(dst)[k] = w[k];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (4 * k + i < nbytes) dst[4 * k + i] = (uint8_t)(w[k] >> (8 * i));
+      }
+    }
+  } else {
+    // not word aligned: up to three head bytes, then the words of the byte sequence shifted by the head (funnel
+    // shifts over neighbouring words), then up to three tail bytes - instead of a byte store per byte
+    const int head = (4 - (int)(a & 3u)) & 3, sh = 8 * head;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      if (i < head && i < nbytes) dst[i] = (uint8_t)(w[0] >> (8 * i));
+    const int nw = nbytes > head ? (nbytes - head) >> 2 : 0;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+    uint32_t tail = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+      const uint32_t v = __funnelshift_r(w[k], k + 1 < NW ? w[k + 1] : 0u, sh);  // bytes head + 4k .. head + 4k + 3
+      if (k < nw) d32[k] = v;
+      if (k == nw) tail = v;
+    }
+    const int done = head + 4 * nw;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      if (done + i < nbytes) dst[done + i] = (uint8_t)(tail >> (8 * i));
+  }
+}
+// ------------------------------------------------------------------------------------------------
+// J4: dequantise + IDCT + colour in ONE kernel for RGB24 output of 4:4:4 images (north_star: "dequantisation, 8x8
+// IDCT, upsampling and YCbCr->RGB as one fused kernel"; for 4:4:4 Planar_444 is the identity).  The three blocks of an
+// MCU sit in the same tile, so the samples never travel through HBM as planes:
+//   1. every thread takes its block's coefficients into registers;           barrier: the staged tile is free
+//   2. transform as in the planar path; the 8 x 8 samples go to an exchange area laid out as 24 rows (component,
+//      row of the tile) of 8 * 42 samples inside the just-emptied stage;    barrier
+//   3. the threads convert units of 8 horizontally adjacent pixels (three 8-byte reads, 24 bytes of RGB out).
+// Blocks flagged for the 64-bit IDCT are transformed with the 32-bit one here like all others and put right
+// afterwards by k_rgb444_fix (the rare path must not cost this one registers); images whose quant tables need the
+// 64-bit path throughout are not fused (HcjImageDesc::fused_rgb is decided on the host).
+// ------------------------------------------------------------------------------------------------
+constexpr int FUSED_ROW_PITCH = 8 * (IDCT_MAX_THREADS / 3);  // 336 bytes: one sample row of the widest 4:4:4 tile
+
+// YCbCr -> RGB (the stated formula) for one pixel, packed 0x00BBGGRR.  The -128 offsets of Cb / Cr are
+// folded into the rounding constants, so a channel is one multiply-add, one shift and one add.
+__device__ __forceinline__ uint32_t ycc_to_rgb_raw(int Y, int Cb, int Cr) {
+  const int r = Y + ((91881 * Cr + (32768 - 91881 * 128)) >> 16);
+  const int g = Y + ((-22554 * Cb - 46802 * Cr + (32768 + (22554 + 46802) * 128)) >> 16);
+  const int bl = Y + ((116130 * Cb + (32768 - 116130 * 128)) >> 16);
+  uint32_t t, px;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(0), "r"(bl), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(t));
+  return px;
+}
+
+__device__ __forceinline__ void idct_tile_rgb444(const DecodeBatchDev &b, const IdctTile &t, IdctStage &st, const IdctMap &mp, int tid) {
+  uint8_t *xch = reinterpret_cast<uint8_t *>(st.tile);
+  const bool mine = (mp.misc & (1u << 10)) != 0u;
+  const int slot = (int)(mp.misc & 255u);
+  const int c = (int)((mp.misc >> 8) & 3u);
+  // (the threads beyond the tile's blocks run along on block 0 and store nothing: no conditionally defined registers
+  // across the barrier, which the compiler would keep in local memory)
+  uint32_t cw[32];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint4 u = st.tile[slot * 8 + (j ^ (slot & 7))];
+    cw[4 * j] = u.x, cw[4 * j + 1] = u.y, cw[4 * j + 2] = u.z, cw[4 * j + 3] = u.w;
+  }
+  __syncthreads();  // every block of the tile is in registers: the stage becomes the exchange area
+  {
+    uint32_t pix[16];
+    reconstruct_fast<false>(cw, st.q + c * 128 + 64, pix);
+    uint8_t *dst = xch + c * 8 * FUSED_ROW_PITCH + (mp.xy & 0xffffu);  // x inside the tile = 8 * MCU
+    if (mine) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(dst + r * FUSED_ROW_PITCH) = make_uint2(pix[2 * r], pix[2 * r + 1]);
+    }
+  }
+  __syncthreads();
+  const HcjImageDesc &d = b.descs[t.img];
+  const int tm = t.tm, width = d.width, height = d.height;
+  const int x_tile = (int)t.m0 * 8, y_tile = (int)t.my * 8;
+  uint8_t *out = b.out + d.out_off;
+  for (int u = tid; u < 8 * tm; u += IDCT_MAX_THREADS) {
+    const int r = u / tm, m = u - r * tm;
+    const int x = x_tile + m * 8, y = y_tile + r;
+    if (y >= height || x >= width) continue;
+    const uint2 vy = *reinterpret_cast<const uint2 *>(xch + r * FUSED_ROW_PITCH + m * 8);
+    const uint2 vu = *reinterpret_cast<const uint2 *>(xch + (8 + r) * FUSED_ROW_PITCH + m * 8);
+    const uint2 vv = *reinterpret_cast<const uint2 *>(xch + (16 + r) * FUSED_ROW_PITCH + m * 8);
+    uint32_t o[6];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {  // 4 pixels -> 12 bytes = 3 words
+      const uint32_t wy = k ? vy.y : vy.x, wu = k ? vu.y : vu.x, wv = k ? vv.y : vv.x;
+      uint32_t px[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) px[i] = ycc_to_rgb_raw((int)byte_of(wy, i), (int)byte_of(wu, i), (int)byte_of(wv, i));
+      o[3 * k + 0] = px[0] | (px[1] << 24);
+      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
+      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    uint8_t *dst = out + ((size_t)y * width + x) * 3;
+    const int n = min(8, width - x);
+    if (n == 8 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
+      reinterpret_cast<uint2 *>(dst)[0] = make_uint2(o[0], o[1]);
+      reinterpret_cast<uint2 *>(dst)[1] = make_uint2(o[2], o[3]);
+      reinterpret_cast<uint2 *>(dst)[2] = make_uint2(o[4], o[5]);
+    } else {
+      store_any<6>(dst, o, 3 * n);
+    }
+  }
+}
+
+// FUSED = true is the instance launched for RGB24 batches that hold 4:4:4 images: their tiles take the fused path
+// (idct_tile_rgb444 below); every other tile, and every tile of the FUSED = false instance, takes the planar path.
+template <bool FUSED>
 __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
     k_idct_persistent(const __grid_constant__ DecodeBatchDev b, int mode) {
   extern __shared__ uint4 s_dyn[];
@@ -1460,7 +1782,9 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
     int tnow;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tnow));
     const IdctMap mp = s_map.get(tnow);
-    if (mp.misc & (1u << 10)) {
+    if (FUSED && t.fused) {  // CTA-uniform
+      idct_tile_rgb444(b, t, st, mp, tnow);
+    } else if (mp.misc & (1u << 10)) {
       const int slot = (int)(mp.misc & 255u);
       uint32_t cw[32];
 #pragma unroll
@@ -1496,7 +1820,9 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   const int grid = HCJ_IDCT_CTAS_PER_SM * (b.sm_count > 0 ? b.sm_count : 148);
   k_idct_plan<<<dim3((b.max_idct_tiles + 127) / 128, b.img_hi - b.img_lo), 128, 0, s>>>(b);
   const uint32_t total = b.tile_hi - b.tile_lo;
-  k_idct_persistent<<<(unsigned)(total < (uint32_t)grid ? total : grid), IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
+  const unsigned ctas = (unsigned)(total < (uint32_t)grid ? total : grid);
+  if (mode == 2 && b.has_fused) k_idct_persistent<true><<<ctas, IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
+  else k_idct_persistent<false><<<ctas, IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
 }
 
 // The coefficient buffer as the TMA unit sees it: uint16 [total blocks][64], box = HCJ_IDCT_THREADS blocks x 64,
@@ -1597,47 +1923,6 @@ __device__ __forceinline__ uint32_t ycc_to_rgb(int Y, int Cb, int Cr) {
   return px;
 }
 
-// NW words to `nbytes` bytes at any address: 16-byte stores when the address allows and all bytes are wanted,
-// 4-byte stores when it is word aligned, bytes otherwise (and for the tail).
-template <int NW>
-__device__ __forceinline__ void store_any(uint8_t *dst, const uint32_t (&w)[NW], int nbytes) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-  if ((a & 15u) == 0 && nbytes == NW * 4) {
-#pragma unroll
-    for (int k = 0; k < NW / 4; k++) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-  } else if ((a & 3u) == 0) {
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-      if (4 * k + 4 <= nbytes) {
-        reinterpret_cast<uint32_t *>(dst)[k] = w[k];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          if (4 * k + i < nbytes) dst[4 * k + i] = (uint8_t)(w[k] >> (8 * i));
-      }
-    }
-  } else {
-    // not word aligned: up to three head bytes, then the words of the byte sequence shifted by the head (funnel
-    // shifts over neighbouring words), then up to three tail bytes - instead of a byte store per byte
-    const int head = (4 - (int)(a & 3u)) & 3, sh = 8 * head;
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-      if (i < head && i < nbytes) dst[i] = (uint8_t)(w[0] >> (8 * i));
-    const int nw = nbytes > head ? (nbytes - head) >> 2 : 0;
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
-    uint32_t tail = 0;
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-      const uint32_t v = __funnelshift_r(w[k], k + 1 < NW ? w[k + 1] : 0u, sh);  // bytes head + 4k .. head + 4k + 3
-      if (k < nw) d32[k] = v;
-      if (k == nw) tail = v;
-    }
-    const int done = head + 4 * nw;
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-      if (done + i < nbytes) dst[done + i] = (uint8_t)(tail >> (8 * i));
-  }
-}
 // 16 bytes from an 8-byte aligned address
 __device__ __forceinline__ void load16(const uint8_t *p, uint32_t (&w)[4]) {
   if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
@@ -1733,7 +2018,7 @@ __device__ __forceinline__ bool rgb_sub_group(const DecodeBatchDev &b, const Hcj
 template <bool PLANAR, bool SUB>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
 __global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
-  if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB) return;
+  if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB || (!PLANAR && d.fused_rgb)) return;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
   if (y >= d.height || x0 >= d.width) return;
   const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off,
@@ -1802,8 +2087,43 @@ __global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
   }
 }
 
+// Fused RGB24 images: the 8 x 8 pixels of every MCU that holds a block flagged for the 64-bit IDCT (pathological
+// coefficient sums, see HCJ_IDCT_L1_LIMIT) are recomputed with the model's arithmetic verbatim.  One thread per 32
+// blocks of an image looks at their flags; almost all of them find nothing.  grid (ceil(max blocks / 32 / 128), images)
+__global__ void __launch_bounds__(128) k_rgb444_fix(DecodeBatchDev b) {
+  const HcjImageDesc &d = b.descs[blockIdx.y + b.img_lo];
+  if (!d.valid || !d.fused_rgb) return;
+  const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) * 32u;
+  if (first >= d.nblocks) return;
+  const uint64_t g0 = d.coef_off + first;
+  const uint32_t w0 = b.wide_flags[g0 >> 5], w1 = b.wide_flags[(g0 >> 5) + 1];
+  uint32_t bits = __funnelshift_r(w0, w1, (uint32_t)(g0 & 31u));
+  if (first + 32u > d.nblocks) bits &= (1u << (d.nblocks - first)) - 1u;
+  uint32_t done_mcu = 0xffffffffu;
+  while (bits) {
+    const uint32_t blk = first + (uint32_t)__ffs((int)bits) - 1u;
+    bits &= bits - 1u;
+    const uint32_t mcu = blk / 3u;
+    if (mcu == done_mcu) continue;
+    done_mcu = mcu;
+    uint32_t pix[3][16];
+    for (int c = 0; c < 3; c++)
+      reconstruct_wide(reinterpret_cast<const uint32_t *>(b.coefs + (d.coef_off + (uint64_t)mcu * 3u + c) * 64), b.qtables + d.qt_off + c * 128, pix[c]);
+    const int x0 = (int)(mcu % (uint32_t)d.mcus_wide) * 8, y0 = (int)(mcu / (uint32_t)d.mcus_wide) * 8;
+    for (int r = 0; r < 8 && y0 + r < d.height; r++)
+      for (int i = 0; i < 8 && x0 + i < d.width; i++) {
+        const int w = 2 * r + (i >> 2), sh = 8 * (i & 3);
+        const uint32_t px = ycc_to_rgb((int)((pix[0][w] >> sh) & 0xffu), (int)((pix[1][w] >> sh) & 0xffu), (int)((pix[2][w] >> sh) & 0xffu));
+        uint8_t *dst = b.out + d.out_off + ((size_t)(y0 + r) * d.width + x0 + i) * 3;
+        dst[0] = (uint8_t)px, dst[1] = (uint8_t)(px >> 8), dst[2] = (uint8_t)(px >> 16);
+      }
+  }
+}
+
 void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
+  if (!planar444 && b.has_fused && b.max_blocks)
+    k_rgb444_fix<<<dim3((b.max_blocks + 32 * 128 - 1) / (32 * 128), b.img_hi - b.img_lo), 128, 0, s>>>(b);
   dim3 block(128);
   dim3 grid((b.max_width / 16 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
   if (b.has_444) {
@@ -1985,7 +2305,8 @@ int configure_device(int *sm_count) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_spec_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(base + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t)));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_idct_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_idct_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_idct_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDCT_SMEM);
   if (sm_count) *sm_count = sms;
   return (int)e;
 }

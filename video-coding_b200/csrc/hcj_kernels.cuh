@@ -21,6 +21,7 @@ struct DecodeBatchDev {
   uint32_t *seg_offs;             // per image: nseg_expected + 1 byte offsets into its entropy bytes
   struct DsTile *ds_tiles;        // per 4 KiB tile of every scan: counts, then offsets (k_destuff_*)
   uint32_t max_ds_tiles;          // max tiles of any image
+  uint32_t total_ds_tiles;        // records in ds_tiles (zeroed before every decode: the look-back reads their status)
   const HcjTableSet *table_sets;
   const uint16_t *lut_primary;    // primary LUT pool
   const uint16_t *lut_full;       // full LUT pool
@@ -53,7 +54,9 @@ struct DecodeBatchDev {
   uint32_t tile_lo, tile_hi;      // tiles of the images [img_lo, img_hi)
   int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
   uint32_t max_rgb_rows;          // max image height (RGB mode)
-  int has_444, has_subsampled;    // the batch holds 4:4:4 / sub-sampled images: which instances of k_rgb to launch
+  int has_444, has_subsampled;    // the batch holds 4:4:4 / sub-sampled images that go through k_rgb: which instances to launch
+  int has_fused;                  // ... 4:4:4 images whose RGB24 is produced inside k_idct_persistent (HcjImageDesc::fused_rgb)
+  uint32_t max_blocks;            // max blocks of any image
   uint32_t max_width;
   uint64_t total_blocks;
   // sub-range of the batch handled by one launch (the pipelined host path decodes chunk by chunk)
@@ -65,6 +68,9 @@ struct DecodeBatchDev {
 // Once per context, with its device current: shared-memory opt-ins of the kernels (a per-device attribute) and the
 // SM count.  Returns a cudaError_t-compatible code.
 int configure_device(int *sm_count);
+// Clears what a decode pass expects to find cleared (wide-block flags, image states, destuff tile records); once per
+// decode of the batch, before the first launch_destuff.  Returns a cudaError_t-compatible code.
+int decode_prologue(const DecodeBatchDev &b, cudaStream_t s);
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
 int destuff_kernel_count();
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
