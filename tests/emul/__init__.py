@@ -32,6 +32,8 @@ def lib():
         L.emu_idct32_unguarded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.emu_decode_segments.argtypes = [C.c_char_p, C.c_int64, C.c_uint, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.emu_decode_speculative.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+        L.emu_decode_units.argtypes = [C.c_char_p, C.c_int64, C.c_uint, C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
+                                       C.POINTER(C.c_int), C.c_void_p]
         L.emu_fdct_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_quantize_check.argtypes = [C.c_int]
         L.emu_quantize_check.restype = C.c_int64
@@ -97,6 +99,18 @@ def decode_speculative(jpeg, nblocks, scan_start, T=64, S=1024):
     wide = np.zeros(nblocks // 32 + 2, np.uint32)
     st = lib().emu_decode_speculative(jpeg, len(jpeg), ent, len(ent), T, S, coefs.ctypes.data, C.byref(rounds), wide.ctypes.data)
     decode_speculative.wide = wide
+    return st, coefs, rounds.value
+
+
+def decode_units(jpeg, nblocks, scan_start, T=64, S=1024, flags=1):
+    """Restart intervals decoded as units of the speculative decoder (long intervals, k_spec_*)."""
+    ent, segs = split_entropy(jpeg, scan_start, True)
+    so = np.array(segs, np.uint32)
+    coefs = np.full((nblocks, 64), 0x5A5A, np.int16)
+    rounds = C.c_int()
+    wide = np.zeros(nblocks // 32 + 2, np.uint32)
+    st = lib().emu_decode_units(jpeg, len(jpeg), flags, ent, so.ctypes.data, len(segs) - 1, T, S, coefs.ctypes.data, C.byref(rounds), wide.ctypes.data)
+    decode_units.wide = wide
     return st, coefs, rounds.value
 
 

@@ -22,13 +22,14 @@ struct HostTables {
   // what the kernels keep in shared memory (table index = comp * 2 + (0 = dc, 1 = ac))
   std::vector<uint32_t> fast;
   std::vector<uint32_t> sub;
+  std::vector<uint32_t> multi;  // multi-symbol AC entries of the synchronisation passes, [comp][HCJ_LUT_SIZE]
   uint32_t max_bits[HCJ_MAX_COMP * 2];
   const uint16_t *full[HCJ_MAX_COMP * 2];
   BlkInfo blkinfo[HCJ_MAX_BPM + 2];
   Tables tab[HCJ_MAX_COMP];
   int32_t quant[HCJ_MAX_COMP * 128];
   uint8_t blk_comp[HCJ_MAX_BPM + 2];
-  FastTables fast_tables() const { return FastTables{fast.data(), sub.data(), max_bits, full, blkinfo, quant}; }
+  FastTables fast_tables() const { return FastTables{fast.data(), sub.data(), max_bits, full, blkinfo, quant, multi.data()}; }
   Local local() const { return Local{fast_tables(), quant, blk_comp}; }
 };
 
@@ -60,7 +61,8 @@ int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj:
       for (int i = 0; i < HCJ_LUT_SIZE; i++)
         ht->fast[(size_t)ti * HCJ_LUT_SIZE + i] = fast_entry_from_primary(l.primary[i], (uint32_t)l.max_bits, k == 0);
       for (int i = 0; i < HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE; i++)
-        ht->sub[(size_t)ti * HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE + i] = fast_entry_or_none(l.primary[HCJ_LUT_SIZE + i], k == 0);
+        ht->sub[(size_t)ti * HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE + i] = fast_entry_or_none(
+            l.primary[HCJ_LUT_SIZE + ((i & ~(HCJ_LUT_SUB_SIZE - 1)) | (int)sub_source_index((uint32_t)i & (HCJ_LUT_SUB_SIZE - 1), (uint32_t)l.max_bits))], k == 0);
     }
     Tables &t = ht->tab[c];
     t.dc_off = (uint32_t)(c * 2) * HCJ_LUT_SIZE;
@@ -68,6 +70,10 @@ int prepare(const uint8_t *jpeg, size_t len, unsigned flags, hcj_header *h, hcj:
     t.dc_max_bits = ht->luts[c * 2].max_bits;
     t.ac_max_bits = ht->luts[c * 2 + 1].max_bits;
   }
+  ht->multi.assign((size_t)plan->info.ncomp * HCJ_LUT_SIZE, 0);
+  for (int c = 0; c < plan->info.ncomp; c++)  // build_multi_tables in hcj_kernels.cu
+    for (uint32_t i = 0; i < HCJ_LUT_SIZE; i++)
+      ht->multi[(size_t)c * HCJ_LUT_SIZE + i] = multi_sync_entry(ht->fast.data() + (size_t)(c * 2 + 1) * HCJ_LUT_SIZE, i);
   for (int k = 0; k < plan->info.blocks_per_mcu; k++) {
     const int c = plan->blk_comp[k];
     ht->blk_comp[k] = (uint8_t)c;
@@ -94,8 +100,9 @@ void store_sparse(const int16_t *row, int16_t *blk) {
 
 // Returns 0, or the status the fast pass itself reports (a run past coefficient 63), with *err_pos set.
 int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t end_bits, int64_t nblocks_end,
-                    int16_t *coefs, int64_t prezeroed_blk, ExactState &st, uint32_t *err_pos) {
-  const uint32_t lim = std::min(hi, end_bits >= 32u ? end_bits - 32u : 0u);
+                    int16_t *coefs, ExactState &st, uint32_t *err_pos) {
+  const uint32_t lim = end_bits >= 32u ? end_bits - 32u : 0u;
+  if (st.p >= lim) return 0;
   ExactLane s;
   s.br.init(sc.words, st.p);
   s.c = st.cz >> 8;
@@ -105,13 +112,11 @@ int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t
   s.share = st.share;
   s.sumabs = 0;
   exact_bind_block(s, T);
-  bool leading = s.z != 0u;
-  if (leading && st.blk >= nblocks_end) return 0;
   int16_t row[64];
   memset(row, 0, sizeof(row));
   for (;;) {
     if (s.z == 0u) {
-      if (s.blk + 1 >= nblocks_end || s.br.pos >= lim) break;
+      if (s.blk + 1 >= nblocks_end || s.br.pos >= lim || s.br.pos >= hi) break;
       if (!exact_dc_step(s, T, row)) break;
     } else {
       if (s.br.pos >= lim) break;
@@ -126,18 +131,15 @@ int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t
           return HCJ_DEV_COEF_INDEX;
         }
         if (exact_share_may_be_wide(s) && exact_share(s, T, row) >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, s.blk);
-        if (leading) store_sparse(row, coefs + (int64_t)s.blk * 64);
-        else memcpy(coefs + (int64_t)s.blk * 64, row, sizeof(row));
+        memcpy(coefs + (int64_t)s.blk * 64, row, sizeof(row));
         memset(row, 0, sizeof(row));
-        leading = false;
         exact_next_block(s, T, sc.bpm);
       }
     }
   }
   if (s.z != 0u) {  // the literal loop stores straight to memory (in the kernel the block stays staged)
     s.share = exact_share(s, T, row);
-    if (!leading && s.blk != prezeroed_blk) zero_block(coefs + (int64_t)s.blk * 64);
-    store_sparse(row, coefs + (int64_t)s.blk * 64);
+    memcpy(coefs + (int64_t)s.blk * 64, row, sizeof(row));
   }
   exact_save_pred(s);
   st.p = s.br.pos;
@@ -149,29 +151,29 @@ int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t
 }
 
 // subseq_sync with the fast steps in front
-void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
-  const uint32_t lim = std::min(hi, sc.total_bits >= 32u ? sc.total_bits - 32u : 0u);
+void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits) {
+  const uint32_t lim = std::min(hi, end_bits >= 32u ? end_bits - 32u : 0u);
+  const uint32_t lim_m = std::min(lim, hi >= (uint32_t)HCJ_LUT_BITS ? hi - (uint32_t)(HCJ_LUT_BITS - 1) : 0u);
   SyncLane s;
   s.br.init(sc.words, p);
   s.c = cz >> 8;
   s.z = cz & 0xffu;
   s.nstart = 0;
   s.d0 = s.d1 = s.d2 = s.d3 = 0;
+  s.first_p = 0xffffffffu;
+  s.first_c = 0;
   sync_bind_block(s, L.ft);
   for (;;) {
     if (s.br.pos >= lim) break;
     if (s.z == 0u) {
-      if (!sync_dc_step(s, L.ft)) break;
+      sync_dc_step(s, L.ft);
     } else {
-      sync_ac_step(s, L.ft);
-      if (z_no_code(s.z)) {
-        sync_ac_undo_no_code(s);
-        break;
-      }
+      sync_ac_step_multi(s, L.ft, lim_m);
       if (z_block_done(s.z)) sync_next_block(s, L.ft, sc.bpm);
     }
   }
-  subseq_sync(sc, L, s.br.pos, (s.c << 8) | s.z, hi, r);
+  subseq_sync(sc, L, s.br.pos, (s.c << 8) | s.z, hi, r, end_bits);
+  if (s.nstart) r.first_p = s.first_p, r.first_c = s.first_c;
   r.nstart += s.nstart;
   r.dcsum[0] += s.d0;
   r.dcsum[1] += s.d1;
@@ -179,19 +181,18 @@ void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz,
   r.dcsum[3] += s.d3;
 }
 
-// subseq_write with the fast steps in front
-int fast_subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
-                      int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *coefs, int64_t prezeroed_blk, uint32_t *err_pos) {
+// subseq_write with the fast steps in front: a run of whole blocks from the block boundary (p, block-in-MCU c)
+int fast_subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c, uint32_t hi, uint32_t end_bits, int64_t blk,
+                      int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *coefs, uint32_t *err_pos) {
   ExactState st;
   st.p = p;
-  st.cz = cz;
+  st.cz = c << 8;
   st.share = 0;
   st.blk = blk;
   for (int k = 0; k < HCJ_MAX_COMP; k++) st.pred[k] = pred[k];
-  // the fast lane stops at `hi` exactly like the literal loop; with hi = 0xffffffff it runs to the end of the data
-  int err = fast_exact_lane(sc, L.ft, hi, end_bits, nblocks, coefs, prezeroed_blk, st, err_pos);
+  int err = fast_exact_lane(sc, L.ft, hi, end_bits, nblocks, coefs, st, err_pos);
   if (err) return err;
-  return subseq_write(sc, L, st.p, st.cz, hi, end_bits, st.blk, st.pred, nblocks, coefs, prezeroed_blk, err_pos, st.share);
+  return subseq_write(sc, L, st.p, st.cz >> 8, hi, end_bits, st.blk, st.pred, nblocks, coefs, err_pos, st.cz & 0xffu, st.share);
 }
 
 }  // namespace
@@ -246,7 +247,7 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
     if (seg_bits > 16) {
       int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
       err = fast_subseq_write(sc, L, seg_off[seg] * 8, 0, 0xffffffffu, seg_off[seg + 1] * 8, (int64_t)mcu0 * bpm - 1, pred,
-                              (int64_t)mcu1 * bpm, coefs, -2, &err_pos);
+                              (int64_t)mcu1 * bpm, coefs, &err_pos);
     } else {
       BitReader br;
       br.init(words.data(), seg_off[seg] * 8, seg_off[seg + 1] * 8);
@@ -266,61 +267,47 @@ int emu_decode_segments(const uint8_t *jpeg, int64_t len, unsigned flags, const 
   return err_key == ~0ull ? 0 : -(int)(err_key & 0xff);
 }
 
-// k_huff_spec: T emulated threads per chunk, subsequences of S bits.  Returns status; rounds_out gets the
-// largest number of fix-point rounds any chunk needed.
-int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entropy, uint32_t ent_len, int T, uint32_t S,
-                           int16_t *coefs /* zeroed */, int *rounds_out, uint32_t *wide_flags /* zeroed, nblocks / 32 + 1 */) {
-  hcj_header *h = new hcj_header;
-  hcj::ImagePlan plan;
-  HostTables ht;
-  int st = prepare(jpeg, (size_t)len, 0, h, &plan, &ht);
-  delete h;
-  if (st) return st;
-  const hcj_frame_info &f = plan.info;
-  std::vector<uint32_t> words((ent_len + 15) / 4 + 4, 0);
-  memcpy(words.data(), entropy, ent_len);
-  const Local LT = ht.local();
-  const uint8_t *blk_comp = ht.blk_comp;
-  ScanCtx sc;
-  sc.words = words.data();
-  sc.total_bits = ent_len * 8;
-  sc.bpm = (uint32_t)f.blocks_per_mcu;
-  for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
-  sc.wide_flags = wide_flags;
-  sc.blk_base = 0;
-  const uint32_t L = sc.total_bits;
-  const int64_t nblocks = f.nblocks;
-  int max_rounds = 0;
+// k_spec_*: one unit of the speculative decoder = a scan without restart markers, or one (long) restart interval:
+// bits [lo_bits, end_bits) of the image's entropy data hold blocks [blk0, blk_end), DC predictors 0 at the start.
+// T emulated threads per chunk, subsequences of S bits.
+static void spec_unit(const ScanCtx &sc, const Local LT, const uint8_t *blk_comp, uint32_t lo_bits, uint32_t end_bits, int64_t blk0,
+                      int64_t blk_end, int T, uint32_t S, int16_t *coefs, unsigned long long *err_key, int *max_rounds) {
+  const uint32_t L = end_bits - lo_bits;
   if (L <= 16) {
     BitReader br;
-    br.init(sc.words, 0, L);
+    br.init(sc.words, lo_bits, end_bits);
     int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-    for (int64_t blk = 0; blk < nblocks; blk++) {
+    for (int64_t blk = blk0; blk < blk_end; blk++) {
       int comp = blk_comp[blk % sc.bpm];
       int err = decode_block_exact(br, LT, sc.tab[comp], L, pred[comp], coefs + blk * 64);
       flag_wide_block(sc, blk);
-      if (err) return err;
+      if (err) {
+        unsigned long long key = ((unsigned long long)br.pos << 8) | (unsigned long long)(-err);
+        if (key < *err_key) *err_key = key;
+        return;
+      }
     }
-    return 0;
+    return;
   }
   struct Carry {
     uint32_t p = 0, cz = 0;
     int64_t nstart = 0;
     int32_t dc[HCJ_MAX_COMP] = {0, 0, 0, 0};
   } carry;
+  carry.p = lo_bits;
+  carry.nstart = blk0;
   const uint32_t nsub = (L + S - 1) / S;
-  unsigned long long err_key = ~0ull;
   for (uint32_t base = 0; base < nsub; base += T) {
     const int nact = (int)(nsub - base < (uint32_t)T ? nsub - base : (uint32_t)T);
     std::vector<SubResult> r(nact);
     std::vector<uint32_t> sp(nact), scz(nact), endp(nact), endcz(nact), hi(nact);
     // phase A
     for (int t = 0; t < nact; t++) {
-      uint32_t i = base + t, lo = i * S;
-      hi[t] = lo + S < L ? lo + S : L;
+      uint32_t i = base + t, lo = lo_bits + i * S;
+      hi[t] = lo + S < end_bits ? lo + S : end_bits;
       sp[t] = t == 0 ? carry.p : lo;
       scz[t] = t == 0 ? carry.cz : 0;
-      fast_subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t]);
+      fast_subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t], end_bits);
       endp[t] = r[t].p;
       endcz[t] = r[t].cz;
     }
@@ -336,7 +323,7 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
           sp[t] = nsp;
           scz[t] = nscz;
           redo_cnt++;
-          fast_subseq_sync(sc, LT, nsp, nscz, hi[t], r[t]);
+          fast_subseq_sync(sc, LT, nsp, nscz, hi[t], r[t], end_bits);
           if (r[t].p != endp[t] || r[t].cz != endcz[t]) {
             any = true;
             np[t] = r[t].p;
@@ -350,18 +337,9 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       if (getenv("EMU_STATS")) fprintf(stderr, "round %d redo %d of %d\n", rounds, redo_cnt, nact);
       if (!any) break;
     }
-    if (rounds > max_rounds) max_rounds = rounds;
-    // phase C: first every thread clears the block it begins last (its neighbour finishes it) ...
-    {
-      int64_t acc = 0;
-      for (int t = 0; t < nact; t++) {
-        int64_t trailing = r[t].nstart > 0 ? carry.nstart + acc - 1 + (int64_t)r[t].nstart : -2;
-        if (trailing >= 0 && trailing < nblocks) zero_block(coefs + trailing * 64);
-        acc += r[t].nstart;
-      }
-    }
-    // ... then (after the barrier) the exact pass; run the emulated threads in REVERSE order so that a
-    // right neighbour really does store into a shared block before its owner gets to it
+    if (rounds > *max_rounds) *max_rounds = rounds;
+    // phase C: the exact pass; every thread decodes the blocks that begin in its subsequence (emulated threads run in
+    // REVERSE order: nothing may depend on a left neighbour having run first)
     std::vector<int64_t> exn(nact);
     std::vector<int32_t> exd(nact * HCJ_MAX_COMP);
     {
@@ -380,15 +358,14 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
       const int t = nact - 1 - tt;
       ex_n = exn[t];
       for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] = exd[t * HCJ_MAX_COMP + k];
+      if (r[t].first_p == 0xffffffffu) continue;  // no block begins here
       int32_t pred[HCJ_MAX_COMP];
       for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + ex_dc[k];
       int64_t blk = carry.nstart + ex_n - 1;
-      bool last = base + t == nsub - 1;
       uint32_t err_pos = 0;
-      const int64_t trailing = r[t].nstart > 0 ? blk + (int64_t)r[t].nstart : -2;
-      int err = fast_subseq_write(sc, LT, sp[t], scz[t], last ? 0xffffffffu : hi[t], L, blk, pred, nblocks, coefs, trailing, &err_pos);
+      int err = fast_subseq_write(sc, LT, r[t].first_p, r[t].first_c, hi[t], end_bits, blk, pred, blk_end, coefs, &err_pos);
       unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
-      if (err && key < err_key) err_key = key;  // the kernel's atomicMin
+      if (err && key < *err_key) *err_key = key;  // the kernel's atomicMin
     }
     ex_n = exn[nact - 1] + r[nact - 1].nstart;
     for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] = exd[(nact - 1) * HCJ_MAX_COMP + k] + r[nact - 1].dcsum[k];
@@ -397,8 +374,48 @@ int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entr
     carry.nstart += ex_n;
     for (int k = 0; k < HCJ_MAX_COMP; k++) carry.dc[k] += ex_dc[k];
   }
+}
+
+// k_spec_*: a scan without restart markers (nseg = 1, seg_off = {0, ent_len}) or one whose restart intervals are long
+// enough to be decoded speculatively, each interval a unit of its own.  Returns status; rounds_out gets the largest
+// number of fix-point rounds any chunk needed.
+int emu_decode_units(const uint8_t *jpeg, int64_t len, unsigned flags, const uint8_t *entropy, const uint32_t *seg_off, uint32_t nseg,
+                     int T, uint32_t S, int16_t *coefs /* zeroed */, int *rounds_out, uint32_t *wide_flags /* zeroed, nblocks / 32 + 1 */) {
+  hcj_header *h = new hcj_header;
+  hcj::ImagePlan plan;
+  HostTables ht;
+  int st = prepare(jpeg, (size_t)len, flags, h, &plan, &ht);
+  delete h;
+  if (st) return st;
+  const hcj_frame_info &f = plan.info;
+  const uint32_t ent_len = seg_off[nseg];
+  std::vector<uint32_t> words((ent_len + 15) / 4 + 4, 0);
+  memcpy(words.data(), entropy, ent_len);
+  const Local LT = ht.local();
+  ScanCtx sc;
+  sc.words = words.data();
+  sc.total_bits = ent_len * 8;
+  sc.bpm = (uint32_t)f.blocks_per_mcu;
+  for (int c = 0; c < f.ncomp; c++) sc.tab[c] = ht.tab[c];
+  sc.wide_flags = wide_flags;
+  sc.blk_base = 0;
+  const uint32_t nmcu = (uint32_t)(f.mcus_wide * f.mcus_high);
+  const uint32_t ri = nseg > 1 || f.restart_interval ? (uint32_t)f.restart_interval : nmcu;
+  int max_rounds = 0;
+  unsigned long long err_key = ~0ull;
+  for (uint32_t u = 0; u < nseg; u++) {
+    const uint32_t mcu0 = std::min(u * ri, nmcu), mcu1 = std::min(mcu0 + ri, nmcu);
+    spec_unit(sc, LT, ht.blk_comp, seg_off[u] * 8, seg_off[u + 1] * 8, (int64_t)mcu0 * sc.bpm, (int64_t)mcu1 * sc.bpm, T, S, coefs, &err_key,
+              &max_rounds);
+  }
   if (rounds_out) *rounds_out = max_rounds;
   return err_key == ~0ull ? 0 : -(int)(err_key & 0xff);
+}
+
+int emu_decode_speculative(const uint8_t *jpeg, int64_t len, const uint8_t *entropy, uint32_t ent_len, int T, uint32_t S,
+                           int16_t *coefs /* zeroed */, int *rounds_out, uint32_t *wide_flags /* zeroed, nblocks / 32 + 1 */) {
+  const uint32_t seg_off[2] = {0, ent_len};
+  return emu_decode_units(jpeg, len, 0, entropy, seg_off, 1, T, S, coefs, rounds_out, wide_flags);
 }
 
 // k_fdct_quant body for one 8x8 block of pixels (row-major), quant table in zig-zag order.

@@ -124,6 +124,20 @@ def test_restart_interval_decode(orc, ri):
     assert dec.yuv() == twin.yuv()
 
 
+@pytest.mark.parametrize("ri,S", [(1, 128), (3, 128), (13, 256), (40, 512), (200, 1024)])
+def test_restart_intervals_as_speculative_units(orc, ri, S):
+    """Long restart intervals go through the subsequence decoder, every interval a unit with its own block range and
+    DC predictors (north_star: in parallel across restart intervals AND within an interval)."""
+    w, h = 208, 112
+    for chroma, q in ((420, 75), (444, 92)):
+        yuv = synth.frame(11 + ri, w, h, chroma)
+        jpg = orc.encode(yuv, w, h, chroma, q, restart_interval=ri)
+        dec, want = _oracle_coefs(orc, jpg)
+        st, got, _ = emul.decode_units(jpg, dec.nblocks, _scan_start(orc, jpg), T=32, S=S)
+        assert st == 0
+        assert np.array_equal(got, want), (chroma, ri)
+
+
 def test_truncated_stream_zero_extension(orc, data):
     """A scan cut short still decodes (the reader zero-extends, bitstream_reader.ml:19-22); same garbage."""
     jpg = data("mini.jpg")
@@ -138,6 +152,52 @@ def test_truncated_stream_zero_extension(orc, data):
     assert st == 0 and np.array_equal(got, want)
     st, got = emul.decode_segments(cut, dec.nblocks, _scan_start(orc, cut), restart=False)
     assert st == 0 and np.array_equal(got, want)
+
+
+def test_corrupt_short_scans_speculative(orc, data):
+    """Damaged scans of small images, where what is left of the data ends long before the blocks do: the blocks that
+    begin beyond the end of the data (the model's reader delivers zeros there) belong to the thread that gets there,
+    whichever subsequence it started in.  `corrupt_flat_48x98.jpg` is the case the GPU fuzz sweep found."""
+    cases = [data("corrupt_flat_48x98.jpg")]
+    rng = np.random.default_rng(17)
+    for i in range(30):
+        chroma = int(rng.choice([420, 422, 444]))
+        w, h = int(rng.integers(8, 120)), int(rng.integers(8, 100))
+        kind = int(rng.integers(3))
+        n = len(synth.frame(0, w, h, chroma))
+        yuv = synth.frame(i, w, h, chroma) if kind == 0 else bytes([int(rng.integers(256))]) * n if kind == 1 else rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        try:
+            j = bytearray(orc.encode(yuv, w, h, chroma, int(rng.choice([20, 75, 95])), restart_interval=int(rng.choice([0, 0, 5, 40]))))
+        except orc.OracleError:
+            continue
+        start = _scan_start(orc, bytes(j))
+        op = int(rng.integers(3))
+        if op == 0 and len(j) - start > 6:
+            for _ in range(int(rng.integers(1, 5))):
+                j[int(rng.integers(start, len(j) - 2))] = int(rng.integers(0xFF))
+        elif op == 1 and len(j) - start > 8:
+            j = j[: int(rng.integers(start + 1, len(j) - 2))] + b"\xff\xd9"
+        else:
+            p = int(rng.integers(start, len(j) - 2))
+            j = j[:p] + j[p + int(rng.integers(1, 6)):]
+        cases.append(bytes(j))
+    checked = 0
+    for k, j in enumerate(cases):
+        start = _scan_start(orc, j)
+        try:
+            dec, want = _oracle_coefs(orc, j)
+            ost, nblocks = 0, dec.nblocks
+        except orc.OracleError as e:
+            ost, nblocks = e.status, 4096
+        if ost not in (0, -2, -3, -4):
+            continue
+        for T, S in ((16, 128), (64, 1024)):
+            st, got, _ = emul.decode_units(j, nblocks, start, T=T, S=S)
+            assert st == ost, (k, T, S, st, ost)
+            if ost == 0:
+                assert np.array_equal(got, want), (k, T, S)
+                checked += 1
+    assert checked >= 10
 
 
 def test_corrupt_stream_status(orc, data):

@@ -554,6 +554,39 @@ def test_speculative_many_subsequences_and_rounds(hcj, ctx, orc):
         assert bytes(o) == orc.decode(j).yuv()
 
 
+def test_long_restart_intervals(hcj, ctx, orc):
+    """Restart intervals long enough for the subsequence decoder (north_star: in parallel across restart intervals and
+    WITHIN an interval): one MCU row per interval (a camera's DRI), a few rows, one interval for the whole image, an
+    interval count that does not divide the MCUs; next to short-interval and marker-free images in the same batch."""
+    cases = [(420, 75, 640, 368, 40), (420, 75, 640, 368, 22), (444, 92, 400, 240, 50), (422, 60, 512, 200, 32), (420, 85, 800, 608, 1000),
+             (420, 75, 640, 368, 920), (444, 95, 1000, 96, 125), (420, 75, 256, 192, 8), (420, 30, 333, 77, 0), (420, 50, 1920, 64, 120),
+             (444, 75, 333, 177, 100)]
+    jpgs = [orc.encode(synth.frame(5100 + i, w, h, c), w, h, c, q, restart_interval=ri) for i, (c, q, w, h, ri) in enumerate(cases)]
+    for mode in (hcj.OUT_YUV, hcj.OUT_RGB24):
+        outs, st = ctx.decode_batch(jpgs, mode)
+        assert st == [0] * len(jpgs)
+        for case, j, o in zip(cases, jpgs, outs):
+            dec = orc.decode(j)
+            assert bytes(o) == (dec.yuv() if mode == hcj.OUT_YUV else oracle_rgb(orc, dec).tobytes()), case
+    with ctx.batch(jpgs, hcj.OUT_PLANES) as b:
+        b.decode()
+        for i, j in enumerate(jpgs):
+            d = orc.decode(j, want_blocks=True)
+            assert np.array_equal(b.coefficients(i), d.coefs_abs_dc().astype(np.int16)), cases[i]
+    # an interval cut short / a missing marker: whatever the oracle says
+    bad = []
+    for j in jpgs[:6]:
+        h0 = hcj.header_decode(j).scan_byte_pos
+        k = j.find(b"\xff\xd1", h0)
+        bad.append(j[: k - 40] + j[k:] if k > h0 + 80 else j[:-40] + b"\xff\xd9")
+        bad.append(j[:k] + j[k + 2:] if k > 0 else j)
+    outs, st = ctx.decode_batch(bad)
+    for j, o, s_ in zip(bad, outs, st):
+        assert s_ == orc.decode_status(j)
+        if s_ == 0:
+            assert bytes(o) == orc.decode(j).yuv()
+
+
 def test_rgb_colour_vs_pillow(hcj, ctx, orc):
     """D13 on the device: the RGB24 output of 4:4:4 images against Pillow's YCbCr -> RGB applied to the device's own
     planar 4:4:4 output of the same images: +-1 (an independent colour conversion; the oracle's formula is pinned the

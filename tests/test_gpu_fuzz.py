@@ -33,6 +33,21 @@ def ctx(hcj):
     c.close()
 
 
+@pytest.fixture(params=["routing_default", "all_intervals_speculative"])
+def routing(request):
+    """Which entropy kernel decodes images with restart intervals: by default short intervals go one per thread (K2)
+    and long ones through the subsequence decoder (K3, every interval a unit); HCJ_LONG_RI_BLOCKS=1 sends every
+    interval, however short (degenerate ones of <= 16 bits included), through K3."""
+    old = os.environ.get("HCJ_LONG_RI_BLOCKS")
+    if request.param == "all_intervals_speculative":
+        os.environ["HCJ_LONG_RI_BLOCKS"] = "1"
+    yield request.param
+    if old is None:
+        os.environ.pop("HCJ_LONG_RI_BLOCKS", None)
+    else:
+        os.environ["HCJ_LONG_RI_BLOCKS"] = old
+
+
 def random_frame(rng, w, h, chroma, kind):
     cw = w if chroma == 444 else w // 2
     ch = h // 2 if chroma == 420 else h
@@ -78,7 +93,7 @@ def encode_cases(orc, rng, cases):
     return out_cases, jpgs
 
 
-def test_fuzz_decode_all_modes(hcj, ctx, orc):
+def test_fuzz_decode_all_modes(hcj, ctx, orc, routing):
     rng = np.random.default_rng(20261018 + SEED)
     cases, jpgs = encode_cases(orc, rng, random_cases(rng, COUNT, MAX_W, MAX_H))
     # (a restart interval of <= 16 bits makes the model's `show` bound observable: status -9, also a defined result)
@@ -101,7 +116,7 @@ def test_fuzz_decode_all_modes(hcj, ctx, orc):
                 assert bytes(o) == f(d), (mode, case)
 
 
-def test_fuzz_coefficients(hcj, ctx, orc):
+def test_fuzz_coefficients(hcj, ctx, orc, routing):
     rng = np.random.default_rng(7 + SEED)
     cases, jpgs = encode_cases(orc, rng, random_cases(rng, 40, 200, 120))
     with ctx.batch(jpgs, hcj.OUT_PLANES) as b:
@@ -113,7 +128,7 @@ def test_fuzz_coefficients(hcj, ctx, orc):
             assert np.array_equal(b.coefficients(i), d.coefs_abs_dc().astype(np.int16)), case
 
 
-def test_fuzz_corrupt_streams(hcj, ctx, orc):
+def test_fuzz_corrupt_streams(hcj, ctx, orc, routing):
     """Byte flips, insertions and cuts in the entropy-coded segment: the model mostly decodes garbage without raising;
     whatever the oracle does (frame or status), the library does, image by image."""
     rng = np.random.default_rng(99 + SEED)

@@ -257,7 +257,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   size_t total_sub = 0, total_ds_tiles = 0;
   uint32_t max_ds_tiles = 0, max_blocks = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
-  bool sub_log2_env = false;
+  bool sub_log2_env = false, spec_has_units = false;
+  uint64_t long_ri_blocks = 128;  // 4:2:0: intervals of 22 MCUs and more
+  if (const char *e = getenv("HCJ_LONG_RI_BLOCKS")) long_ri_blocks = (uint64_t)std::max(1, atoi(e));  // tuning / test knob
+  uint32_t guess_bits = 2048;
+  if (const char *e = getenv("HCJ_GUESS_BITS")) guess_bits = (uint32_t)std::max(64, atoi(e));
   if (const char *e = getenv("HCJ_SUB_LOG2")) {  // tuning knob: preferred subsequence length, log2 of bits
     sub_log2 = (uint32_t)std::min(15, std::max(8, atoi(e)));
     sub_log2_env = true;
@@ -465,27 +469,33 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       d.blk_bx[k] = (uint8_t)plan.blk_bx[k];
       d.blk_by[k] = (uint8_t)plan.blk_by[k];
     }
-    if (d.ri) {
+    // Restart intervals of at least `long_ri_blocks` blocks (two or more subsequences each) are decoded like scans
+    // without markers, every interval a unit of the speculative decoder; shorter ones by one thread each (K2).
+    if (d.ri && (uint64_t)d.ri * (uint64_t)d.bpm < long_ri_blocks) {
       list_restart.push_back((uint32_t)i);
       max_segments = std::max(max_segments, d.nseg_expected);
     } else {
       list_spec.push_back((uint32_t)i);
+      if (d.ri) spec_has_units = true;
       // subsequences of 2^sub_log2 bits: long enough for the decoder to resynchronise inside one almost always
       // (a couple of MCUs), short enough for one thread each to fill the GPU
       // measured: 4096 bits for 65-bit blocks (1080p q75: 7.8 ms vs 8.0 ms at 8192), 8192 bits for 175-bit blocks
       // (4k 4:4:4 q95: 11.5 ms vs 12.9 ms at 4096): the per-subsequence work is per block, not per bit
-      const uint64_t est_bits = (uint64_t)(d.file_len - d.scan_start) * 8;
+      const uint64_t est_bits = (uint64_t)(d.file_len - d.scan_start) * 8;  // upper bound of the destuffed length
       const uint32_t s0 = sub_log2_env ? 1u << sub_log2 : (est_bits > (uint64_t)d.nblocks * 120 ? 8192u : 4096u);
       // ... and cut so that the subsequences fill whole CTAs of the exact pass (512 threads): 1080p q75 has ~800
-      // subsequences of 4096 bits, i.e. a second CTA with 44 % of its lanes idle; 1024 of ~3150 bits keep all busy
+      // subsequences of 4096 bits, i.e. a second CTA with 44 % of its lanes idle; 1024 of ~3150 bits keep all busy.
+      // (The count is bounded from above here: one subsequence beyond the last full CTA would cost a CTA of its own.)
       const uint64_t ctas = std::max<uint64_t>(1, (est_bits + 256ull * s0) / (512ull * s0));
-      uint64_t sb = (est_bits + 512 * ctas - 1) / (512 * ctas);
+      const uint64_t extra = d.nseg_expected > 1 ? d.nseg_expected : 0;  // every unit ends with a partial subsequence
+      const uint64_t slots = 512 * ctas > 2 * extra ? 512 * ctas - extra : 512 * ctas;
+      uint64_t sb = (est_bits + slots - 1) / slots;
       sb = (sb + 31) & ~31ull;
       d.sub_bits = (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(sb, s0 / 2));
       d.sub_off = (uint32_t)total_sub;
-      const size_t nsub_max = ((size_t)d.ent_cap * 8) / d.sub_bits + 2;
+      const size_t nsub_max = (size_t)((est_bits + d.sub_bits - 1) / d.sub_bits) + (size_t)extra + 1;
       total_sub += nsub_max + 1;
-      max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max + 255) / 256));
+      max_sub_chunks = std::max(max_sub_chunks, (uint32_t)((nsub_max - 1 + 255) / 256));
     }
     int tm_max = std::max(1, std::min(tile_mcus, HCJ_IDCT_THREADS / d.bpm));
     uint32_t tiles = (uint32_t)((d.mcus_wide + tm_max - 1) / tm_max) * (uint32_t)d.mcus_high;
@@ -537,9 +547,11 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   BALLOC(ds_tiles, hcjk::DsTile *, 8 * (total_ds_tiles + 1));
   if (!list_spec.empty()) {
     BALLOC(sub_start, uint16_t *, 2 * total_sub + 16);
-    BALLOC(sub_end, uint16_t *, 2 * total_sub + 16);
+    BALLOC(seg_sub, uint32_t *, 4 * (nsegs + 1));
     BALLOC(sub_end2, uint16_t *, 2 * total_sub + 16);
+    BALLOC(sub_first, uint32_t *, 4 * total_sub + 16);
     BALLOC(sub_nstart, int32_t *, 4 * total_sub + 16);
+    BALLOC(sub_blk, int32_t *, 4 * total_sub + 16);
     BALLOC(sub_dc, int4 *, 16 * total_sub + 16);
     BALLOC(sub_list, uint32_t *, 4 * total_sub + 16);
   }
@@ -579,6 +591,8 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.list_spec = d_ls;
   dv.n_spec = (int)list_spec.size();
   dv.max_sub_chunks = max_sub_chunks;
+  dv.spec_guess_bits = guess_bits;
+  dv.spec_has_units = spec_has_units ? 1 : 0;
   dv.max_ds_tiles = max_ds_tiles;
   dv.total_ds_tiles = (uint32_t)total_ds_tiles;
   dv.max_idct_tiles = max_tiles;
@@ -600,7 +614,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.ls_hi = (uint32_t)list_spec.size();
   b->list_restart = list_restart;
   b->list_spec = list_spec;
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count() : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled + (mode == HCJ_OUT_RGB24 ? dv.has_fused : 0) : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count(dv) : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled + (mode == HCJ_OUT_RGB24 ? dv.has_fused : 0) : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;
@@ -675,6 +689,21 @@ int hcj_batch_decode_stages(hcj_ctx *c, hcj_batch *b, float *ms, int capacity, i
   if (e == cudaSuccess) e = cudaGetLastError();
   for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
   for (auto &x : ev) cudaEventDestroy(x);
+  if (e == cudaSuccess && getenv("HCJ_SPEC_STATS") && !b->list_spec.empty()) {
+    // fix-point statistics of the speculative decoder: rounds and subsequences decoded again per image
+    std::vector<HcjImageState> states(b->n);
+    e = cudaMemcpy(states.data(), b->dev.states, sizeof(HcjImageState) * b->n, cudaMemcpyDeviceToHost);
+    unsigned long long redo = 0, rounds = 0;
+    unsigned max_rounds = 0, with_redo = 0;
+    for (uint32_t i : b->list_spec) {
+      const unsigned r = states[i].pad_ & 255u, n = states[i].pad_ >> 8;
+      redo += n, rounds += r;
+      max_rounds = std::max(max_rounds, r);
+      with_redo += r != 0;
+    }
+    fprintf(stderr, "[spec] images %zu  with redo %u  rounds total %llu max %u  subsequences redone %llu\n", b->list_spec.size(), with_redo,
+            rounds, max_rounds, redo);
+  }
   *nstages = 6;
   return e == cudaSuccess ? HCJ_OK : HCJ_ERR_CUDA - (int)e;
 }

@@ -155,16 +155,25 @@ struct FastTables {
   const uint16_t *const *full;  // [table] -> global memory, (length << 8) | data
   const BlkInfo *blkinfo;       // [block-in-MCU]
   const int32_t *quant;         // [scan component][128]
+  const uint32_t *multi;        // [pair][HCJ_LUT_SIZE] multi-symbol AC entries of the synchronisation passes (or null)
 };
 
-// `e` has HCJ_FAST_SLOW set.  Returns a resolved entry or HCJ_FAST_NONE.
+// `e` has HCJ_FAST_SLOW set.  Returns a resolved entry or HCJ_FAST_NONE.  The sub-tables are kept in a uniform shape
+// (load_tables): HCJ_LUT_SUB_SIZE entries each, indexed by the HCJ_LUT_SUB_BITS bits that follow the primary index,
+// whatever the table's longest code.
 HCJ_HD uint32_t fast_lookup_slow(const FastTables &T, uint32_t toff, uint32_t e, uint32_t win, bool isdc) {
   if (e == HCJ_FAST_NONE) return e;
-  const uint32_t ti = toff >> HCJ_LUT_BITS, mb = T.max_bits[ti];
+  const uint32_t ti = toff >> HCJ_LUT_BITS;
   if (e & HCJ_FAST_SUB)
     return T.sub[ti * (HCJ_LUT_NSUB * HCJ_LUT_SUB_SIZE) + (e & (HCJ_LUT_NSUB - 1)) * HCJ_LUT_SUB_SIZE +
-                 ((win >> (32u - mb)) & ((1u << (mb - HCJ_LUT_BITS)) - 1u))];
-  return fast_entry_or_none(T.full[ti][win >> (32u - mb)], isdc);
+                 ((win >> (32 - HCJ_LUT_BITS - HCJ_LUT_SUB_BITS)) & (HCJ_LUT_SUB_SIZE - 1))];
+  return fast_entry_or_none(T.full[ti][win >> (32u - T.max_bits[ti])], isdc);
+}
+// Entry `i` of a uniform sub-table from the host's (a verbatim slice of the full table: 2^(max_bits - HCJ_LUT_BITS)
+// entries, indexed by the bits between the primary index and the longest code).
+HCJ_HD uint32_t sub_source_index(uint32_t i, uint32_t max_bits) {
+  const uint32_t have = max_bits > (uint32_t)HCJ_LUT_BITS ? max_bits - (uint32_t)HCJ_LUT_BITS : 0u;
+  return have >= (uint32_t)HCJ_LUT_SUB_BITS ? i : i >> ((uint32_t)HCJ_LUT_SUB_BITS - have);
 }
 HCJ_HD uint32_t fast_lookup(const FastTables &T, uint32_t toff, uint32_t win, bool isdc) {
   uint32_t e = T.fast[toff + (win >> (32 - HCJ_LUT_BITS))];
@@ -284,11 +293,10 @@ struct ScanCtx {
   uint64_t blk_base;           // index of the image's first block in the batch
 };
 
-// A block's sum(|dequantised coefficient|) may be accumulated by up to four threads (a block is at most
-// 63 * 31 + 31 bits long, subsequences are at least 1024 bits): each flags the block when its share reaches
-// a quarter of the limit, so an unflagged block is certainly below HCJ_IDCT_L1_LIMIT.
-#define HCJ_WIDE_SHARE (HCJ_IDCT_L1_LIMIT_VALUE / 4)
+// A block is decoded by one thread from its DC symbol to its end, which forms the block's sum(|dequantised
+// coefficient|) and flags the block when it reaches the limit.
 #define HCJ_IDCT_L1_LIMIT_VALUE 60000
+#define HCJ_WIDE_SHARE HCJ_IDCT_L1_LIMIT_VALUE
 
 HCJ_HD void flag_wide_block(const ScanCtx &sc, int64_t blk) {
   uint64_t g = sc.blk_base + (uint64_t)blk;
@@ -303,6 +311,7 @@ struct SubResult {
   uint32_t p, cz;     // end state: cz = (c << 8) | z
   uint32_t nstart;    // DC symbols (blocks begun) decoded
   int32_t dcsum[HCJ_MAX_COMP];
+  uint32_t first_p, first_c;  // where the first of those blocks begins and its block-in-MCU index; first_p = 0xffffffff: none
 };
 
 // One symbol, DC or AC, decoded with the same instruction stream (lanes of a warp are rarely all in the
@@ -328,14 +337,16 @@ HCJ_HD Symbol read_symbol(const BitReader &br, const Local L, const Tables &t, b
   return s;
 }
 
-HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r) {
+HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   uint32_t nstart = 0;
   int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
   BitReader br;
-  br.init(sc.words, p, sc.total_bits);
+  br.init(sc.words, p, end_bits);  // end of the scan / of the restart interval: bits beyond it read as zero
   uint32_t comp = L.blk_comp[c];
   Tables t = sc.tab[comp];
+  r.first_p = 0xffffffffu;
+  r.first_c = 0;
   while (br.pos < hi) {
     const bool isdc = z == 0u;
     const Symbol s = read_symbol(br, L, t, isdc);
@@ -343,6 +354,7 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
       br.skip(1);
       continue;
     }
+    if (isdc && r.first_p == 0xffffffffu) r.first_p = br.pos, r.first_c = c;
     br.skip(s.nbits);
     const int32_t diff = isdc ? s.value : 0;
     d0 += comp == 0u ? diff : 0;
@@ -369,32 +381,28 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   r.dcsum[3] = d3;
 }
 
-// Final pass over one subsequence (or one restart interval) from its exact start state.  `blk` is the
-// index (within the image) of the block in progress (at the start of a block: the index of the previous
-// one), `pred` the DC predictors at the start state.  Stores coefficients (zig-zag, DC resolved) into the
-// `coefs`.  Decodes the symbols that start before `hi` and belong to blocks < `nblocks`;
-// with hi = 0xffffffff it runs until block nblocks - 1 is complete, reading zero bits past the end of
-// the data exactly as the model's reader does.
-// Every block is cleared by the thread that begins it, just before the DC store, except block
-// `prezeroed_blk`: a block this thread begins but another thread finishes must have been cleared before
-// that other thread's pass starts (the speculative kernel does so in a separate step); pass -2 if none.
-HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, uint32_t end_bits, int64_t blk,
-                        int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, int64_t prezeroed_blk,
-                        uint32_t *err_pos, uint32_t share0 = 0) {
-  uint32_t c = cz >> 8, z = cz & 0xffu;
+// Final pass of one thread: a run of whole blocks.  It starts at a block boundary (p, block-in-MCU c, DC next) with the
+// DC predictors `pred`; `blk` is the index (within the image) of the block before the first one it decodes.  It
+// decodes the blocks < `nblocks` that BEGIN before `hi` (the one in progress at `hi` is finished: the thread of the
+// next subsequence starts at the first block that begins in its own bits) or at / beyond `end_bits` (nobody else's:
+// the model's reader delivers zero bits there and the unit's blocks are decoded whatever the bits say); with
+// hi >= end_bits it runs until block nblocks - 1 is complete.  Stores
+// coefficients (zig-zag, DC resolved) into `coefs`; every block is cleared right before its DC store.
+HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c, uint32_t hi, uint32_t end_bits, int64_t blk,
+                        int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, uint32_t *err_pos,
+                        uint32_t z = 0, uint32_t share0 = 0) {
   BitReader br;
   br.init(sc.words, p, end_bits);
   uint32_t comp = L.blk_comp[c];
   Tables t = sc.tab[comp];
   const int32_t *q = L.quant + comp * 128;
   int32_t p0 = pred[0], p1 = pred[1], p2 = pred[2], p3 = pred[3];
-  if (z != 0u && blk >= nblocks) return HCJ_DEV_OK;
   int16_t *out = coefs + blk * 64;
-  uint32_t share = share0;  // this thread's part of the block's sum(|dequantised coefficient|)
+  uint32_t share = share0;  // sum(|dequantised coefficient|) of the block in progress
   int err = HCJ_DEV_OK;
-  while (br.pos < hi) {
+  for (;;) {
     const bool isdc = z == 0u;
-    if (isdc && blk + 1 >= nblocks) break;  // every block is complete
+    if (isdc && (blk + 1 >= nblocks || (br.pos >= hi && br.pos < end_bits))) break;  // every block is complete / the next one is not this thread's
     const Symbol s = read_symbol(br, L, t, isdc);
     if (s.e == 0u) {
       err = isdc ? HCJ_DEV_NO_DC_CODE : HCJ_DEV_NO_AC_CODE;
@@ -421,7 +429,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
       }
       blk++;
       out += 64;
-      if (blk != prezeroed_blk) zero_block(out);
+      zero_block(out);
     }
     if (isdc || (s.size != 0u && !eob)) {
       out[zi] = (int16_t)v;
@@ -429,7 +437,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
     }
     z = eob ? 64u : zi + 1u;
     if (z >= 64u) {
-      if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
+      if (share >= (uint32_t)HCJ_IDCT_L1_LIMIT_VALUE) flag_wide_block(sc, blk);
       share = 0;
       z = 0;
       c = c + 1u == sc.bpm ? 0u : c + 1u;
@@ -438,7 +446,6 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
       q = L.quant + comp * 128;
     }
   }
-  if (share >= (uint32_t)HCJ_WIDE_SHARE) flag_wide_block(sc, blk);
   if (err) *err_pos = br.pos;
   return err;
 }
@@ -612,12 +619,40 @@ HCJ_HD bool exact_dc_step(ExactLane &s, const FastTables T, int16_t *row) {
 }
 
 // ---- synchronisation pass (no coefficients): same symbols, only the state and the prefix-sum inputs
+//
+// The values of AC coefficients do not matter here, so one look-up may swallow SEVERAL AC symbols: entry `idx` of a
+// table's multi-symbol form describes the longest run of symbols whose codes lie wholly inside the HCJ_LUT_BITS
+// index bits (the magnitude bits of the last one may reach beyond them), ending early after an end-of-block (the next
+// symbol is a DC one, other table) and never longer than 31 bits:
+//   [7:0] bits consumed by all of them, [15:8] `pre` = zig-zag advance of all but the last, [31:24] total advance
+//   (capped at 127: any total that takes z to 64 or beyond closes the block, exactly as a single step would).
+// The run is valid for a lane at zig-zag index z iff z + pre < 64 (no symbol before the last one closes the block)
+// and every symbol of it starts before the lane's limit; otherwise the lane takes the single-symbol step.  Entries
+// whose first code is not resolved by the index bits are copied from the single-symbol table (HCJ_FAST_SLOW set).
+HCJ_HD uint32_t multi_sync_entry(const uint32_t *fast_ac /* the table's HCJ_LUT_SIZE single-symbol entries */, uint32_t idx) {
+  const uint32_t e = fast_ac[idx];
+  if (e & HCJ_FAST_SLOW) return e;
+  uint32_t pos = e & 0xffu, pre = 0, adv = e >> 24;
+  while (adv != HCJ_ZADV_EOB && pos < (uint32_t)HCJ_LUT_BITS && pre + adv < 63u) {
+    const uint32_t e2 = fast_ac[(idx << pos) & (HCJ_LUT_SIZE - 1)];
+    if (e2 & HCJ_FAST_SLOW) break;
+    if (pos + ((e2 >> 8) & 0xffu) > (uint32_t)HCJ_LUT_BITS) break;  // the code needs bits the index does not have
+    if (pos + (e2 & 0xffu) > 31u) break;
+    pre += adv;
+    adv = e2 >> 24;
+    pos += e2 & 0xffu;
+  }
+  const uint32_t tot = pre + adv > 127u ? 127u : pre + adv;
+  return pos | (pre << 8) | (tot << 24);
+}
+
 struct SyncLane {
   FastReader br;
   uint32_t c, z;
   uint32_t tdc, tac, comp;
   uint32_t nstart;
   int32_t d0, d1, d2, d3;
+  uint32_t first_p, first_c;  // the first block begun (SubResult)
 };
 HCJ_HD void sync_bind_block(SyncLane &s, const FastTables T) {
   const BlkInfo bi = T.blkinfo[s.c];
@@ -630,27 +665,39 @@ HCJ_HD void sync_next_block(SyncLane &s, const FastTables T, uint32_t bpm) {
   s.z = 0u;
   sync_bind_block(s, T);
 }
-// One AC symbol.  Afterwards: s.z >= 256 = undefined code (nothing consumed; the literal loop skips one
-// bit); any other s.z >= 64 closes the block, overlong runs included, exactly as subseq_sync does.
-HCJ_HD void sync_ac_step(SyncLane &s, const FastTables T) {
-  const uint32_t e = fast_lookup(T, s.tac, s.br.window(), false);
+// One look-up: as many AC symbols as the multi-symbol entry holds, or one (see multi_sync_entry).  `lim_m`: a run
+// may be taken while the position is below it (= all its symbols start before the end of the subsequence).  An
+// undefined code is skipped one bit at a time, as subseq_sync does.  Any s.z >= 64 afterwards closes the block,
+// overlong runs included, exactly as in subseq_sync.
+HCJ_HD void sync_ac_step_multi(SyncLane &s, const FastTables T, uint32_t lim_m) {
+  const uint32_t win = s.br.window();
+  const uint32_t idx = win >> (32 - HCJ_LUT_BITS);
+  uint32_t e = T.multi[((s.tac - HCJ_LUT_SIZE) >> 1) + idx];
+  if (s.z + byte_of(e, 1) >= 64u || s.br.pos >= lim_m) e = T.fast[s.tac + idx];  // the single-symbol entry
+  if (e & HCJ_FAST_SLOW) {
+    e = fast_lookup_slow(T, s.tac, e, win, false);
+    if (e == HCJ_FAST_NONE) e = 1u;  // consume one bit, no advance
+  }
   s.br.consume(byte_of(e, 0));
   s.z += e >> 24;
 }
-HCJ_HD void sync_ac_undo_no_code(SyncLane &s) { s.z -= 255u; }
-HCJ_HD bool sync_dc_step(SyncLane &s, const FastTables T) {
+// The DC symbol that begins the next block (s.z == 0, tables bound); an undefined code is skipped one bit at a time.
+HCJ_HD void sync_dc_step(SyncLane &s, const FastTables T) {
   const uint32_t win = s.br.window();
   const uint32_t e = fast_lookup(T, s.tdc, win, true);
-  if (e == HCJ_FAST_NONE) return false;
+  if (e == HCJ_FAST_NONE) {
+    s.br.consume(1u);
+    return;
+  }
   const int32_t v = fast_value(win, byte_of(e, 1), byte_of(e, 2));
   s.d0 += s.comp == 0u ? v : 0;
   s.d1 += s.comp == 1u ? v : 0;
   s.d2 += s.comp == 2u ? v : 0;
   s.d3 += s.comp == 3u ? v : 0;
+  if (s.nstart == 0u) s.first_p = s.br.pos, s.first_c = s.c;
   s.nstart++;
   s.br.consume(byte_of(e, 0));
   s.z = 1u;
-  return true;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct DecodeBatchDev {
   const uint8_t *files;           // compressed files, each starting at a 16-byte boundary
   uint8_t *entropy;               // destuffed entropy-coded bytes per image
   uint32_t *seg_offs;             // per image: nseg_expected + 1 byte offsets into its entropy bytes
+  uint32_t *seg_sub;              // same indexing, speculatively decoded images with restart intervals: first subsequence of every interval (k_spec_units)
   struct DsTile *ds_tiles;        // per 4 KiB tile of every scan: counts, then offsets (k_destuff_*)
   uint32_t max_ds_tiles;          // max tiles of any image
   uint32_t total_ds_tiles;        // records in ds_tiles (zeroed before every decode: the look-back reads their status)
@@ -42,12 +43,15 @@ struct DecodeBatchDev {
   int n_spec;
   // per subsequence of those images (index = HcjImageDesc::sub_off + subsequence):
   uint16_t *sub_start;            // packed decoder state the subsequence was last decoded from
-  uint16_t *sub_end;              // packed state at its end after the first pass
-  uint16_t *sub_end2;             // ... after the later passes (the current one)
-  int32_t *sub_nstart;            // blocks begun; after the scan: exclusive prefix within the image
+  uint16_t *sub_end2;             // packed state at its end (decoded from sub_start)
+  uint32_t *sub_first;            // where the first block begun inside the subsequence starts, and its block-in-MCU index
+  int32_t *sub_nstart;            // blocks begun
+  int32_t *sub_blk;               // index (within the image) of the first of them: segmented exclusive prefix (k_spec_fix)
   int4 *sub_dc;                   // DC differential sums per scan component; after the scan: exclusive prefix
   uint32_t *sub_list;             // scratch: subsequences to decode again in the current fix-point round
   uint32_t max_sub_chunks;        // max over list_spec of ceil(subsequences / 256)
+  uint32_t spec_guess_bits;       // bits in front of a subsequence that k_spec_sync decodes from a guessed state
+  int spec_has_units;             // list_spec holds images with (long) restart intervals: k_spec_units runs
   uint32_t max_idct_tiles;        // max over images of tiles_per_row * mcus_high
   struct IdctTile *idct_plan;     // one record per IDCT tile of the batch (k_idct_plan), image after image
   uint32_t total_idct_tiles;
@@ -75,7 +79,7 @@ void launch_destuff(const DecodeBatchDev &b, cudaStream_t s);
 int destuff_kernel_count();
 void launch_huff_restart(const DecodeBatchDev &b, cudaStream_t s);
 void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s);
-int huff_spec_kernel_count();
+int huff_spec_kernel_count(const DecodeBatchDev &b);
 void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s);
 int idct_kernel_count();
 size_t idct_plan_bytes(uint32_t tiles);

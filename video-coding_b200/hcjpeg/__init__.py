@@ -15,6 +15,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_ROOT, "lib", "libhcjpeg.so")
+if os.environ.get("HCJ_LIB_PATH"):  # A/B measurements of a variant build (make -C csrc OUT=../lib_x EXTRA=-D...)
+    LIB_PATH = os.path.abspath(os.environ["HCJ_LIB_PATH"])
 
 OUT_YUV, OUT_PLANES, OUT_RGB24, OUT_YUV444 = 0, 1, 2, 3
 FLAG_RESTART_EXT = 1
@@ -243,6 +245,8 @@ def build(force=False):
     """Compile libhcjpeg.so for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU).
     The library is rebuilt when the sources differ from the ones it was built from (a content stamp next to
     it: file times do not survive being copied to another machine)."""
+    if os.environ.get("HCJ_LIB_PATH"):
+        return LIB_PATH  # a variant build made by hand
     csrc = os.path.join(_ROOT, "csrc")
     stamp = LIB_PATH + ".stamp"
     digest = _source_digest()
