@@ -681,6 +681,17 @@ HCJ_HD void sync_ac_step_multi(SyncLane &s, const FastTables T, uint32_t lim_m) 
   s.br.consume(byte_of(e, 0));
   s.z += e >> 24;
 }
+// The same, one symbol per look-up (kernels that do not keep the multi-symbol tables).
+HCJ_HD void sync_ac_step_single(SyncLane &s, const FastTables T) {
+  const uint32_t win = s.br.window();
+  uint32_t e = T.fast[s.tac + (win >> (32 - HCJ_LUT_BITS))];
+  if (e & HCJ_FAST_SLOW) {
+    e = fast_lookup_slow(T, s.tac, e, win, false);
+    if (e == HCJ_FAST_NONE) e = 1u;  // consume one bit, no advance
+  }
+  s.br.consume(byte_of(e, 0));
+  s.z += e >> 24;
+}
 // The DC symbol that begins the next block (s.z == 0, tables bound); an undefined code is skipped one bit at a time.
 HCJ_HD void sync_dc_step(SyncLane &s, const FastTables T) {
   const uint32_t win = s.br.window();

@@ -1029,6 +1029,7 @@ static inline size_t multi_smem_bytes(const DecodeBatchDev &b) { return (size_t)
 // Synchronisation decode of one subsequence per lane (the semantics of subseq_sync): the fast steps run
 // warp-synchronously with the per-block work batched as in warp_exact_fast; the literal loop finishes
 // what is left (the last 32 bits of the unit, undefined codes met while speculating).
+template <bool MULTI = true>
 __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local L, bool valid, uint32_t p, uint32_t cz,
                                                  uint32_t hi, uint32_t end_bits, SubResult &r) {
   const FastTables T = L.ft;
@@ -1050,15 +1051,22 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   // Unlike the exact pass, the per-block code is light here (no write-out), and when decoding from a
   // guessed state the "blocks" of the lanes are of wildly different lengths: lanes at a block boundary are
   // served as soon as a quarter of the running lanes are waiting (measured against a half and an eighth).
-  const int thr = 2;
+#ifndef HCJ_SYNC_THR
+#define HCJ_SYNC_THR 2
+#endif
+#ifndef HCJ_SYNC_UNROLL
+#define HCJ_SYNC_UNROLL 2
+#endif
+  const int thr = HCJ_SYNC_THR;
   for (;;) {
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < HCJ_SYNC_UNROLL; u++) {
       if (st == 0) {
         if (s.br.pos >= lim) {
           st = 2;
         } else {
-          sync_ac_step_multi(s, T, lim_m);
+          if (MULTI) sync_ac_step_multi(s, T, lim_m);
+          else sync_ac_step_single(s, T);
           st = z_block_done(s.z) ? 1 : 0;
         }
       }
@@ -1197,7 +1205,183 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spec_units(DecodeBatchDev b) {
   if (t == 0) unit_sub[d.nseg_expected] = carry;
 }
 
-// Shared memory of the K3 kernels that only synchronise: [SmemTables][ScanCtx][tables][multi-symbol tables]
+// One value of the segmented scans of k_spec_fix: blocks begun and DC sums per component of a subsequence; `flag` =
+// it is the first one of its unit (the sums start again from the unit's first block and predictors 0).
+struct SegVal {
+  int32_t v[5];
+  uint32_t flag;
+};
+__device__ __forceinline__ void seg_combine(SegVal &right, const SegVal &left) {  // right = left (+) right
+  if (!right.flag) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) right.v[k] += left.v[k];
+  }
+  right.flag |= left.flag;
+}
+
+// The image-wide step between the synchronisation decode and the exact pass: one small CTA per image.  The step is
+// bound by the latency of a handful of lanes decoding a subsequence each (a round takes as long as one subsequence
+// takes one lane), so what matters is how many images are in flight per SM: 128 threads and no more shared memory
+// than the single-symbol tables (8 CTAs per SM).  (Run as the tail of the image's last k_spec_sync CTA instead - tables already loaded, no launch -
+// it took the same time in total: 2.64 ms against 1.95 + 0.65 ms; the CTA slots are the bottleneck, not the issue
+// slots.)
+constexpr int SPEC_FIX_THREADS = 128;
+__global__ void __launch_bounds__(SPEC_FIX_THREADS, 8) k_spec_fix(DecodeBatchDev b) {
+  extern __shared__ uint4 s_dyn4[];
+  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
+  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
+  void *lut_smem = reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15));
+  __shared__ SegVal s_seg[SPEC_FIX_THREADS / 32];
+  __shared__ uint32_t s_count;
+  SpecImage si;
+  if (!spec_image(b, blockIdx.x, si)) return;
+  const HcjImageDesc &d = *si.d;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int16_t *coefs = b.coefs + d.coef_off * 64;
+  const int n = (int)si.nsub;
+  uint32_t *list = b.sub_list + d.sub_off;
+
+  // ---- which subsequences were decoded from a state that is not their left neighbour's end state?
+  auto collect = [&]() {
+    if (t == 0) s_count = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n; j0 += SPEC_FIX_THREADS) {
+      const int j = j0 + t;
+      // (the first subsequence of a unit has the packed start state 0 and no left neighbour: its `start` entry is
+      // compared with the end of the previous unit's last subsequence only if jl > 0)
+      bool need = false;
+      if (j >= 1 && j < n && __ldcg(si.end2 + j - 1) != __ldcg(si.start + j)) need = si.nunits <= 1u || spec_sub(si, (uint32_t)j).jl > 0u;
+      const uint32_t mask = __ballot_sync(0xffffffffu, need);
+      if (mask) {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&s_count, (uint32_t)__popc(mask));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (need) list[at + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)j;
+      }
+    }
+    __syncthreads();
+    return (int)s_count;
+  };
+  int nredo = collect();
+  uint32_t rounds = 0, redone = 0;  // diagnostics (HcjImageState::pad_, printed under HCJ_SPEC_STATS)
+  // units of <= 16 bits (the model's `show` bound, bitstream_reader.ml:32, is in play): decoded serially below
+  bool tiny = false;
+  for (uint32_t u = t; u < si.nunits; u += SPEC_FIX_THREADS) tiny = tiny || (si.segs[u + 1] - si.segs[u]) * 8u <= 16u;
+  if (si.nunits == 1u) tiny = si.state->ent_len * 8u <= 16u;
+  const bool any_tiny = __syncthreads_or(tiny);
+
+  if (nredo || any_tiny) {  // CTA-uniform; the tables are only loaded now
+    const FastTables T = load_tables(st, lut_smem, b, d);
+    __syncthreads();
+    fill_scan_ctx(sc, st, b, d, si.state->ent_len * 8u);
+    __syncthreads();
+    const Local LT{T, st.quant, st.blk_comp};
+    if (any_tiny) {
+      const uint32_t ri = d.ri ? d.ri : d.nmcu;
+      for (uint32_t u = t; u < si.nunits; u += SPEC_FIX_THREADS) {
+        const uint32_t b0 = si.nunits > 1u ? si.segs[u] : 0u, b1 = si.nunits > 1u ? si.segs[u + 1] : si.state->ent_len;
+        const uint32_t bits = (b1 - b0) * 8u;
+        if (bits > 16u) continue;
+        BitReader br;
+        br.init(sc.words, b0 * 8u, b1 * 8u);
+        int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
+        const uint32_t mcu0 = min(u * ri, d.nmcu), mcu1 = min(mcu0 + ri, d.nmcu);
+        for (int64_t blk = (int64_t)mcu0 * d.bpm; blk < (int64_t)mcu1 * d.bpm; blk++) {
+          const uint32_t comp = st.blk_comp[blk % d.bpm];
+          const int err = decode_block_exact(br, LT, sc.tab[comp], bits, pred[comp], coefs + blk * 64);
+          flag_wide_block(sc, blk);
+          if (err) {
+            raise_status(si.state, err, br.pos);
+            break;
+          }
+        }
+      }
+    }
+    // ---- fix-point rounds over the compacted list
+    while (nredo) {
+      rounds++;
+      redone += (uint32_t)nredo;
+      for (int k0 = 0; k0 < nredo; k0 += SPEC_FIX_THREADS) {
+        const int k = k0 + t;
+        const bool valid = k < nredo;
+        const uint32_t j = valid ? __ldcg(list + k) : 1u;
+        const uint32_t ns = __ldcg(si.end2 + j - 1);  // reads within a round are unsynchronised (chaotic relaxation): the fix-point is unique
+        const SpecSub q = spec_sub(si, min(j, (uint32_t)n - 1u));
+        uint32_t p, cz;
+        spec_unpack(ns, q.lo, p, cz);
+        SubResult r;
+        warp_subseq_sync<false>(sc, LT, valid, p, cz, q.hi, q.uend, r);
+        if (valid) {
+          si.start[j] = (uint16_t)ns;
+          si.end2[j] = (uint16_t)spec_pack(r.p, q.hi, r.cz);
+          si.first[j] = spec_pack_first(r, q.lo);
+          si.nstart[j] = (int32_t)r.nstart;
+          si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
+        }
+      }
+      __syncthreads();
+      nredo = collect();
+    }
+  }
+
+  if (t == 0) si.state->pad_ = min(rounds, 255u) | (redone << 8);
+  // ---- segmented exclusive scans over the image's subsequences, in place: index of the first block begun in every
+  // subsequence (a unit's count starts at its first block) and the DC predictors there.
+  SegVal carry;
+#pragma unroll
+  for (int k = 0; k < 5; k++) carry.v[k] = 0;
+  carry.flag = 0;
+  for (int j0 = 0; j0 < n; j0 += SPEC_FIX_THREADS) {
+    const int j = j0 + t;
+    SegVal own, x;
+#pragma unroll
+    for (int k = 0; k < 5; k++) own.v[k] = 0;
+    own.flag = 0;
+    if (j < n) {
+      const int4 dc = __ldcg(si.dc + j);
+      own.v[0] = __ldcg(si.nstart + j), own.v[1] = dc.x, own.v[2] = dc.y, own.v[3] = dc.z, own.v[4] = dc.w;
+      if (si.nunits > 1u) {
+        const SpecSub q = spec_sub(si, (uint32_t)j);
+        own.flag = q.jl == 0u;
+        x = own;
+        if (own.flag) x.v[0] += q.blk0;
+      } else {
+        own.flag = j == 0;
+        x = own;
+      }
+    } else {
+      x = own;
+    }
+    // inclusive segmented scan of x inside the warp
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      SegVal o;
+#pragma unroll
+      for (int k = 0; k < 5; k++) o.v[k] = __shfl_up_sync(0xffffffffu, x.v[k], dlt);
+      o.flag = __shfl_up_sync(0xffffffffu, x.flag, dlt);
+      if (lane >= dlt) seg_combine(x, o);
+    }
+    __syncthreads();  // s_seg may still be read from the previous chunk
+    if (lane == 31) s_seg[warp] = x;
+    __syncthreads();
+    SegVal before = carry, total = carry;  // everything before this warp / the whole chunk, carried from chunk to chunk
+    for (int k = 0; k < SPEC_FIX_THREADS / 32; k++) {
+      SegVal w = s_seg[k];
+      seg_combine(w, total);
+      total = w;
+      if (k + 1 == warp) before = w;
+    }
+    seg_combine(x, before);
+    carry = total;
+    carry.flag = 0;
+    if (j < n) {
+      si.blk[j] = x.v[0] - own.v[0];  // exclusive (si.nstart keeps the counts: k_spec_write sorts by them)
+      si.dc[j] = make_int4(x.v[1] - own.v[1], x.v[2] - own.v[2], x.v[3] - own.v[3], x.v[4] - own.v[4]);
+    }
+  }
+}
+
+// Shared memory of k_spec_sync: [SmemTables][ScanCtx][tables][multi-symbol tables]
 #ifndef HCJ_SPEC_SYNC_CTAS
 #define HCJ_SPEC_SYNC_CTAS 4
 #endif
@@ -1229,184 +1413,14 @@ __global__ void __launch_bounds__(SPEC_THREADS, HCJ_SPEC_SYNC_CTAS) k_spec_sync(
     const uint32_t p0 = q.lo - q.ulo > b.spec_guess_bits ? q.lo - b.spec_guess_bits : q.ulo;
     warp_subseq_sync(sc, LT, warm, p0, 0u, q.lo, q.uend, r);
     if (warm) p = r.p, cz = r.cz;
+    warp_subseq_sync(sc, LT, valid, p, cz, q.hi, q.uend, r);
   }
-  warp_subseq_sync(sc, LT, valid, p, cz, q.hi, q.uend, r);
   if (valid) {
     si.start[j] = (uint16_t)spec_pack(p, q.lo, cz);
     si.end2[j] = (uint16_t)spec_pack(r.p, q.hi, r.cz);
     si.first[j] = spec_pack_first(r, q.lo);
     si.nstart[j] = (int32_t)r.nstart;
     si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
-  }
-}
-
-// One value of the segmented scans of k_spec_fix: blocks begun and DC sums per component of a subsequence; `flag` =
-// it is the first one of its unit (the sums start again from the unit's first block and predictors 0).
-struct SegVal {
-  int32_t v[5];
-  uint32_t flag;
-};
-__device__ __forceinline__ void seg_combine(SegVal &right, const SegVal &left) {  // right = left (+) right
-  if (!right.flag) {
-#pragma unroll
-    for (int k = 0; k < 5; k++) right.v[k] += left.v[k];
-  }
-  right.flag |= left.flag;
-}
-
-__global__ void __launch_bounds__(SPEC_THREADS, 4) k_spec_fix(DecodeBatchDev b) {
-  extern __shared__ uint4 s_dyn4[];
-  SmemTables &st = *reinterpret_cast<SmemTables *>(s_dyn4);
-  ScanCtx &sc = *reinterpret_cast<ScanCtx *>(reinterpret_cast<char *>(s_dyn4) + ((sizeof(SmemTables) + 15) & ~size_t(15)));
-  void *lut_smem = reinterpret_cast<char *>(&sc) + ((sizeof(ScanCtx) + 15) & ~size_t(15));
-  __shared__ SegVal s_seg[SPEC_THREADS / 32];
-  __shared__ uint32_t s_count;
-  SpecImage si;
-  if (!spec_image(b, blockIdx.x, si)) return;
-  const HcjImageDesc &d = *si.d;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int16_t *coefs = b.coefs + d.coef_off * 64;
-  const int n = (int)si.nsub;
-  uint32_t *list = b.sub_list + d.sub_off;
-
-  // ---- which subsequences were decoded from a state that is not their left neighbour's end state?
-  auto collect = [&]() {
-    if (t == 0) s_count = 0;
-    __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
-      const int j = j0 + t;
-      // (the first subsequence of a unit has the packed start state 0 and no left neighbour: its `start` entry is
-      // compared with the end of the previous unit's last subsequence only if jl > 0)
-      bool need = false;
-      if (j >= 1 && j < n && si.end2[j - 1] != si.start[j]) need = si.nunits <= 1u || spec_sub(si, (uint32_t)j).jl > 0u;
-      const uint32_t mask = __ballot_sync(0xffffffffu, need);
-      if (mask) {
-        uint32_t at = 0;
-        if (lane == 0) at = atomicAdd(&s_count, (uint32_t)__popc(mask));
-        at = __shfl_sync(0xffffffffu, at, 0);
-        if (need) list[at + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)j;
-      }
-    }
-    __syncthreads();
-    return (int)s_count;
-  };
-  int nredo = collect();
-  uint32_t rounds = 0, redone = 0;  // diagnostics (HcjImageState::pad_, printed under HCJ_SPEC_STATS)
-  // units of <= 16 bits (the model's `show` bound, bitstream_reader.ml:32, is in play): decoded serially below
-  bool tiny = false;
-  for (uint32_t u = t; u < si.nunits; u += SPEC_THREADS) tiny = tiny || (si.segs[u + 1] - si.segs[u]) * 8u <= 16u;
-  if (si.nunits == 1u) tiny = si.state->ent_len * 8u <= 16u;
-  const bool any_tiny = __syncthreads_or(tiny);
-
-  if (nredo || any_tiny) {  // CTA-uniform; rare: the tables are only loaded now
-    FastTables T = load_tables(st, lut_smem, b, d);
-    __syncthreads();
-    build_multi_tables(T, b, d);
-    fill_scan_ctx(sc, st, b, d, si.state->ent_len * 8u);
-    __syncthreads();
-    const Local LT{T, st.quant, st.blk_comp};
-    if (any_tiny) {
-      const uint32_t ri = d.ri ? d.ri : d.nmcu;
-      for (uint32_t u = t; u < si.nunits; u += SPEC_THREADS) {
-        const uint32_t b0 = si.nunits > 1u ? si.segs[u] : 0u, b1 = si.nunits > 1u ? si.segs[u + 1] : si.state->ent_len;
-        const uint32_t bits = (b1 - b0) * 8u;
-        if (bits > 16u) continue;
-        BitReader br;
-        br.init(sc.words, b0 * 8u, b1 * 8u);
-        int32_t pred[HCJ_MAX_COMP] = {0, 0, 0, 0};
-        const uint32_t mcu0 = min(u * ri, d.nmcu), mcu1 = min(mcu0 + ri, d.nmcu);
-        for (int64_t blk = (int64_t)mcu0 * d.bpm; blk < (int64_t)mcu1 * d.bpm; blk++) {
-          const uint32_t comp = st.blk_comp[blk % d.bpm];
-          const int err = decode_block_exact(br, LT, sc.tab[comp], bits, pred[comp], coefs + blk * 64);
-          flag_wide_block(sc, blk);
-          if (err) {
-            raise_status(si.state, err, br.pos);
-            break;
-          }
-        }
-      }
-    }
-    // ---- fix-point rounds over the compacted list
-    while (nredo) {
-      rounds++;
-      redone += (uint32_t)nredo;
-      for (int k0 = 0; k0 < nredo; k0 += SPEC_THREADS) {
-        const int k = k0 + t;
-        const bool valid = k < nredo;
-        const uint32_t j = valid ? list[k] : 1u;
-        const uint32_t ns = si.end2[j - 1];  // reads within a round are unsynchronised (chaotic relaxation): the fix-point is unique
-        const SpecSub q = spec_sub(si, min(j, (uint32_t)n - 1u));
-        uint32_t p, cz;
-        spec_unpack(ns, q.lo, p, cz);
-        SubResult r;
-        warp_subseq_sync(sc, LT, valid, p, cz, q.hi, q.uend, r);
-        if (valid) {
-          si.start[j] = (uint16_t)ns;
-          si.end2[j] = (uint16_t)spec_pack(r.p, q.hi, r.cz);
-          si.first[j] = spec_pack_first(r, q.lo);
-          si.nstart[j] = (int32_t)r.nstart;
-          si.dc[j] = make_int4(r.dcsum[0], r.dcsum[1], r.dcsum[2], r.dcsum[3]);
-        }
-      }
-      __syncthreads();
-      nredo = collect();
-    }
-  }
-
-  if (t == 0) si.state->pad_ = min(rounds, 255u) | (redone << 8);
-  // ---- segmented exclusive scans over the image's subsequences, in place: index of the first block begun in every
-  // subsequence (a unit's count starts at its first block) and the DC predictors there.
-  SegVal carry;
-#pragma unroll
-  for (int k = 0; k < 5; k++) carry.v[k] = 0;
-  carry.flag = 0;
-  for (int j0 = 0; j0 < n; j0 += SPEC_THREADS) {
-    const int j = j0 + t;
-    SegVal own, x;
-#pragma unroll
-    for (int k = 0; k < 5; k++) own.v[k] = 0;
-    own.flag = 0;
-    if (j < n) {
-      const int4 dc = si.dc[j];
-      own.v[0] = si.nstart[j], own.v[1] = dc.x, own.v[2] = dc.y, own.v[3] = dc.z, own.v[4] = dc.w;
-      if (si.nunits > 1u) {
-        const SpecSub q = spec_sub(si, (uint32_t)j);
-        own.flag = q.jl == 0u;
-        x = own;
-        if (own.flag) x.v[0] += q.blk0;
-      } else {
-        own.flag = j == 0;
-        x = own;
-      }
-    } else {
-      x = own;
-    }
-    // inclusive segmented scan of x inside the warp
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      SegVal o;
-#pragma unroll
-      for (int k = 0; k < 5; k++) o.v[k] = __shfl_up_sync(0xffffffffu, x.v[k], dlt);
-      o.flag = __shfl_up_sync(0xffffffffu, x.flag, dlt);
-      if (lane >= dlt) seg_combine(x, o);
-    }
-    __syncthreads();  // s_seg may still be read from the previous chunk
-    if (lane == 31) s_seg[warp] = x;
-    __syncthreads();
-    SegVal before = carry, total = carry;  // everything before this warp / the whole chunk, carried from chunk to chunk
-    for (int k = 0; k < SPEC_THREADS / 32; k++) {
-      SegVal w = s_seg[k];
-      seg_combine(w, total);
-      total = w;
-      if (k + 1 == warp) before = w;
-    }
-    seg_combine(x, before);
-    carry = total;
-    carry.flag = 0;
-    if (j < n) {
-      si.blk[j] = x.v[0] - own.v[0];  // exclusive (si.nstart keeps the counts: k_spec_write sorts by them)
-      si.dc[j] = make_int4(x.v[1] - own.v[1], x.v[2] - own.v[2], x.v[3] - own.v[3], x.v[4] - own.v[4]);
-    }
   }
 }
 
@@ -1470,7 +1484,7 @@ void launch_huff_spec(const DecodeBatchDev &b, cudaStream_t s) {
   const dim3 grid(b.max_sub_chunks, b.ls_hi - b.ls_lo);
   if (b.spec_has_units) k_spec_units<<<b.ls_hi - b.ls_lo, SPEC_THREADS, 0, s>>>(b);
   k_spec_sync<<<grid, SPEC_THREADS, smem_sync, s>>>(b);
-  k_spec_fix<<<b.ls_hi - b.ls_lo, SPEC_THREADS, smem_sync, s>>>(b);
+  k_spec_fix<<<b.ls_hi - b.ls_lo, SPEC_FIX_THREADS, base, s>>>(b);
   const dim3 grid_w((b.max_sub_chunks * SPEC_THREADS + SPEC_WRITE_THREADS - 1) / SPEC_WRITE_THREADS, b.ls_hi - b.ls_lo);
   k_spec_write<<<grid_w, SPEC_WRITE_THREADS, smem_write, s>>>(b);
 }
@@ -2411,7 +2425,7 @@ int configure_device(int *sm_count) {
   const size_t stage = (HR_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_huff_restart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + stage));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + multi_smem_bytes(worst)));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + multi_smem_bytes(worst)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_spec_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(base + (SPEC_WRITE_THREADS / 32) * HR_STAGE_WORDS * sizeof(uint32_t)));
