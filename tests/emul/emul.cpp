@@ -116,7 +116,7 @@ int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t
   memset(row, 0, sizeof(row));
   for (;;) {
     if (s.z == 0u) {
-      if (s.blk + 1 >= nblocks_end || s.br.pos >= lim || s.br.pos >= hi) break;
+      if (s.blk + 1 >= nblocks_end || s.br.pos >= lim || (s.c == 0u && s.br.pos >= hi)) break;
       if (!exact_dc_step(s, T, row)) break;
     } else {
       if (s.br.pos >= lim) break;
@@ -151,7 +151,7 @@ int fast_exact_lane(const ScanCtx &sc, const FastTables T, uint32_t hi, uint32_t
 }
 
 // subseq_sync with the fast steps in front
-void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits) {
+void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits, int32_t *dpre) {
   const uint32_t lim = std::min(hi, end_bits >= 32u ? end_bits - 32u : 0u);
   const uint32_t lim_m = std::min(lim, hi >= (uint32_t)HCJ_LUT_BITS ? hi - (uint32_t)(HCJ_LUT_BITS - 1) : 0u);
   SyncLane s;
@@ -161,19 +161,25 @@ void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz,
   s.nstart = 0;
   s.d0 = s.d1 = s.d2 = s.d3 = 0;
   s.first_p = 0xffffffffu;
-  s.first_c = 0;
+  s.nbefore = 0;
   sync_bind_block(s, L.ft);
   for (;;) {
     if (s.br.pos >= lim) break;
     if (s.z == 0u) {
-      sync_dc_step(s, L.ft);
+      sync_dc_step(s, L.ft, dpre);
     } else {
       sync_ac_step_multi(s, L.ft, lim_m);
       if (z_block_done(s.z)) sync_next_block(s, L.ft, sc.bpm);
     }
   }
-  subseq_sync(sc, L, s.br.pos, (s.c << 8) | s.z, hi, r, end_bits);
-  if (s.nstart) r.first_p = s.first_p, r.first_c = s.first_c;
+  int32_t dpre2[HCJ_MAX_COMP];
+  subseq_sync(sc, L, s.br.pos, (s.c << 8) | s.z, hi, r, end_bits, dpre2);
+  if (s.first_p != 0xffffffffu) {
+    r.first_p = s.first_p, r.nbefore = s.nbefore;
+  } else if (r.first_p != 0xffffffffu) {
+    r.nbefore += s.nstart;
+    dpre[0] = s.d0 + dpre2[0], dpre[1] = s.d1 + dpre2[1], dpre[2] = s.d2 + dpre2[2], dpre[3] = s.d3 + dpre2[3];
+  }
   r.nstart += s.nstart;
   r.dcsum[0] += s.d0;
   r.dcsum[1] += s.d1;
@@ -181,7 +187,7 @@ void fast_subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz,
   r.dcsum[3] += s.d3;
 }
 
-// subseq_write with the fast steps in front: a run of whole blocks from the block boundary (p, block-in-MCU c)
+// subseq_write with the fast steps in front: a run of whole MCUs from the MCU boundary at p (c = 0)
 int fast_subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c, uint32_t hi, uint32_t end_bits, int64_t blk,
                       int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *coefs, uint32_t *err_pos) {
   ExactState st;
@@ -300,6 +306,7 @@ static void spec_unit(const ScanCtx &sc, const Local LT, const uint8_t *blk_comp
   for (uint32_t base = 0; base < nsub; base += T) {
     const int nact = (int)(nsub - base < (uint32_t)T ? nsub - base : (uint32_t)T);
     std::vector<SubResult> r(nact);
+    std::vector<int32_t> dpre(nact * HCJ_MAX_COMP);
     std::vector<uint32_t> sp(nact), scz(nact), endp(nact), endcz(nact), hi(nact);
     // phase A
     for (int t = 0; t < nact; t++) {
@@ -307,7 +314,7 @@ static void spec_unit(const ScanCtx &sc, const Local LT, const uint8_t *blk_comp
       hi[t] = lo + S < end_bits ? lo + S : end_bits;
       sp[t] = t == 0 ? carry.p : lo;
       scz[t] = t == 0 ? carry.cz : 0;
-      fast_subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t], end_bits);
+      fast_subseq_sync(sc, LT, sp[t], scz[t], hi[t], r[t], end_bits, &dpre[t * HCJ_MAX_COMP]);
       endp[t] = r[t].p;
       endcz[t] = r[t].cz;
     }
@@ -323,7 +330,7 @@ static void spec_unit(const ScanCtx &sc, const Local LT, const uint8_t *blk_comp
           sp[t] = nsp;
           scz[t] = nscz;
           redo_cnt++;
-          fast_subseq_sync(sc, LT, nsp, nscz, hi[t], r[t], end_bits);
+          fast_subseq_sync(sc, LT, nsp, nscz, hi[t], r[t], end_bits, &dpre[t * HCJ_MAX_COMP]);
           if (r[t].p != endp[t] || r[t].cz != endcz[t]) {
             any = true;
             np[t] = r[t].p;
@@ -358,12 +365,12 @@ static void spec_unit(const ScanCtx &sc, const Local LT, const uint8_t *blk_comp
       const int t = nact - 1 - tt;
       ex_n = exn[t];
       for (int k = 0; k < HCJ_MAX_COMP; k++) ex_dc[k] = exd[t * HCJ_MAX_COMP + k];
-      if (r[t].first_p == 0xffffffffu) continue;  // no block begins here
+      if (r[t].first_p == 0xffffffffu) continue;  // no MCU begins here
       int32_t pred[HCJ_MAX_COMP];
-      for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + ex_dc[k];
-      int64_t blk = carry.nstart + ex_n - 1;
+      for (int k = 0; k < HCJ_MAX_COMP; k++) pred[k] = carry.dc[k] + ex_dc[k] + dpre[t * HCJ_MAX_COMP + k];
+      int64_t blk = carry.nstart + ex_n + r[t].nbefore - 1;
       uint32_t err_pos = 0;
-      int err = fast_subseq_write(sc, LT, r[t].first_p, r[t].first_c, hi[t], end_bits, blk, pred, blk_end, coefs, &err_pos);
+      int err = fast_subseq_write(sc, LT, r[t].first_p, 0, hi[t], end_bits, blk, pred, blk_end, coefs, &err_pos);
       unsigned long long key = ((unsigned long long)err_pos << 8) | (unsigned long long)(-err);
       if (err && key < *err_key) *err_key = key;  // the kernel's atomicMin
     }

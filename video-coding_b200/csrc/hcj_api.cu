@@ -553,6 +553,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     BALLOC(sub_nstart, int32_t *, 4 * total_sub + 16);
     BALLOC(sub_blk, int32_t *, 4 * total_sub + 16);
     BALLOC(sub_dc, int4 *, 16 * total_sub + 16);
+    BALLOC(sub_dpre, int4 *, 16 * total_sub + 16);
     BALLOC(sub_list, uint32_t *, 4 * total_sub + 16);
   }
   b->coef_bytes = (size_t)total_blocks * 128;

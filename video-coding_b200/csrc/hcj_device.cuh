@@ -311,7 +311,9 @@ struct SubResult {
   uint32_t p, cz;     // end state: cz = (c << 8) | z
   uint32_t nstart;    // DC symbols (blocks begun) decoded
   int32_t dcsum[HCJ_MAX_COMP];
-  uint32_t first_p, first_c;  // where the first of those blocks begins and its block-in-MCU index; first_p = 0xffffffff: none
+  // The first MCU that begins here (DC symbol of block-in-MCU 0): its position (0xffffffff: none) and how many
+  // blocks were begun before it; the DC sums up to it go to the `dpre` argument of the decode functions.
+  uint32_t first_p, nbefore;
 };
 
 // One symbol, DC or AC, decoded with the same instruction stream (lanes of a warp are rarely all in the
@@ -337,7 +339,8 @@ HCJ_HD Symbol read_symbol(const BitReader &br, const Local L, const Tables &t, b
   return s;
 }
 
-HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits) {
+HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t cz, uint32_t hi, SubResult &r, uint32_t end_bits,
+                        int32_t *dpre /* [HCJ_MAX_COMP], written when the first MCU start is met */) {
   uint32_t c = cz >> 8, z = cz & 0xffu;
   uint32_t nstart = 0;
   int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
@@ -346,7 +349,7 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   uint32_t comp = L.blk_comp[c];
   Tables t = sc.tab[comp];
   r.first_p = 0xffffffffu;
-  r.first_c = 0;
+  r.nbefore = 0;
   while (br.pos < hi) {
     const bool isdc = z == 0u;
     const Symbol s = read_symbol(br, L, t, isdc);
@@ -354,7 +357,10 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
       br.skip(1);
       continue;
     }
-    if (isdc && r.first_p == 0xffffffffu) r.first_p = br.pos, r.first_c = c;
+    if (isdc && c == 0u && r.first_p == 0xffffffffu) {
+      r.first_p = br.pos, r.nbefore = nstart;
+      dpre[0] = d0, dpre[1] = d1, dpre[2] = d2, dpre[3] = d3;
+    }
     br.skip(s.nbits);
     const int32_t diff = isdc ? s.value : 0;
     d0 += comp == 0u ? diff : 0;
@@ -381,12 +387,13 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   r.dcsum[3] = d3;
 }
 
-// Final pass of one thread: a run of whole blocks.  It starts at a block boundary (p, block-in-MCU c, DC next) with the
-// DC predictors `pred`; `blk` is the index (within the image) of the block before the first one it decodes.  It
-// decodes the blocks < `nblocks` that BEGIN before `hi` (the one in progress at `hi` is finished: the thread of the
-// next subsequence starts at the first block that begins in its own bits) or at / beyond `end_bits` (nobody else's:
-// the model's reader delivers zero bits there and the unit's blocks are decoded whatever the bits say); with
-// hi >= end_bits it runs until block nblocks - 1 is complete.  Stores
+// Final pass of one thread: a run of whole MCUs.  It starts at an MCU boundary (p, block-in-MCU c = 0, DC next) with
+// the DC predictors `pred`; `blk` is the index (within the image) of the block before the first one it decodes.  It
+// decodes the MCUs (blocks < `nblocks`) that BEGIN before `hi` (the one in progress at `hi` is finished: the thread of
+// the next subsequence starts at the first MCU that begins in its own bits - so the lanes of a warp, which run in lock
+// step block by block, are all in the same block-in-MCU, luma with luma and chroma with chroma) or at / beyond
+// `end_bits` (nobody else's: the model's reader delivers zero bits there and the unit's blocks are decoded whatever
+// the bits say); with hi >= end_bits it runs until block nblocks - 1 is complete.  Stores
 // coefficients (zig-zag, DC resolved) into `coefs`; every block is cleared right before its DC store.
 HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c, uint32_t hi, uint32_t end_bits, int64_t blk,
                         int32_t pred[HCJ_MAX_COMP], int64_t nblocks, int16_t *__restrict__ coefs, uint32_t *err_pos,
@@ -402,7 +409,7 @@ HCJ_HD int subseq_write(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   int err = HCJ_DEV_OK;
   for (;;) {
     const bool isdc = z == 0u;
-    if (isdc && (blk + 1 >= nblocks || (br.pos >= hi && br.pos < end_bits))) break;  // every block is complete / the next one is not this thread's
+    if (isdc && (blk + 1 >= nblocks || (c == 0u && br.pos >= hi && br.pos < end_bits))) break;  // every block is complete / the next MCU is not this thread's
     const Symbol s = read_symbol(br, L, t, isdc);
     if (s.e == 0u) {
       err = isdc ? HCJ_DEV_NO_DC_CODE : HCJ_DEV_NO_AC_CODE;
@@ -652,7 +659,7 @@ struct SyncLane {
   uint32_t tdc, tac, comp;
   uint32_t nstart;
   int32_t d0, d1, d2, d3;
-  uint32_t first_p, first_c;  // the first block begun (SubResult)
+  uint32_t first_p, nbefore;  // the first MCU begun (SubResult)
 };
 HCJ_HD void sync_bind_block(SyncLane &s, const FastTables T) {
   const BlkInfo bi = T.blkinfo[s.c];
@@ -693,19 +700,23 @@ HCJ_HD void sync_ac_step_single(SyncLane &s, const FastTables T) {
   s.z += e >> 24;
 }
 // The DC symbol that begins the next block (s.z == 0, tables bound); an undefined code is skipped one bit at a time.
-HCJ_HD void sync_dc_step(SyncLane &s, const FastTables T) {
+// The first MCU start met is recorded, with the DC sums up to it in `dpre` (int32 [HCJ_MAX_COMP]).
+HCJ_HD void sync_dc_step(SyncLane &s, const FastTables T, int32_t *dpre) {
   const uint32_t win = s.br.window();
   const uint32_t e = fast_lookup(T, s.tdc, win, true);
   if (e == HCJ_FAST_NONE) {
     s.br.consume(1u);
     return;
   }
+  if (s.c == 0u && s.first_p == 0xffffffffu) {
+    s.first_p = s.br.pos, s.nbefore = s.nstart;
+    dpre[0] = s.d0, dpre[1] = s.d1, dpre[2] = s.d2, dpre[3] = s.d3;
+  }
   const int32_t v = fast_value(win, byte_of(e, 1), byte_of(e, 2));
   s.d0 += s.comp == 0u ? v : 0;
   s.d1 += s.comp == 1u ? v : 0;
   s.d2 += s.comp == 2u ? v : 0;
   s.d3 += s.comp == 3u ? v : 0;
-  if (s.nstart == 0u) s.first_p = s.br.pos, s.first_c = s.c;
   s.nstart++;
   s.br.consume(byte_of(e, 0));
   s.z = 1u;

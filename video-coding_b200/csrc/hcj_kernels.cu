@@ -670,8 +670,9 @@ constexpr int HR_STAGE_WORDS = 32 * HR_ROW_WORDS;  // per warp
 // ------------------------------------------------------------------------------------------------
 // Warp-synchronous exact pass (the symbol semantics of subseq_write), shared by K2 and K3.
 //
-// Every lane decodes its own run of WHOLE blocks: from a block boundary (bit position p, block-in-MCU c) it decodes
-// the blocks < nblocks_end that begin before `hi` or at / beyond the end of the data (subseq_write).  The block in progress is staged in the lane's row of
+// Every lane decodes its own run of WHOLE MCUs: from an MCU boundary at bit position p it decodes the MCUs (blocks <
+// nblocks_end) that begin before `hi` or at / beyond the end of the data (subseq_write).  All lanes of a warp are
+// therefore in the same block-in-MCU at every step: luma blocks run in lock step with luma blocks.  The block in progress is staged in the lane's row of
 // `stage` (shared memory, 36-word stride) and, once complete, written out by the warp as one 128-byte line:
 // scattered 2-byte stores cost one L2 partial-sector transaction per symbol and were the bottleneck of the entropy
 // kernels.  (K3's threads used to start mid-block at their subsequence boundary and share that block with their left
@@ -769,7 +770,7 @@ __device__ __forceinline__ int warp_exact_fast(const ScanCtx &sc, const FastTabl
       warp_store_full(__ballot_sync(0xffffffffu, have), s.blk, stage, lane, coefs);
       if (have) exact_next_block(s, T, bpm);
       if (st == 1) {
-        if (s.blk + 1 >= in.nblocks_end || s.br.pos >= lim || s.br.pos >= in.hi) st = 2;
+        if (s.blk + 1 >= in.nblocks_end || s.br.pos >= lim || (s.c == 0u && s.br.pos >= in.hi)) st = 2;
         else st = exact_dc_step(s, T, row) ? 0 : 2;
       }
     }
@@ -816,7 +817,7 @@ __device__ __forceinline__ int warp_exact_pass(const ScanCtx &sc, const SmemTabl
     bool done_blk = false;
     if (active) {
       const bool isdc = z == 0u;
-      if (isdc && ((br.pos >= in.hi && br.pos < in.end_bits) || blk + 1 >= in.nblocks_end)) {
+      if (isdc && ((c == 0u && br.pos >= in.hi && br.pos < in.end_bits) || blk + 1 >= in.nblocks_end)) {
         active = false;
       } else {
         const Symbol s = read_symbol(br, L, t, isdc);
@@ -1031,7 +1032,7 @@ static inline size_t multi_smem_bytes(const DecodeBatchDev &b) { return (size_t)
 // what is left (the last 32 bits of the unit, undefined codes met while speculating).
 template <bool MULTI = true>
 __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local L, bool valid, uint32_t p, uint32_t cz,
-                                                 uint32_t hi, uint32_t end_bits, SubResult &r) {
+                                                 uint32_t hi, uint32_t end_bits, SubResult &r, int32_t *dpre) {
   const FastTables T = L.ft;
   const uint32_t bpm = sc.bpm;
   const uint32_t lim = min(hi, end_bits >= 32u ? end_bits - 32u : 0u);
@@ -1042,7 +1043,7 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   s.nstart = 0;
   s.d0 = s.d1 = s.d2 = s.d3 = 0;
   s.first_p = 0xffffffffu;
-  s.first_c = 0;
+  s.nbefore = 0;
   const bool entered = valid && p < lim;
   s.br.init(sc.words, entered ? p : 0u);
   s.br.pos = p;
@@ -1080,7 +1081,7 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
         if (s.br.pos >= lim) {
           st = 2;
         } else {
-          sync_dc_step(s, T);
+          sync_dc_step(s, T, dpre);
           st = s.z != 0u ? 0 : 1;  // (an undefined code: one bit was skipped, still at the boundary)
         }
       }
@@ -1090,13 +1091,18 @@ __device__ __forceinline__ void warp_subseq_sync(const ScanCtx &sc, const Local 
   r.cz = (s.c << 8) | s.z;
   r.nstart = s.nstart;
   r.dcsum[0] = s.d0, r.dcsum[1] = s.d1, r.dcsum[2] = s.d2, r.dcsum[3] = s.d3;
-  r.first_p = s.first_p, r.first_c = s.first_c;
+  r.first_p = s.first_p, r.nbefore = s.nbefore;
   if (valid && s.br.pos < hi) {
     SubResult r2;
-    subseq_sync(sc, L, s.br.pos, r.cz, hi, r2, end_bits);
+    int32_t dpre2[HCJ_MAX_COMP];
+    subseq_sync(sc, L, s.br.pos, r.cz, hi, r2, end_bits, dpre2);
     r.p = r2.p;
     r.cz = r2.cz;
-    if (r.nstart == 0u) r.first_p = r2.first_p, r.first_c = r2.first_c;
+    if (r.first_p == 0xffffffffu && r2.first_p != 0xffffffffu) {
+      r.first_p = r2.first_p, r.nbefore = r.nstart + r2.nbefore;
+#pragma unroll
+      for (int k = 0; k < HCJ_MAX_COMP; k++) dpre[k] = r.dcsum[k] + dpre2[k];
+    }
     r.nstart += r2.nstart;
 #pragma unroll
     for (int k = 0; k < HCJ_MAX_COMP; k++) r.dcsum[k] += r2.dcsum[k];
@@ -1111,13 +1117,14 @@ struct SpecImage {
   const uint32_t *segs;      // unit u = bytes [segs[u], segs[u + 1]) of the image's entropy data
   const uint32_t *unit_sub;  // nunits > 1: index of every unit's first subsequence (nunits + 1 entries, k_spec_units)
   uint16_t *start, *end2;
-  uint32_t *first;           // where the first block begun in the subsequence starts (spec_pack_first)
+  uint32_t *first;           // where the first MCU begun in the subsequence starts (spec_pack_first)
   int32_t *nstart, *blk;     // blocks begun in the subsequence; index of the first of them (k_spec_fix)
-  int4 *dc;
+  int4 *dc, *dpre;           // DC sums per component of the subsequence / of its part in front of that first MCU
 };
-// position (relative to the subsequence's first bit: < 2^15) and block-in-MCU index of the first block begun; bit 31: none
+// position (relative to the subsequence's first bit: < 2^15) of the first MCU begun and the blocks begun before it (< 16);
+// bit 31: none
 __device__ __forceinline__ uint32_t spec_pack_first(const SubResult &r, uint32_t lo) {
-  return r.first_p == 0xffffffffu ? 0x80000000u : (r.first_p - lo) | (r.first_c << 16);
+  return r.first_p == 0xffffffffu ? 0x80000000u : (r.first_p - lo) | (r.nbefore << 16);
 }
 __device__ __forceinline__ uint32_t spec_unit_subs(uint32_t bits, uint32_t S) { return bits <= 16u ? 0u : (bits + S - 1u) / S; }
 __device__ __forceinline__ bool spec_image(const DecodeBatchDev &b, uint32_t list_index, SpecImage &si) {
@@ -1136,6 +1143,7 @@ __device__ __forceinline__ bool spec_image(const DecodeBatchDev &b, uint32_t lis
   si.nstart = b.sub_nstart + si.d->sub_off;
   si.blk = b.sub_blk + si.d->sub_off;
   si.dc = b.sub_dc + si.d->sub_off;
+  si.dpre = b.sub_dpre + si.d->sub_off;
   return true;
 }
 
@@ -1310,7 +1318,7 @@ __global__ void __launch_bounds__(SPEC_FIX_THREADS, 8) k_spec_fix(DecodeBatchDev
         uint32_t p, cz;
         spec_unpack(ns, q.lo, p, cz);
         SubResult r;
-        warp_subseq_sync<false>(sc, LT, valid, p, cz, q.hi, q.uend, r);
+        warp_subseq_sync<false>(sc, LT, valid, p, cz, q.hi, q.uend, r, reinterpret_cast<int32_t *>(si.dpre + j));
         if (valid) {
           si.start[j] = (uint16_t)ns;
           si.end2[j] = (uint16_t)spec_pack(r.p, q.hi, r.cz);
@@ -1411,9 +1419,11 @@ __global__ void __launch_bounds__(SPEC_THREADS, HCJ_SPEC_SYNC_CTAS) k_spec_sync(
   {
     const bool warm = valid && q.jl > 0u;
     const uint32_t p0 = q.lo - q.ulo > b.spec_guess_bits ? q.lo - b.spec_guess_bits : q.ulo;
-    warp_subseq_sync(sc, LT, warm, p0, 0u, q.lo, q.uend, r);
+    // (dpre: the DC sums in front of the first MCU start go straight to their place; the warm-up's are overwritten)
+    int32_t *dpre = reinterpret_cast<int32_t *>(si.dpre + (valid ? j : 0u));
+    warp_subseq_sync(sc, LT, warm, p0, 0u, q.lo, q.uend, r, dpre);
     if (warm) p = r.p, cz = r.cz;
-    warp_subseq_sync(sc, LT, valid, p, cz, q.hi, q.uend, r);
+    warp_subseq_sync(sc, LT, valid, p, cz, q.hi, q.uend, r, dpre);
   }
   if (valid) {
     si.start[j] = (uint16_t)spec_pack(p, q.lo, cz);
@@ -1454,14 +1464,14 @@ __global__ void __launch_bounds__(SPEC_WRITE_THREADS, 2) k_spec_write(DecodeBatc
   in.valid = j < si.nsub;
   const uint32_t jj = in.valid ? j : 0u;
   const SpecSub q = spec_sub(si, jj);
-  // the thread decodes the blocks that begin in its subsequence (and finishes the last of them beyond its end)
+  // the thread decodes the MCUs that begin in its subsequence (and finishes the last of them beyond its end)
   const uint32_t first = si.first[jj];
   in.valid = in.valid && (first >> 31) == 0u;
   in.p = q.lo + (first & 0xffffu);
-  in.cz = ((first >> 16) & 15u) << 8;
-  const int4 dc = si.dc[jj];
-  in.pred[0] = dc.x, in.pred[1] = dc.y, in.pred[2] = dc.z, in.pred[3] = dc.w;
-  in.blk = si.blk[jj] - 1;
+  in.cz = 0u;
+  const int4 dc = si.dc[jj], dpre = si.dpre[jj];
+  in.pred[0] = dc.x + dpre.x, in.pred[1] = dc.y + dpre.y, in.pred[2] = dc.z + dpre.z, in.pred[3] = dc.w + dpre.w;
+  in.blk = si.blk[jj] + (int32_t)((first >> 16) & 15u) - 1;
   in.hi = q.hi;  // (blocks that begin at or beyond the unit's end are decoded by the thread that gets there)
   in.end_bits = q.uend;
   in.nblocks_end = q.blk_end;

@@ -44,7 +44,8 @@ struct DecodeBatchDev {
   // per subsequence of those images (index = HcjImageDesc::sub_off + subsequence):
   uint16_t *sub_start;            // packed decoder state the subsequence was last decoded from
   uint16_t *sub_end2;             // packed state at its end (decoded from sub_start)
-  uint32_t *sub_first;            // where the first block begun inside the subsequence starts, and its block-in-MCU index
+  uint32_t *sub_first;            // where the first MCU begun inside the subsequence starts, and the blocks begun in front of it
+  int4 *sub_dpre;                 // DC differential sums of those blocks in front
   int32_t *sub_nstart;            // blocks begun
   int32_t *sub_blk;               // index (within the image) of the first of them: segmented exclusive prefix (k_spec_fix)
   int4 *sub_dc;                   // DC differential sums per scan component; after the scan: exclusive prefix
