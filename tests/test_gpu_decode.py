@@ -694,3 +694,32 @@ def test_fused_rgb444(hcj, ctx, orc, data):
         b.decode()
         outs, st = b.fetch()
         assert st == [0] * len(jpgs) and [bytes(o) for o in outs] == want
+
+
+def test_fused_rgb_subsampled(hcj, ctx, orc, data):
+    """J4 for 4:2:0 / 4:2:2 (HCJ_FUSED_SUB=1): RGB24 of even-sized images comes out of the IDCT kernel (Planar_444
+    up-sampling and the colour conversion inside the tile; the units that need another tile's chroma go through
+    k_rgb_deferred), and the default two-kernel form with two pixel rows per thread.  Widths
+    that are not a multiple of 16 (crop inside the last unit), several tiles per MCU row (> 21 / 32 MCUs wide), one
+    MCU row, tiny images, blocks flagged for the 64-bit IDCT, and odd sizes (not fused) in the same batch."""
+    from test_emul_device_logic import _patch_dqt
+
+    cases = [(420, 256, 192, 75), (420, 1000, 40, 90), (420, 1004, 38, 60), (420, 52, 44, 95), (420, 16, 16, 75), (420, 2, 2, 75),
+             (420, 34, 18, 50), (422, 200, 120, 75), (422, 1030, 24, 85), (422, 18, 9, 75), (420, 1920, 64, 75), (420, 640, 368, 30),
+             (420, 333, 77, 75), (422, 131, 70, 75), (444, 64, 48, 75), (420, 700, 34, 100), (420, 354, 64, 75)]
+    jpgs = [orc.encode(synth.frame(1700 + i, w, h, c), w, h, c, q, restart_interval=(8 if i % 2 else 0)) for i, (c, w, h, q) in enumerate(cases)]
+    jpgs += [_patch_dqt(orc.encode(synth.frame(9, 96, 64, 420), 96, 64, 420, 100, restart_interval=2), 200),
+             _patch_dqt(orc.encode(synth.frame(10, 704, 32, 422), 704, 32, 422, 100), 255)]
+    want = [oracle_rgb(orc, orc.decode(j)).tobytes() for j in jpgs]
+    os_env = __import__("os").environ
+    os_env["HCJ_FUSED_SUB"] = "1"  # the fused form is opt-in for sub-sampled images (slower than the two kernels: hcj_api.cu)
+    try:
+        outs, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
+    finally:
+        del os_env["HCJ_FUSED_SUB"]
+    assert st == [0] * len(jpgs)
+    for k, (o, w_) in enumerate(zip(outs, want)):
+        assert bytes(o) == w_, (k, (cases + ["wide420", "wide422"])[k])
+    # the default: k_idct_persistent to planes, then k_rgb_sub_pairs (even sizes) / k_rgb (odd sizes)
+    outs, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
+    assert st == [0] * len(jpgs) and [bytes(o) for o in outs] == want

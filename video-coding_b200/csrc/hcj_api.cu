@@ -255,7 +255,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   uint32_t total_tiles = 0;
   uint32_t max_segments = 0, max_tiles = 0, max_rows = 0, max_width = 0, max_sub_chunks = 0;
   size_t total_sub = 0, total_ds_tiles = 0;
-  uint32_t max_ds_tiles = 0, max_blocks = 0;
+  uint32_t max_ds_tiles = 0, max_blocks = 0, max_deferred = 0;
   uint32_t sub_log2 = 12;  // measured on 1080p q75: 1024 -> 11.0 ms, 2048 -> 9.4 ms, 4096 -> 8.9 ms for the four K3 kernels
   bool sub_log2_env = false, spec_has_units = false;
   uint64_t long_ri_blocks = 128;  // 4:2:0: intervals of 22 MCUs and more
@@ -507,10 +507,28 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
     {
       bool unit_sampling = f.ncomp == 3;
       for (int k = 0; k < f.ncomp; k++) unit_sampling = unit_sampling && f.hs[k] == 1 && f.vs[k] == 1;
-      d.fused_rgb = mode == HCJ_OUT_RGB24 && f.chroma == 444 && unit_sampling && !d.wide_idct && !getenv("HCJ_NO_FUSED_RGB");
+      const bool fusable = mode == HCJ_OUT_RGB24 && f.ncomp == 3 && !d.wide_idct && !getenv("HCJ_NO_FUSED_RGB");
+      // sub-sampled: luma 2x2 or 2x1, chroma 1x1, even size (the chroma planes are exactly half)
+      const bool sub = f.ncomp == 3 && f.hs[0] == 2 && f.hs[1] == 1 && f.hs[2] == 1 && f.vs[1] == 1 && f.vs[2] == 1 &&
+                       ((f.chroma == 420 && f.vs[0] == 2 && f.height % 2 == 0) || (f.chroma == 422 && f.vs[0] == 1)) && f.width % 2 == 0;
+      // Measured on 1024 x 1080p 4:2:0 (gpurun_out/r02s_*): fused 4.89 ms + 0.64 ms for the deferred units against
+      // 2.20 + 2.39 ms for k_idct_persistent + k_rgb_sub_pairs.  Both forms are bound by the instructions of the
+      // conversion (about 24 per pixel: interpolation, four multiply-adds, shifts, saturating packs), which fusing does
+      // not remove, and the deferred units cost more than the plane round trip saves: the two-kernel form stays the
+      // default for sub-sampled images; HCJ_FUSED_SUB=1 selects the fused one.
+      d.fused_rgb = !fusable ? 0 : (f.chroma == 444 && unit_sampling) ? 1 : (sub && getenv("HCJ_FUSED_SUB")) ? 2 : 0;
     }
-    if (d.fused_rgb) b->dev.has_fused = 1;
-    else (f.chroma == 444 ? b->dev.has_444 : b->dev.has_subsampled) = 1;
+    if (d.fused_rgb == 1) b->dev.has_fused = 1;
+    else if (d.fused_rgb == 2) {
+      b->dev.has_fused_sub = 1;
+      // what k_rgb_deferred enumerates: a pixel row per MCU row with a chroma row below it, 16 pixels per row and tile boundary
+      const uint32_t tm_max_i = (uint32_t)std::max(1, std::min(tile_mcus, HCJ_IDCT_THREADS / d.bpm));
+      const uint32_t tpr = ((uint32_t)d.mcus_wide + tm_max_i - 1) / tm_max_i;
+      const uint32_t def_rows = f.vs[0] == 2 ? (uint32_t)(f.actual_height[1] - 1) / 8 : 0;
+      max_deferred = std::max(max_deferred, def_rows * (((uint32_t)f.width + 15) / 16) + (tpr - 1) * (uint32_t)f.height);
+    }
+    else if (f.chroma == 444) b->dev.has_444 = 1;
+    else b->dev.has_subsampled |= ((f.width & 1) || (f.chroma == 420 && (f.height & 1))) ? 2 : 1;
     max_blocks = std::max(max_blocks, d.nblocks);
     max_width = std::max(max_width, (uint32_t)f.width);
   }
@@ -605,6 +623,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.tile_mcus = tile_mcus;
   dv.max_rgb_rows = max_rows;
   dv.max_blocks = max_blocks;
+  dv.max_deferred_groups = max_deferred;
   dv.max_width = max_width;
   dv.total_blocks = total_blocks;
   dv.img_lo = 0;
@@ -615,7 +634,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
   dv.ls_hi = (uint32_t)list_spec.size();
   b->list_restart = list_restart;
   b->list_spec = list_spec;
-  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count(dv) : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + dv.has_subsampled + (mode == HCJ_OUT_RGB24 ? dv.has_fused : 0) : 0);
+  b->kernels = hcjk::destuff_kernel_count() + (dv.n_restart ? 1 : 0) + (dv.n_spec ? hcjk::huff_spec_kernel_count(dv) : 0) + hcjk::idct_kernel_count() + (post_444(mode) ? dv.has_444 + (mode == HCJ_OUT_RGB24 ? (dv.has_subsampled & 1) + (dv.has_subsampled >> 1) + dv.has_fused + dv.has_fused_sub : (dv.has_subsampled ? 1 : 0)) : 0);
 
   // ---- upload
   cudaStream_t s = c->stream;

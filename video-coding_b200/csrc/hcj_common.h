@@ -85,7 +85,7 @@ struct HcjImageDesc {
   uint8_t blk_by[HCJ_MAX_BPM + 2];
   uint8_t wide_idct;     // 1: some quant entry > 255 -> always take the 64-bit IDCT
   uint8_t valid;         // 0: header/geometry failed on the host; kernels skip the image
-  uint8_t fused_rgb;     // RGB24 output of a 4:4:4 image without 16-bit quant entries: k_idct_persistent converts to RGB itself
+  uint8_t fused_rgb;     // RGB24 output, no 16-bit quant entries: k_idct_persistent converts to RGB itself (1 = 4:4:4, 2 = 4:2:0 / 4:2:2 of even size)
   uint8_t pad_[1];
   uint32_t table_set;    // index into the batch table sets
   uint32_t qt_off;       // offset (uint16 entries) of this image's quant tables [nqt][64], zig-zag order

@@ -1623,7 +1623,7 @@ struct alignas(16) IdctTile {
   uint16_t tm, nblk; // MCUs and blocks in the tile
   uint16_t qbytes;   // bytes of quant tables (512 per component)
   uint16_t remap;    // the thread -> block mapping differs from the previous tile's (first tile of an image, other width)
-  uint32_t fused;    // RGB24 output of a 4:4:4 image: colour conversion inside the tile (HcjImageDesc::fused_rgb)
+  uint32_t fused;    // RGB24 output: colour conversion inside the tile (HcjImageDesc::fused_rgb: 1 = 4:4:4, 2 = sub-sampled)
 };
 static_assert(sizeof(IdctTile) == 32, "two 16-byte cp.async per record");
 
@@ -1783,6 +1783,41 @@ __device__ __forceinline__ uint32_t ycc_to_rgb_raw(int Y, int Cb, int Cr) {
   return px;
 }
 
+// 4 pixels -> 12 bytes of RGB: the stated formula with the "+ Y" and the rounding constant folded into the
+// accumulator of the multiply-adds: Y + ((k * C + 32768) >> 16) == ((Y << 16 | 0x8000) + k * C) >> 16 exactly (the shift
+// is arithmetic and Y << 16 is a multiple of 65536).  wcb_s / wcr_s: the chroma bytes with bit 7 flipped (= C - 128 as
+// signed bytes); one PRMT each extracts a sign-extended sample, one the accumulator.
+// byte I of x, sign extended (prmt's replicate-sign selector; __byte_perm documents three selector bits only)
+template <int I>
+__device__ __forceinline__ int sext_byte(uint32_t x) {
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0x8880u | I | (I << 4) | (I << 8) | (I << 12)));
+  return r;
+}
+template <int I>
+__device__ __forceinline__ uint32_t ycc_pixel(uint32_t wy, uint32_t wcb_s, uint32_t wcr_s) {
+  const int t = (int)__byte_perm(wy, 0x00008000u, 0x4054 | (I << 8));
+  const int cb = sext_byte<I>(wcb_s), cr = sext_byte<I>(wcr_s);
+  const int r = (91881 * cr + t) >> 16;
+  const int g = (-46802 * cr + (-22554 * cb + t)) >> 16;
+  const int bl = (116130 * cb + t) >> 16;
+  uint32_t u, px;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(u) : "r"(0), "r"(bl), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(u));
+  return px;
+}
+__device__ __forceinline__ void ycc4_to_rgb12(uint32_t wy, uint32_t wcb, uint32_t wcr, uint32_t *o) {
+  const uint32_t sb = wcb ^ 0x80808080u, sr = wcr ^ 0x80808080u;
+  const uint32_t p0 = ycc_pixel<0>(wy, sb, sr), p1 = ycc_pixel<1>(wy, sb, sr), p2 = ycc_pixel<2>(wy, sb, sr), p3 = ycc_pixel<3>(wy, sb, sr);
+  o[0] = __byte_perm(p0, p1, 0x4210);  // p0 | p1 << 24
+  o[1] = __byte_perm(p1, p2, 0x5421);  // p1 >> 8 | p2 << 16
+  o[2] = __byte_perm(p2, p3, 0x6542);  // p2 >> 16 | p3 << 8
+}
+// 8 pixels -> 24 bytes of RGB
+__device__ __forceinline__ void ycc8_to_rgb24(uint2 vy, const uint32_t (&cb)[2], const uint32_t (&cr)[2], uint32_t (&o)[6]) {
+  ycc4_to_rgb12(vy.x, cb[0], cr[0], o);
+  ycc4_to_rgb12(vy.y, cb[1], cr[1], o + 3);
+}
 __device__ __forceinline__ void idct_tile_rgb444(const DecodeBatchDev &b, const IdctTile &t, IdctStage &st, const IdctMap &mp, int tid) {
   uint8_t *xch = reinterpret_cast<uint8_t *>(st.tile);
   const bool mine = (mp.misc & (1u << 10)) != 0u;
@@ -1819,15 +1854,9 @@ __device__ __forceinline__ void idct_tile_rgb444(const DecodeBatchDev &b, const 
     const uint2 vu = *reinterpret_cast<const uint2 *>(xch + (8 + r) * FUSED_ROW_PITCH + m * 8);
     const uint2 vv = *reinterpret_cast<const uint2 *>(xch + (16 + r) * FUSED_ROW_PITCH + m * 8);
     uint32_t o[6];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {  // 4 pixels -> 12 bytes = 3 words
-      const uint32_t wy = k ? vy.y : vy.x, wu = k ? vu.y : vu.x, wv = k ? vv.y : vv.x;
-      uint32_t px[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) px[i] = ycc_to_rgb_raw((int)byte_of(wy, i), (int)byte_of(wu, i), (int)byte_of(wv, i));
-      o[3 * k + 0] = px[0] | (px[1] << 24);
-      o[3 * k + 1] = (px[1] >> 8) | (px[2] << 16);
-      o[3 * k + 2] = (px[2] >> 16) | (px[3] << 8);
+    {
+      const uint32_t cb[2] = {vu.x, vu.y}, cr[2] = {vv.x, vv.y};
+      ycc8_to_rgb24(vy, cb, cr, o);
     }
     uint8_t *dst = out + ((size_t)y * width + x) * 3;
     const int n = min(8, width - x);
@@ -1838,6 +1867,168 @@ __device__ __forceinline__ void idct_tile_rgb444(const DecodeBatchDev &b, const 
     } else {
       store_any<6>(dst, o, 3 * n);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// J4 for sub-sampled images (4:2:0 / 4:2:2 of even size): dequantise + IDCT + Planar_444 up-sampling + colour in the
+// same kernel.  The tile's samples go to the exchange area (luma rows, then Cb rows, then Cr rows); units of 8 luma
+// pixels are then converted with Planar_444's interpolation (tools/src/planar_444.ml:25-33,82-103: the chroma sample,
+// its right neighbour, the row below and its right neighbour, clamped at the cropped plane's edge) done four samples
+// at a time in SIMD-within-a-register form.  Two kinds of units need chroma samples of another tile - the last pixel
+// row of an MCU row (the chroma row below) and the last unit of a tile's rows (the chroma column to the right): for
+// those the tile writes its luma samples to the plane buffer instead, every tile writes its chroma blocks there, and
+// k_rgb_deferred converts them (about 9 % of the pixels of a 1080p frame) once all tiles are done.
+// Blocks flagged for the 64-bit IDCT are redone from the coefficient buffer inside the tile (wide_block_to_xch).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void wide_block_to_xch(const int16_t *coefs_blk, const int32_t *q, uint8_t *dst, int pitch) {
+  uint32_t pix[16];
+  reconstruct_wide(reinterpret_cast<const uint32_t *>(coefs_blk), q, pix);
+  for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(pix[2 * r], pix[2 * r + 1]);
+}
+
+// (a + b + 1) >> 1 of the four bytes of each word
+__device__ __forceinline__ uint32_t avg2_bytes(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }
+// (a + b + c + d + 2) >> 2 of the four bytes of each word, in two 16-bit lanes per word
+__device__ __forceinline__ uint32_t avg4_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const uint32_t m = 0x00ff00ffu;
+  const uint32_t lo = (a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u;
+  const uint32_t hi = ((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u;
+  return ((lo >> 2) & m) | (((hi >> 2) & m) << 8);
+}
+// Planar_444's chroma for 8 horizontally adjacent pixels: A = the four chroma samples under them, a4 = the next one to
+// the right (already clamped), B / b4 = the same of the chroma row below (or of the same row); oy: odd luma row of a
+// vertically sub-sampled plane.  w[0] = pixels 0..3, w[1] = pixels 4..7.
+__device__ __forceinline__ void upsample8(uint32_t A, uint32_t a4, uint32_t B, uint32_t b4, bool oy, uint32_t (&w)[2]) {
+  const uint32_t A1 = (A >> 8) | (a4 << 24), B1 = (B >> 8) | (b4 << 24);
+  uint32_t even, odd;
+  if (!oy) {
+    even = A;
+    odd = avg2_bytes(A, A1);
+  } else {
+    even = avg2_bytes(A, B);
+    odd = avg4_bytes(A, A1, B, B1);
+  }
+  w[0] = __byte_perm(even, odd, 0x5140);
+  w[1] = __byte_perm(even, odd, 0x7362);
+}
+// chroma samples cx0 .. cx0 + 8 of a row (8-byte aligned), clamped at the plane's last column (nvalid = samples from
+// cx0 that exist, >= 1): the eight under a unit of 16 pixels and their right neighbour
+__device__ __forceinline__ void chroma9(const uint8_t *row, int nvalid, uint32_t &c0, uint32_t &c1, uint32_t &c8) {
+  const uint2 v = *reinterpret_cast<const uint2 *>(row);
+  c0 = v.x, c1 = v.y;
+  if (nvalid >= 9) {
+    c8 = *reinterpret_cast<const uint32_t *>(row + 8) & 0xffu;  // (the exchange area / the padded plane continues behind the last sample)
+  } else {
+    uint64_t w = (uint64_t)c0 | (uint64_t)c1 << 32;
+    const uint64_t last = (w >> (8 * (nvalid - 1))) & 0xffull;
+    for (int k = nvalid; k < 8; k++) w = (w & ~(0xffull << (8 * k))) | (last << (8 * k));
+    c0 = (uint32_t)w, c1 = (uint32_t)(w >> 32), c8 = (uint32_t)last;
+  }
+}
+// The chroma samples of a unit of 16 pixels: eight and their right neighbour
+struct Chroma9 {
+  uint32_t c0, c1, c8;
+};
+__device__ __forceinline__ Chroma9 load_chroma9(const uint8_t *row, int nvalid) {
+  Chroma9 c;
+  chroma9(row, nvalid, c.c0, c.c1, c.c8);
+  return c;
+}
+// A unit of 16 pixels: Planar_444's up-sampling of a chroma row (and, for an odd luma row of a vertically sub-sampled
+// plane, the row below) + colour conversion -> 48 bytes of RGB in o[12]
+__device__ __forceinline__ void sub_unit16_convert(const uint4 vy, const Chroma9 &ba, const Chroma9 &bb, const Chroma9 &ra, const Chroma9 &rb,
+                                                   bool oy, uint32_t (&o)[12]) {
+  uint32_t wb[4], wr[4], w[2];
+  upsample8(ba.c0, ba.c1 & 0xffu, bb.c0, bb.c1 & 0xffu, oy, w);
+  wb[0] = w[0], wb[1] = w[1];
+  upsample8(ba.c1, ba.c8, bb.c1, bb.c8, oy, w);
+  wb[2] = w[0], wb[3] = w[1];
+  upsample8(ra.c0, ra.c1 & 0xffu, rb.c0, rb.c1 & 0xffu, oy, w);
+  wr[0] = w[0], wr[1] = w[1];
+  upsample8(ra.c1, ra.c8, rb.c1, rb.c8, oy, w);
+  wr[2] = w[0], wr[3] = w[1];
+  ycc4_to_rgb12(vy.x, wb[0], wr[0], o);
+  ycc4_to_rgb12(vy.y, wb[1], wr[1], o + 3);
+  ycc4_to_rgb12(vy.z, wb[2], wr[2], o + 6);
+  ycc4_to_rgb12(vy.w, wb[3], wr[3], o + 9);
+}
+__device__ __forceinline__ void sub_unit16_to_rgb(const uint4 vy, const uint8_t *cb_a, const uint8_t *cb_b, const uint8_t *cr_a,
+                                                  const uint8_t *cr_b, int nvalid, bool oy, uint32_t (&o)[12]) {
+  const Chroma9 ba = load_chroma9(cb_a, nvalid), ra = load_chroma9(cr_a, nvalid);
+  Chroma9 bb = ba, rb = ra;
+  if (oy) bb = load_chroma9(cb_b, nvalid), rb = load_chroma9(cr_b, nvalid);
+  sub_unit16_convert(vy, ba, bb, ra, rb, oy, o);
+}
+
+__device__ __forceinline__ void idct_tile_rgb_sub(const DecodeBatchDev &b, const IdctTile &t, IdctStage &st, const IdctMap &mp, int tid) {
+  uint8_t *xch = reinterpret_cast<uint8_t *>(st.tile);
+  const bool mine = (mp.misc & (1u << 10)) != 0u;
+  const int slot = (int)(mp.misc & 255u);
+  const int c = (int)((mp.misc >> 8) & 3u);
+  const uint32_t fbit = (uint32_t)(t.blk0 & 127u) + slot;  // bit index inside the staged flag chunks
+  const bool wide = mine && ((reinterpret_cast<const uint32_t *>(st.flags)[fbit >> 5] >> (fbit & 31u)) & 1u);
+  uint32_t cw[32];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint4 u = st.tile[slot * 8 + (j ^ (slot & 7))];
+    cw[4 * j] = u.x, cw[4 * j + 1] = u.y, cw[4 * j + 2] = u.z, cw[4 * j + 3] = u.w;
+  }
+  const bool any_wide = __syncthreads_or(wide);  // every block of the tile is in registers: the stage becomes the exchange area
+  const HcjImageDesc &d = b.descs[t.img];
+  const int tm = t.tm, vs_log = d.comp[0].vs == 2 ? 1 : 0;
+  const int rows = 8 << vs_log, pitch_l = 16 * tm, pitch_c = 8 * tm;
+  uint8_t *xcb = xch + rows * pitch_l, *xcr = xcb + 8 * pitch_c;
+  const int x = (int)t.m0 * (int)((mp.misc >> 12) & 63u) + (int)(mp.xy & 0xffffu);  // the block's place in its padded plane
+  const int y = (int)t.my * (int)((mp.misc >> 18) & 63u) + (int)(mp.xy >> 16);
+  uint8_t *dst = c == 0 ? xch + (mp.xy >> 16) * pitch_l + (mp.xy & 0xffffu) : (c == 1 ? xcb : xcr) + (mp.xy & 0xffffu);
+  const int pitch = c == 0 ? pitch_l : pitch_c;
+  {
+    uint32_t pix[16];
+    reconstruct_fast<false>(cw, st.q + c * 128 + 64, pix);
+    if (mine && !wide) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(pix[2 * r], pix[2 * r + 1]);
+      if (c != 0) store_block_rows(pix, mp.plane, mp.stride, x, y, mp.stride, mp.h_limit);  // for the neighbours' deferred units
+    }
+  }
+  if (any_wide && wide) {  // rare
+    const int16_t *cb = b.coefs + (t.blk0 + (uint64_t)slot) * 64;
+    wide_block_to_xch(cb, st.q + c * 128, dst, pitch);
+    if (c != 0) wide_block_store(reinterpret_cast<const uint32_t *>(cb), st.q + c * 128, mp.plane, mp.stride, x, y, mp.stride, mp.h_limit);
+  }
+  __syncthreads();
+  const int width = d.width, height = d.height, cwid = d.comp[1].actual_w, chh = d.comp[1].actual_h;
+  const int x_tile = (int)t.m0 * 16, y_tile = (int)t.my * rows, cx_tile = (int)t.m0 * 8, cy_tile = (int)t.my * 8;
+  const bool right_deferred = cx_tile + 8 * tm < cwid;           // the chroma column right of the tile exists
+  const bool bottom_deferred = vs_log && cy_tile + 8 < chh;      // the chroma row below the tile exists
+  uint8_t *out = b.out + d.out_off;
+  uint8_t *plane_y = b.planes + d.comp[0].plane_off;
+  const int stride_y = d.comp[0].decoded_w;
+  // Units of 16 pixels (one MCU column of one pixel row), all even rows first, then all odd rows: the lanes of a warp
+  // run the same interpolation code.
+  const int nunits = rows * tm, nhalf = vs_log ? 8 * tm : nunits;
+  const uint32_t recip = 65536u / (uint32_t)tm + 1u;  // k / tm for k < 2^11, tm <= 32
+  for (int idx = tid; idx < nunits; idx += IDCT_MAX_THREADS) {
+    const int k = idx < nhalf ? idx : idx - nhalf;
+    const int rk = (int)(((uint32_t)k * recip) >> 16), m = k - rk * tm;
+    const int r = vs_log ? 2 * rk + (idx < nhalf ? 0 : 1) : rk;
+    const int px = x_tile + 16 * m, py = y_tile + r;
+    if (py >= height || px >= width) continue;
+    const uint4 vy = *reinterpret_cast<const uint4 *>(xch + r * pitch_l + 16 * m);
+    if ((right_deferred && m == tm - 1) || (bottom_deferred && r == rows - 1)) {
+      *reinterpret_cast<uint4 *>(plane_y + (size_t)py * stride_y + px) = vy;  // k_rgb_deferred converts the group
+      continue;
+    }
+    const int crow = r >> vs_log;
+    const bool oy = vs_log && (r & 1);
+    // the row below, clamped at the cropped plane's last row (inside the tile here: the other case is deferred)
+    const int crow1 = (oy && cy_tile + crow + 1 <= chh - 1) ? crow + 1 : crow;
+    const int nvalid = cwid - (cx_tile + 8 * m);
+    uint32_t o[12];
+    sub_unit16_to_rgb(vy, xcb + crow * pitch_c + 8 * m, xcb + crow1 * pitch_c + 8 * m, xcr + crow * pitch_c + 8 * m,
+                      xcr + crow1 * pitch_c + 8 * m, nvalid, oy, o);
+    store_any<12>(out + ((size_t)py * width + px) * 3, o, 3 * min(16, width - px));
   }
 }
 
@@ -1916,8 +2107,10 @@ __global__ void __launch_bounds__(IDCT_MAX_THREADS, HCJ_IDCT_CTAS_PER_SM)
     int tnow;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tnow));
     const IdctMap mp = s_map.get(tnow);
-    if (FUSED && t.fused) {  // CTA-uniform
+    if (FUSED && t.fused == 1u) {  // CTA-uniform
       idct_tile_rgb444(b, t, st, mp, tnow);
+    } else if (FUSED && t.fused == 2u) {
+      idct_tile_rgb_sub(b, t, st, mp, tnow);
     } else if (mp.misc & (1u << 10)) {
       const int slot = (int)(mp.misc & 255u);
       uint32_t cw[32];
@@ -1955,7 +2148,7 @@ void launch_idct(const DecodeBatchDev &b, int mode, cudaStream_t s) {
   k_idct_plan<<<dim3((b.max_idct_tiles + 127) / 128, b.img_hi - b.img_lo), 128, 0, s>>>(b);
   const uint32_t total = b.tile_hi - b.tile_lo;
   const unsigned ctas = (unsigned)(total < (uint32_t)grid ? total : grid);
-  if (mode == 2 && b.has_fused) k_idct_persistent<true><<<ctas, IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
+  if (mode == 2 && (b.has_fused || b.has_fused_sub)) k_idct_persistent<true><<<ctas, IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
   else k_idct_persistent<false><<<ctas, IDCT_MAX_THREADS, IDCT_SMEM, s>>>(b, mode);
 }
 
@@ -2076,8 +2269,17 @@ __device__ __forceinline__ bool rgb_sub_group(const DecodeBatchDev &b, const Hcj
                                               int sv, int cw, int chh, int vs_log, int x0, int y, int n, const uint32_t (&wy)[4],
                                               uint32_t (&wu)[4], uint32_t (&wv)[4]) {
   const int cy = y >> vs_log, cx0 = x0 >> 1;
-  const bool below = cy >= chh;  // odd height: no chroma row for the last luma row
   const bool oy = vs_log && (y & 1);
+  if (!PLANAR && (d.width & 1) == 0 && (!vs_log || (d.height & 1) == 0)) {
+    // even sizes (every luma sample has its chroma sample): interpolation and colour four samples at a time
+    const int cy1 = oy ? min(cy + 1, chh - 1) : cy;
+    uint32_t o[12];
+    sub_unit16_to_rgb(make_uint4(wy[0], wy[1], wy[2], wy[3]), pu + (size_t)cy * su + cx0, pu + (size_t)cy1 * su + cx0,
+                      pv + (size_t)cy * sv + cx0, pv + (size_t)cy1 * sv + cx0, cw - cx0, oy, o);
+    store_any<12>(b.out + d.out_off + ((size_t)y * d.width + x0) * 3, o, 3 * n);
+    return true;
+  }
+  const bool below = cy >= chh;  // odd height: no chroma row for the last luma row
   const int cy1 = min(cy + 1, chh - 1), cx8 = max(min(cx0 + 8, cw - 1), 0);
   int cu[2][9], cv[2][9];
 #pragma unroll
@@ -2150,11 +2352,7 @@ __device__ __forceinline__ bool rgb_sub_group(const DecodeBatchDev &b, const Hcj
 // the instances the batch needs).  (Planes that are not 8-byte aligned - never produced by the library - go pixel by
 // pixel through up_sample.)
 template <bool PLANAR, bool SUB>  // PLANAR: planar 4:4:4 Y,U,V (Planar_444.convert_from_420 / _422 of the frame) instead of RGB24
-__global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
-  const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
-  if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB || (!PLANAR && d.fused_rgb)) return;
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
-  if (y >= d.height || x0 >= d.width) return;
+__device__ __forceinline__ void rgb_group(const DecodeBatchDev &b, const HcjImageDesc &d, int x0, int y) {
   const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off,
                 *pv = b.planes + d.comp[2].plane_off;
   const int sy = d.comp[0].decoded_w, su = d.comp[1].decoded_w, sv = d.comp[2].decoded_w;
@@ -2221,12 +2419,87 @@ __global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
   }
 }
 
+template <bool PLANAR, bool SUB>
+__global__ void __launch_bounds__(128, SUB ? 10 : 12) k_rgb(DecodeBatchDev b) {
+  const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
+  if (!d.valid || d.chroma == 0 || (d.chroma != 444) != SUB || (!PLANAR && d.fused_rgb)) return;
+  if (!PLANAR && SUB && !(d.width & 1) && !(d.chroma == 420 && (d.height & 1))) return;  // k_rgb_sub_pairs
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
+  if (y >= d.height || x0 >= d.width) return;
+  rgb_group<PLANAR, SUB>(b, d, x0, y);
+}
+
+// RGB24 of sub-sampled images of even size, two pixel rows (2 * blockIdx.y and the next) of a 16-pixel column per thread:
+// everything the pair needs - 32 luma samples, two chroma rows of nine samples per component - is requested before
+// anything is computed (the one-row form of k_rgb is bound by the latency of its loads: 49 % of the HBM peak), and for
+// 4:2:0 the two rows share their chroma rows.
+__global__ void __launch_bounds__(128, 8) k_rgb_sub_pairs(DecodeBatchDev b) {
+  const HcjImageDesc &d = b.descs[blockIdx.z + b.img_lo];
+  if (!d.valid || d.chroma == 0 || d.chroma == 444 || d.fused_rgb) return;
+  const int vs_log = d.chroma == 420 ? 1 : 0;
+  if ((d.width & 1) || (vs_log && (d.height & 1))) return;  // odd sizes: k_rgb
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y0 = blockIdx.y * 2;
+  if (y0 >= d.height || x0 >= d.width) return;
+  const uint8_t *py = b.planes + d.comp[0].plane_off, *pu = b.planes + d.comp[1].plane_off, *pv = b.planes + d.comp[2].plane_off;
+  const int sy = d.comp[0].decoded_w, su = d.comp[1].decoded_w, sv = d.comp[2].decoded_w;
+  const int cw = d.comp[1].actual_w, chh = d.comp[1].actual_h;
+  const bool two = y0 + 1 < d.height;
+  const int cx0 = x0 >> 1, nvalid = cw - cx0;
+  // chroma rows of the first and of the second pixel row (4:2:0: the same row, and the clamped row below it)
+  const int ca = vs_log ? blockIdx.y : y0, cb_ = vs_log ? min((int)blockIdx.y + 1, chh - 1) : min(y0 + 1, chh - 1);
+  uint32_t w0[4], w1[4] = {0u, 0u, 0u, 0u};
+  load16(py + (size_t)y0 * sy + x0, w0);
+  if (two) load16(py + (size_t)(y0 + 1) * sy + x0, w1);
+  const Chroma9 ua = load_chroma9(pu + (size_t)ca * su + cx0, nvalid), va = load_chroma9(pv + (size_t)ca * sv + cx0, nvalid);
+  const Chroma9 ub = load_chroma9(pu + (size_t)cb_ * su + cx0, nvalid), vb = load_chroma9(pv + (size_t)cb_ * sv + cx0, nvalid);
+  const int n = min(16, d.width - x0);
+  uint8_t *dst = b.out + d.out_off + ((size_t)y0 * d.width + x0) * 3;
+  uint32_t o[12];
+  sub_unit16_convert(make_uint4(w0[0], w0[1], w0[2], w0[3]), ua, ua, va, va, false, o);
+  store_any<12>(dst, o, 3 * n);
+  if (two) {
+    if (vs_log) sub_unit16_convert(make_uint4(w1[0], w1[1], w1[2], w1[3]), ua, ub, va, vb, true, o);
+    else sub_unit16_convert(make_uint4(w1[0], w1[1], w1[2], w1[3]), ub, ub, vb, vb, false, o);
+    store_any<12>(dst + (size_t)d.width * 3, o, 3 * n);
+  }
+}
+
+// The units that the fused tiles of sub-sampled images (idct_tile_rgb_sub) left over: the last pixel row of every MCU
+// row that has a chroma row below it, and the last 16 pixels of the rows of every tile that has a tile to its right.
+// One thread per group of 16 pixels, converted from the plane buffer like everything else in k_rgb.
+// grid (ceil(max groups of an image / 128), images)
+__global__ void __launch_bounds__(128, 10) k_rgb_deferred(DecodeBatchDev b) {
+  const HcjImageDesc &d = b.descs[blockIdx.y + b.img_lo];
+  if (!d.valid || d.fused_rgb != 2) return;
+  const int vs_log = d.comp[0].vs == 2 ? 1 : 0, rows = 8 << vs_log;
+  const int chh = d.comp[1].actual_h;
+  const int ngroups = (d.width + 15) / 16;
+  const int def_rows = vs_log ? (chh - 1) / 8 : 0;  // MCU rows my with a chroma row 8 * my + 8 below them
+  int tpr;
+  const int tm_bal = idct_tile_width(b, d, tpr);
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  int x0, y;
+  if (id < def_rows * ngroups) {
+    const int k = id / ngroups;
+    x0 = (id - k * ngroups) * 16;
+    y = rows * k + rows - 1;
+  } else {
+    const int id2 = id - def_rows * ngroups;
+    const int tx = id2 / d.height;
+    if (tx >= tpr - 1) return;
+    y = id2 - tx * d.height;
+    x0 = 16 * tm_bal * (tx + 1) - 16;
+  }
+  if (y >= d.height || x0 >= d.width) return;
+  rgb_group<false, true>(b, d, x0, y);
+}
+
 // Fused RGB24 images: the 8 x 8 pixels of every MCU that holds a block flagged for the 64-bit IDCT (pathological
 // coefficient sums, see HCJ_IDCT_L1_LIMIT) are recomputed with the model's arithmetic verbatim.  One thread per 32
 // blocks of an image looks at their flags; almost all of them find nothing.  grid (ceil(max blocks / 32 / 128), images)
 __global__ void __launch_bounds__(128) k_rgb444_fix(DecodeBatchDev b) {
   const HcjImageDesc &d = b.descs[blockIdx.y + b.img_lo];
-  if (!d.valid || !d.fused_rgb) return;
+  if (!d.valid || d.fused_rgb != 1) return;
   const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) * 32u;
   if (first >= d.nblocks) return;
   const uint64_t g0 = d.coef_off + first;
@@ -2258,6 +2531,9 @@ void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   if (b.img_hi <= b.img_lo || b.max_rgb_rows == 0) return;
   if (!planar444 && b.has_fused && b.max_blocks)
     k_rgb444_fix<<<dim3((b.max_blocks + 32 * 128 - 1) / (32 * 128), b.img_hi - b.img_lo), 128, 0, s>>>(b);
+  if (!planar444 && b.has_fused_sub) {
+    k_rgb_deferred<<<dim3((b.max_deferred_groups + 127) / 128, b.img_hi - b.img_lo), 128, 0, s>>>(b);
+  }
   dim3 block(128);
   dim3 grid((b.max_width / 16 + 127 + 1) / 128, b.max_rgb_rows, b.img_hi - b.img_lo);
   if (b.has_444) {
@@ -2266,7 +2542,10 @@ void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s) {
   }
   if (b.has_subsampled) {
     if (planar444) k_rgb<true, true><<<grid, block, 0, s>>>(b);
-    else k_rgb<false, true><<<grid, block, 0, s>>>(b);
+    else {
+      if (b.has_subsampled & 1) k_rgb_sub_pairs<<<dim3(grid.x, (b.max_rgb_rows + 1) / 2, grid.z), block, 0, s>>>(b);
+      if (b.has_subsampled & 2) k_rgb<false, true><<<grid, block, 0, s>>>(b);
+    }
   }
 }
 

@@ -60,8 +60,11 @@ struct DecodeBatchDev {
   int tile_mcus;                  // MCUs per IDCT tile (upper bound; per-image value derived in-kernel)
   uint32_t max_rgb_rows;          // max image height (RGB mode)
   int has_444, has_subsampled;    // the batch holds 4:4:4 / sub-sampled images that go through k_rgb: which instances to launch
-  int has_fused;                  // ... 4:4:4 images whose RGB24 is produced inside k_idct_persistent (HcjImageDesc::fused_rgb)
+                                  // (has_subsampled: bit 0 = of even size, bit 1 = of odd size)
+  int has_fused;                  // ... 4:4:4 images whose RGB24 is produced inside k_idct_persistent (HcjImageDesc::fused_rgb == 1)
+  int has_fused_sub;              // ... sub-sampled images of even size likewise (fused_rgb == 2; k_rgb_deferred finishes them)
   uint32_t max_blocks;            // max blocks of any image
+  uint32_t max_deferred_groups;   // max over fused sub-sampled images of the 16-pixel groups k_rgb_deferred converts
   uint32_t max_width;
   uint64_t total_blocks;
   // sub-range of the batch handled by one launch (the pipelined host path decodes chunk by chunk)
