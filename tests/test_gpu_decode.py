@@ -723,3 +723,29 @@ def test_fused_rgb_subsampled(hcj, ctx, orc, data):
     # the default: k_idct_persistent to planes, then k_rgb_sub_pairs (even sizes) / k_rgb (odd sizes)
     outs, st = ctx.decode_batch(jpgs, hcj.OUT_RGB24)
     assert st == [0] * len(jpgs) and [bytes(o) for o in outs] == want
+
+
+def test_destuff_three_kernel_form(hcj, ctx, orc, data):
+    """K1 has two forms: the chained scan with decoupled look-back (one kernel, the default) and count / scan / write
+    (HCJ_DESTUFF_3PASS=1).  Same results: files of many tiles, restart markers, stuffed bytes at tile boundaries,
+    terminators in the middle of a scan, truncated files."""
+    jpgs = [orc.encode(synth.frame(7300 + i, w, h, c), w, h, c, q, restart_interval=ri)
+            for i, (c, w, h, q, ri) in enumerate([(444, 640, 480, 98, 0), (420, 800, 608, 75, 8), (422, 512, 200, 100, 1), (420, 64, 48, 50, 0)])]
+    jpgs += [jpgs[0][: len(jpgs[0]) // 2] + b"\xff\xd9" + jpgs[0][len(jpgs[0]) // 2:], jpgs[1][:-300], data("Mouse480.jpg")]
+    os_env = __import__("os").environ
+    res = []
+    for three in (False, True):
+        if three:
+            os_env["HCJ_DESTUFF_3PASS"] = "1"
+        try:
+            with ctx.batch(jpgs, hcj.OUT_YUV) as b:
+                b.decode()
+                outs, st = b.fetch()
+                res.append((st, [None if o is None else bytes(o) for o in outs], [b.entropy(i) for i in range(len(jpgs)) if st[i] == 0]))
+        finally:
+            os_env.pop("HCJ_DESTUFF_3PASS", None)
+    assert res[0] == res[1]
+    for j, o, s_ in zip(jpgs, res[0][1], res[0][0]):
+        assert s_ == orc.decode_status(j)
+        if s_ == 0:
+            assert o == orc.decode(j).yuv()

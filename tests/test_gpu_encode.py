@@ -238,3 +238,29 @@ def test_encode_block_log(hcj, ctx, orc, case):
 ZIGZAG_INVERSE = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47,
                   55, 62, 63]
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 3])
+def test_encode_chunk_pipeline(hcj, ctx, orc, chunk):
+    """hcj_encode_batch moves its frames through the device in chunks (upload, kernels and download of neighbouring
+    chunks overlap; source frames and finished files are double-buffered): more chunks than buffers, a last chunk that
+    is short, and byte buffers that have to grow for a later chunk (flat frames first, noise at quality 100 last)."""
+    import os
+
+    w, h, chroma = 176, 96, 420
+    rng = np.random.default_rng(5)
+    n = len(synth.frame(0, w, h, chroma))
+    frames = [bytes([90 + i]) * n for i in range(3)] + [synth.frame(40 + i, w, h, chroma) for i in range(3)] + [rng.integers(0, 256, n, dtype=np.uint8).tobytes()]
+    old = os.environ.get("HCJ_ENC_CHUNK")
+    os.environ["HCJ_ENC_CHUNK"] = str(chunk)
+    try:
+        for q, ri in ((100, 0), (60, 5)):
+            outs, st = ctx.encode_batch(frames, w, h, chroma, q, ri)
+            assert st == [0] * len(frames)
+            for f, o in zip(frames, outs):
+                assert o == orc.encode(f, w, h, chroma, q, restart_interval=ri)
+    finally:
+        if old is None:
+            del os.environ["HCJ_ENC_CHUNK"]
+        else:
+            os.environ["HCJ_ENC_CHUNK"] = old

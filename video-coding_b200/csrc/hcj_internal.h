@@ -30,6 +30,7 @@ struct hcj_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t enc0 = nullptr, enc1 = nullptr;  // around the device work of the latest hcj_encode_batch
   bool enc_timed = false;
+  float enc_ms = 0.f;  // kernel time of the latest hcj_encode_batch, summed over its chunks
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the kernels of the next chunk
   cudaStream_t up_stream = nullptr;    // H2D of the next chunk's files overlaps both
   std::vector<cudaEvent_t> up_events;

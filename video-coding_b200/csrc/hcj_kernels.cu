@@ -407,13 +407,17 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
   __shared__ uint32_t s_warp[DS_THREADS / 32];
   __shared__ uint32_t s_min[DS_THREADS / 32];
   __shared__ unsigned long long s_prefix;
-  __shared__ __align__(16) uint32_t s_out[(DS_TILE + 32) / 4];
-  const uint32_t img = blockIdx.y + b.img_lo;
+  __shared__ __align__(16) uint32_t s_out[(DS_TILE + 32) / 4];  // the tile's kept bytes, compacted from offset 0
+  // grid (images, tiles): CTAs are dispatched image-fastest, so the tiles in flight at any moment are about the same
+  // tile of many images and a tile's predecessors have long published their inclusive records (tile-fastest, all tiles
+  // of one large image start together and every look-back walks back through hundreds of records: 2.08 ms against
+  // 1.94 ms for the three kernels on 128 x 4k 4:4:4)
+  const uint32_t img = blockIdx.x + b.img_lo;
   const HcjImageDesc *d = &b.descs[img];
   if (!d->valid) return;
   const uint32_t base0 = d->scan_start & ~15u;
   const uint32_t ntiles = d->file_len > base0 ? (d->file_len - base0 + DS_TILE - 1) / DS_TILE : 0;
-  const uint32_t t = blockIdx.x;
+  const uint32_t t = blockIdx.y;
   if (t >= ntiles) {
     if (t == 0 && threadIdx.x == 0) ds_write_state(b, d, img, 0, 0, false);  // a scan of zero bytes has no terminator
     return;
@@ -437,16 +441,54 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
     total += x;
   }
   const uint32_t excl = wbase + incl - cnt;
-  // ---- what lies before this tile
+  // ---- publish this tile's own counts at once: the tiles behind it can look back while this one compacts
   unsigned long long *recs = reinterpret_cast<unsigned long long *>(b.ds_tiles + d->ds_off);
-  if (warp == 0) {
-    const unsigned long long mine = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32) |
-                                    (tmin != 0xffffffffu ? DSR_TERM : 0ull);
-    unsigned long long before = 0;  // value and terminator bit of everything before this tile
-    if (t == 0) {
-      if (lane == 0) dsr_store(recs, mine | (2ull << 62));
+  const unsigned long long mine = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32) |
+                                  (tmin != 0xffffffffu ? DSR_TERM : 0ull);
+  if (tid == 0) dsr_store(recs + t, mine | ((t == 0 ? 2ull : 1ull) << 62));
+  // ---- compact the tile's kept bytes into shared memory, from offset 0
+  const uint32_t so = excl & 0xffffu;
+  if (c.anyff == 0u) {
+    const uint32_t q = so >> 2, sh = (so & 3u) * 8u;
+    if (sh == 0u) {
+      s_out[q] = c.w[0], s_out[q + 1] = c.w[1], s_out[q + 2] = c.w[2], s_out[q + 3] = c.w[3];
     } else {
-      if (lane == 0) dsr_store(recs + t, mine | (1ull << 62));
+      atomicOr(&s_out[q], c.w[0] << sh);
+      s_out[q + 1] = __funnelshift_l(c.w[0], c.w[1], sh);
+      s_out[q + 2] = __funnelshift_l(c.w[1], c.w[2], sh);
+      s_out[q + 3] = __funnelshift_l(c.w[2], c.w[3], sh);
+      atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
+    }
+  } else {
+    uint32_t o = so;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (c.emit[k] == 0x80808080u && c.ffz[k] == 0u) {
+        const uint32_t sh = (o & 3u) * 8u;
+        if (sh == 0u) {
+          s_out[o >> 2] = c.w[k];
+        } else {
+          atomicOr(&s_out[o >> 2], c.w[k] << sh);
+          atomicOr(&s_out[(o >> 2) + 1], c.w[k] >> (32u - sh));
+        }
+        o += 4;
+      } else if (c.emit[k] != 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t bit = 0x80u << (8 * i);
+          if (c.emit[k] & bit) {
+            const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
+            atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
+            o++;
+          }
+        }
+      }
+    }
+  }
+  // ---- what lies before this tile (warp 0; by now the predecessors have mostly published)
+  if (warp == 0) {
+    unsigned long long before = 0;  // value and terminator bit of everything before this tile
+    if (t != 0) {
       int base = (int)t - 1;
       for (;;) {
         const int idx = base - lane;
@@ -476,80 +518,54 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
   const uint32_t out0 = (uint32_t)before, mk0 = (uint32_t)((before & DSR_VALUE) >> 32);
   if (tid == 0 && (tmin != 0xffffffffu || t + 1 == ntiles))
     ds_write_state(b, d, img, out0 + (total & 0xffffu), mk0 + (total >> 16), tmin != 0xffffffffu);
-  // ---- compact the tile (as k_destuff_write)
-  uint8_t *ent = b.entropy + d->ent_off;
-  uint32_t *segs = b.seg_offs + d->seg_off;
-  const uint32_t nseg_expected = d->nseg_expected;
-  const uint32_t phase = out0 & 15u;
-  const uint32_t so = phase + (excl & 0xffffu);
-  if (c.anyff == 0u) {
-    const uint32_t q = so >> 2, sh = (so & 3u) * 8u;
-    if (sh == 0u) {
-      s_out[q] = c.w[0], s_out[q + 1] = c.w[1], s_out[q + 2] = c.w[2], s_out[q + 3] = c.w[3];
-    } else {
-      atomicOr(&s_out[q], c.w[0] << sh);
-      s_out[q + 1] = __funnelshift_l(c.w[0], c.w[1], sh);
-      s_out[q + 2] = __funnelshift_l(c.w[1], c.w[2], sh);
-      s_out[q + 3] = __funnelshift_l(c.w[2], c.w[3], sh);
-      atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
-    }
-  } else {
-    uint32_t o = so, opos = out0 + (excl & 0xffffu), mk = mk0 + (excl >> 16);
+  // ---- restart markers: interval mk starts at the output position of the byte behind the marker
+  if (c.mark[0] | c.mark[1] | c.mark[2] | c.mark[3]) {
+    uint32_t *segs = b.seg_offs + d->seg_off;
+    const uint32_t nseg_expected = d->nseg_expected;
+    uint32_t opos = out0 + (excl & 0xffffu), mk = mk0 + (excl >> 16);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (c.emit[k] == 0x80808080u && c.ffz[k] == 0u) {
-        const uint32_t sh = (o & 3u) * 8u;
-        if (sh == 0u) {
-          s_out[o >> 2] = c.w[k];
-        } else {
-          atomicOr(&s_out[o >> 2], c.w[k] << sh);
-          atomicOr(&s_out[(o >> 2) + 1], c.w[k] >> (32u - sh));
-        }
-        o += 4;
-        opos += 4;
-      } else if ((c.emit[k] | c.mark[k]) != 0u) {
+    for (int k = 0; k < 4; k++)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t bit = 0x80u << (8 * i);
-          if (c.emit[k] & bit) {
-            const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
-            atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
-            o++;
-            opos++;
-          } else if (c.mark[k] & bit) {
-            mk++;
-            if (mk < nseg_expected) segs[mk] = opos;  // interval mk starts here
-          }
+      for (int i = 0; i < 4; i++) {
+        const uint32_t bit = 0x80u << (8 * i);
+        if (c.emit[k] & bit) opos++;
+        else if (c.mark[k] & bit) {
+          mk++;
+          if (mk < nseg_expected) segs[mk] = opos;
         }
       }
-    }
   }
-  __syncthreads();
-  const uint8_t *s_bytes = reinterpret_cast<const uint8_t *>(s_out);
-  const uint32_t nbytes = total & 0xffffu, avail = phase + nbytes;
+  // ---- copy out: destination word k (16 bytes, aligned) takes the tile's bytes [16 k - phase, 16 k - phase + 16)
+  uint8_t *ent = b.entropy + d->ent_off;
+  const uint32_t phase = out0 & 15u, nbytes = total & 0xffffu, avail = phase + nbytes;
   uint8_t *dst0 = ent + (out0 - phase);  // 16-byte aligned
+  const uint8_t *s_bytes = reinterpret_cast<const uint8_t *>(s_out);
   const uint32_t w_lo = phase ? 1u : 0u, w_hi = avail >> 4;  // words [w_lo, w_hi) are wholly this tile's
-  for (uint32_t k = w_lo + tid; k < w_hi; k += DS_THREADS)
-    reinterpret_cast<uint4 *>(dst0)[k] = reinterpret_cast<const uint4 *>(s_out)[k];
+  for (uint32_t k = w_lo + tid; k < w_hi; k += DS_THREADS) {
+    const uint32_t sb = 16u * k - phase;  // first source byte
+    const uint32_t q = sb >> 2, sh = (sb & 3u) * 8u;
+    const uint32_t a0 = s_out[q], a1 = s_out[q + 1], a2 = s_out[q + 2], a3 = s_out[q + 3], a4 = s_out[q + 4];
+    reinterpret_cast<uint4 *>(dst0)[k] = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                                                    __funnelshift_r(a3, a4, sh));
+  }
   // partial words at both ends (shared with the neighbouring tiles): byte by byte
-  if (phase && (uint32_t)tid < 16u - phase && phase + tid < avail) dst0[phase + tid] = s_bytes[phase + tid];
+  if (phase && (uint32_t)tid < 16u - phase && (uint32_t)tid < nbytes) dst0[phase + tid] = s_bytes[tid];
   const uint32_t tail0 = max(w_hi << 4, w_lo << 4);
-  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_bytes[tail0 + tid];
+  if (tail0 + tid < avail && tail0 + tid >= phase && (uint32_t)tid < 16u) dst0[tail0 + tid] = s_bytes[tail0 + tid - phase];
 }
 
 static bool destuff_three_pass() {
-  // Measured on a B200 (gpurun_out/r02c_*): the one-pass kernel reads the input once but pays for the look-back with
-  // the whole CTA waiting at the barrier behind it: 1.07 ms against 0.885 ms for the three kernels on 1024 x 1080p
-  // (2.89 against 1.94 ms on 128 x 4k 4:4:4 q95).  The three-pass form stays the default; HCJ_DESTUFF_1PASS=1 selects
-  // the chained scan for A/B measurements.
-  static const bool v = getenv("HCJ_DESTUFF_1PASS") == nullptr;
-  return v;
+  // Measured on a B200 (gpurun_out/r02x_*, 1024 x 1080p / 128 x 4k 4:4:4 q95): three kernels 0.886 / 1.94 ms; the chained
+  // scan with the look-back in front of the compaction and a tile-fastest grid 1.07 / 2.89 ms; with every tile's own
+  // counts published before it compacts, the look-back behind the compaction and an image-fastest grid 0.74 / 1.58 ms.
+  // HCJ_DESTUFF_3PASS=1 selects the three kernels (A/B measurements, tests).
+  return getenv("HCJ_DESTUFF_3PASS") != nullptr;
 }
 
 void launch_destuff(const DecodeBatchDev &b, cudaStream_t s) {
-  if (!destuff_three_pass()) {
+  if (!destuff_three_pass() && b.max_ds_tiles <= 65535u) {  // (tiles are the grid's y dimension)
     if (b.img_hi <= b.img_lo) return;
-    k_destuff<<<dim3(b.max_ds_tiles ? b.max_ds_tiles : 1u, b.img_hi - b.img_lo), DS_THREADS, 0, s>>>(b);
+    k_destuff<<<dim3(b.img_hi - b.img_lo, b.max_ds_tiles ? b.max_ds_tiles : 1u), DS_THREADS, 0, s>>>(b);
     return;
   }
   if (b.img_hi <= b.img_lo) return;
