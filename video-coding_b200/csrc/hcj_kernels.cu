@@ -1,19 +1,23 @@
 // hcj_kernels.cu — decode kernels for sm_100a.
 //
-//   k_destuff_count / _scan / _write   D3  extract_entropy_coded_bits (decoder.ml:261-281) + restart-marker
-//                                          scan, tile-parallel
-//   k_huff_restart                     D6  huffman_decode per restart interval (stated extension), DC
+//   k_destuff                          D3  extract_entropy_coded_bits (decoder.ml:261-281) + restart-marker scan in one
+//                                          pass: a chained scan with decoupled look-back over 4 KiB tiles
+//                                          (k_destuff_count / _scan / _write: the three-kernel form, HCJ_DESTUFF_3PASS)
+//   k_huff_restart                     D6  huffman_decode per SHORT restart interval (stated extension), DC
 //                                          resolved in-thread: fast steps in lock step per block
-//   k_spec_sync x2 / _fix / _write     D6  huffman_decode of a scan without restart markers: self-synchronising
-//                                          speculative subsequence decode over the whole batch, per-image
-//                                          fix-point on a compacted list, prefix sums for block indices and
-//                                          DC predictors (decoder.ml:118-165,347-397), exact pass
-//   k_idct_persistent                  D7-D11 dequantise + inverse zig-zag + Chen IDCT + clip + store (+ crop)
-//   k_rgb                              D12/D13 Planar_444 up-sampling + stated YCbCr->RGB
-//   k_idct_blocks, k_compare           debug tap (Component.recon), Ocompare on the device
+//   k_spec_units / _sync / _fix /      D6  huffman_decode of scans without restart markers and of LONG restart
+//   _write                                 intervals: self-synchronising speculative subsequence decode over the whole
+//                                          batch (one pass with a guessed-state warm-up, multi-symbol AC look-ups),
+//                                          per-image fix-point on a compacted list, segmented prefix sums for block
+//                                          indices and DC predictors (decoder.ml:118-165,347-397), exact pass on whole MCUs
+//   k_idct_persistent                  D7-D11 dequantise + inverse zig-zag + Chen IDCT + clip/level-shift + crop + store;
+//                                          the FUSED instance also converts to RGB24 inside the tile (4:4:4; sub-sampled
+//                                          opt-in, k_rgb_deferred / k_rgb444_fix finish it)
+//   k_rgb, k_rgb_sub_pairs             D12/D13 Planar_444 up-sampling + stated YCbCr->RGB from the plane buffer
+//   k_idct_blocks, k_block_log, k_compare*  debug taps (Component.recon, Component.Summary), Ocompare on the device
 //
 // None of this is GEMM-shaped: no tensor cores.  The entropy kernels are bound by instruction issue and
-// shared-memory table look-ups, the IDCT kernel by integer issue at 50 % of the HBM roofline (DESIGN.md has
+// shared-memory table look-ups, the IDCT kernel by integer issue at 67 % of the HBM roofline (DESIGN.md has
 // the byte counts and the ncu numbers).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -1520,9 +1524,9 @@ int huff_spec_kernel_count(const DecodeBatchDev &b) { return 3 + (b.spec_has_uni
 // K5: fused dequantise + inverse zig-zag + Chen IDCT + clip/level shift + store (+ crop).
 //
 // A CTA owns up to `tile_mcus` consecutive MCUs of one MCU row.  Their coefficient blocks are one
-// contiguous run in HBM (block order = decode_seq order) and are staged into shared memory with
-// 16-byte cp.async copies; block rows are padded to 144 bytes so that the per-thread 16-byte reads are
-// bank-conflict free.  One thread reconstructs one 8x8 block entirely in registers; threads are ordered
+// contiguous run in HBM (block order = decode_seq order) and are staged into shared memory by ONE TMA tensor
+// copy per tile (cp.async.bulk.tensor.2d, 128-byte swizzle: the per-thread 16-byte reads of a quarter-warp are
+// bank-conflict free in a dense tile).  One thread reconstructs one 8x8 block entirely in registers; threads are ordered
 // (component, block row, MCU, block column) so that a warp stores 32 horizontally adjacent blocks:
 // every store instruction writes 256 contiguous bytes of one image row.
 // ================================================================================================
