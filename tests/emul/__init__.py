@@ -104,7 +104,7 @@ def decode_speculative(jpeg, nblocks, scan_start, T=64, S=1024):
 
 def decode_units(jpeg, nblocks, scan_start, T=64, S=1024, flags=1):
     """Restart intervals decoded as units of the speculative decoder (long intervals, k_spec_*)."""
-    ent, segs = split_entropy(jpeg, scan_start, True)
+    ent, segs = split_entropy(jpeg, scan_start, b"\xff\xdd" in jpeg[:scan_start])  # RSTn only splits files that carry a DRI segment
     so = np.array(segs, np.uint32)
     coefs = np.full((nblocks, 64), 0x5A5A, np.int16)
     rounds = C.c_int()

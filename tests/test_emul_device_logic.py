@@ -157,8 +157,10 @@ def test_truncated_stream_zero_extension(orc, data):
 def test_corrupt_short_scans_speculative(orc, data):
     """Damaged scans of small images, where what is left of the data ends long before the blocks do: the blocks that
     begin beyond the end of the data (the model's reader delivers zeros there) belong to the thread that gets there,
-    whichever subsequence it started in.  `corrupt_flat_48x98.jpg` is the case the GPU fuzz sweep found."""
-    cases = [data("corrupt_flat_48x98.jpg")]
+    whichever subsequence it started in.  `corrupt_flat_48x98.jpg` is the case the GPU fuzz sweep found;
+    `corrupt_undefined_dc_at_mcu_start.jpg` the soak's: an undefined DC code exactly where a subsequence's first MCU
+    begins (the thread that starts there must raise it, so the start is where the DC symbol is looked for)."""
+    cases = [data("corrupt_flat_48x98.jpg"), data("corrupt_undefined_dc_at_mcu_start.jpg")]
     rng = np.random.default_rng(17)
     for i in range(30):
         chroma = int(rng.choice([420, 422, 444]))

@@ -353,13 +353,16 @@ HCJ_HD void subseq_sync(const ScanCtx &sc, const Local L, uint32_t p, uint32_t c
   while (br.pos < hi) {
     const bool isdc = z == 0u;
     const Symbol s = read_symbol(br, L, t, isdc);
-    if (s.e == 0u) {  // undefined code: resynchronise one bit later
-      br.skip(1);
-      continue;
-    }
+    // The first MCU start is where its DC symbol is LOOKED FOR: if the code there is undefined, the exact pass of the
+    // thread that starts here raises what the model raises (found by the soak: the position used to be recorded after
+    // the skipped bits, and the error was lost).
     if (isdc && c == 0u && r.first_p == 0xffffffffu) {
       r.first_p = br.pos, r.nbefore = nstart;
       dpre[0] = d0, dpre[1] = d1, dpre[2] = d2, dpre[3] = d3;
+    }
+    if (s.e == 0u) {  // undefined code: resynchronise one bit later
+      br.skip(1);
+      continue;
     }
     br.skip(s.nbits);
     const int32_t diff = isdc ? s.value : 0;
@@ -704,13 +707,13 @@ HCJ_HD void sync_ac_step_single(SyncLane &s, const FastTables T) {
 HCJ_HD void sync_dc_step(SyncLane &s, const FastTables T, int32_t *dpre) {
   const uint32_t win = s.br.window();
   const uint32_t e = fast_lookup(T, s.tdc, win, true);
+  if (s.c == 0u && s.first_p == 0xffffffffu) {  // (where the DC symbol is looked for, defined or not: see subseq_sync)
+    s.first_p = s.br.pos, s.nbefore = s.nstart;
+    dpre[0] = s.d0, dpre[1] = s.d1, dpre[2] = s.d2, dpre[3] = s.d3;
+  }
   if (e == HCJ_FAST_NONE) {
     s.br.consume(1u);
     return;
-  }
-  if (s.c == 0u && s.first_p == 0xffffffffu) {
-    s.first_p = s.br.pos, s.nbefore = s.nstart;
-    dpre[0] = s.d0, dpre[1] = s.d1, dpre[2] = s.d2, dpre[3] = s.d3;
   }
   const int32_t v = fast_value(win, byte_of(e, 1), byte_of(e, 2));
   s.d0 += s.comp == 0u ? v : 0;
