@@ -482,7 +482,10 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       // measured: 4096 bits for 65-bit blocks (1080p q75: 7.8 ms vs 8.0 ms at 8192), 8192 bits for 175-bit blocks
       // (4k 4:4:4 q95: 11.5 ms vs 12.9 ms at 4096): the per-subsequence work is per block, not per bit
       const uint64_t est_bits = (uint64_t)(d.file_len - d.scan_start) * 8;  // upper bound of the destuffed length
-      const uint32_t s0 = sub_log2_env ? 1u << sub_log2 : (est_bits > (uint64_t)d.nblocks * 120 ? 8192u : 4096u);
+      // round 2 (one synchronisation pass with a 2048-bit warm-up in front of every subsequence, exact pass on whole MCUs):
+      // longer subsequences pay less warm-up per bit and leave the lanes of the exact pass more alike: 1080p q75 K3
+      // 5.80 / 5.25 / 4.88 / 5.73 ms at 2048 / 4096 / 8192 / 16384 bits (gpurun_out/r03f_*), so 8192 from 2 Mbit up
+      const uint32_t s0 = sub_log2_env ? 1u << sub_log2 : ((est_bits > (uint64_t)d.nblocks * 120 || est_bits >= (1ull << 21)) ? 8192u : 4096u);
       // ... and cut so that the subsequences fill whole CTAs of the exact pass (512 threads): 1080p q75 has ~800
       // subsequences of 4096 bits, i.e. a second CTA with 44 % of its lanes idle; 1024 of ~3150 bits keep all busy.
       // (The count is bounded from above here: one subsequence beyond the last full CTA would cost a CTA of its own.)
