@@ -1531,7 +1531,6 @@ int huff_spec_kernel_count(const DecodeBatchDev &b) { return 3 + (b.spec_has_uni
 // every store instruction writes 256 contiguous bytes of one image row.
 // ================================================================================================
 constexpr int IDCT_MAX_THREADS = HCJ_IDCT_THREADS;
-constexpr int IDCT_ROW_U4 = 9;  // 144 bytes per staged block
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
