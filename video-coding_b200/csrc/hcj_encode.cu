@@ -746,8 +746,12 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
   auto upload = [&](int k) {  // frames of chunk k -> their slot, behind the kernels that last read it
     const int lo = k * ch, hi = std::min(n, lo + ch);
     if (k >= 2 && err == cudaSuccess) err = cudaStreamWaitEvent(us, ev_src_free[k - 2], 0);
-    for (int i = lo; i < hi && err == cudaSuccess; i++)
-      err = cudaMemcpyAsync(src_slot[k & 1] + (uint64_t)(i - lo) * e.frame_bytes, yuv[i], e.frame_bytes, cudaMemcpyHostToDevice, us);
+    for (int i = lo; i < hi && err == cudaSuccess;) {  // frames that lie back to back in host memory go up as one copy
+      int j = i + 1;
+      while (j < hi && yuv[j] == yuv[j - 1] + e.frame_bytes) j++;
+      err = cudaMemcpyAsync(src_slot[k & 1] + (uint64_t)(i - lo) * e.frame_bytes, yuv[i], e.frame_bytes * (uint64_t)(j - i), cudaMemcpyHostToDevice, us);
+      i = j;
+    }
     if (err == cudaSuccess) err = cudaEventRecord(ev_up[k], us);
   };
   if (st == HCJ_OK && nchunks > 0) upload(0);
