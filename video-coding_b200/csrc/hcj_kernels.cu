@@ -1805,18 +1805,14 @@ __device__ __forceinline__ uint32_t ycc_to_rgb_raw(int Y, int Cb, int Cr) {
 // 4 pixels -> 12 bytes of RGB: the stated formula with the "+ Y" and the rounding constant folded into the
 // accumulator of the multiply-adds: Y + ((k * C + 32768) >> 16) == ((Y << 16 | 0x8000) + k * C) >> 16 exactly (the shift
 // is arithmetic and Y << 16 is a multiple of 65536).  wcb_s / wcr_s: the chroma bytes with bit 7 flipped (= C - 128 as
-// signed bytes); one PRMT each extracts a sign-extended sample, one the accumulator.
-// byte I of x, sign extended (prmt's replicate-sign selector; __byte_perm documents three selector bits only)
-template <int I>
-__device__ __forceinline__ int sext_byte(uint32_t x) {
-  int r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0x8880u | I | (I << 4) | (I << 8) | (I << 12)));
-  return r;
-}
+// signed bytes); one dp4a each extracts a sign-extended sample, one PRMT builds the accumulator.
 template <int I>
 __device__ __forceinline__ uint32_t ycc_pixel(uint32_t wy, uint32_t wcb_s, uint32_t wcr_s) {
   const int t = (int)__byte_perm(wy, 0x00008000u, 0x4054 | (I << 8));
-  const int cb = sext_byte<I>(wcb_s), cr = sext_byte<I>(wcr_s);
+  // the sign-extended chroma bytes come from dp4a (x . one-hot byte selector), not from a PRMT: the colour kernels are bound
+  // by the alu pipe (78 % busy against 18 % for the fma pipe), k_rgb_sub_pairs 2.39 -> 2.27 ms per 1024 x 1080p; the
+  // accumulator built the same way (dp4a + IMAD for one PRMT) 2.25 ms: not kept
+  const int cb = __dp4a((int)wcb_s, 1 << (8 * I), 0), cr = __dp4a((int)wcr_s, 1 << (8 * I), 0);
   const int r = (91881 * cr + t) >> 16;
   const int g = (-46802 * cr + (-22554 * cb + t)) >> 16;
   const int bl = (116130 * cb + t) >> 16;
