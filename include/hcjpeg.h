@@ -223,7 +223,10 @@ int hcj_idct_blocks(hcj_ctx *ctx, const int16_t *coefs, size_t nblocks, const ui
  * plane linearly, so a width that is not a multiple of 8 shears the image: Plane.blit, plane.ml:20).
  * restart_interval 0 reproduces the model byte-for-byte; >0 is the stated DRI/RSTn extension.
  * out_len[i] is the length of frame i's file whether or not it fitted: with HCJ_ERR_BUFFER_TOO_SMALL in status[i] it is
- * the capacity a second call needs (hcj_encode_bound is the bound that never fails). */
+ * the capacity a second call needs (hcj_encode_bound is the bound that never fails).
+ * The frames go through the device in chunks (64 by default) on three streams - upload of the next chunk, kernels,
+ * download of the previous chunk's files - so with pinned frame buffers (hcj_host_alloc) the call runs at the link's
+ * host-to-device rate; frames that lie back to back in host memory go up as one copy per chunk. */
 int hcj_encode_batch(hcj_ctx *ctx, const uint8_t *const *yuv, int n, int width, int height, int chroma, int quality,
                      int restart_interval, uint8_t *const *out, const size_t *out_capacity, size_t *out_len,
                      int *status);
@@ -304,8 +307,8 @@ int hcj_batch_compare(hcj_ctx *ctx, hcj_batch *b, const uint8_t *const *ref, con
  * ms[0..*nstages) in launch order and synchronises.  Stage names: hcj_decode_stage_name(i). */
 int hcj_batch_decode_stages(hcj_ctx *ctx, hcj_batch *b, float *ms, int capacity, int *nstages);
 const char *hcj_decode_stage_name(int i);
-/* Device time of the latest hcj_encode_batch on this context: from the first kernel (frames already in HBM)
- * to the last one (files complete in HBM), including the one host round trip that sizes the byte buffers. */
+/* Kernel time of the latest hcj_encode_batch on this context, summed over its chunks (CUDA events around the two
+ * kernel phases of every chunk; the host's sizing step between them is not device work). */
 int hcj_encode_last_device_ms(hcj_ctx *ctx, float *ms);
 /* ms between two points on the context's stream */
 int hcj_timer_start(hcj_ctx *ctx);
