@@ -484,7 +484,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       const uint64_t est_bits = (uint64_t)(d.file_len - d.scan_start) * 8;  // upper bound of the destuffed length
       // round 2 (one synchronisation pass with a 2048-bit warm-up in front of every subsequence, exact pass on whole MCUs):
       // longer subsequences pay less warm-up per bit and leave the lanes of the exact pass more alike: 1080p q75 K3
-      // 5.80 / 5.25 / 4.88 / 5.73 ms at 2048 / 4096 / 8192 / 16384 bits (gpurun_out/r03f_*), so 8192 from 2 Mbit up
+      // 5.80 / 5.25 / 4.88 / 5.73 ms at 2048 / 4096 / 8192 / 16384 bits (profiles/r02_experiments/r03f_*), so 8192 from 2 Mbit up
       const uint32_t s0 = sub_log2_env ? 1u << sub_log2 : ((est_bits > (uint64_t)d.nblocks * 120 || est_bits >= (1ull << 21)) ? 8192u : 4096u);
       // ... and cut so that the subsequences fill whole CTAs of the exact pass (512 threads): 1080p q75 has ~800
       // subsequences of 4096 bits, i.e. a second CTA with 44 % of its lanes idle; 1024 of ~3150 bits keep all busy.
@@ -514,7 +514,7 @@ static int batch_create(hcj_ctx *c, const uint8_t *const *jpeg, const size_t *le
       // sub-sampled: luma 2x2 or 2x1, chroma 1x1, even size (the chroma planes are exactly half)
       const bool sub = f.ncomp == 3 && f.hs[0] == 2 && f.hs[1] == 1 && f.hs[2] == 1 && f.vs[1] == 1 && f.vs[2] == 1 &&
                        ((f.chroma == 420 && f.vs[0] == 2 && f.height % 2 == 0) || (f.chroma == 422 && f.vs[0] == 1)) && f.width % 2 == 0;
-      // Measured on 1024 x 1080p 4:2:0 (gpurun_out/r02s_*): fused 4.89 ms + 0.64 ms for the deferred units against
+      // Measured on 1024 x 1080p 4:2:0 (profiles/r02s_*): fused 4.89 ms + 0.64 ms for the deferred units against
       // 2.20 + 2.39 ms for k_idct_persistent + k_rgb_sub_pairs.  Both forms are bound by the instructions of the
       // conversion (about 24 per pixel: interpolation, four multiply-adds, shifts, saturating packs), which fusing does
       // not remove, and the deferred units cost more than the plane round trip saves: the two-kernel form stays the

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
 }
 
 static bool destuff_three_pass() {
-  // Measured on a B200 (gpurun_out/r02x_*, 1024 x 1080p / 128 x 4k 4:4:4 q95): three kernels 0.886 / 1.94 ms; the chained
+  // Measured on a B200 (profiles/r02_experiments/r02x_*, 1024 x 1080p / 128 x 4k 4:4:4 q95): three kernels 0.886 / 1.94 ms; the chained
   // scan with the look-back in front of the compaction and a tile-fastest grid 1.07 / 2.89 ms; with every tile's own
   // counts published before it compacts, the look-back behind the compaction and an image-fastest grid 0.74 / 1.58 ms.
   // HCJ_DESTUFF_3PASS=1 selects the three kernels (A/B measurements, tests).
