@@ -45,6 +45,15 @@ def expect_blocks(text):
     return re.findall(r"\[%expect\s*\{\|(.*?)\|\}\]", text, re.S)
 
 
+def dedent_sexp(block, start):
+    """The text `print_s` wrote: from the line that begins with `start`, without the indentation ppx_expect adds."""
+    i = block.index(start)
+    pad = i - (block.rfind("\n", 0, i) + 1)
+    lines = block[i - pad :].rstrip().split("\n")
+    assert all(l[:pad].strip() == "" for l in lines)
+    return "\n".join(l[pad:] for l in lines) + "\n"
+
+
 g = {"_about": "goldens lifted from hardcamls/video-coding's own tests by make_golden.py"}
 
 # ---- data files (jpeg/test_data) ---------------------------------------------------------
@@ -129,6 +138,8 @@ g["header_480x320_q20_420"] = {
     "source": "jpeg/model/test/test_encode_headers.ml:%d" % line_of(t, '"example header"'),
     "hex": hdr.hex(),
     "parsed": sexp_tables(sexp),
+    # the text itself: print_s [%message (header : Decoder.Header.t)] as Sexp.to_string_hum lays it out
+    "sexp_text": dedent_sexp(blk, "(header"),
 }
 
 # ---- Mouse480 header + first 64 destuffed entropy bytes (hardcaml/test/test_codeblock_decoder.ml)
@@ -142,6 +153,7 @@ g["mouse480"] = {
     "source": "jpeg/hardcaml/test/test_codeblock_decoder.ml:%d" % line_of(t, '("String.subo entropy_bits ~len:64"'),
     "entropy_first64_hex": first64.hex(),
     "parsed": sexp_tables(blk[blk.index("(headers") :]),
+    "sexp_text": dedent_sexp(blk, "(headers"),  # print_s [%message (headers : Model.Header.t)]
 }
 
 # ---- encoder code tables (test_tables.ml) --------------------------------------------------
@@ -250,6 +262,54 @@ for m in re.finditer(r'let%expect_test "([^"]+)" =(.*?)\n;;', t, re.S):
     name, body = m.groups()
     ups[name] = [ints(b) for b in expect_blocks(body)]
 g["planar_444"] = {"source": "tools/src/planar_444.ml:139-249", "dumps": ups}
+
+# ---- every multi-line s-expression any expect test of the reference holds, as laid out by Sexp.to_string_hum ------
+# (pins the layout engine of hcjpeg/sexp.py: parse the text, print it again, compare)
+def top_level_sexps(block):
+    """(start, end) of the balanced top-level lists of an expect block; None if the block is not made of s-expressions."""
+    spans, depth, start, i, n = [], 0, None, 0, len(block)
+    while i < n:
+        c = block[i]
+        if c == '"':
+            i += 1
+            while i < n and block[i] != '"':
+                i += 2 if block[i] == "\\" else 1
+        elif c == "(":
+            if depth == 0:
+                start = i
+            depth += 1
+        elif c == ")":
+            depth -= 1
+            if depth < 0:
+                return None
+            if depth == 0:
+                spans.append((start, i + 1))
+        i += 1
+    return spans if depth == 0 else None
+
+
+layouts = []
+for root, _, names in sorted(os.walk(REF)):
+    for name in sorted(names):
+        if not name.endswith(".ml"):
+            continue
+        rel = os.path.relpath(os.path.join(root, name), REF)
+        t = read(rel)
+        for m in re.finditer(r"\[%expect\s*\{\|(.*?)\|\}\]", t, re.S):
+            blk = m.group(1)
+            spans = top_level_sexps(blk)
+            for a, b in spans or []:
+                src = blk[a:b]
+                if "\n" not in src:
+                    continue
+                col = a - (blk.rfind("\n", 0, a) + 1)
+                lines = src.split("\n")
+                if any(l[:col].strip() for l in lines[1:]):
+                    continue  # not the output of one print_s
+                layouts.append({"source": "%s:%d" % (rel, line_of(t, src)), "text": "\n".join([lines[0]] + [l[col:] for l in lines[1:]])})
+with open(os.path.join(OUT, "sexp_layouts.json"), "w") as f:
+    json.dump({"_about": "multi-line print_s outputs of the reference's expect tests (make_golden.py)", "layouts": layouts}, f, indent=1)
+print("wrote", f.name, len(layouts), "layouts")
 
 with open(os.path.join(OUT, "reference_goldens.json"), "w") as f:
     json.dump(g, f, indent=1, sort_keys=True)
