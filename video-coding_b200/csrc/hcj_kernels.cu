@@ -113,7 +113,8 @@ __device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off
     // the byte at `start` sees prev = 0 even if the byte before it is FF
     if (start > off && start < off + 16u) {
       const uint32_t k = (start - off) >> 2, i = (start - off) & 3u, bit = 0x80u << (8 * i);
-      const uint32_t ch = (c.w[k] >> (8 * i)) & 0xffu;
+      const uint32_t wk = k == 0 ? c.w[0] : k == 1 ? c.w[1] : k == 2 ? c.w[2] : c.w[3];  // (no run-time index: the words stay in registers)
+      const uint32_t ch = (wk >> (8 * i)) & 0xffu;
 #pragma unroll
       for (int kk = 0; kk < 4; kk++)
         if ((uint32_t)kk == k) {
@@ -412,6 +413,16 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
   __shared__ uint32_t s_min[DS_THREADS / 32];
   __shared__ unsigned long long s_prefix;
   __shared__ __align__(16) uint32_t s_out[(DS_TILE + 32) / 4];  // the tile's kept bytes, compacted from offset 0
+  __shared__ uint32_t s_sel[16];  // byte-permute selector that squeezes a word's kept bytes (flags = index) to its low end
+  if (threadIdx.x < 16) {
+    uint32_t sel = 0x4444u, n = 0;  // 4 = a byte of the zero operand
+    for (uint32_t i = 0; i < 4; i++)
+      if (threadIdx.x >> i & 1u) {
+        sel = (sel & ~(0xfu << (4 * n))) | (i << (4 * n));
+        n++;
+      }
+    s_sel[threadIdx.x] = sel;  // published by the barrier inside ds_classify
+  }
   // grid (images, tiles): CTAs are dispatched image-fastest, so the tiles in flight at any moment are about the same
   // tile of many images and a tile's predecessors have long published their inclusive records (tile-fastest, all tiles
   // of one large image start together and every look-back walks back through hundreds of records: 2.08 ms against
@@ -464,29 +475,21 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
       atomicOr(&s_out[q + 4], c.w[3] >> (32u - sh));
     }
   } else {
+    // some byte goes (or an FF arrives late, behind its 00): every word is squeezed by ONE byte permute whose selector
+    // comes from a 16-entry table indexed by the word's four keep flags, and ORed in at its byte offset.  No branches:
+    // the few lanes of a warp that are here (6 % of the threads, but some lane of 86 % of the warps) run in step,
+    // whatever word their FF sits in (the byte loop this replaces ran its four cases one after the other).
     uint32_t o = so;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (c.emit[k] == 0x80808080u && c.ffz[k] == 0u) {
-        const uint32_t sh = (o & 3u) * 8u;
-        if (sh == 0u) {
-          s_out[o >> 2] = c.w[k];
-        } else {
-          atomicOr(&s_out[o >> 2], c.w[k] << sh);
-          atomicOr(&s_out[(o >> 2) + 1], c.w[k] >> (32u - sh));
-        }
-        o += 4;
-      } else if (c.emit[k] != 0u) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t bit = 0x80u << (8 * i);
-          if (c.emit[k] & bit) {
-            const uint32_t ch = (c.ffz[k] & bit) ? 0xffu : (c.w[k] >> (8 * i)) & 0xffu;
-            atomicOr(&s_out[o >> 2], ch << ((o & 3u) * 8u));
-            o++;
-          }
-        }
-      }
+      const uint32_t e = c.emit[k];
+      const uint32_t w2 = c.w[k] | ((c.ffz[k] >> 7) * 0xffu);                  // the 00 behind an FF emits the FF
+      const uint32_t sel = s_sel[((e >> 7) * 0x10204080u) >> 28];              // flags of bytes 0..3 -> bits 0..3
+      const uint32_t v = __byte_perm(w2, 0u, sel);                             // kept bytes at the low end, zeros above
+      const uint32_t sh = (o & 3u) * 8u;
+      atomicOr(&s_out[o >> 2], v << sh);
+      atomicOr(&s_out[(o >> 2) + 1], __funnelshift_l(v, 0u, sh));              // v >> (32 - sh); 0 for sh = 0
+      o += (uint32_t)__popc(e);
     }
   }
   // ---- what lies before this tile (warp 0; by now the predecessors have mostly published)
@@ -527,17 +530,19 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
     uint32_t *segs = b.seg_offs + d->seg_off;
     const uint32_t nseg_expected = d->nseg_expected;
     uint32_t opos = out0 + (excl & 0xffffu), mk = mk0 + (excl >> 16);
+    // one iteration per marker (a lane rarely holds more than one), not one per byte: the interval starts at the
+    // output position of the bytes kept in front of the marker
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint32_t bit = 0x80u << (8 * i);
-        if (c.emit[k] & bit) opos++;
-        else if (c.mark[k] & bit) {
-          mk++;
-          if (mk < nseg_expected) segs[mk] = opos;
-        }
+    for (int k = 0; k < 4; k++) {
+      uint32_t m = c.mark[k] & ~c.emit[k];  // (a flag is never both; the byte loop this replaces gave emit precedence)
+      while (m) {
+        const uint32_t bit = m & (0u - m);  // the lowest flag = the first marker of the word
+        mk++;
+        if (mk < nseg_expected) segs[mk] = opos + (uint32_t)__popc(c.emit[k] & (bit - 1u));
+        m ^= bit;
       }
+      opos += (uint32_t)__popc(c.emit[k]);
+    }
   }
   // ---- copy out: destination word k (16 bytes, aligned) takes the tile's bytes [16 k - phase, 16 k - phase + 16)
   uint8_t *ent = b.entropy + d->ent_off;
