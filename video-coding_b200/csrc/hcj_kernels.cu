@@ -68,15 +68,14 @@ struct DsClass {
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {  // 0x80 in every byte of x that is 0 (exact)
   return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
 }
-__device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off, uint32_t start, uint32_t flen, bool restart,
-                                               uint8_t *s_last, int tid) {
+__device__ __forceinline__ DsClass ds_classify(const uint8_t *file, uint32_t off, uint32_t start, uint32_t flen, bool restart) {
   DsClass c;
   uint4 v = make_uint4(0, 0, 0, 0);
   if (off < flen) v = __ldg(reinterpret_cast<const uint4 *>(file + off));
+  // the byte in front of the 16: its own load (the line is the neighbour thread's, an L1 hit) instead of an exchange
+  // through shared memory and a CTA barrier
+  const uint32_t prev = (off > start && off - 1 < flen) ? (uint32_t)__ldg(file + off - 1) : 0u;
   c.w[0] = v.x, c.w[1] = v.y, c.w[2] = v.z, c.w[3] = v.w;
-  s_last[tid] = (uint8_t)(v.w >> 24);
-  __syncthreads();
-  const uint32_t prev = tid == 0 ? (off > start && off - 1 < flen ? (uint32_t)__ldg(file + off - 1) : 0u) : s_last[tid - 1];
   // the model starts with prev = '\x00' (decoder.ml:279): the byte before `start` does not count
   uint32_t pff = (prev == 0xffu && off != start) ? 0x80u : 0u;  // "the previous byte is FF", for byte 0 of the word
   c.anyff = pff;
@@ -133,6 +132,8 @@ __device__ __forceinline__ uint32_t ds_count(const uint32_t m[4]) {
 // first terminator of the tile (block-wide min), 0xffffffff if none; drops everything at or after it
 __device__ __forceinline__ uint32_t ds_cut_at_terminator(DsClass &c, uint32_t off, uint32_t *s_min, int lane, int warp) {
   uint32_t tpos = 0xffffffffu;
+  // a terminating marker is in the last tile of a scan only: every other tile leaves after one barrier
+  if (!__syncthreads_or((c.term[0] | c.term[1] | c.term[2] | c.term[3]) != 0u)) return tpos;
   if (c.term[0] | c.term[1] | c.term[2] | c.term[3]) {
 #pragma unroll
     for (int k = 3; k >= 0; k--)
@@ -176,14 +177,13 @@ __device__ __forceinline__ bool ds_tile_setup(const DecodeBatchDev &b, const Hcj
 }
 
 __global__ void __launch_bounds__(DS_THREADS) k_destuff_count(DecodeBatchDev b) {
-  __shared__ uint8_t s_last[DS_THREADS];
   __shared__ uint32_t s_min[DS_THREADS / 32];
   __shared__ uint32_t s_cnt[DS_THREADS / 32];
   const HcjImageDesc *d;
   uint32_t off;
   if (!ds_tile_setup(b, d, off)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0);
   const uint32_t tmin = ds_cut_at_terminator(c, off, s_min, lane, warp);
   uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
 #pragma unroll
@@ -279,7 +279,6 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_scan(DecodeBatchDev b) {
 }
 
 __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) {
-  __shared__ uint8_t s_last[DS_THREADS];
   __shared__ uint32_t s_warp[DS_THREADS / 32];
   __shared__ uint32_t s_min[DS_THREADS / 32];
   // Compacted bytes of the tile, placed at the same 16-byte phase as their destination.  Zeroed first:
@@ -296,7 +295,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff_write(DecodeBatchDev b) 
   uint8_t *ent = b.entropy + d->ent_off;
   uint32_t *segs = b.seg_offs + d->seg_off;
   const uint32_t nseg_expected = d->nseg_expected;
-  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0);
   ds_cut_at_terminator(c, off, s_min, lane, warp);
   // block exclusive scan of (markers << 16 | kept bytes): at most 4096 bytes and 2048 markers per tile
   const uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
@@ -408,7 +407,6 @@ __device__ __forceinline__ void ds_write_state(const DecodeBatchDev &b, const Hc
 }
 
 __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
-  __shared__ uint8_t s_last[DS_THREADS];
   __shared__ uint32_t s_warp[DS_THREADS / 32];
   __shared__ uint32_t s_min[DS_THREADS / 32];
   __shared__ unsigned long long s_prefix;
@@ -421,7 +419,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
         sel = (sel & ~(0xfu << (4 * n))) | (i << (4 * n));
         n++;
       }
-    s_sel[threadIdx.x] = sel;  // published by the barrier inside ds_classify
+    s_sel[threadIdx.x] = sel;  // published by the barrier inside ds_cut_at_terminator
   }
   // grid (images, tiles): CTAs are dispatched image-fastest, so the tiles in flight at any moment are about the same
   // tile of many images and a tile's predecessors have long published their inclusive records (tile-fastest, all tiles
@@ -441,7 +439,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_destuff(DecodeBatchDev b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   reinterpret_cast<uint4 *>(s_out)[tid] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 2) reinterpret_cast<uint4 *>(s_out)[DS_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
-  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0, s_last, tid);
+  DsClass c = ds_classify(b.files + d->file_off, off, d->scan_start, d->file_len, d->ri > 0);
   const uint32_t tmin = ds_cut_at_terminator(c, off, s_min, lane, warp);
   // block exclusive scan of (markers << 16 | kept bytes): at most 4096 bytes and 2048 markers per tile
   const uint32_t cnt = (ds_count(c.mark) << 16) | ds_count(c.emit);
