@@ -280,6 +280,9 @@ int hcj_magnitude(int size, int value);
 /* Ocompare.square_error / max_difference per plane (tools/src/ocompare.ml:8-52) of two host frames. */
 int hcj_compare_planes(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,
                        int *max_difference);
+/* The same with Ocompare.total_difference (tools/src/ocompare.ml:20-30): what `oyuv compare mean-difference` divides. */
+int hcj_compare_planes_ex(hcj_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error,
+                          int *max_difference, int64_t *total_difference);
 
 /* `oyuv convert` on the device (tools/src/oconv.ml:111-133): a planar frame of `chroma` (420 / 422 / 444, planes as
  * Frame.create lays them out) is taken to 4:4:4 (Planar_444.convert_from_420 / _422), cropped to dst_width x dst_height

@@ -263,6 +263,23 @@ for m in re.finditer(r'let%expect_test "([^"]+)" =(.*?)\n;;', t, re.S):
     ups[name] = [ints(b) for b in expect_blocks(body)]
 g["planar_444"] = {"source": "tools/src/planar_444.ml:139-249", "dumps": ups}
 
+# ---- the cram tests as they are written: the `model` / `oyuv` command lines and the output they must print ----
+# (ffmpeg is not in this image: its commands and the comparisons against its output are left out and counted)
+cram = {}
+for name in ["model-encode-and-decode.t", "test-nonstandard-sizes.t", "mouse-decode.t"]:
+    t = read("jpeg/test/" + name)
+    steps, skipped = [], 0
+    for line in t.split("\n"):
+        if line.startswith("  $ "):
+            cmd = line[4:].strip()
+            keep = cmd.split()[0] in ("model", "oyuv") and "out_ffmpeg" not in cmd
+            skipped += 0 if keep or cmd.startswith(".") else 1
+            steps.append({"cmd": cmd, "out": []}) if keep else steps.append(None)
+        elif line.startswith("  ") and steps and steps[-1] is not None:
+            steps[-1]["out"].append(line[2:])
+    cram[name] = {"source": "jpeg/test/" + name, "steps": [x for x in steps if x], "skipped_ffmpeg_steps": skipped}
+g["cram_scripts"] = cram
+
 # ---- every multi-line s-expression any expect test of the reference holds, as laid out by Sexp.to_string_hum ------
 # (pins the layout engine of hcjpeg/sexp.py: parse the text, print it again, compare)
 def top_level_sexps(block):

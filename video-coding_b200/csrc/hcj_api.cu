@@ -1167,24 +1167,29 @@ int hcj_batch_compare(hcj_ctx *c, hcj_batch *b, const uint8_t *const *ref, const
 }
 
 int hcj_compare_planes(hcj_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error, int *max_difference) {
-  if (!c || !a || !b || !square_error || !max_difference) return HCJ_ERR_INVALID_ARG;
+  int64_t total = 0;
+  return hcj_compare_planes_ex(c, a, b, n, square_error, max_difference, &total);
+}
+
+int hcj_compare_planes_ex(hcj_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, int64_t *square_error, int *max_difference,
+                          int64_t *total_difference) {
+  if (!c || !a || !b || !square_error || !max_difference || !total_difference) return HCJ_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(c->device));
   void *d_a = nullptr, *d_b = nullptr, *d_r = nullptr;
   int st = c->alloc(&d_a, n + 16);
   if (st == HCJ_OK) st = c->alloc(&d_b, n + 16);
   if (st == HCJ_OK) st = c->alloc(&d_r, 256);
   cudaError_t e = cudaSuccess;
-  unsigned long long res[2] = {0, 0};
+  unsigned long long res[3] = {0, 0, 0};
   if (st == HCJ_OK) {
     e = cudaMemcpyAsync(d_a, a, n, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, b, n, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_r, 0, 16, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_r, 0, 24, c->stream);
     if (e == cudaSuccess) {
-      hcjk::launch_compare((const uint8_t *)d_a, (const uint8_t *)d_b, n, (unsigned long long *)d_r,
-                           (int *)((char *)d_r + 8), c->stream);
+      hcjk::launch_compare((const uint8_t *)d_a, (const uint8_t *)d_b, n, (unsigned long long *)d_r, c->stream);
       e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(res, d_r, 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res, d_r, 24, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   }
   c->release(d_a);
@@ -1194,6 +1199,7 @@ int hcj_compare_planes(hcj_ctx *c, const uint8_t *a, const uint8_t *b, size_t n,
   if (e != cudaSuccess) return HCJ_ERR_CUDA - (int)e;
   *square_error = (int64_t)res[0];
   *max_difference = (int)(res[1] & 0xffffffffu);
+  *total_difference = (int64_t)res[2];
   return HCJ_OK;
 }
 

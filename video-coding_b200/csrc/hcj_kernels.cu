@@ -2660,22 +2660,26 @@ void launch_block_log(const DecodeBatchDev &b, uint32_t img, uint32_t first, uin
 }
 
 // Ocompare.square_error / max_difference (tools/src/ocompare.ml:8-52).
-__global__ void k_compare(const uint8_t *a, const uint8_t *bb, size_t n, unsigned long long *sse, int *maxdiff) {
-  unsigned long long acc = 0;
+// res[0] = square error, res[1] = max difference, res[2] = total difference (Ocompare, tools/src/ocompare.ml:8-52)
+__global__ void k_compare(const uint8_t *a, const uint8_t *bb, size_t n, unsigned long long *res) {
+  unsigned long long acc = 0, tot = 0;
   int mx = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int dlt = abs((int)a[i] - (int)bb[i]);
     acc += (unsigned long long)(dlt * dlt);
+    tot += (unsigned long long)dlt;
     mx = max(mx, dlt);
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    tot += __shfl_xor_sync(0xffffffffu, tot, s);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(sse, acc);
-    atomicMax(maxdiff, mx);
+    atomicAdd(res, acc);
+    atomicMax(reinterpret_cast<int *>(res + 1), mx);
+    atomicAdd(res + 2, tot);
   }
 }
 
@@ -2712,11 +2716,11 @@ void launch_compare_planes(const uint8_t *out, const uint8_t *ref, const Compare
   k_compare_planes<<<dim3(32, 4, images), 256, 0, s>>>(out, ref, planes, acc);
 }
 
-void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff, cudaStream_t s) {
+void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *res, cudaStream_t s) {
   if (n == 0) return;
   size_t want = (n + 255) / 256;
   unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-  k_compare<<<blocks, 256, 0, s>>>(a, b, n, sse, maxdiff);
+  k_compare<<<blocks, 256, 0, s>>>(a, b, n, res);
 }
 
 // Per-device launch configuration, done once per context right after cudaSetDevice (hcj_ctx_create): the opt-in to

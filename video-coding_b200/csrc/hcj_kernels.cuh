@@ -92,8 +92,7 @@ int make_coef_tensor_map(DecodeBatchDev *b);
 void launch_rgb(const DecodeBatchDev &b, bool planar444, cudaStream_t s);
 void launch_idct_blocks(const int16_t *coefs, size_t nblocks, const uint16_t *qt, bool force_wide, uint8_t *out,
                         cudaStream_t s);
-void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *sse, int *maxdiff,
-                    cudaStream_t s);
+void launch_compare(const uint8_t *a, const uint8_t *b, size_t n, unsigned long long *res /* sse, max, total */, cudaStream_t s);
 
 size_t yuv_frame_bytes(int w, int h, int chroma);
 void launch_yuv_convert(const uint8_t *src, int sw, int sh, int schroma, int x_off, int y_off, uint8_t *dst, int dw, int dh, int dchroma,

@@ -178,6 +178,7 @@ _SIGS = {
     "hcj_write_headers": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "hcj_encode_quantized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "hcj_compare_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "hcj_compare_planes_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int), _P(C.c_int64)]),
     "hcj_quant_scale": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "hcj_encoder_code": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "hcj_mag": (C.c_int, [C.c_int, C.c_int]),
@@ -491,6 +492,15 @@ class Context:
         sse, mx = C.c_int64(), C.c_int()
         _check(lib().hcj_compare_planes(self._h, a.ctypes.data, b.ctypes.data, a.size, C.byref(sse), C.byref(mx)))
         return sse.value, mx.value
+
+    def compare_planes_ex(self, a, b):
+        """(square_error, max_difference, total_difference) of two planes (tools/src/ocompare.ml:8-52) on the device."""
+        a = np.ascontiguousarray(a, np.uint8).ravel()
+        b = np.ascontiguousarray(b, np.uint8).ravel()
+        assert a.size == b.size
+        sse, mx, tot = C.c_int64(), C.c_int(), C.c_int64()
+        _check(lib().hcj_compare_planes_ex(self._h, a.ctypes.data, b.ctypes.data, a.size, C.byref(sse), C.byref(mx), C.byref(tot)))
+        return sse.value, mx.value, tot.value
 
 
 def device_count():
