@@ -116,6 +116,7 @@ void launch_compare_planes(const uint8_t *out, const uint8_t *ref, const Compare
                            cudaStream_t s);
 
 // ---- encoder ----
+constexpr int HCJ_ENC_SLOT_WORDS = 16;  // blocks of up to 512 bits are packed once (k_block_bits) and only shifted into place (k_place)
 struct EncodeBatchDev {
   int n;                      // frames
   int ncomp, bpm;
@@ -138,6 +139,7 @@ struct EncodeBatchDev {
   const uint32_t *ac_codes;   // [2][256]
   int16_t *quant;             // [n][nblocks][64] zig-zag, DC absolute
   uint32_t *blk_bits;         // [n][nblocks] bit length of each block's code, later exclusive offsets per segment
+  uint32_t *blk_words;        // [n][nblocks][HCJ_ENC_SLOT_WORDS] every block's own bit string, first bit in bit 31 of word 0 (k_block_bits)
   uint32_t *seg_bytes;        // [n][nseg * seg_chunks + 1] stuffed byte length of every unit, later exclusive offsets
   uint8_t *raw;               // [n][raw_stride] unstuffed packed bits, segments byte-aligned
   uint64_t raw_stride;
