@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *statu
   pk.finish();
   if (!ok) atomicCAS(status + frame, 0, HCJ_ERR_ENCODER_PARAMS);
   e.blk_bits[(uint64_t)frame * (e.nblocks + 1) + blk] = pk.bits;
+  if (pk.bits > (uint32_t)HCJ_ENC_SLOT_WORDS * 32u) *e.long_blocks = 1u;  // (every writer stores the same value)
 }
 
 // ---- K7b: in-place exclusive scan of blk_bits per frame; entry [nblocks] receives the total ---------
@@ -531,10 +532,10 @@ static void launch_bit_lengths(const EncodeBatchDev &e, int *d_status, uint32_t 
   k_gather_totals<<<(e.n + 127) / 128, 128, 0, s>>>(e, d_totals);
 }
 
-static void launch_entropy(const EncodeBatchDev &e, cudaStream_t s) {
+static void launch_entropy(const EncodeBatchDev &e, bool long_blocks, cudaStream_t s) {
   dim3 gb((e.nblocks + 127) / 128, e.n);
   k_place<<<gb, 128, 0, s>>>(e);
-  k_pack<<<gb, 128, 0, s>>>(e);
+  if (long_blocks) k_pack<<<gb, 128, 0, s>>>(e);  // (0.1 ms per 512 x 1080p even when every CTA leaves at once)
   dim3 gs((e.nseg * e.seg_chunks + 3) / 4, e.n);
   k_seg_count<<<gs, 128, 0, s>>>(e);
   k_seg_scan<<<e.n, SCAN_THREADS, 0, s>>>(e);
@@ -703,7 +704,8 @@ int setup_encode(hcj_ctx *c, int n, int width, int height, int chroma, int quali
   if (entropy) {
     alloc((void **)&e.blk_bits, (uint64_t)n * (e.nblocks + 1) * 4);
     alloc((void **)&e.blk_words, (uint64_t)n * e.nblocks * hcjk::HCJ_ENC_SLOT_WORDS * 4);
-    alloc((void **)&e.out_len, 4 * (size_t)std::max(n, 1));
+    alloc((void **)&e.out_len, 4 * (size_t)std::max(n, 1) + 4);
+    if (st == HCJ_OK) e.long_blocks = e.out_len + std::max(n, 1);  // one flag behind the lengths
   }
   if (st != HCJ_OK) return st;
   e.qrecip = reinterpret_cast<const uint32_t *>(d_tables);
@@ -837,6 +839,7 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
     // phase 1: coefficients and the bit length of every block; the totals size the byte buffers
     if (err == cudaSuccess) err = cudaStreamWaitEvent(s, ev_up[k], 0);
     if (err == cudaSuccess) err = cudaMemsetAsync(S.d_status, 0, 4 * (size_t)m, s);
+    if (err == cudaSuccess) err = cudaMemsetAsync(e.long_blocks, 0, 4, s);
     cudaEventRecord(ev_t[4 * k + 0], s);
     hcjk::launch_encode(e, s);
     hcjk::launch_bit_lengths(e, S.d_status, e.out_len, s);
@@ -844,6 +847,8 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaEventRecord(ev_src_free[k], s);
     if (err == cudaSuccess) err = cudaMemcpyAsync(lens.data(), e.out_len, 4 * (size_t)m, cudaMemcpyDeviceToHost, s);
+    uint32_t long_blocks = 1;
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&long_blocks, e.long_blocks, 4, cudaMemcpyDeviceToHost, s);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) break;
     uint64_t max_bits = 0;
@@ -871,7 +876,7 @@ int hcj_encode_batch(hcj_ctx *c, const uint8_t *const *yuv, int n, int width, in
     if (k >= 2) err = cudaStreamWaitEvent(s, ev_down[k - 2], 0);
     if (err == cudaSuccess) err = cudaMemsetAsync(e.raw, 0, (uint64_t)m * e.raw_stride, s);  // the packer ORs into zeroed words
     cudaEventRecord(ev_t[4 * k + 2], s);
-    hcjk::launch_entropy(e, s);
+    hcjk::launch_entropy(e, long_blocks != 0, s);
     cudaEventRecord(ev_t[4 * k + 3], s);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaMemcpyAsync(lens.data(), e.out_len, 4 * (size_t)m, cudaMemcpyDeviceToHost, s);

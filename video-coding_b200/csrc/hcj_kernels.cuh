@@ -146,6 +146,7 @@ struct EncodeBatchDev {
   uint8_t *out;               // [n][out_stride] finished files
   uint64_t out_stride;
   uint32_t *out_len;          // [n]
+  uint32_t *long_blocks;      // != 0: some block of the chunk is longer than its slot (k_pack has work)
   const uint8_t *header;      // shared header bytes
   uint32_t header_len;
 };
