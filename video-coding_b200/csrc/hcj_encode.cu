@@ -1,13 +1,16 @@
 // hcj_encode.cu — encoder mirror (Encoder.encode_420/422/444, jpeg/model/src/encoder.ml) for sm_100a.
 //
 //   k_fdct_quant   E2,E4-E6  zero-padded block fetch, level shift, Chen FDCT, quantise, zig-zag
-//   k_block_bits   E7,E8     per block: DC differential + (run, size) symbols -> code length in bits
+//   k_block_bits   E7,E8     per block: DC differential + (run, size) symbols -> the block's code + magnitude fields packed
+//                            into its own 512-bit slot, and their length in bits (the field loop runs once per block:
+//                            the block staged in shared memory, one iteration per non-zero coefficient,
+//                            encode_block_fields_sparse)
 //   k_scan_bits    per frame: exclusive prefix sum of block bit lengths (one CTA walks the frame)
-//   (k_block_bits and k_pack stage the block in shared memory and walk its non-zero map: one loop iteration per
-//    non-zero coefficient, encode_block_fields_sparse)
-//   k_pack         E8,E9     per block: write code + magnitude fields at their bit offset (big-endian
-//                            32-bit words, atomicOr only on the two boundary words), 1-fill at the end of
-//                            every segment (flush_with_1s, bitstream_writer.ml:45-49)
+//   k_place        E8,E9     per block: the finished bit string shifted to its bit offset (big-endian 32-bit words,
+//                            atomicOr only on the two boundary words), 1-fill at the end of every segment
+//                            (flush_with_1s, bitstream_writer.ml:45-49)
+//   k_pack         E8,E9     blocks longer than their slot: the field loop again, straight to the bit offset (only
+//                            launched when a chunk holds such a block)
 //   k_seg_count    E9        per unit (segment, or 1 KiB of a lone segment): stuffed byte count
 //   k_seg_scan     per frame: prefix sum of unit sizes -> output offsets; copies the header
 //   k_stuff        E9,E10    per unit: byte copy with FF -> FF 00, RSTn between segments, EOI
