@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(128) k_block_bits(EncodeBatchDev e, int *statu
 // ---- K7b: in-place exclusive scan of blk_bits per frame; entry [nblocks] receives the total ---------
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bits(EncodeBatchDev e) {
-  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];  // inclusive sums of the warps, then their exclusive prefix
+  __shared__ uint32_t s_total;
   uint32_t *bits = e.blk_bits + (uint64_t)blockIdx.x * (e.nblocks + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t carry = 0;
@@ -247,16 +248,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bits(EncodeBatchDev e) {
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    // the 32 warp sums are scanned by warp 0 (every thread used to add them up itself: 32 shared-memory reads and 64
+    // additions per thread and round)
+    if (warp == 0) {
+      const uint32_t w = s_warp[lane];
+      uint32_t wi = w;
 #pragma unroll
-    for (int k = 0; k < SCAN_THREADS / 32; k++) {
-      uint32_t t = s_warp[k];
-      if (k < warp) wbase += t;
-      total += t;
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      s_warp[lane] = wi - w;
+      if (lane == 31) s_total = wi;
     }
-    if (i < e.nblocks) bits[i] = carry + wbase + incl - v;
-    carry += total;
     __syncthreads();
+    if (i < e.nblocks) bits[i] = carry + s_warp[warp] + incl - v;
+    carry += s_total;
+    __syncthreads();  // s_warp / s_total are written again in the next round
   }
   if (threadIdx.x == 0) bits[e.nblocks] = carry;
 }
