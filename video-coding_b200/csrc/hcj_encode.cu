@@ -528,7 +528,7 @@ void launch_encode(const EncodeBatchDev &e, cudaStream_t s) {
   k_fdct_quant<<<gb, 128, 0, s>>>(e);
 }
 
-int encode_kernel_count() { return 9; }
+int encode_kernel_count() { return 8; }  // k_fdct_quant, k_block_bits, k_scan_bits, k_gather_totals, k_place, k_seg_count, k_seg_scan, k_stuff (+ k_pack for chunks with long blocks)
 
 // Gathers the per-frame totals of the bit scan into a dense array for one small D2H copy.
 __global__ void k_gather_totals(EncodeBatchDev e, uint32_t *totals) {
