@@ -35,6 +35,27 @@ def test_cli_argument_forms():
     assert _ocaml_float(3.0) == "3" and _ocaml_float(0.5) == "0.5" and _ocaml_float(float("inf")) == "INF" and _ocaml_float(1e-5) == "1E-05"
 
 
+def test_cli_without_a_device_fails_loudly(tmp_path, monkeypatch, capsys):
+    """No CPU path behind the commands: without CUDA `model decode frame` leaves with status 1 and writes nothing; the host-only
+    `model decode header` still prints the pinned text (header parsing is host code in the library, as in the reference)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import hcjpeg.model
+
+    monkeypatch.setattr(hcjpeg.model, "_default_ctx", None)
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "m.jpg").write_bytes(open(os.path.join(GOLDEN, "mini.jpg"), "rb").read())
+    rc, out = run_cli(["model", "decode", "frame", "m.jpg", "o.yuv"])
+    assert rc == 1 and out == "" and not (tmp_path / "o.yuv").exists()
+    assert capsys.readouterr().err.strip() != ""  # the library's status text
+    rc, out = run_cli(["model", "decode", "header", "m.jpg"])
+    assert rc == 0 and out.startswith("(header\n ((frame\n   (((length 17) (sample_precision 8) (width 64) (height 64)")
+    with pytest.raises(SystemExit):
+        run_cli(["model", "frobnicate"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("script", ["model-encode-and-decode.t", "test-nonstandard-sizes.t", "mouse-decode.t"])
 def test_cram_script(script, goldens, orc, tmp_path, monkeypatch):
